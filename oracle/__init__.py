@@ -1,0 +1,202 @@
+"""CPU oracle for the VBD hot path -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end over ``liboracle_port.so`` (restated arithmetic) and, when present,
+``_ref/liboracle_ref.so`` (per-vertex arithmetic compiled from the reference's own headers).
+See ``vbd_oracle.cpp`` for the reference file:line each routine follows.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` legs may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_LIB = os.path.join(_HERE, "liboracle_port.so")
+REF_LIB = os.path.join(_HERE, "_ref", "liboracle_ref.so")
+
+# enums shared with the product (sim/vbd/Enums.h:9-28, graph/Enums.h)
+POSITION, INERTIA, KINETIC_ENERGY_MINIMUM, ADAPTIVE_VBD, ADAPTIVE_PBAT = range(5)
+ACCEL_NONE, ACCEL_CHEBYSHEV = 0, 1
+ORDER_NATURAL, ORDER_SMALLEST_DEGREE, ORDER_LARGEST_DEGREE = range(3)
+SELECT_LEAST_USED, SELECT_FIRST_AVAILABLE = range(2)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle(s). ``_ref`` is only (re)built where /root/reference exists."""
+    targets = ["port"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-C", _HERE, "-s"] + targets, check=True)
+
+
+class _Desc(C.Structure):
+    _fields_ = [
+        ("nV", C.c_int64), ("nT", C.c_int64),
+        ("X", C.c_void_p), ("E", C.c_void_p), ("v", C.c_void_p), ("aext", C.c_void_p),
+        ("rhoe", C.c_void_p), ("lame", C.c_void_p), ("dbc", C.c_void_p), ("nDbc", C.c_int64),
+        ("colors", C.c_void_p),
+        ("ordering", C.c_int), ("selection", C.c_int),
+        ("strategy", C.c_int), ("accel", C.c_int), ("omegaMode", C.c_int),
+        ("kD", C.c_double), ("detHZero", C.c_double), ("rho", C.c_double),
+    ]
+
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def _load(kind: str) -> C.CDLL:
+    if kind in _libs:
+        return _libs[kind]
+    path = PORT_LIB if kind == "port" else REF_LIB
+    if not os.path.exists(path):
+        if kind == "port":
+            build(ref=False)
+        else:
+            raise FileNotFoundError(f"{path} not built (needs /root/reference; run `make -C oracle ref`)")
+    lib = C.CDLL(path)
+    lib.vbdo_kind.restype = C.c_char_p
+    lib.vbdo_last_error.restype = C.c_char_p
+    lib.vbdo_create.restype = C.c_void_p
+    lib.vbdo_create.argtypes = [C.POINTER(_Desc)]
+    lib.vbdo_destroy.argtypes = [C.c_void_p]
+    lib.vbdo_step.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_int64]
+    lib.vbdo_sweeps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
+    lib.vbdo_size.restype = C.c_int64
+    lib.vbdo_size.argtypes = [C.c_void_p, C.c_char_p]
+    lib.vbdo_get_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    lib.vbdo_get_i64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    lib.vbdo_set_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    lib.vbdo_set_params.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.vbdo_objective.restype = C.c_double
+    lib.vbdo_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    lib.vbdo_objective_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    lib.vbdo_snh_eval.restype = C.c_double
+    lib.vbdo_snh_eval.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.vbdo_num_threads.restype = C.c_int
+    lib.vbdo_set_num_threads.argtypes = [C.c_int]
+    _libs[kind] = lib
+    return lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+_F64 = ("x", "v", "aext", "xt", "xtilde", "vt", "X", "m", "GP", "wg", "lame")
+_I64 = ("GVGp", "GVGe", "GVGilocal", "colors", "Pptr", "Padj")
+
+
+class Oracle:
+    """Double-precision CPU VBD integrator with the reference's semantics.
+
+    ``X`` is 3 x nV, ``E`` is 4 x nT (the reference's column-per-vertex / column-per-tet
+    convention, sim/vbd/Data.h:167-170).  ``kind`` = "port" | "reference".
+    """
+
+    def __init__(self, X, E, *, v=None, aext=None, rhoe=None, mue=None, lambdae=None, dbc=None,
+                 colors=None, ordering=ORDER_LARGEST_DEGREE, selection=SELECT_LEAST_USED,
+                 strategy=ADAPTIVE_PBAT, accel=ACCEL_NONE, rho=1.0, omega_mode=0, kD=0.0,
+                 detH_zero=1e-7, kind="port"):
+        self.lib = _load("port" if kind == "port" else "ref")
+        X = np.asarray(X, dtype=np.float64)
+        E = np.asarray(E, dtype=np.int64)
+        assert X.shape[0] == 3 and E.shape[0] == 4
+        self.nV, self.nT = X.shape[1], E.shape[1]
+        keep = []
+
+        def colmajor(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(a, dtype=dt).T)  # (n, rows): column-major of rows x n
+            keep.append(a)
+            return a
+
+        Xc, Ec = colmajor(X, np.float64), colmajor(E, np.int64)
+        vc, ac = colmajor(v, np.float64), colmajor(aext, np.float64)
+        lame = None
+        if mue is not None:
+            lame = np.ascontiguousarray(np.stack([np.asarray(mue, np.float64),
+                                                  np.asarray(lambdae, np.float64)], axis=1))
+        rhoe = None if rhoe is None else np.ascontiguousarray(rhoe, dtype=np.float64)
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, dtype=np.int64)
+        colors = None if colors is None else np.ascontiguousarray(colors, dtype=np.int64)
+        d = _Desc(self.nV, self.nT, _ptr(Xc), _ptr(Ec), _ptr(vc), _ptr(ac), _ptr(rhoe), _ptr(lame),
+                  _ptr(dbc), 0 if dbc is None else dbc.size, _ptr(colors), ordering, selection,
+                  strategy, accel, omega_mode, kD, detH_zero, rho)
+        self.h = self.lib.vbdo_create(C.byref(d))
+        if not self.h:
+            raise ValueError(self.lib.vbdo_last_error().decode())
+        self.kind = self.lib.vbdo_kind().decode()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.vbdo_destroy(self.h)
+            self.h = None
+
+    def step(self, dt, iterations, substeps=1):
+        self.lib.vbdo_step(self.h, dt, iterations, substeps)
+
+    def sweeps(self, dt, reps):
+        self.lib.vbdo_sweeps(self.h, dt, reps)
+
+    def get(self, name):
+        n = self.lib.vbdo_size(self.h, name.encode())
+        if name in _F64:
+            out = np.empty(n, dtype=np.float64)
+            rc = self.lib.vbdo_get_f64(self.h, name.encode(), _ptr(out))
+        elif name in _I64:
+            out = np.empty(n, dtype=np.int64)
+            rc = self.lib.vbdo_get_i64(self.h, name.encode(), _ptr(out))
+        else:
+            raise KeyError(name)
+        assert rc == 0
+        if name in ("x", "v", "aext", "xt", "xtilde", "vt", "X"):
+            return out.reshape(self.nV, 3).T.copy()
+        if name == "GP":
+            # 4 x 3nT, element e = columns 3e..3e+2 (sim/vbd/Data.h:191-192)
+            return out.reshape(3 * self.nT, 4).T.copy()
+        if name == "lame":
+            return out.reshape(self.nT, 2).T.copy()
+        return out
+
+    def set(self, name, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)
+        assert self.lib.vbdo_set_f64(self.h, name.encode(), _ptr(a)) == 0
+
+    def set_params(self, strategy, kD, detH_zero):
+        self.lib.vbdo_set_params(self.h, strategy, kD, detH_zero)
+
+    x = property(lambda s: s.get("x"), lambda s, a: s.set("x", a))
+    v = property(lambda s: s.get("v"), lambda s, a: s.set("v", a))
+
+    def objective(self, xk, xtilde, dt):
+        a = np.ascontiguousarray(np.asarray(xk, np.float64).T)
+        b = np.ascontiguousarray(np.asarray(xtilde, np.float64).T)
+        return self.lib.vbdo_objective(self.h, _ptr(a), _ptr(b), dt)
+
+    def objective_gradient(self, xk, xtilde, dt):
+        a = np.ascontiguousarray(np.asarray(xk, np.float64).T)
+        b = np.ascontiguousarray(np.asarray(xtilde, np.float64).T)
+        out = np.empty(3 * self.nV)
+        self.lib.vbdo_objective_gradient(self.h, _ptr(a), _ptr(b), dt, _ptr(out))
+        return out
+
+    @property
+    def num_threads(self):
+        return self.lib.vbdo_num_threads()
+
+    def set_num_threads(self, n):
+        self.lib.vbdo_set_num_threads(n)
+
+
+def snh_eval(F, mu, lam, kind="port"):
+    lib = _load("port" if kind == "port" else "ref")
+    f = np.ascontiguousarray(np.asarray(F, np.float64).T).reshape(-1)  # column-major
+    return lib.vbdo_snh_eval(_ptr(f), mu, lam)
