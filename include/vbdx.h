@@ -1,0 +1,207 @@
+/*
+ * vbdx.h -- C ABI of the B200-native Vertex Block Descent integrator.
+ *
+ * This is the drop-in boundary for the reference's VBD path.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/source/pbat unless
+ * they start with bindings/).  Conventions at the boundary are the reference's:
+ *   - matrices are column-major with one column per vertex / element
+ *     (X: 3 x nV, E: 4 x nT, F: 3 x nF;  sim/vbd/Data.h:167-176), i.e. interleaved xyz;
+ *   - construction data is double / int64 like pbat::sim::vbd::Data (Aliases.h:17-18);
+ *     run-time state crosses as float (GpuScalar, gpu/Aliases.h:19-20) or double;
+ *   - the caller owns every host buffer; nothing is retained after a call returns;
+ *   - calls on one handle are not thread-safe; every call returns after its work is
+ *     complete unless its name ends in _async.
+ * Errors: every function returns a vbdx_status; vbdx_last_error() gives the message.  The
+ * C++ / Python wrappers rethrow VBDX_INVALID_ARGUMENT as std::invalid_argument / ValueError
+ * (the reference throws std::invalid_argument from Data::Construct, sim/vbd/Data.cpp:245-306).
+ * There is no CPU fallback: without a CUDA device vbdx_create fails with VBDX_NO_DEVICE.
+ */
+#ifndef VBDX_H
+#define VBDX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBDX_ABI_VERSION 1
+
+typedef enum vbdx_status {
+    VBDX_OK               = 0,
+    VBDX_INVALID_ARGUMENT = 1,
+    VBDX_NO_DEVICE        = 2,
+    VBDX_CUDA_ERROR       = 3,
+    VBDX_OUT_OF_MEMORY    = 4,
+    VBDX_UNSUPPORTED      = 5
+} vbdx_status;
+
+/* sim/vbd/Enums.h:9-15 */
+typedef enum vbdx_initialization_strategy {
+    VBDX_INIT_POSITION               = 0,
+    VBDX_INIT_INERTIA                = 1,
+    VBDX_INIT_KINETIC_ENERGY_MINIMUM = 2,
+    VBDX_INIT_ADAPTIVE_VBD           = 3,
+    VBDX_INIT_ADAPTIVE_PBAT          = 4
+} vbdx_initialization_strategy;
+
+/* sim/vbd/Enums.h:21-28 (only None and Chebyshev are implemented; the others return
+ * VBDX_UNSUPPORTED at creation -- SURVEY.md section 8f) */
+typedef enum vbdx_acceleration_strategy {
+    VBDX_ACCEL_NONE         = 0,
+    VBDX_ACCEL_CHEBYSHEV    = 1,
+    VBDX_ACCEL_ANDERSON     = 2,
+    VBDX_ACCEL_NESTEROV     = 3,
+    VBDX_ACCEL_BROYDEN      = 4,
+    VBDX_ACCEL_TRUST_REGION = 5
+} vbdx_acceleration_strategy;
+
+/* graph/Enums.h: EGreedyColorOrderingStrategy / EGreedyColorSelectionStrategy */
+typedef enum vbdx_color_ordering { VBDX_ORDER_NATURAL = 0, VBDX_ORDER_SMALLEST_DEGREE = 1, VBDX_ORDER_LARGEST_DEGREE = 2 } vbdx_color_ordering;
+typedef enum vbdx_color_selection { VBDX_SELECT_LEAST_USED = 0, VBDX_SELECT_FIRST_AVAILABLE = 1 } vbdx_color_selection;
+
+/* How the Chebyshev weight omega_k is computed.  REFERENCE reproduces what
+ * sim/vbd/Kernels.h:96-102 evaluates to (omega_k = 1 - rho^2*omega_{k-1} for k >= 2, an operator
+ * precedence slip shared by the reference's CPU and GPU integrators); TEXTBOOK is
+ * 4/(4 - rho^2*omega_{k-1}). */
+typedef enum vbdx_omega_mode { VBDX_OMEGA_REFERENCE = 0, VBDX_OMEGA_TEXTBOOK = 1 } vbdx_omega_mode;
+
+/* hyper-elastic energy of the elastic term.  The reference hard-codes Stable Neo-Hookean
+ * (sim/vbd/Integrator.cpp:120, gpu/impl/vbd/Kernels.cuh:178); StVK
+ * (physics/SaintVenantKirchhoffEnergy.h) is offered as an extension with the same (mu,lambda). */
+typedef enum vbdx_material { VBDX_MATERIAL_STABLE_NEO_HOOKEAN = 0, VBDX_MATERIAL_STVK = 1 } vbdx_material;
+
+/*
+ * POD mirror of the fields of pbat::sim::vbd::Data (sim/vbd/Data.h:167-246) that the
+ * reference's GPU integrator consumes in its constructor (gpu/impl/vbd/Integrator.cu:22-80,
+ * gpu/impl/vbd/ChebyshevIntegrator.cu:16-22).  Not taken from the caller, by design: the
+ * vertex->tet adjacency (GVGp/GVGe/GVGilocal), shape-function gradients GP and quadrature
+ * weights wg -- they are rebuilt on the device from X and E.
+ * Optional pointers may be NULL (defaults = Data::Construct's, sim/vbd/Data.cpp:182-209).
+ */
+typedef struct vbdx_data_desc {
+    uint32_t abi_version;  /* VBDX_ABI_VERSION */
+    uint32_t struct_size;  /* sizeof(vbdx_data_desc) */
+    int64_t nV, nT;
+    const double* X;       /* 3 x nV rest positions (Data::X); also the initial x */
+    const int64_t* E;      /* 4 x nT tetrahedra (Data::E) */
+    const double* v;       /* 3 x nV initial velocities, default 0 */
+    const double* aext;    /* 3 x nV external accelerations, default (0,0,-9.81) */
+    const double* m;       /* nV lumped masses; NULL = rho_e*V_e/4 summed on the device */
+    const double* rhoe;    /* nT mass densities, default 1e3 (ignored when m is given) */
+    const double* lame;    /* 2 x nT (mu_e, lambda_e), default Y=1e6, nu=0.45 */
+    const int64_t* dbc;    /* Dirichlet vertices (need not be sorted) */
+    int64_t nDbc;
+    const int64_t* colors; /* nV vertex colours (Data::colors); NULL = greedy colouring below */
+    int32_t ordering;      /* vbdx_color_ordering, reference default LargestDegree */
+    int32_t selection;     /* vbdx_color_selection, reference default LeastUsed */
+    int32_t strategy;      /* vbdx_initialization_strategy, reference default AdaptivePbat */
+    int32_t acceleration;  /* vbdx_acceleration_strategy */
+    int32_t omega_mode;    /* vbdx_omega_mode */
+    int32_t material;      /* vbdx_material */
+    double kD;             /* Rayleigh damping (Data::kD, default 0) */
+    double detHZero;       /* Data::detHZero, default 1e-7 */
+    double rho;            /* Chebyshev spectral radius estimate, 0 < rho < 1 */
+    /* collision mesh (Data::B, V, F) and contact parameters (Data::muC, muF, epsv,
+     * mActiveSetUpdateFrequency).  nF == 0 disables contact. */
+    const int64_t* B;      /* nV body ids, default all equal */
+    const int64_t* V;      /* nCV collision vertices */
+    int64_t nCV;
+    const int64_t* F;      /* 3 x nF collision triangles */
+    int64_t nF;
+    double muC, muF, epsv;
+    int32_t active_set_update_frequency;
+    /* execution */
+    int32_t device;        /* CUDA device ordinal, -1 = current device */
+    int32_t tile_iters;    /* tuning: target incident tets per lane (0 = default) */
+    int32_t flags;         /* VBDX_FLAG_* */
+} vbdx_data_desc;
+
+#define VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY 1 /* AdaptiveVbd uses the stored v(t-1) like the reference's GPU
+                                                path (gpu/impl/vbd/Integrator.cu:333) instead of the CPU path's
+                                                vt == v (sim/vbd/Integrator.cpp:32,61-68) */
+#define VBDX_FLAG_NATURAL_VERTEX_ORDER 2     /* keep vertices in colour-major natural order (no Morton) */
+
+typedef struct vbdx_integrator vbdx_integrator;
+
+/* Fill a descriptor with the reference's defaults (sim/vbd/Data.h:206-246). */
+void vbdx_data_desc_init(vbdx_data_desc* desc);
+
+/* pbat::gpu::vbd::Integrator::Integrator(Data const&)   gpu/vbd/Integrator.h:45, gpu/vbd/Integrator.cu:15-33
+ * pbat::sim::vbd::Integrator::Integrator(Data)          sim/vbd/Integrator.h:22 */
+vbdx_status vbdx_create(const vbdx_data_desc* desc, vbdx_integrator** out);
+/* ~Integrator   gpu/vbd/Integrator.h:62 */
+vbdx_status vbdx_destroy(vbdx_integrator* h);
+
+/* Integrator::Step(dt, iterations, substeps)   gpu/vbd/Integrator.h:72, sim/vbd/Integrator.h:29 */
+vbdx_status vbdx_step(vbdx_integrator* h, double dt, int32_t iterations, int32_t substeps);
+/* same, returns once the work is enqueued on the handle's stream */
+vbdx_status vbdx_step_async(vbdx_integrator* h, double dt, int32_t iterations, int32_t substeps);
+vbdx_status vbdx_synchronize(vbdx_integrator* h);
+
+/* Integrator::SetPositions / SetVelocities / SetExternalAcceleration   gpu/vbd/Integrator.h:95-105
+ * (float = the GPU wrapper's GpuMatrixX; double = sim::vbd::Integrator's data.x / data.v,
+ *  bindings/pypbat/sim/vbd/Integrator.cpp:60-71).  3 x nV column-major, caller's vertex order. */
+vbdx_status vbdx_set_positions_f32(vbdx_integrator* h, const float* x, int64_t nV);
+vbdx_status vbdx_set_positions_f64(vbdx_integrator* h, const double* x, int64_t nV);
+vbdx_status vbdx_set_velocities_f32(vbdx_integrator* h, const float* v, int64_t nV);
+vbdx_status vbdx_set_velocities_f64(vbdx_integrator* h, const double* v, int64_t nV);
+vbdx_status vbdx_set_external_acceleration_f32(vbdx_integrator* h, const float* a, int64_t nV);
+vbdx_status vbdx_set_external_acceleration_f64(vbdx_integrator* h, const double* a, int64_t nV);
+/* Integrator::GetPositions / GetVelocities   gpu/vbd/Integrator.h:139-144 */
+vbdx_status vbdx_get_positions_f32(vbdx_integrator* h, float* x, int64_t nV);
+vbdx_status vbdx_get_positions_f64(vbdx_integrator* h, double* x, int64_t nV);
+vbdx_status vbdx_get_velocities_f32(vbdx_integrator* h, float* v, int64_t nV);
+vbdx_status vbdx_get_velocities_f64(vbdx_integrator* h, double* v, int64_t nV);
+
+/* Integrator::SetNumericalZeroForHessianDeterminant   gpu/vbd/Integrator.h:111 */
+vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero);
+/* Integrator::SetRayleighDampingCoefficient           gpu/vbd/Integrator.h:116 */
+vbdx_status vbdx_set_rayleigh_damping(vbdx_integrator* h, double kD);
+/* Integrator::SetInitializationStrategy               gpu/vbd/Integrator.h:121 */
+vbdx_status vbdx_set_initialization_strategy(vbdx_integrator* h, int32_t strategy);
+/* Integrator::SetBlockSize                            gpu/vbd/Integrator.h:126
+ * accepted for compatibility; the sweep is warp-tiled, so this is only a tuning hint */
+vbdx_status vbdx_set_block_size(vbdx_integrator* h, int32_t block_size);
+/* Integrator::SetSceneBoundingBox                     gpu/vbd/Integrator.h:132-134 */
+vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3], const float max3[3]);
+
+/* Use a caller-provided cudaStream_t for all subsequent work (NULL = the handle's own). */
+vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream);
+
+/* Introspection used by tests, bench.py and the roofline accounting. */
+typedef struct vbdx_info {
+    int64_t nV, nT, nActiveVertices; /* nActiveVertices = vertices that are swept (non-Dirichlet) */
+    int64_t nIncidences;             /* sum over swept vertices of incident tets */
+    int64_t nRecordSlots;            /* incidence record slots incl. padding (x 64 B = streamed bytes/sweep) */
+    int32_t nColors, nTiles;
+    int32_t gridBlocks, blockThreads; /* persistent launch shape */
+    int32_t device, smCount;
+    int64_t deviceBytes;             /* device memory held by the handle */
+    int64_t kernelLaunches;          /* CUDA kernels launched by this handle since creation */
+    double  lastStepMs;              /* device time of the last vbdx_step (CUDA events on its stream) */
+} vbdx_info;
+vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out);
+
+/* Debug / parity access to what the device built (caller's vertex and element numbering):
+ * the vertex->tet CSR (GVGp nV+1, GVGe and GVGilocal 4 nT; sim/vbd/Data.h:196-204), shape function
+ * gradients GP (4 x 3nT as Data::GP), quadrature weights wg (nT), lumped masses m (nV), and
+ * colours (nV).  Any pointer may be NULL. */
+vbdx_status vbdx_get_adjacency(vbdx_integrator* h, int64_t* GVGp, int64_t* GVGe, int64_t* GVGilocal);
+vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, double* m);
+vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
+
+/* Host-only helpers (no device needed): the reference's greedy colouring of the mesh primal
+ * graph, graph/Color.h:45-135 on graph/Mesh.h:116-123, as Data::Construct calls it
+ * (sim/vbd/Data.cpp:228-231). */
+vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int64_t* colors_out);
+
+const char* vbdx_last_error(void);
+int32_t vbdx_abi_version(void);
+/* number of CUDA devices visible (0 when there is no driver/GPU) */
+int32_t vbdx_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBDX_H */

@@ -1,0 +1,163 @@
+"""Shared ctypes front-end of the two integrator classes: owns one ``vbdx_integrator`` handle."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _interleaved(a, dtype, nV, name):
+    """3 x nV (reference convention) -> contiguous nV x 3, which is the column-major 3 x nV the
+    C-ABI expects."""
+    a = np.asarray(a, dtype=dtype)
+    if a.shape != (3, nV):
+        raise ValueError(f"{name} must be 3 x {nV}, got {a.shape}")  # gpu/impl/common/Eigen.cuh:28-35
+    return np.ascontiguousarray(a.T)
+
+
+class DeviceIntegrator:
+    _dtype = np.float32
+
+    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None):
+        L = _lib.lib()
+        if data.x.size == 0:
+            raise ValueError("Data.construct() must be called before creating an integrator")
+        nV, nT = data.X.shape[1], data.E.shape[1]
+        d = _lib.DataDesc()
+        L.vbdx_data_desc_init(C.byref(d))
+        keep = []
+
+        def ptr(a, dtype, transpose=False):
+            if a is None or np.size(a) == 0:
+                return None
+            a = np.asarray(a, dtype=dtype)
+            a = np.ascontiguousarray(a.T if transpose else a)
+            keep.append(a)
+            return a.ctypes.data
+
+        d.nV, d.nT = nV, nT
+        d.X = ptr(data.x, np.float64, True)       # the reference uploads data.x (gpu/impl/vbd/Integrator.cu:27)
+        d.E = ptr(data.E, np.int64, True)
+        d.v = ptr(data.v, np.float64, True)
+        d.aext = ptr(data.aext, np.float64, True)
+        d.m = ptr(data.m, np.float64)
+        d.rhoe = ptr(data.rhoe, np.float64)
+        d.lame = ptr(data.lame, np.float64, True)
+        d.dbc = ptr(data.dbc, np.int64)
+        d.nDbc = int(np.size(data.dbc))
+        cols = data.colors if colors is None else colors
+        d.colors = ptr(cols, np.int64)
+        d.ordering = int(data.vertex_coloring_ordering)
+        d.selection = int(data.vertex_coloring_selection)
+        d.strategy = int(data.strategy)
+        d.acceleration = int(data.accelerator)
+        d.omega_mode = int(getattr(data, "omega_mode", 0))
+        d.kD, d.detHZero, d.rho = float(data.kD), float(data.detH_zero), float(data.rho)
+        d.B = ptr(data.B, np.int64)
+        d.V = ptr(data.V, np.int64)
+        d.nCV = int(np.size(data.V))
+        d.F = ptr(data.F, np.int64, True)
+        d.nF = int(data.F.shape[1]) if np.ndim(data.F) == 2 else 0
+        d.muC, d.muF, d.epsv = float(data.muC), float(data.muF), float(data.epsv)
+        d.active_set_update_frequency = int(data.active_set_update_frequency)
+        d.device, d.tile_iters, d.flags = int(device), int(tile_iters), int(flags)
+        # rest positions differ from x only if the caller edited data.x after construct(); the
+        # element rest data must come from X (sim/vbd/Data.cpp:220-221)
+        self._rest_differs = not np.array_equal(data.x, data.X)
+        if self._rest_differs:
+            d.X = ptr(data.X, np.float64, True)
+        self._h = C.c_void_p()
+        self._L = L
+        _lib.check(L.vbdx_create(C.byref(d), C.byref(self._h)))
+        self.nV, self.nT = nV, nT
+        self._strategy, self._kD, self._detH = int(data.strategy), float(data.kD), float(data.detH_zero)
+        if self._rest_differs:
+            self.x = data.x
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.vbdx_destroy(h)
+            self._h = None
+
+    # ---- stepping -------------------------------------------------------------------------
+    def _step(self, dt, iterations, substeps):
+        _lib.check(self._L.vbdx_step(self._h, float(dt), int(iterations), int(substeps)))
+
+    def step_async(self, dt, iterations, substeps=1):
+        """Extension: enqueue a step on the handle's stream and return immediately."""
+        _lib.check(self._L.vbdx_step_async(self._h, float(dt), int(iterations), int(substeps)))
+
+    def synchronize(self):
+        _lib.check(self._L.vbdx_synchronize(self._h))
+
+    def use_stream(self, cuda_stream_ptr):
+        """Extension: run on a caller-provided ``cudaStream_t`` (e.g. torch's current stream)."""
+        _lib.check(self._L.vbdx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- state ----------------------------------------------------------------------------
+    def _sfx(self):
+        return "f32" if self._dtype == np.float32 else "f64"
+
+    def _get(self, what):
+        out = np.empty((self.nV, 3), dtype=self._dtype)
+        _lib.check(getattr(self._L, f"vbdx_get_{what}_{self._sfx()}")(self._h, out.ctypes.data, self.nV))
+        return np.ascontiguousarray(out.T)
+
+    def _set(self, what, a):
+        a = _interleaved(a, self._dtype, self.nV, what)
+        _lib.check(getattr(self._L, f"vbdx_set_{what}_{self._sfx()}")(self._h, a.ctypes.data, self.nV))
+
+    x = property(lambda s: s._get("positions"), lambda s, a: s._set("positions", a))
+    v = property(lambda s: s._get("velocities"), lambda s, a: s._set("velocities", a))
+
+    def _set_acceleration(self, a):
+        self._set("external_acceleration", a)
+
+    def _set_detH(self, zero):
+        _lib.check(self._L.vbdx_set_detH_zero(self._h, float(zero)))
+        self._detH = float(zero)
+
+    def _set_kD(self, kD):
+        _lib.check(self._L.vbdx_set_rayleigh_damping(self._h, float(kD)))
+        self._kD = float(kD)
+
+    def _set_strategy(self, strategy):
+        _lib.check(self._L.vbdx_set_initialization_strategy(self._h, int(strategy)))
+        self._strategy = int(strategy)
+
+    def _set_block_size(self, n):
+        _lib.check(self._L.vbdx_set_block_size(self._h, int(n)))
+
+    def _set_scene_bounding_box(self, lo, hi):
+        lo = np.ascontiguousarray(lo, dtype=np.float32)
+        hi = np.ascontiguousarray(hi, dtype=np.float32)
+        _lib.check(self._L.vbdx_set_scene_bounding_box(self._h, lo.ctypes.data, hi.ctypes.data))
+
+    # ---- introspection (extensions used by tests / bench) -----------------------------------
+    @property
+    def info(self):
+        out = _lib.Info()
+        _lib.check(self._L.vbdx_get_info(self._h, C.byref(out)))
+        return {k: getattr(out, k) for k, _ in out._fields_}
+
+    def adjacency(self):
+        p = np.empty(self.nV + 1, np.int64)
+        e = np.empty(4 * self.nT, np.int64)
+        il = np.empty(4 * self.nT, np.int64)
+        _lib.check(self._L.vbdx_get_adjacency(self._h, p.ctypes.data, e.ctypes.data, il.ctypes.data))
+        return p, e, il
+
+    def element_data(self):
+        GP = np.empty(12 * self.nT)
+        wg = np.empty(self.nT)
+        m = np.empty(self.nV)
+        _lib.check(self._L.vbdx_get_element_data(self._h, GP.ctypes.data, wg.ctypes.data, m.ctypes.data))
+        return GP.reshape(3 * self.nT, 4).T.copy(), wg, m
+
+    def colors(self):
+        c = np.empty(self.nV, np.int64)
+        _lib.check(self._L.vbdx_get_colors(self._h, c.ctypes.data))
+        return c

@@ -1,0 +1,281 @@
+// Host-side planning for the B200 VBD integrator: vertex colouring (when the caller supplies
+// none) and the colour-major / warp-tile vertex order the sweep kernel streams through.
+// Pure C++ (no CUDA) so that it can be unit-tested on a CPU-only machine through the C-ABI.
+#include "vbdx_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace vbdx {
+
+namespace {
+
+inline uint32_t ExpandBits10(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+}  // namespace
+
+// Greedy colouring of the mesh primal graph with the reference's semantics
+// (graph/Color.h:45-135; visiting order = stable sort by vertex degree in the primal graph
+// G*G^T, self loop included, graph/Mesh.h:116-123; colour choice = usable colour with the fewest
+// vertices, ties to the lowest colour index; a new colour only when all are blocked).
+void GreedyColorMesh(
+    int64_t nV,
+    int64_t nT,
+    const int64_t* E,
+    int ordering,
+    int selection,
+    std::vector<int64_t>& colors)
+{
+    // vertex -> tet lists by counting sort
+    std::vector<int64_t> vtPtr(nV + 1, 0);
+    for (int64_t k = 0; k < 4 * nT; ++k)
+        ++vtPtr[E[k] + 1];
+    for (int64_t i = 0; i < nV; ++i)
+        vtPtr[i + 1] += vtPtr[i];
+    std::vector<int32_t> vt(static_cast<size_t>(4 * nT));
+    {
+        std::vector<int64_t> cursor(vtPtr.begin(), vtPtr.end() - 1);
+        for (int64_t e = 0; e < nT; ++e)
+            for (int a = 0; a < 4; ++a)
+                vt[cursor[E[4 * e + a]]++] = static_cast<int32_t>(e);
+    }
+    // 1-ring (self included) via a visit stamp; two passes: sizes, then entries
+    std::vector<int64_t> ringPtr(nV + 1, 0);
+    std::vector<int64_t> stamp(nV, -1);
+    for (int64_t u = 0; u < nV; ++u)
+    {
+        int64_t cnt = 0;
+        stamp[u]    = u;
+        ++cnt;
+        for (int64_t k = vtPtr[u]; k < vtPtr[u + 1]; ++k)
+            for (int a = 0; a < 4; ++a)
+            {
+                int64_t const w = E[4 * static_cast<int64_t>(vt[k]) + a];
+                if (stamp[w] != u)
+                {
+                    stamp[w] = u;
+                    ++cnt;
+                }
+            }
+        ringPtr[u + 1] = ringPtr[u] + cnt;
+    }
+    std::vector<int32_t> ring(static_cast<size_t>(ringPtr[nV]));
+    std::fill(stamp.begin(), stamp.end(), int64_t(-1));
+    for (int64_t u = 0; u < nV; ++u)
+    {
+        int64_t pos = ringPtr[u];
+        stamp[u]    = u;
+        ring[pos++] = static_cast<int32_t>(u);
+        for (int64_t k = vtPtr[u]; k < vtPtr[u + 1]; ++k)
+            for (int a = 0; a < 4; ++a)
+            {
+                int64_t const w = E[4 * static_cast<int64_t>(vt[k]) + a];
+                if (stamp[w] != u)
+                {
+                    stamp[w]    = u;
+                    ring[pos++] = static_cast<int32_t>(w);
+                }
+            }
+    }
+    // visiting order: stable by degree == counting sort over degrees
+    std::vector<int64_t> order(nV);
+    if (ordering == 0 /* Natural */)
+        std::iota(order.begin(), order.end(), int64_t(0));
+    else
+    {
+        int64_t maxDeg = 0;
+        for (int64_t u = 0; u < nV; ++u)
+            maxDeg = std::max(maxDeg, ringPtr[u + 1] - ringPtr[u]);
+        std::vector<int64_t> bucket(maxDeg + 2, 0);
+        bool const largestFirst = (ordering == 2);
+        auto slot = [&](int64_t u) {
+            int64_t const d = ringPtr[u + 1] - ringPtr[u];
+            return largestFirst ? (maxDeg - d) : d;
+        };
+        for (int64_t u = 0; u < nV; ++u)
+            ++bucket[slot(u) + 1];
+        for (int64_t d = 0; d <= maxDeg; ++d)
+            bucket[d + 1] += bucket[d];
+        for (int64_t u = 0; u < nV; ++u)
+            order[bucket[slot(u)]++] = u;
+    }
+    colors.assign(nV, -1);
+    std::vector<int64_t> used;     // vertices per colour
+    std::vector<uint8_t> blocked;  // per colour, for the vertex being coloured
+    for (int64_t u : order)
+    {
+        std::fill(blocked.begin(), blocked.end(), uint8_t(0));
+        size_t nBlocked = 0;
+        for (int64_t k = ringPtr[u]; k < ringPtr[u + 1]; ++k)
+        {
+            int64_t const c = colors[ring[k]];
+            if (c >= 0 && !blocked[c])
+            {
+                blocked[c] = 1;
+                ++nBlocked;
+            }
+        }
+        if (nBlocked == used.size())
+        {
+            colors[u] = static_cast<int64_t>(used.size());
+            used.push_back(1);
+            blocked.push_back(0);
+            continue;
+        }
+        int64_t pick = -1;
+        for (int64_t c = 0; c < static_cast<int64_t>(used.size()); ++c)
+        {
+            if (blocked[c])
+                continue;
+            if (pick < 0 || (selection == 0 /* LeastUsed */ && used[c] < used[pick]))
+                pick = c;
+        }
+        colors[u] = pick;
+        ++used[pick];
+    }
+}
+
+void BuildPlan(
+    int64_t nV,
+    const int32_t* deg,
+    const int64_t* colors,
+    const uint8_t* isDbc,
+    const double* X,
+    int tileIters,
+    int gridBlocks,
+    bool naturalOrder,
+    Plan& plan)
+{
+    plan      = Plan{};
+    plan.nV   = nV;
+    tileIters = std::max(1, tileIters);
+    // bounding box for the Morton order
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < nV; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = std::min(lo[d], X[3 * i + d]);
+            hi[d] = std::max(hi[d], X[3 * i + d]);
+        }
+    double ext = 0;
+    for (int d = 0; d < 3; ++d)
+        ext = std::max(ext, hi[d] - lo[d]);
+    if (!(ext > 0))
+        ext = 1;
+    struct Item {
+        uint64_t key;
+        int32_t v;
+        uint8_t lw;
+        uint16_t iters;
+    };
+    std::vector<Item> items;
+    items.reserve(nV);
+    int64_t nColors = 0;
+    for (int64_t i = 0; i < nV; ++i)
+    {
+        nColors = std::max<int64_t>(nColors, colors[i] + 1);
+        if (isDbc[i])
+            continue;
+        int const d = deg[i];
+        int lw      = 0;
+        while (lw < 5 && (int64_t(1) << lw) * tileIters < d)
+            ++lw;
+        int const w     = 1 << lw;
+        int const iters = std::max(1, (d + w - 1) / w);
+        uint32_t morton = 0;
+        if (!naturalOrder)
+        {
+            uint32_t q[3];
+            for (int k = 0; k < 3; ++k)
+                q[k] = static_cast<uint32_t>(
+                    std::min(1023.0, std::max(0.0, (X[3 * i + k] - lo[k]) / ext * 1024.0)));
+            morton = (ExpandBits10(q[0]) << 2) | (ExpandBits10(q[1]) << 1) | ExpandBits10(q[2]);
+        }
+        uint64_t const itKey = 4095u - static_cast<uint32_t>(std::min(iters, 4095));
+        uint64_t const key   = (static_cast<uint64_t>(colors[i]) << 45) |
+                             (static_cast<uint64_t>(5 - lw) << 42) | (itKey << 30) | morton;
+        items.push_back({key, static_cast<int32_t>(i), static_cast<uint8_t>(lw),
+                         static_cast<uint16_t>(std::min(iters, 65535))});
+        plan.nIncidences += d;
+    }
+    std::stable_sort(items.begin(), items.end(), [](Item const& a, Item const& b) { return a.key < b.key; });
+    plan.nActive = static_cast<int64_t>(items.size());
+    plan.nColors = static_cast<int32_t>(nColors);
+    plan.new2old.resize(nV);
+    plan.old2new.resize(nV);
+    plan.colorTileBegin.assign(nColors + 1, 0);
+    // tiles
+    int64_t pos = 0, block = 0;
+    int64_t curColor = 0;
+    while (pos < plan.nActive)
+    {
+        int64_t const c = colors[items[pos].v];
+        while (curColor < c)
+            plan.colorTileBegin[++curColor] = static_cast<uint32_t>(plan.tiles.size());
+        int const lw = items[pos].lw;
+        int const G  = 32 >> lw;
+        int n = 0, iters = 0;
+        while (n < G && pos + n < plan.nActive && colors[items[pos + n].v] == c &&
+               items[pos + n].lw == lw)
+        {
+            iters = std::max<int>(iters, items[pos + n].iters);
+            ++n;
+        }
+        TileDesc t;
+        t.blockStart = static_cast<uint32_t>(block);
+        t.vbase      = static_cast<uint32_t>(pos);
+        t.meta       = static_cast<uint32_t>(lw) | (static_cast<uint32_t>(iters) << 8) |
+                 (static_cast<uint32_t>(n) << 24);
+        t.pad = 0;
+        plan.tiles.push_back(t);
+        for (int k = 0; k < n; ++k)
+        {
+            plan.new2old[pos + k]             = items[pos + k].v;
+            plan.old2new[items[pos + k].v]    = static_cast<int32_t>(pos + k);
+        }
+        pos += n;
+        block += iters;
+    }
+    while (curColor < nColors)
+        plan.colorTileBegin[++curColor] = static_cast<uint32_t>(plan.tiles.size());
+    plan.nBlocks = block;
+    // Dirichlet vertices last
+    int64_t tail = plan.nActive;
+    for (int64_t i = 0; i < nV; ++i)
+        if (isDbc[i])
+        {
+            plan.new2old[tail]   = static_cast<int32_t>(i);
+            plan.old2new[i]      = static_cast<int32_t>(tail);
+            ++tail;
+        }
+    // per colour, split the tile range between CTAs by equal record-block counts
+    gridBlocks = std::max(1, gridBlocks);
+    plan.ctaTileRange.assign(static_cast<size_t>(nColors) * (gridBlocks + 1), 0);
+    for (int64_t c = 0; c < nColors; ++c)
+    {
+        uint32_t const tb = plan.colorTileBegin[c], te = plan.colorTileBegin[c + 1];
+        uint32_t* range   = &plan.ctaTileRange[c * (gridBlocks + 1)];
+        int64_t const b0  = (tb < te) ? plan.tiles[tb].blockStart : 0;
+        int64_t const b1  = (tb < te) ? (te < plan.tiles.size() ? plan.tiles[te].blockStart : plan.nBlocks) : 0;
+        int64_t const total = b1 - b0;
+        uint32_t t = tb;
+        for (int b = 0; b < gridBlocks; ++b)
+        {
+            range[b] = t;
+            int64_t const limit = b0 + (total * (b + 1)) / gridBlocks;
+            while (t < te && static_cast<int64_t>(plan.tiles[t].blockStart) < limit)
+                ++t;
+        }
+        range[gridBlocks] = te;
+    }
+}
+
+}  // namespace vbdx

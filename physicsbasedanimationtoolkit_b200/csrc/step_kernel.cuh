@@ -1,0 +1,370 @@
+// The persistent VBD step kernel for sm_100a: one cooperative launch runs every substep,
+// every iteration and every colour of a time step, with software grid barriers between
+// colours.  Replaces, from scratch, the reference's per-colour launch pair
+// (gpu/impl/vbd/Kernels.cuh:148-233 VbdIteration + gpu/impl/vbd/Integrator.cu:317-325 copy-back),
+// its three thrust pre/post passes (gpu/impl/vbd/Integrator.cu:190-248,329-347) and the
+// per-iteration Chebyshev pass (gpu/impl/vbd/ChebyshevIntegrator.cu:38-59).
+//
+// Arithmetic follows the reference CPU path (the parity oracle):
+//   InertialTarget / InitialPositionsForSolve   sim/vbd/Kernels.h:29-94
+//   SolveVertex                                 sim/vbd/Integrator.cpp:98-136
+//   AddDamping / AddInertiaDerivatives / IntegratePositions   sim/vbd/Kernels.h:179-191,310-339
+//   ChebyshevUpdate                             sim/vbd/Kernels.h:104-119, ChebyshevIntegrator.cpp:15-32
+// with the Stable Neo-Hookean vertex block in closed form (DESIGN.md "Math").
+#pragma once
+
+#include "vbdx_internal.h"
+
+#include <cuda_runtime.h>
+
+namespace vbdx {
+
+struct StepParams {
+    // static topology
+    const float4* __restrict__ records;        // [nBlocks][4][32] float4
+    const uint4* __restrict__ tiles;           // TileDesc
+    const uint32_t* __restrict__ ctaTileRange; // [nColors][gridDim.x + 1]
+    int nColors;
+    int nVerts;   // all internal vertices (swept first, Dirichlet last)
+    // state (internal vertex order, float4 per vertex)
+    float4* pos;           // current-iterate buffer Q at [0,nVerts); previous-iterate buffer P at [pOff, pOff+nVerts)
+    uint32_t pOff;         // 0 (P aliases Q) or nVerts (Chebyshev)
+    float4* hist;          // Chebyshev: blended iterate of two iterations ago
+    float4* xtildeM;       // inertial target xyz, mass in w
+    float4* xt;            // positions at the start of the substep
+    float4* vel;           // velocities
+    float4* vtm1;          // previous velocities (only with VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY), else null
+    const float4* __restrict__ aext;
+    const float* __restrict__ omega;  // Chebyshev weights per iteration
+    // scalars
+    float sdt, sdt2;
+    float dampD;       // kD / sdt
+    float detHZero;
+    int strategy;
+    int iterations, substeps;
+    unsigned int* barrier;  // zeroed before launch
+};
+
+__device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void AddRelease(unsigned int* p, unsigned int v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// All CTAs of the (cooperatively launched, fully resident) grid meet here.  The release/acquire
+// pair at gpu scope orders every position written before the barrier against every weak load
+// after it, and invalidates this SM's L1 so those loads may use the default cached path.
+__device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int& target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        target += gridDim.x;
+        AddRelease(counter, 1u);
+        while (LoadAcquire(counter) < target)
+        {
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 LoadPos(const float4* p)
+{
+    return __ldcg(p);  // L2-coherent load: positions change between colours
+}
+
+// InitialPositionsForSolve (sim/vbd/Kernels.h:45-94)
+__device__ __forceinline__ float3 InitialPosition(
+    float3 xt,
+    float3 vtm1,
+    float3 vt,
+    float3 a,
+    float dt,
+    float dt2,
+    int strategy)
+{
+    if (strategy == 0)
+        return xt;
+    float3 x = make_float3(xt.x + dt * vt.x, xt.y + dt * vt.y, xt.z + dt * vt.z);
+    if (strategy == 1)
+        return x;
+    float atilde = 1.f;
+    if (strategy >= 3)
+    {
+        float const an2 = a.x * a.x + a.y * a.y + a.z * a.z;
+        atilde          = 0.f;
+        if (an2 != 0.f)
+        {
+            if (strategy == 3)
+            {
+                float const d = ((vt.x - vtm1.x) / dt) * a.x + ((vt.y - vtm1.y) / dt) * a.y +
+                                ((vt.z - vtm1.z) / dt) * a.z;
+                atilde = fminf(fmaxf(d / an2, 0.f), 1.f);
+            }
+            else
+            {
+                float const nrm = sqrtf(vt.x * vt.x + vt.y * vt.y + vt.z * vt.z) + 1.17549435e-38f;
+                float const d   = (vt.x / nrm) * a.x + (vt.y / nrm) * a.y + (vt.z / nrm) * a.z;
+                atilde          = fminf(fabsf(d / an2), 1.f);
+            }
+        }
+    }
+    float const s = dt2 * atilde;
+    return make_float3(x.x + s * a.x, x.y + s * a.y, x.z + s * a.z);
+}
+
+// Sweep of one colour: every warp walks its share of the colour's tiles.
+template <bool kChebyshev, bool kDamping>
+__device__ __forceinline__ void SweepColor(StepParams const& p, int color, int k, float omega)
+{
+    uint32_t const* range = p.ctaTileRange + static_cast<size_t>(color) * (gridDim.x + 1);
+    uint32_t const tBegin = range[blockIdx.x], tEnd = range[blockIdx.x + 1];
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    float4 const* __restrict__ posQ = p.pos;
+    float4 const* __restrict__ posP = p.pos + p.pOff;
+
+    for (uint32_t T = tBegin + warp; T < tEnd; T += nWarps)
+    {
+        uint4 const td        = __ldg(p.tiles + T);
+        uint32_t const lw     = td.z & 0xffu;
+        uint32_t const iters  = (td.z >> 8) & 0xffffu;
+        uint32_t const nverts = td.z >> 24;
+        uint32_t const grp    = lane >> lw;
+        bool const valid      = grp < nverts;
+        uint32_t const vi     = td.y + (valid ? grp : 0u);
+        // own position: the previous iterate (P); nobody has written vertex vi in this sweep
+        float4 const xi = LoadPos(posP + vi);
+
+        float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        float4 const* rec = p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane;
+#pragma unroll 1
+        for (uint32_t t = 0; t < iters; ++t, rec += kBlockFloat4)
+        {
+            float4 const c0 = __ldcs(rec);
+            float4 const c1 = __ldcs(rec + 32);
+            float4 const c2 = __ldcs(rec + 64);
+            float4 const c3 = __ldcs(rec + 96);
+            uint32_t const j1 = __float_as_uint(c0.x), j2 = __float_as_uint(c0.y),
+                           j3 = __float_as_uint(c0.z);
+            float4 const p1 = LoadPos(posQ + (j1 & ~kPrevFlag) + ((j1 & kPrevFlag) ? p.pOff : 0u));
+            float4 const p2 = LoadPos(posQ + (j2 & ~kPrevFlag) + ((j2 & kPrevFlag) ? p.pOff : 0u));
+            float4 const p3 = LoadPos(posQ + (j3 & ~kPrevFlag) + ((j3 & kPrevFlag) ? p.pOff : 0u));
+            // gradients of the three other vertices
+            float const a0 = c0.w, a1 = c1.x, a2 = c1.y;
+            float const b0 = c1.z, b1 = c1.w, b2 = c2.x;
+            float const e0 = c2.y, e1 = c2.z, e2 = c2.w;
+            float const wmu = c3.x, wlam = c3.y, alpha = c3.z, gh2 = c3.w;
+            // edge vectors relative to this vertex:  F = sum_a (x_a - x_i) (x) grad_a
+            float const d1x = p1.x - xi.x, d1y = p1.y - xi.y, d1z = p1.z - xi.z;
+            float const d2x = p2.x - xi.x, d2y = p2.y - xi.y, d2z = p2.z - xi.z;
+            float const d3x = p3.x - xi.x, d3y = p3.y - xi.y, d3z = p3.z - xi.z;
+            float const F00 = d1x * a0 + d2x * b0 + d3x * e0;
+            float const F01 = d1x * a1 + d2x * b1 + d3x * e1;
+            float const F02 = d1x * a2 + d2x * b2 + d3x * e2;
+            float const F10 = d1y * a0 + d2y * b0 + d3y * e0;
+            float const F11 = d1y * a1 + d2y * b1 + d3y * e1;
+            float const F12 = d1y * a2 + d2y * b2 + d3y * e2;
+            float const F20 = d1z * a0 + d2z * b0 + d3z * e0;
+            float const F21 = d1z * a1 + d2z * b1 + d3z * e1;
+            float const F22 = d1z * a2 + d2z * b2 + d3z * e2;
+            // cofactors
+            float const C00 = F11 * F22 - F12 * F21;
+            float const C01 = F12 * F20 - F10 * F22;
+            float const C02 = F10 * F21 - F11 * F20;
+            float const C10 = F02 * F21 - F01 * F22;
+            float const C11 = F00 * F22 - F02 * F20;
+            float const C12 = F01 * F20 - F00 * F21;
+            float const C20 = F01 * F12 - F02 * F11;
+            float const C21 = F02 * F10 - F00 * F12;
+            float const C22 = F00 * F11 - F01 * F10;
+            float const J   = F00 * C00 + F01 * C01 + F02 * C02;
+            // gradient of this vertex' shape function
+            float const q0 = -(a0 + b0 + e0), q1 = -(a1 + b1 + e1), q2 = -(a2 + b2 + e2);
+            float const Fq0 = F00 * q0 + F01 * q1 + F02 * q2;
+            float const Fq1 = F10 * q0 + F11 * q1 + F12 * q2;
+            float const Fq2 = F20 * q0 + F21 * q1 + F22 * q2;
+            float const Cq0 = C00 * q0 + C01 * q1 + C02 * q2;
+            float const Cq1 = C10 * q0 + C11 * q1 + C12 * q2;
+            float const Cq2 = C20 * q0 + C21 * q1 + C22 * q2;
+            float const s   = wlam * (J - alpha);
+            g0 += wmu * Fq0 + s * Cq0;
+            g1 += wmu * Fq1 + s * Cq1;
+            g2 += wmu * Fq2 + s * Cq2;
+            float const t0 = wlam * Cq0, t1 = wlam * Cq1, t2 = wlam * Cq2;
+            h00 += t0 * Cq0;
+            h01 += t0 * Cq1;
+            h02 += t0 * Cq2;
+            h11 += t1 * Cq1;
+            h12 += t1 * Cq2;
+            h22 += t2 * Cq2;
+            hd += wmu * gh2;
+        }
+        // butterfly over the w lanes that share a vertex (fixed order => deterministic)
+        for (uint32_t o = (1u << lw) >> 1; o > 0; o >>= 1)
+        {
+            h00 += __shfl_xor_sync(0xffffffffu, h00, o);
+            h01 += __shfl_xor_sync(0xffffffffu, h01, o);
+            h02 += __shfl_xor_sync(0xffffffffu, h02, o);
+            h11 += __shfl_xor_sync(0xffffffffu, h11, o);
+            h12 += __shfl_xor_sync(0xffffffffu, h12, o);
+            h22 += __shfl_xor_sync(0xffffffffu, h22, o);
+            hd += __shfl_xor_sync(0xffffffffu, hd, o);
+            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+            g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+        }
+        if (valid && (lane & ((1u << lw) - 1u)) == 0u)
+        {
+            h00 += hd;
+            h11 += hd;
+            h22 += hd;
+            float x = xi.x, y = xi.y, z = xi.z;
+            if constexpr (kDamping)
+            {
+                float4 const xt = __ldcg(p.xt + vi);
+                float const D   = p.dampD;
+                float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
+                g0 += D * (h00 * ex + h01 * ey + h02 * ez);
+                g1 += D * (h01 * ex + h11 * ey + h12 * ez);
+                g2 += D * (h02 * ex + h12 * ey + h22 * ez);
+                float const sc = 1.f + D;
+                h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
+            }
+            float4 const xm = __ldcg(p.xtildeM + vi);
+            float const K   = xm.w / p.sdt2;
+            h00 += K, h11 += K, h22 += K;
+            g0 += K * (x - xm.x);
+            g1 += K * (y - xm.y);
+            g2 += K * (z - xm.z);
+            // Newton step with the explicit cofactor inverse of the symmetric 3x3
+            float const i00 = h11 * h22 - h12 * h12;
+            float const i01 = h02 * h12 - h01 * h22;
+            float const i02 = h01 * h12 - h02 * h11;
+            float const det = h00 * i00 + h01 * i01 + h02 * i02;
+            if (fabsf(det) > p.detHZero)
+            {
+                float const i11 = h00 * h22 - h02 * h02;
+                float const i12 = h01 * h02 - h00 * h12;
+                float const i22 = h00 * h11 - h01 * h01;
+                float const r   = 1.f / det;
+                x -= r * (i00 * g0 + i01 * g1 + i02 * g2);
+                y -= r * (i01 * g0 + i11 * g1 + i12 * g2);
+                z -= r * (i02 * g0 + i12 * g1 + i22 * g2);
+            }
+            float4 const raw = make_float4(x, y, z, 0.f);
+            if constexpr (kChebyshev)
+            {
+                // Q <- raw sweep result (read by higher colours in this iteration);
+                // P <- blended iterate (read by lower colours in the next iteration and as this
+                // vertex' own start); hist <- previous blended iterate.
+                float4 out = raw;
+                if (k > 1)
+                {
+                    float4 const h2 = __ldcg(p.hist + vi);
+                    out.x = omega * (x - h2.x) + h2.x;
+                    out.y = omega * (y - h2.y) + h2.y;
+                    out.z = omega * (z - h2.z) + h2.z;
+                }
+                p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
+                p.pos[vi]          = raw;
+                p.pos[p.pOff + vi] = out;
+            }
+            else
+            {
+                p.pos[vi] = raw;
+            }
+        }
+    }
+}
+
+template <bool kChebyshev, bool kDamping>
+__global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ StepParams p)
+{
+    unsigned int target = 0;
+    uint32_t const gtid    = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t const gstride = gridDim.x * blockDim.x;
+    for (int s = 0; s < p.substeps; ++s)
+    {
+        // pre-step (fused with the velocity update of the previous substep):
+        //   v = (x - xt)/h; xt = x; xtilde = xt + h v + h^2 a; x = initial guess
+        for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+        {
+            float4 const x4 = __ldcg(p.pos + p.pOff + i);
+            float4 v4       = __ldcg(p.vel + i);
+            float3 vprev    = make_float3(v4.x, v4.y, v4.z);
+            if (s > 0)
+            {
+                float4 const xt4 = __ldcg(p.xt + i);
+                v4.x = (x4.x - xt4.x) / p.sdt;
+                v4.y = (x4.y - xt4.y) / p.sdt;
+                v4.z = (x4.z - xt4.z) / p.sdt;
+                p.vel[i] = v4;
+            }
+            // "previous velocity" of InitialPositionsForSolve: the CPU reference passes vt == v
+            // (sim/vbd/Integrator.cpp:32,61-68); the GPU reference keeps a real v(t-1)
+            float3 vtm1 = make_float3(v4.x, v4.y, v4.z);
+            if (p.vtm1 != nullptr)
+            {
+                if (s > 0)
+                    vtm1 = vprev;
+                else
+                {
+                    float4 const q = __ldcg(p.vtm1 + i);
+                    vtm1           = make_float3(q.x, q.y, q.z);
+                }
+            }
+            float4 const a4 = __ldg(p.aext + i);
+            float4 xm       = __ldcg(p.xtildeM + i);
+            xm.x            = x4.x + p.sdt * v4.x + p.sdt2 * a4.x;
+            xm.y            = x4.y + p.sdt * v4.y + p.sdt2 * a4.y;
+            xm.z            = x4.z + p.sdt * v4.z + p.sdt2 * a4.z;
+            p.xtildeM[i]    = xm;
+            p.xt[i]         = x4;
+            float3 const x0 = InitialPosition(
+                make_float3(x4.x, x4.y, x4.z),
+                vtm1,
+                make_float3(v4.x, v4.y, v4.z),
+                make_float3(a4.x, a4.y, a4.z),
+                p.sdt,
+                p.sdt2,
+                p.strategy);
+            float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
+            p.pos[i]       = o;
+            if constexpr (kChebyshev)
+                p.pos[p.pOff + i] = o;
+        }
+        GridBarrier(p.barrier, target);
+        for (int k = 0; k < p.iterations; ++k)
+        {
+            float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            for (int c = 0; c < p.nColors; ++c)
+            {
+                SweepColor<kChebyshev, kDamping>(p, c, k, omega);
+                GridBarrier(p.barrier, target);
+            }
+        }
+    }
+    // velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
+    // v(t-1) <- v like the reference's UpdateBdfState (gpu/impl/vbd/Integrator.cu:329-347)
+    for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+    {
+        float4 const x4  = __ldcg(p.pos + p.pOff + i);
+        float4 const xt4 = __ldcg(p.xt + i);
+        float4 v4        = __ldcg(p.vel + i);
+        if (p.vtm1 != nullptr)
+            p.vtm1[i] = v4;
+        v4.x     = (x4.x - xt4.x) / p.sdt;
+        v4.y     = (x4.y - xt4.y) / p.sdt;
+        v4.z     = (x4.z - xt4.z) / p.sdt;
+        p.vel[i] = v4;
+    }
+}
+
+}  // namespace vbdx

@@ -1,0 +1,762 @@
+// C-ABI layer and host driver of the B200 VBD integrator (include/vbdx.h).
+// Host code is C++20; every device computation is a hand-written sm_100a kernel from
+// setup_kernels.cuh / step_kernel.cuh.  No Thrust/CUB dispatch, no CPU fallback.
+#include "../../include/vbdx.h"
+
+#include "setup_kernels.cuh"
+#include "step_kernel.cuh"
+#include "vbdx_internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace vbdx {
+
+struct Error : std::runtime_error {
+    vbdx_status status;
+    Error(vbdx_status s, std::string const& what) : std::runtime_error(what), status(s) {}
+};
+
+#define VBDX_CUDA(call)                                                                          \
+    do                                                                                           \
+    {                                                                                            \
+        cudaError_t const err__ = (call);                                                        \
+        if (err__ != cudaSuccess)                                                                \
+            throw ::vbdx::Error(                                                                 \
+                err__ == cudaErrorMemoryAllocation ? VBDX_OUT_OF_MEMORY : VBDX_CUDA_ERROR,       \
+                std::string(#call) + ": " + cudaGetErrorString(err__));                          \
+    } while (0)
+
+static void Require(bool cond, char const* what)
+{
+    if (!cond)
+        throw Error(VBDX_INVALID_ARGUMENT, what);
+}
+
+// plain device allocation with byte accounting
+template <class T>
+struct DevBuf {
+    T* p     = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(DevBuf const&)            = delete;
+    DevBuf& operator=(DevBuf const&) = delete;
+    ~DevBuf() { Free(); }
+    void Alloc(size_t count, int64_t* accounting = nullptr)
+    {
+        Free();
+        n = count;
+        if (count == 0)
+            return;
+        VBDX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        if (accounting)
+            *accounting += static_cast<int64_t>(count * sizeof(T));
+    }
+    void Free()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void Upload(T const* src, size_t count, cudaStream_t s)
+    {
+        VBDX_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void Download(T* dst, size_t count, cudaStream_t s) const
+    {
+        VBDX_CUDA(cudaMemcpyAsync(dst, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+static inline int Blocks(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+using StepKernelFn = void (*)(StepParams);
+
+struct Integrator {
+    int device = 0, smCount = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+    int64_t nV = 0, nT = 0;
+    int64_t deviceBytes = 0, kernelLaunches = 0;
+    double lastStepMs = 0;
+    bool stepTimed    = false;
+
+    Plan plan;
+    int gridBlocks = 0, blockThreads = 256;
+    int64_t nRecordSlots = 0;
+
+    // parameters
+    int strategy = VBDX_INIT_ADAPTIVE_PBAT, acceleration = VBDX_ACCEL_NONE, omegaMode = 0;
+    double kD = 0, detHZero = 1e-7, rho = 1;
+    int flags = 0;
+    std::vector<float> omegaHost;
+    int omegaIterations = -1;
+
+    // setup products kept for introspection (caller numbering)
+    DevBuf<int32_t> dE;
+    DevBuf<uint32_t> dPtr, dAdj;
+    DevBuf<double> dJinv, dVol, dMass;
+    DevBuf<int32_t> dColor;
+    DevBuf<uint8_t> dIsDbc;
+    std::vector<int64_t> colors;
+
+    // static sweep data
+    DevBuf<float4> dRecords;
+    DevBuf<TileDesc> dTiles;
+    DevBuf<uint32_t> dCtaRange;
+    DevBuf<int32_t> dNew2Old, dOld2New;
+
+    // state
+    DevBuf<float4> dPos, dHist, dXtildeM, dXt, dVel, dVtm1, dAext;
+    DevBuf<float> dOmega;
+    DevBuf<unsigned int> dBarrier;
+    DevBuf<double> dStaging;  // 3 nV doubles
+
+    ~Integrator()
+    {
+        if (evBegin)
+            cudaEventDestroy(evBegin);
+        if (evEnd)
+            cudaEventDestroy(evEnd);
+        if (ownStream)
+            cudaStreamDestroy(ownStream);
+    }
+
+    StepKernelFn Kernel() const
+    {
+        bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+        bool const damp = kD != 0.0;
+        if (cheb)
+            return damp ? StepKernel<true, true> : StepKernel<true, false>;
+        return damp ? StepKernel<false, true> : StepKernel<false, false>;
+    }
+
+    void Create(vbdx_data_desc const& d);
+    void Step(double dt, int iterations, int substeps, bool sync);
+    template <class T>
+    void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1);
+    template <class T>
+    void GetVertexField(float4 const* src, T* dst, int64_t n);
+};
+
+void Integrator::Create(vbdx_data_desc const& d)
+{
+    Require(d.abi_version == VBDX_ABI_VERSION && d.struct_size == sizeof(vbdx_data_desc),
+            "vbdx_data_desc: ABI version / struct size mismatch");
+    Require(d.nV > 0 && d.nT > 0 && d.X && d.E, "need a volume mesh: X (3 x nV) and E (4 x nT)");
+    Require(d.nV < (int64_t(1) << 31) - 1 && d.nT < (int64_t(1) << 29), "mesh too large for 32-bit device indices");
+    Require(d.acceleration >= VBDX_ACCEL_NONE && d.acceleration <= VBDX_ACCEL_TRUST_REGION, "unknown acceleration strategy");
+    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV)
+        throw Error(VBDX_UNSUPPORTED, "only the base and Chebyshev-accelerated VBD solves are implemented");
+    if (d.material != VBDX_MATERIAL_STABLE_NEO_HOOKEAN)
+        throw Error(VBDX_UNSUPPORTED, "only the Stable Neo-Hookean energy is implemented");
+    if (d.acceleration == VBDX_ACCEL_CHEBYSHEV)
+        Require(d.rho > 0 && d.rho < 1, "Expected 0 < rho < 1");  // sim/vbd/Data.cpp:272-276
+    Require(d.strategy >= 0 && d.strategy <= VBDX_INIT_ADAPTIVE_PBAT, "unknown initialization strategy");
+    Require(d.nDbc >= 0 && (d.nDbc == 0 || d.dbc), "dbc pointer missing");
+    nV = d.nV, nT = d.nT;
+    strategy = d.strategy, acceleration = d.acceleration, omegaMode = d.omega_mode;
+    kD = d.kD, detHZero = d.detHZero, rho = d.rho, flags = d.flags;
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        throw Error(VBDX_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (d.device >= 0)
+    {
+        Require(d.device < count, "device ordinal out of range");
+        VBDX_CUDA(cudaSetDevice(d.device));
+    }
+    VBDX_CUDA(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    VBDX_CUDA(cudaGetDeviceProperties(&prop, device));
+    smCount = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch)
+        throw Error(VBDX_UNSUPPORTED, "device does not support cooperative launches");
+    VBDX_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+    stream = ownStream;
+    VBDX_CUDA(cudaEventCreate(&evBegin));
+    VBDX_CUDA(cudaEventCreate(&evEnd));
+
+    // ---- host-side validation and narrowing of the connectivity
+    std::vector<int32_t> E32(static_cast<size_t>(4 * nT));
+    for (int64_t k = 0; k < 4 * nT; ++k)
+    {
+        int64_t const v = d.E[k];
+        Require(v >= 0 && v < nV, "element index out of range");
+        E32[k] = static_cast<int32_t>(v);
+    }
+    std::vector<uint8_t> isDbc(static_cast<size_t>(nV), 0);
+    for (int64_t k = 0; k < d.nDbc; ++k)
+    {
+        Require(d.dbc[k] >= 0 && d.dbc[k] < nV, "Dirichlet vertex index out of range");
+        isDbc[d.dbc[k]] = 1;
+    }
+    if (d.colors)
+    {
+        colors.assign(d.colors, d.colors + nV);
+        for (int64_t c : colors)
+            Require(c >= 0 && c < (int64_t(1) << 18), "vertex colours must be in [0, 2^18)");
+    }
+    else
+        GreedyColorMesh(nV, nT, d.E, d.ordering, d.selection, colors);
+    std::vector<int32_t> color32(colors.begin(), colors.end());
+
+    // ---- device: CSR, element data
+    dE.Alloc(4 * nT, &deviceBytes);
+    dE.Upload(E32.data(), E32.size(), stream);
+    DevBuf<double> dX;
+    dX.Alloc(3 * nV);
+    dX.Upload(d.X, 3 * nV, stream);
+    dColor.Alloc(nV, &deviceBytes);
+    dColor.Upload(color32.data(), nV, stream);
+    dIsDbc.Alloc(nV, &deviceBytes);
+    dIsDbc.Upload(isDbc.data(), nV, stream);
+
+    dPtr.Alloc(nV + 1, &deviceBytes);
+    dAdj.Alloc(4 * nT, &deviceBytes);
+    DevBuf<uint32_t> dCursor, dScratch, dErr;
+    dCursor.Alloc(nV + 1);
+    dScratch.Alloc((nV + 1 + kScanTile - 1) / kScanTile + 1);
+    dErr.Alloc(1);
+    VBDX_CUDA(cudaMemsetAsync(dCursor.p, 0, (nV + 1) * sizeof(uint32_t), stream));
+    VBDX_CUDA(cudaMemsetAsync(dErr.p, 0, sizeof(uint32_t), stream));
+    CountIncidences<<<Blocks(4 * nT, 256), 256, 0, stream>>>(dE.p, 4 * nT, dCursor.p);
+    ExclusiveScanU32(dCursor.p, dPtr.p, nV + 1, dScratch.p, stream);
+    VBDX_CUDA(cudaMemsetAsync(dCursor.p, 0, (nV + 1) * sizeof(uint32_t), stream));
+    FillIncidences<<<Blocks(4 * nT, 256), 256, 0, stream>>>(dE.p, 4 * nT, dPtr.p, dCursor.p, dAdj.p);
+    SortRows<<<Blocks(nV, 128), 128, 0, stream>>>(dPtr.p, dAdj.p, nV);
+    dJinv.Alloc(9 * nT, &deviceBytes);
+    dVol.Alloc(nT, &deviceBytes);
+    ElementQuantities<<<Blocks(nT, 128), 128, 0, stream>>>(dX.p, dE.p, nT, dColor.p, dIsDbc.p, dJinv.p, dVol.p, dErr.p);
+    kernelLaunches += 7;
+
+    DevBuf<double> dLame, dRho;
+    // default material: Y = 1e6, nu = 0.45 (sim/vbd/Data.cpp:199-205, physics/HyperElasticity.cpp:6-11)
+    double const Y = 1e6, nu = 0.45;
+    double const muDefault = Y / (2. * (1. + nu)), lamDefault = (Y * nu) / ((1. + nu) * (1. - 2. * nu));
+    if (d.lame)
+    {
+        for (int64_t e = 0; e < nT; ++e)
+            Require(d.lame[2 * e + 1] != 0.0, "lambda must be non-zero (alpha = 1 + mu/lambda)");
+        dLame.Alloc(2 * nT);
+        dLame.Upload(d.lame, 2 * nT, stream);
+    }
+    dMass.Alloc(nV, &deviceBytes);
+    if (d.m)
+        dMass.Upload(d.m, nV, stream);
+    else
+    {
+        if (d.rhoe)
+        {
+            dRho.Alloc(nT);
+            dRho.Upload(d.rhoe, nT, stream);
+        }
+        VertexMass<<<Blocks(nV, 128), 128, 0, stream>>>(dPtr.p, dAdj.p, dVol.p, dRho.p, 1e3, dMass.p, nV);
+        ++kernelLaunches;
+    }
+
+    std::vector<uint32_t> ptrHost(static_cast<size_t>(nV + 1));
+    uint32_t err = 0;
+    dPtr.Download(ptrHost.data(), nV + 1, stream);
+    dErr.Download(&err, 1, stream);
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+    if (err & 1u)
+        throw Error(VBDX_INVALID_ARGUMENT, "inverted or degenerate tetrahedron in the rest mesh (det J <= 1e-10)");
+    if (err & 2u)
+        throw Error(VBDX_INVALID_ARGUMENT, "invalid colouring: two swept vertices of one tetrahedron share a colour");
+
+    // ---- launch shape, then the host plan
+    bool const cheb0 = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    // the damping variant can be switched on later (SetRayleighDampingCoefficient), so size the
+    // persistent grid for the least-resident variant of this acceleration mode
+    int perSm = 1 << 30;
+    for (StepKernelFn fn : {cheb0 ? StepKernel<true, false> : StepKernel<false, false>,
+                            cheb0 ? StepKernel<true, true> : StepKernel<false, true>})
+    {
+        int n = 0;
+        VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, 0));
+        perSm = std::min(perSm, n);
+    }
+    if (perSm < 1)
+        throw Error(VBDX_CUDA_ERROR, "step kernel does not fit on an SM");
+    gridBlocks = perSm * smCount;
+
+    std::vector<int32_t> deg(static_cast<size_t>(nV));
+    for (int64_t i = 0; i < nV; ++i)
+        deg[i] = static_cast<int32_t>(ptrHost[i + 1] - ptrHost[i]);
+    int const tileIters = d.tile_iters > 0 ? d.tile_iters : 4;
+    BuildPlan(nV, deg.data(), colors.data(), isDbc.data(), d.X, tileIters, gridBlocks,
+              (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, plan);
+    nRecordSlots = plan.nBlocks * 32;
+
+    dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
+    dTiles.Upload(plan.tiles.data(), plan.tiles.size(), stream);
+    dCtaRange.Alloc(plan.ctaTileRange.size() + 1, &deviceBytes);
+    dCtaRange.Upload(plan.ctaTileRange.data(), plan.ctaTileRange.size(), stream);
+    dNew2Old.Alloc(nV, &deviceBytes);
+    dNew2Old.Upload(plan.new2old.data(), nV, stream);
+    dOld2New.Alloc(nV, &deviceBytes);
+    dOld2New.Upload(plan.old2new.data(), nV, stream);
+    dRecords.Alloc(static_cast<size_t>(plan.nBlocks) * kBlockFloat4 + 1, &deviceBytes);
+    if (!plan.tiles.empty())
+    {
+        int const nTiles = static_cast<int>(plan.tiles.size());
+        FillRecords<<<Blocks(static_cast<int64_t>(nTiles) * 32, 256), 256, 0, stream>>>(
+            dTiles.p, nTiles, dNew2Old.p, dOld2New.p, dPtr.p, dAdj.p, dE.p, dJinv.p, dVol.p, dLame.p,
+            muDefault, lamDefault, dColor.p, dRecords.p);
+        ++kernelLaunches;
+    }
+
+    // ---- state
+    bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    dPos.Alloc(static_cast<size_t>(nV) * (cheb ? 2 : 1), &deviceBytes);
+    if (cheb)
+        dHist.Alloc(nV, &deviceBytes);
+    dXtildeM.Alloc(nV, &deviceBytes);
+    dXt.Alloc(nV, &deviceBytes);
+    dVel.Alloc(nV, &deviceBytes);
+    dAext.Alloc(nV, &deviceBytes);
+    if (flags & VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY)
+        dVtm1.Alloc(nV, &deviceBytes);
+    dBarrier.Alloc(1, &deviceBytes);
+    dStaging.Alloc(3 * nV, &deviceBytes);
+    DevBuf<double> dV0, dA0;
+    if (d.v)
+    {
+        dV0.Alloc(3 * nV);
+        dV0.Upload(d.v, 3 * nV, stream);
+    }
+    if (d.aext)
+    {
+        dA0.Alloc(3 * nV);
+        dA0.Upload(d.aext, 3 * nV, stream);
+    }
+    InitState<<<Blocks(nV, 256), 256, 0, stream>>>(
+        nV, dNew2Old.p, dX.p, dV0.p, dA0.p, dMass.p, dIsDbc.p, cheb ? static_cast<uint32_t>(nV) : 0u, dPos.p,
+        dHist.p, dXtildeM.p, dXt.p, dVel.p, dVtm1.p, dAext.p);
+    ++kernelLaunches;
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+    VBDX_CUDA(cudaGetLastError());
+}
+
+void Integrator::Step(double dt, int iterations, int substeps, bool sync)
+{
+    Require(dt > 0 && iterations >= 0 && substeps >= 1, "Step: need dt > 0, iterations >= 0, substeps >= 1");
+    VBDX_CUDA(cudaSetDevice(device));
+    bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    if (cheb && omegaIterations != iterations)
+    {
+        // ChebyshevOmega, evaluated in double like the reference's CPU integrator and rounded once
+        omegaHost.assign(std::max(iterations, 1), 1.f);
+        double const rho2 = rho * rho;
+        double omega      = 0;
+        for (int k = 0; k < iterations; ++k)
+        {
+            if (k == 0)
+                omega = 1.0;
+            else if (k == 1)
+                omega = 2.0 / (2.0 - rho2);
+            else
+                omega = (omegaMode == VBDX_OMEGA_REFERENCE) ? (4.0 / 4.0 - rho2 * omega) : 4.0 / (4.0 - rho2 * omega);
+            omegaHost[k] = static_cast<float>(omega);
+        }
+        if (dOmega.n < omegaHost.size())
+            dOmega.Alloc(omegaHost.size(), &deviceBytes);
+        dOmega.Upload(omegaHost.data(), omegaHost.size(), stream);
+        VBDX_CUDA(cudaStreamSynchronize(stream));  // omegaHost must outlive the copy
+        omegaIterations = iterations;
+    }
+    double const sdt = dt / static_cast<double>(substeps);
+    StepParams p{};
+    p.records      = dRecords.p;
+    p.tiles        = reinterpret_cast<uint4 const*>(dTiles.p);
+    p.ctaTileRange = dCtaRange.p;
+    p.nColors      = plan.nColors;
+    p.nVerts       = static_cast<int>(nV);
+    p.pos          = dPos.p;
+    p.pOff         = cheb ? static_cast<uint32_t>(nV) : 0u;
+    p.hist         = dHist.p;
+    p.xtildeM      = dXtildeM.p;
+    p.xt           = dXt.p;
+    p.vel          = dVel.p;
+    p.vtm1         = dVtm1.p;
+    p.aext         = dAext.p;
+    p.omega        = dOmega.p;
+    p.sdt          = static_cast<float>(sdt);
+    p.sdt2         = static_cast<float>(sdt * sdt);
+    p.dampD        = static_cast<float>(kD / sdt);
+    p.detHZero     = static_cast<float>(detHZero);
+    p.strategy     = strategy;
+    p.iterations   = iterations;
+    p.substeps     = substeps;
+    p.barrier      = dBarrier.p;
+    VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
+    VBDX_CUDA(cudaEventRecord(evBegin, stream));
+    void* args[] = {&p};
+    VBDX_CUDA(cudaLaunchCooperativeKernel(
+        reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, 0, stream));
+    VBDX_CUDA(cudaEventRecord(evEnd, stream));
+    ++kernelLaunches;
+    stepTimed = true;
+    if (sync)
+    {
+        VBDX_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
+        lastStepMs = ms;
+    }
+}
+
+template <class T>
+void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1)
+{
+    Require(src != nullptr && n == nV, "expected a 3 x nV array");  // gpu/impl/common/Eigen.cuh:28-35
+    VBDX_CUDA(cudaSetDevice(device));
+    T* staging = reinterpret_cast<T*>(dStaging.p);
+    VBDX_CUDA(cudaMemcpyAsync(staging, src, 3 * nV * sizeof(T), cudaMemcpyHostToDevice, stream));
+    ScatterFromCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, staging, dst0, dst1);
+    ++kernelLaunches;
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+}
+
+template <class T>
+void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n)
+{
+    Require(dst != nullptr && n == nV, "expected a 3 x nV array");
+    VBDX_CUDA(cudaSetDevice(device));
+    T* staging = reinterpret_cast<T*>(dStaging.p);
+    GatherToCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, src, staging);
+    ++kernelLaunches;
+    VBDX_CUDA(cudaMemcpyAsync(dst, staging, 3 * nV * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace vbdx
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+using vbdx::Integrator;
+
+struct vbdx_integrator {
+    Integrator impl;
+};
+
+static thread_local std::string gLastError;
+
+template <class F>
+static vbdx_status Guard(F&& f)
+{
+    try
+    {
+        f();
+        return VBDX_OK;
+    }
+    catch (vbdx::Error const& e)
+    {
+        gLastError = e.what();
+        return e.status;
+    }
+    catch (std::bad_alloc const&)
+    {
+        gLastError = "host allocation failed";
+        return VBDX_OUT_OF_MEMORY;
+    }
+    catch (std::exception const& e)
+    {
+        gLastError = e.what();
+        return VBDX_CUDA_ERROR;
+    }
+}
+
+static vbdx_status NeedHandle(vbdx_integrator* h)
+{
+    if (h)
+        return VBDX_OK;
+    gLastError = "null integrator handle";
+    return VBDX_INVALID_ARGUMENT;
+}
+
+extern "C" {
+
+const char* vbdx_last_error(void) { return gLastError.c_str(); }
+int32_t vbdx_abi_version(void) { return VBDX_ABI_VERSION; }
+
+int32_t vbdx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void vbdx_data_desc_init(vbdx_data_desc* d)
+{
+    std::memset(d, 0, sizeof(*d));
+    d->abi_version  = VBDX_ABI_VERSION;
+    d->struct_size  = sizeof(vbdx_data_desc);
+    d->ordering     = VBDX_ORDER_LARGEST_DEGREE;  // sim/vbd/Data.h:211-216
+    d->selection    = VBDX_SELECT_LEAST_USED;
+    d->strategy     = VBDX_INIT_ADAPTIVE_PBAT;    // sim/vbd/Data.h:222-223
+    d->acceleration = VBDX_ACCEL_NONE;
+    d->omega_mode   = VBDX_OMEGA_REFERENCE;
+    d->material     = VBDX_MATERIAL_STABLE_NEO_HOOKEAN;
+    d->kD           = 0.0;
+    d->detHZero     = 1e-7;
+    d->rho          = 1.0;
+    d->muC          = 1e6;
+    d->muF          = 0.3;
+    d->epsv         = 1e-3;
+    d->active_set_update_frequency = 1;
+    d->device       = -1;
+}
+
+vbdx_status vbdx_create(const vbdx_data_desc* desc, vbdx_integrator** out)
+{
+    if (!desc || !out)
+    {
+        gLastError = "vbdx_create: null argument";
+        return VBDX_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    std::unique_ptr<vbdx_integrator> h;
+    vbdx_status const st = Guard([&] {
+        h = std::make_unique<vbdx_integrator>();
+        h->impl.Create(*desc);
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+vbdx_status vbdx_destroy(vbdx_integrator* h)
+{
+    if (h)
+    {
+        cudaSetDevice(h->impl.device);
+        cudaStreamSynchronize(h->impl.stream);
+        delete h;
+    }
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_step(vbdx_integrator* h, double dt, int32_t iterations, int32_t substeps)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] { h->impl.Step(dt, iterations, substeps, true); });
+}
+
+vbdx_status vbdx_step_async(vbdx_integrator* h, double dt, int32_t iterations, int32_t substeps)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] { h->impl.Step(dt, iterations, substeps, false); });
+}
+
+vbdx_status vbdx_synchronize(vbdx_integrator* h)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        VBDX_CUDA(cudaSetDevice(h->impl.device));
+        VBDX_CUDA(cudaStreamSynchronize(h->impl.stream));
+        if (h->impl.stepTimed)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->impl.evBegin, h->impl.evEnd) == cudaSuccess)
+                h->impl.lastStepMs = ms;
+        }
+    });
+}
+
+#define VBDX_SETTER(name, T, dst0, dst1)                                                         \
+    vbdx_status name(vbdx_integrator* h, const T* a, int64_t nV)                                 \
+    {                                                                                            \
+        if (vbdx_status s = NeedHandle(h))                                                       \
+            return s;                                                                            \
+        return Guard([&] { h->impl.SetVertexField<T>(a, nV, dst0, dst1); });                     \
+    }
+#define VBDX_GETTER(name, T, src)                                                                \
+    vbdx_status name(vbdx_integrator* h, T* a, int64_t nV)                                       \
+    {                                                                                            \
+        if (vbdx_status s = NeedHandle(h))                                                       \
+            return s;                                                                            \
+        return Guard([&] { h->impl.GetVertexField<T>(src, a, nV); });                            \
+    }
+// positions live in Q (and in P when the Chebyshev double buffer exists); the step result is P
+#define VBDX_POS_Q (h->impl.dPos.p)
+#define VBDX_POS_P (h->impl.dHist.p ? h->impl.dPos.p + h->impl.nV : nullptr)
+VBDX_SETTER(vbdx_set_positions_f32, float, VBDX_POS_Q, VBDX_POS_P)
+VBDX_SETTER(vbdx_set_positions_f64, double, VBDX_POS_Q, VBDX_POS_P)
+VBDX_SETTER(vbdx_set_velocities_f32, float, h->impl.dVel.p, nullptr)
+VBDX_SETTER(vbdx_set_velocities_f64, double, h->impl.dVel.p, nullptr)
+VBDX_SETTER(vbdx_set_external_acceleration_f32, float, h->impl.dAext.p, nullptr)
+VBDX_SETTER(vbdx_set_external_acceleration_f64, double, h->impl.dAext.p, nullptr)
+VBDX_GETTER(vbdx_get_positions_f32, float, (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_Q))
+VBDX_GETTER(vbdx_get_positions_f64, double, (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_Q))
+VBDX_GETTER(vbdx_get_velocities_f32, float, h->impl.dVel.p)
+VBDX_GETTER(vbdx_get_velocities_f64, double, h->impl.dVel.p)
+
+vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    h->impl.detHZero = zero;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_set_rayleigh_damping(vbdx_integrator* h, double kD)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    h->impl.kD = kD;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_set_initialization_strategy(vbdx_integrator* h, int32_t strategy)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    if (strategy < 0 || strategy > VBDX_INIT_ADAPTIVE_PBAT)
+    {
+        gLastError = "unknown initialization strategy";
+        return VBDX_INVALID_ARGUMENT;
+    }
+    h->impl.strategy = strategy;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_set_block_size(vbdx_integrator* h, int32_t block_size)
+{
+    (void)block_size;  // the sweep is warp-tiled; the reference's knob has no equivalent here
+    return NeedHandle(h);
+}
+
+vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3], const float max3[3])
+{
+    (void)min3;
+    (void)max3;
+    return NeedHandle(h);
+}
+
+vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        VBDX_CUDA(cudaStreamSynchronize(h->impl.stream));
+        h->impl.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->impl.ownStream;
+    });
+}
+
+vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    auto const& I        = h->impl;
+    out->nV              = I.nV;
+    out->nT              = I.nT;
+    out->nActiveVertices = I.plan.nActive;
+    out->nIncidences     = I.plan.nIncidences;
+    out->nRecordSlots    = I.nRecordSlots;
+    out->nColors         = I.plan.nColors;
+    out->nTiles          = static_cast<int32_t>(I.plan.tiles.size());
+    out->gridBlocks      = I.gridBlocks;
+    out->blockThreads    = I.blockThreads;
+    out->device          = I.device;
+    out->smCount         = I.smCount;
+    out->deviceBytes     = I.deviceBytes;
+    out->kernelLaunches  = I.kernelLaunches;
+    out->lastStepMs      = I.lastStepMs;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_get_adjacency(vbdx_integrator* h, int64_t* GVGp, int64_t* GVGe, int64_t* GVGilocal)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        std::vector<uint32_t> ptr(I.nV + 1), adj(4 * I.nT);
+        I.dPtr.Download(ptr.data(), ptr.size(), I.stream);
+        I.dAdj.Download(adj.data(), adj.size(), I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        if (GVGp)
+            for (size_t k = 0; k < ptr.size(); ++k)
+                GVGp[k] = ptr[k];
+        for (size_t k = 0; k < adj.size(); ++k)
+        {
+            if (GVGe)
+                GVGe[k] = adj[k] >> 2;
+            if (GVGilocal)
+                GVGilocal[k] = adj[k] & 3u;
+        }
+    });
+}
+
+vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, double* m)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        if (GP)
+        {
+            std::vector<double> ji(9 * I.nT);
+            I.dJinv.Download(ji.data(), ji.size(), I.stream);
+            VBDX_CUDA(cudaStreamSynchronize(I.stream));
+            // Data::GP layout: 4 x 3nT column-major, GP[12e + 4d + i] (sim/vbd/Data.h:191-192)
+            for (int64_t e = 0; e < I.nT; ++e)
+                for (int d = 0; d < 3; ++d)
+                {
+                    double const* J = &ji[9 * e];
+                    GP[12 * e + 4 * d + 0] = -(J[d] + J[3 + d] + J[6 + d]);
+                    for (int i = 1; i < 4; ++i)
+                        GP[12 * e + 4 * d + i] = J[3 * (i - 1) + d];
+                }
+        }
+        if (wg)
+            I.dVol.Download(wg, I.nT, I.stream);
+        if (m)
+            I.dMass.Download(m, I.nV, I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+    });
+}
+
+vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    if (colors)
+        std::memcpy(colors, h->impl.colors.data(), h->impl.colors.size() * sizeof(int64_t));
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int64_t* colors_out)
+{
+    return Guard([&] {
+        vbdx::Require(nV > 0 && nT >= 0 && E && colors_out, "vbdx_greedy_color: bad arguments");
+        for (int64_t k = 0; k < 4 * nT; ++k)
+            vbdx::Require(E[k] >= 0 && E[k] < nV, "element index out of range");
+        std::vector<int64_t> colors;
+        vbdx::GreedyColorMesh(nV, nT, E, ordering, selection, colors);
+        std::memcpy(colors_out, colors.data(), colors.size() * sizeof(int64_t));
+    });
+}
+
+}  // extern "C"

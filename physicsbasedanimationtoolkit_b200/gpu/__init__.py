@@ -1,0 +1,2 @@
+"""``pbat.gpu`` -- only the ``vbd`` sub-module is in scope."""
+from . import vbd  # noqa: F401

@@ -1,0 +1,304 @@
+"""``pbat.sim.vbd``: the problem description (``Data``) and the double-precision-interface
+integrator, mirroring bindings/pypbat/sim/vbd/{Data,Integrator}.cpp.
+
+``Data`` is a host-side (numpy) mirror of ``pbat::sim::vbd::Data`` (sim/vbd/Data.h:27-246):
+same fluent ``with_*`` builder, same field names, same defaults, same validation errors
+(``ValueError`` where the reference throws ``std::invalid_argument``).  ``Integrator`` runs on
+the GPU -- there is no CPU integrator in this package.
+"""
+from __future__ import annotations
+
+import enum
+
+import numpy as np
+
+from .. import graph as _graph
+from .._device import DeviceIntegrator
+
+
+class InitializationStrategy(enum.IntEnum):
+    """sim/vbd/Enums.h:9-15"""
+    Position = 0
+    Inertia = 1
+    KineticEnergyMinimum = 2
+    AdaptiveVbd = 3
+    AdaptivePbat = 4
+
+
+class AccelerationStrategy(enum.IntEnum):
+    """sim/vbd/Enums.h:21-28 (Python names: bindings/pypbat/sim/vbd/Data.cpp:24-30)"""
+    Base = 0
+    Chebyshev = 1
+    Anderson = 2
+    Nesterov = 3
+    Broyden = 4
+    TrustRegion = 5
+
+
+def lame_coefficients(Y, nu):
+    """physics/HyperElasticity.cpp:6-11"""
+    mu = Y / (2.0 * (1.0 + nu))
+    lam = (Y * nu) / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    return mu, lam
+
+
+def _cols(a, rows, dtype, name):
+    a = np.asarray(a, dtype=dtype)
+    if a.ndim != 2 or a.shape[0] != rows:
+        raise ValueError(f"{name} must have {rows} rows, got shape {a.shape}")
+    return a
+
+
+class Data:
+    """Mirror of ``pbat::sim::vbd::Data``.  Arrays are numpy, one column per vertex/element."""
+
+    def __init__(self):
+        e = np.empty
+        self.X = e((3, 0))
+        self.E = e((4, 0), dtype=np.int64)
+        self.B = e(0, dtype=np.int64)
+        self.V = e(0, dtype=np.int64)
+        self.F = e((3, 0), dtype=np.int64)
+        self.XVA = e(0)
+        self.FA = e(0)
+        self.x = e((3, 0))
+        self.v = e((3, 0))
+        self.aext = e((3, 0))
+        self.m = e(0)
+        self.xt = e((3, 0))
+        self.xtilde = e((3, 0))
+        self.vt = e((3, 0))
+        self.wg = e(0)
+        self.GP = e((4, 0))
+        self.rhoe = e(0)
+        self.lame = e((2, 0))
+        self.GVGp = e(0, dtype=np.int64)
+        self.GVGe = e(0, dtype=np.int64)
+        self.GVGilocal = e(0, dtype=np.int64)
+        self.muD = 1.0
+        self.dbc = e(0, dtype=np.int64)
+        self.vertex_coloring_ordering = _graph.GreedyColorOrderingStrategy.LargestDegree
+        self.vertex_coloring_selection = _graph.GreedyColorSelectionStrategy.LeastUsed
+        self.colors = e(0, dtype=np.int64)
+        self.Pptr = e(0, dtype=np.int64)
+        self.Padj = e(0, dtype=np.int64)
+        # sim/vbd/Data.h:222-246
+        self.strategy = InitializationStrategy.AdaptivePbat
+        self.kD = 0.0
+        self.muC = 1e6
+        self.muF = 0.3
+        self.epsv = 1e-3
+        self.active_set_update_frequency = 1
+        self.detH_zero = 1e-7
+        self.accelerator = AccelerationStrategy.Base
+        self.rho = 1.0
+        self.manderson = 5
+        self.nesterov_L = 1.0
+        self.nesterov_start = 3
+        self.eta = 0.2
+        self.tau = 2.0
+        self.curved = True
+        # extension (not in the reference): which omega recurrence the Chebyshev solve uses,
+        # 0 = as the reference evaluates it, 1 = textbook (include/vbdx.h vbdx_omega_mode)
+        self.omega_mode = 0
+
+    # ---- fluent builder (sim/vbd/Data.cpp:20-177) ----------------------------------------
+    def with_volume_mesh(self, X, T):
+        self.X = _cols(X, 3, np.float64, "X").copy()
+        self.E = _cols(T, 4, np.int64, "T").copy()
+        if self.B.size == 0:
+            self.B = np.ones(self.X.shape[1], dtype=np.int64)
+        return self
+
+    def with_surface_mesh(self, V, F):
+        # vertex areas XVA and triangle areas FA as sim/vbd/Data.cpp:34-54
+        self.V = np.asarray(V, dtype=np.int64).reshape(-1).copy()
+        self.F = _cols(F, 3, np.int64, "F").copy()
+        X = self.X
+        AB = X[:, self.F[1]] - X[:, self.F[0]]
+        AC = X[:, self.F[2]] - X[:, self.F[0]]
+        dbl = np.linalg.norm(np.cross(AB, AC, axis=0), axis=0)
+        self.XVA = np.zeros(X.shape[1])
+        for r in range(3):
+            np.add.at(self.XVA, self.F[r], dbl / 6.0)
+        self.FA = dbl / 2.0
+        return self
+
+    def with_bodies(self, B):
+        self.B = np.asarray(B, dtype=np.int64).reshape(-1).copy()
+        return self
+
+    def with_velocity(self, v):
+        self.v = _cols(v, 3, np.float64, "v").copy()
+        return self
+
+    def with_acceleration(self, a):
+        self.aext = _cols(a, 3, np.float64, "a").copy()
+        return self
+
+    def with_material(self, rhoe, mue, lambdae):
+        self.rhoe = np.asarray(rhoe, dtype=np.float64).reshape(-1).copy()
+        self.lame = np.stack([np.asarray(mue, np.float64).reshape(-1),
+                              np.asarray(lambdae, np.float64).reshape(-1)])
+        return self
+
+    def with_dirichlet_vertices(self, dbc, muD=1.0, input_sorted=True):
+        self.dbc = np.asarray(dbc, dtype=np.int64).reshape(-1).copy()
+        self.muD = float(muD)
+        if not input_sorted:
+            self.dbc.sort()
+        return self
+
+    def with_vertex_coloring_strategy(self, ordering, selection):
+        self.vertex_coloring_ordering = _graph.GreedyColorOrderingStrategy(ordering)
+        self.vertex_coloring_selection = _graph.GreedyColorSelectionStrategy(selection)
+        return self
+
+    def with_initialization_strategy(self, strategy):
+        self.strategy = InitializationStrategy(strategy)
+        return self
+
+    def with_rayleigh_damping(self, kD):
+        self.kD = float(kD)
+        return self
+
+    def with_contact_parameters(self, muC, muF, epsv):
+        self.muC, self.muF, self.epsv = float(muC), float(muF), float(epsv)
+        return self
+
+    def with_active_set_update_frequency(self, frequency):
+        self.active_set_update_frequency = int(frequency)
+        return self
+
+    def with_hessian_determinant_zero(self, zero):
+        self.detH_zero = float(zero)
+        return self
+
+    def with_chebyshev_acceleration(self, rho):
+        self.rho = float(rho)
+        self.accelerator = AccelerationStrategy.Chebyshev
+        return self
+
+    def with_anderson_acceleration(self, window_size):
+        self.manderson = int(window_size)
+        self.accelerator = AccelerationStrategy.Anderson
+        return self
+
+    def with_broyden_acceleration(self, window_size):
+        self.manderson = int(window_size)
+        self.accelerator = AccelerationStrategy.Broyden
+        return self
+
+    def with_nesterov_acceleration(self, L, start):
+        self.nesterov_L, self.nesterov_start = float(L), int(start)
+        self.accelerator = AccelerationStrategy.Nesterov
+        return self
+
+    def with_trust_region_acceleration(self, eta, tau, curved):
+        self.eta, self.tau, self.curved = float(eta), float(tau), bool(curved)
+        self.accelerator = AccelerationStrategy.TrustRegion
+        return self
+
+    # ---- Data::Construct (sim/vbd/Data.cpp:179-308) --------------------------------------
+    def construct(self, validate=True):
+        X, E = self.X, self.E
+        nV, nT = X.shape[1], E.shape[1]
+        if nT and (E.min() < 0 or E.max() >= nV):
+            raise ValueError("element index out of range")
+        self.x = X.copy()
+        if self.xt.size == 0:
+            self.xt = self.x.copy()
+        if self.v.size == 0:
+            self.v = np.zeros_like(self.x)
+        if self.aext.size == 0:
+            self.aext = np.zeros_like(self.x)
+            self.aext[2] = -9.81
+        self.xtilde = np.zeros_like(self.x)
+        self.vt = np.zeros_like(self.x)
+        if self.lame.size == 0:
+            mu, lam = lame_coefficients(1e6, 0.45)
+            self.lame = np.empty((2, nT))
+            self.lame[0], self.lame[1] = mu, lam
+        if self.rhoe.size == 0:
+            self.rhoe = np.full(nT, 1e3)
+        # shape function gradients (fem/ShapeFunctions.h:267-297), quadrature weights
+        # (fem/MeshQuadrature.h:75-88) and lumped mass (fem/Mass.h:791-830) for linear tets
+        J = np.stack([X[:, E[a]] - X[:, E[0]] for a in (1, 2, 3)], axis=2).transpose(1, 0, 2)  # nT x 3 x 3
+        det = np.linalg.det(J)
+        if np.any(det <= 1e-10):
+            raise ValueError("inverted or degenerate tetrahedron in the rest mesh")  # fem/Jacobian.h:68-80
+        Jinv = np.linalg.inv(J)                      # rows = gradients of local vertices 1..3
+        G = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)  # nT x 4 x 3
+        self.GP = np.ascontiguousarray(G.transpose(1, 0, 2).reshape(4, 3 * nT))
+        self.wg = det / 6.0
+        self.m = np.bincount(E.reshape(-1), weights=np.tile(self.rhoe * self.wg / 4.0, 4), minlength=nV)
+        # vertex -> tet adjacency, ascending element id per vertex (sim/vbd/Data.cpp:223-226)
+        flat = E.T.reshape(-1)                       # entry k = 4 e + ilocal
+        order = np.argsort(flat, kind="stable")
+        self.GVGp = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=nV))]).astype(np.int64)
+        self.GVGe = (order // 4).astype(np.int64)
+        self.GVGilocal = (order % 4).astype(np.int64)
+        # colouring and partitions (sim/vbd/Data.cpp:228-231)
+        self.colors = _graph.mesh_greedy_color(E, nV, self.vertex_coloring_ordering,
+                                               self.vertex_coloring_selection)
+        nC = int(self.colors.max()) + 1 if nV else 0
+        keep = np.ones(nV, dtype=bool)
+        if self.dbc.size:  # sim/vbd/Data.cpp:236-243
+            if self.dbc.min() < 0 or self.dbc.max() >= nV:
+                raise ValueError("Dirichlet vertex index out of range")
+            self.v[:, self.dbc] = 0.0
+            self.aext[:, self.dbc] = 0.0
+            keep[self.dbc] = False
+        verts = np.flatnonzero(keep)
+        part = np.argsort(self.colors[verts], kind="stable")
+        self.Padj = verts[part].astype(np.int64)
+        self.Pptr = np.concatenate([[0], np.cumsum(np.bincount(self.colors[verts], minlength=nC))]).astype(np.int64)
+        if validate:  # sim/vbd/Data.cpp:245-306
+            ok = (self.xt.shape == self.x.shape and self.v.shape == self.x.shape and
+                  self.aext.shape == self.x.shape and self.m.size == nV and self.B.size == nV and
+                  self.x.shape[0] == 3)
+            if not ok:
+                raise ValueError(
+                    f"x, v, aext, m and B must have same #columns={nV} as x, and 3 rows (except m and B)")
+            A = AccelerationStrategy
+            if self.accelerator == A.Chebyshev and not (0 < self.rho < 1):
+                raise ValueError("Expected 0 < rho < 1")
+            if self.accelerator in (A.Anderson, A.Broyden) and self.manderson < 1:
+                raise ValueError("Expected m > 0")
+            if self.accelerator == A.Nesterov:
+                if self.nesterov_L <= 0:
+                    raise ValueError("Expected L > 0")
+                if self.nesterov_start < 0:
+                    raise ValueError("Expected start >= 0")
+            if self.accelerator == A.TrustRegion:
+                if self.eta < 0:
+                    raise ValueError("Expected eta >= 0")
+                if self.tau <= 1:
+                    raise ValueError("Expected tau > 1")
+        return self
+
+
+class Integrator(DeviceIntegrator):
+    """``pbat.sim.vbd.Integrator`` (bindings/pypbat/sim/vbd/Integrator.cpp:30-90): positions and
+    velocities cross the boundary as float64 3 x nV arrays.  Dispatch on ``data.accelerator``
+    happens at construction like the reference's factory; strategies other than Base and
+    Chebyshev raise ``NotImplementedError``."""
+
+    _dtype = np.float64
+
+    def __init__(self, data: Data, **tuning):
+        super().__init__(data, **tuning)
+        self.data = data
+
+    def step(self, dt, iterations, substeps=1):
+        self._step(dt, iterations, substeps)
+        # keep the public `data` member in sync, like the reference whose Step mutates data.x / data.v
+        self.data.x = self.x
+        self.data.v = self.v
+
+    def trace_next_step(self, path=".", t=-1):
+        raise NotImplementedError("iterate tracing is not implemented (SURVEY.md section 8f, rank 3)")
+
+    strategy = property(lambda s: InitializationStrategy(s._strategy), lambda s, v: s._set_strategy(v))
+    kD = property(lambda s: s._kD, lambda s, v: s._set_kD(v))
+    detH_residual = property(lambda s: s._detH, lambda s, v: s._set_detH(v))
