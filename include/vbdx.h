@@ -115,7 +115,17 @@ typedef struct vbdx_data_desc {
     int32_t device;        /* CUDA device ordinal, -1 = current device */
     int32_t tile_iters;    /* tuning: target incident tets per lane (0 = default) */
     int32_t flags;         /* VBDX_FLAG_* */
+    int32_t kernel_variant;/* tuning: vbdx_kernel_variant (0 = default) */
+    int32_t ring_slots;    /* tuning: shared-memory ring capacity in 2 KB record blocks (0 = default) */
 } vbdx_data_desc;
+
+/* Which persistent step kernel runs the sweeps.  Both compute the same arithmetic in the same order. */
+typedef enum vbdx_kernel_variant {
+    VBDX_KERNEL_DEFAULT = 0,
+    VBDX_KERNEL_DIRECT  = 1, /* every warp loads its records straight from global memory */
+    VBDX_KERNEL_TMA     = 2  /* warp-specialised: a producer warp streams records into a shared-memory ring with
+                                bulk asynchronous copies (TMA) across the colour barriers */
+} vbdx_kernel_variant;
 
 #define VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY 1 /* AdaptiveVbd uses the stored v(t-1) like the reference's GPU
                                                 path (gpu/impl/vbd/Integrator.cu:333) instead of the CPU path's
@@ -190,6 +200,11 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out);
 vbdx_status vbdx_get_adjacency(vbdx_integrator* h, int64_t* GVGp, int64_t* GVGe, int64_t* GVGilocal);
 vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, double* m);
 vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
+
+/* Diagnostics: with out == NULL, arm phase tracing of sweep `iteration` for the following steps (direct kernel
+ * variant); with out != NULL, read back nColors x gridBlocks x 4 %globaltimer stamps (phase start, warp 0 done,
+ * CTA done, barrier released) and disarm. */
+vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned long long* out, int64_t capacity);
 
 /* Host-only helpers (no device needed): the reference's greedy colouring of the mesh primal
  * graph, graph/Color.h:45-135 on graph/Mesh.h:116-123, as Data::Construct calls it

@@ -20,7 +20,7 @@ def _interleaved(a, dtype, nV, name):
 class DeviceIntegrator:
     _dtype = np.float32
 
-    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None):
+    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0):
         L = _lib.lib()
         if data.x.size == 0:
             raise ValueError("Data.construct() must be called before creating an integrator")
@@ -63,6 +63,7 @@ class DeviceIntegrator:
         d.muC, d.muF, d.epsv = float(data.muC), float(data.muF), float(data.epsv)
         d.active_set_update_frequency = int(data.active_set_update_frequency)
         d.device, d.tile_iters, d.flags = int(device), int(tile_iters), int(flags)
+        d.kernel_variant, d.ring_slots = int(kernel_variant), int(ring_slots)
         # rest positions differ from x only if the caller edited data.x after construct(); the
         # element rest data must come from X (sim/vbd/Data.cpp:220-221)
         self._rest_differs = not np.array_equal(data.x, data.X)
@@ -161,3 +162,13 @@ class DeviceIntegrator:
         c = np.empty(self.nV, np.int64)
         _lib.check(self._L.vbdx_get_colors(self._h, c.ctypes.data))
         return c
+
+    def trace_phases(self, iteration, dt, iterations, substeps=1):
+        """Diagnostics (direct kernel): %globaltimer stamps [colour, CTA, 4] of one sweep iteration."""
+        info = self.info
+        n = info["nColors"] * info["gridBlocks"] * 4
+        _lib.check(self._L.vbdx_debug_trace(self._h, int(iteration), None, 0))
+        self._step(dt, iterations, substeps)
+        out = np.zeros(n, dtype=np.uint64)
+        _lib.check(self._L.vbdx_debug_trace(self._h, int(iteration), out.ctypes.data, n))
+        return out.reshape(info["nColors"], info["gridBlocks"], 4)

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvbdx.so")
 VBDX_OK, VBDX_INVALID_ARGUMENT, VBDX_NO_DEVICE, VBDX_CUDA_ERROR, VBDX_OUT_OF_MEMORY, VBDX_UNSUPPORTED = range(6)
 FLAG_ADAPTIVE_VBD_GPU_HISTORY = 1
 FLAG_NATURAL_VERTEX_ORDER = 2
+KERNEL_DEFAULT, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 
 
 class DataDesc(C.Structure):
@@ -32,6 +33,7 @@ class DataDesc(C.Structure):
         ("muC", C.c_double), ("muF", C.c_double), ("epsv", C.c_double),
         ("active_set_update_frequency", C.c_int32),
         ("device", C.c_int32), ("tile_iters", C.c_int32), ("flags", C.c_int32),
+        ("kernel_variant", C.c_int32), ("ring_slots", C.c_int32),
     ]
 
 
@@ -72,6 +74,7 @@ SYMBOLS = {
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),
     "vbdx_set_scene_bounding_box": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_debug_trace": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_get_info": (C.c_int, [_H, C.POINTER(Info)]),
     "vbdx_get_adjacency": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_get_element_data": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),

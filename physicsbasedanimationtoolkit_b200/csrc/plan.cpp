@@ -259,6 +259,7 @@ void BuildPlan(
     // per colour, split the tile range between CTAs by equal record-block counts
     gridBlocks = std::max(1, gridBlocks);
     plan.ctaTileRange.assign(static_cast<size_t>(nColors) * (gridBlocks + 1), 0);
+    plan.ctaBlockBegin.assign(static_cast<size_t>(nColors) * (gridBlocks + 1), 0);
     for (int64_t c = 0; c < nColors; ++c)
     {
         uint32_t const tb = plan.colorTileBegin[c], te = plan.colorTileBegin[c + 1];
@@ -275,6 +276,9 @@ void BuildPlan(
                 ++t;
         }
         range[gridBlocks] = te;
+        uint32_t* blk = &plan.ctaBlockBegin[c * (gridBlocks + 1)];
+        for (int b = 0; b <= gridBlocks; ++b)
+            blk[b] = static_cast<uint32_t>(range[b] < te ? plan.tiles[range[b]].blockStart : b1);
     }
 }
 

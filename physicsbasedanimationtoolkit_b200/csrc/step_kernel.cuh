@@ -43,6 +43,8 @@ struct StepParams {
     int strategy;
     int iterations, substeps;
     unsigned int* barrier;  // zeroed before launch
+    unsigned long long* trace;  // optional [nColors][gridDim.x][4] timestamps of one iteration (diagnostics)
+    int traceIteration;
 };
 
 __device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p)
@@ -60,16 +62,27 @@ __device__ __forceinline__ void AddRelease(unsigned int* p, unsigned int v)
 // All CTAs of the (cooperatively launched, fully resident) grid meet here.  The release/acquire
 // pair at gpu scope orders every position written before the barrier against every weak load
 // after it, and invalidates this SM's L1 so those loads may use the default cached path.
-__device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int& target)
+__device__ __forceinline__ unsigned long long GlobalTimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr)
 {
     __syncthreads();
     if (threadIdx.x == 0)
     {
+        if (trace)
+            trace[2] = GlobalTimer();  // every warp of this CTA has finished the phase
         target += gridDim.x;
         AddRelease(counter, 1u);
         while (LoadAcquire(counter) < target)
         {
         }
+        if (trace)
+            trace[3] = GlobalTimer();  // barrier released
     }
     __syncthreads();
 }
@@ -346,8 +359,17 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
             float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
             for (int c = 0; c < p.nColors; ++c)
             {
+                unsigned long long* tr = nullptr;
+                if (p.trace != nullptr && k == p.traceIteration)
+                {
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 4;
+                    if (threadIdx.x == 0)
+                        tr[0] = GlobalTimer();
+                }
                 SweepColor<kChebyshev, kDamping>(p, c, k, omega);
-                GridBarrier(p.barrier, target);
+                if (tr != nullptr && threadIdx.x == 0)
+                    tr[1] = GlobalTimer();  // warp 0 done
+                GridBarrier(p.barrier, target, tr);
             }
         }
     }

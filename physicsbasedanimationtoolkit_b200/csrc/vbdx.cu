@@ -5,6 +5,7 @@
 
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
+#include "step_kernel_tma.cuh"
 #include "vbdx_internal.h"
 
 #include <cmath>
@@ -77,6 +78,7 @@ struct DevBuf {
 static inline int Blocks(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
 using StepKernelFn = void (*)(StepParams);
+using TmaKernelFn  = void (*)(TmaParams);
 
 struct Integrator {
     int device = 0, smCount = 0;
@@ -89,6 +91,9 @@ struct Integrator {
 
     Plan plan;
     int gridBlocks = 0, blockThreads = 256;
+    int variant = VBDX_KERNEL_DIRECT;
+    uint32_t ringSlots = 0;
+    size_t smemBytes   = 0;
     int64_t nRecordSlots = 0;
 
     // parameters
@@ -109,7 +114,7 @@ struct Integrator {
     // static sweep data
     DevBuf<float4> dRecords;
     DevBuf<TileDesc> dTiles;
-    DevBuf<uint32_t> dCtaRange;
+    DevBuf<uint32_t> dCtaRange, dCtaBlockBegin;
     DevBuf<int32_t> dNew2Old, dOld2New;
 
     // state
@@ -117,6 +122,8 @@ struct Integrator {
     DevBuf<float> dOmega;
     DevBuf<unsigned int> dBarrier;
     DevBuf<double> dStaging;  // 3 nV doubles
+    DevBuf<unsigned long long> dTrace;
+    int traceIteration = -1;
 
     ~Integrator()
     {
@@ -135,6 +142,15 @@ struct Integrator {
         if (cheb)
             return damp ? StepKernel<true, true> : StepKernel<true, false>;
         return damp ? StepKernel<false, true> : StepKernel<false, false>;
+    }
+
+    TmaKernelFn KernelTma() const
+    {
+        bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+        bool const damp = kD != 0.0;
+        if (cheb)
+            return damp ? StepKernelTma<true, true> : StepKernelTma<true, false>;
+        return damp ? StepKernelTma<false, true> : StepKernelTma<false, false>;
     }
 
     void Create(vbdx_data_desc const& d);
@@ -278,13 +294,38 @@ void Integrator::Create(vbdx_data_desc const& d)
     bool const cheb0 = acceleration == VBDX_ACCEL_CHEBYSHEV;
     // the damping variant can be switched on later (SetRayleighDampingCoefficient), so size the
     // persistent grid for the least-resident variant of this acceleration mode
+    variant = d.kernel_variant == VBDX_KERNEL_DEFAULT ? VBDX_KERNEL_TMA : d.kernel_variant;
+    Require(variant == VBDX_KERNEL_DIRECT || variant == VBDX_KERNEL_TMA, "unknown kernel variant");
     int perSm = 1 << 30;
-    for (StepKernelFn fn : {cheb0 ? StepKernel<true, false> : StepKernel<false, false>,
-                            cheb0 ? StepKernel<true, true> : StepKernel<false, true>})
+    if (variant == VBDX_KERNEL_TMA)
     {
-        int n = 0;
-        VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, 0));
-        perSm = std::min(perSm, n);
+        blockThreads = kTmaThreads;
+        int maxOptin = 0;
+        VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - 1024) / (kBlockBytes + 16));
+        ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : 104u;
+        ringSlots = std::max(2u, std::min(ringSlots, maxSlots));
+        smemBytes = static_cast<size_t>(ringSlots) * (kBlockBytes + 16);
+        for (TmaKernelFn fn : {cheb0 ? StepKernelTma<true, false> : StepKernelTma<false, false>,
+                               cheb0 ? StepKernelTma<true, true> : StepKernelTma<false, true>})
+        {
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            int n = 0;
+            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
+            perSm = std::min(perSm, n);
+        }
+        perSm = std::min(perSm, 1);  // the ring is sized for one CTA per SM
+    }
+    else
+    {
+        blockThreads = 256;
+        for (StepKernelFn fn : {cheb0 ? StepKernel<true, false> : StepKernel<false, false>,
+                                cheb0 ? StepKernel<true, true> : StepKernel<false, true>})
+        {
+            int n = 0;
+            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, 0));
+            perSm = std::min(perSm, n);
+        }
     }
     if (perSm < 1)
         throw Error(VBDX_CUDA_ERROR, "step kernel does not fit on an SM");
@@ -302,6 +343,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     dTiles.Upload(plan.tiles.data(), plan.tiles.size(), stream);
     dCtaRange.Alloc(plan.ctaTileRange.size() + 1, &deviceBytes);
     dCtaRange.Upload(plan.ctaTileRange.data(), plan.ctaTileRange.size(), stream);
+    dCtaBlockBegin.Alloc(plan.ctaBlockBegin.size() + 1, &deviceBytes);
+    dCtaBlockBegin.Upload(plan.ctaBlockBegin.data(), plan.ctaBlockBegin.size(), stream);
     dNew2Old.Alloc(nV, &deviceBytes);
     dNew2Old.Upload(plan.new2old.data(), nV, stream);
     dOld2New.Alloc(nV, &deviceBytes);
@@ -399,11 +442,26 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.iterations   = iterations;
     p.substeps     = substeps;
     p.barrier      = dBarrier.p;
+    p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
+    p.traceIteration = traceIteration;
     VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
-    void* args[] = {&p};
-    VBDX_CUDA(cudaLaunchCooperativeKernel(
-        reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, 0, stream));
+    if (variant == VBDX_KERNEL_TMA)
+    {
+        TmaParams tp{};
+        tp.base          = p;
+        tp.ctaBlockBegin = dCtaBlockBegin.p;
+        tp.ringSlots     = ringSlots;
+        void* args[]     = {&tp};
+        VBDX_CUDA(cudaLaunchCooperativeKernel(
+            reinterpret_cast<void const*>(KernelTma()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+    }
+    else
+    {
+        void* args[] = {&p};
+        VBDX_CUDA(cudaLaunchCooperativeKernel(
+            reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, 0, stream));
+    }
     VBDX_CUDA(cudaEventRecord(evEnd, stream));
     ++kernelLaunches;
     stepTimed = true;
@@ -659,6 +717,30 @@ vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream)
     return Guard([&] {
         VBDX_CUDA(cudaStreamSynchronize(h->impl.stream));
         h->impl.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->impl.ownStream;
+    });
+}
+
+vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned long long* out, int64_t capacity)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        size_t const n = static_cast<size_t>(I.plan.nColors) * I.gridBlocks * 4;
+        if (out == nullptr)
+        {
+            // arm: the next steps record the timestamps of `iteration` (direct kernel only)
+            if (I.dTrace.n < n)
+                I.dTrace.Alloc(n, &I.deviceBytes);
+            VBDX_CUDA(cudaMemsetAsync(I.dTrace.p, 0, n * sizeof(unsigned long long), I.stream));
+            I.traceIteration = iteration;
+            return;
+        }
+        vbdx::Require(capacity >= static_cast<int64_t>(n) && I.dTrace.p != nullptr, "trace buffer too small or tracing not armed");
+        I.dTrace.Download(out, n, I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        I.traceIteration = -1;
     });
 }
 

@@ -47,6 +47,7 @@ struct Plan {
     std::vector<TileDesc> tiles;
     std::vector<uint32_t> colorTileBegin;    // nColors + 1
     std::vector<uint32_t> ctaTileRange;      // nColors x (gridBlocks + 1): tiles of colour c for CTA b
+    std::vector<uint32_t> ctaBlockBegin;     // nColors x (gridBlocks + 1): first record block of CTA b in colour c
     int64_t nBlocks = 0;
     int64_t nIncidences = 0;                 // over swept vertices
 };

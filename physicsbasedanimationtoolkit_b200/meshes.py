@@ -50,7 +50,7 @@ def boundary_facets(T: np.ndarray):
     """Boundary triangles of a tet mesh, oriented outward (normal points away from the tet).
     Returns F (3 x nF)."""
     # faces opposite each local vertex, outward for a positively oriented tet
-    loc = np.array([[1, 3, 2], [0, 2, 3], [0, 3, 1], [0, 1, 2]])
+    loc = np.array([[1, 2, 3], [0, 3, 2], [0, 1, 3], [0, 2, 1]])
     faces = np.concatenate([T[loc[a]] for a in range(4)], axis=1)  # 3 x 4nT
     key = np.sort(faces, axis=0)
     _, inv, cnt = np.unique(key, axis=1, return_inverse=True, return_counts=True)

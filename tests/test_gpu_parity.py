@@ -19,7 +19,8 @@ def rel_l2(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
-def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile_iters=0, klass=None, flags=0, v=None):
+def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile_iters=0, klass=None, flags=0, v=None,
+         kernel_variant=0, ring_slots=0):
     d = pbat.sim.vbd.Data().with_volume_mesh(X, T)
     if dbc is not None:
         d = d.with_dirichlet_vertices(dbc)
@@ -32,7 +33,7 @@ def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile
     d.omega_mode = omega_mode
     d = d.with_rayleigh_damping(kD).construct()
     klass = klass or pbat.gpu.vbd.Integrator
-    vbd = klass(d, tile_iters=tile_iters, flags=flags)
+    vbd = klass(d, tile_iters=tile_iters, flags=flags, kernel_variant=kernel_variant, ring_slots=ring_slots)
     ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, v=v,
                         accel=oracle.ACCEL_CHEBYSHEV if cheb else oracle.ACCEL_NONE, rho=cheb or 1.0,
                         omega_mode=omega_mode, kD=kD,
@@ -174,3 +175,57 @@ def test_errors():
     d2 = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_anderson_acceleration(5).construct()
     with pytest.raises(NotImplementedError):
         pbat.gpu.vbd.Integrator(d2)
+
+
+@pytest.mark.parametrize("name", ["cube_base", "cube_cheb", "beam_small_base", "beam_small_cheb",
+                                  "beam_small_cheb_textbook", "beam_small_substeps_damped", "beam_small_position",
+                                  "beam_small_inertia", "beam_small_kinetic", "beam_small_adaptive_vbd",
+                                  "config1_base", "config1_cheb"])
+def test_against_reference_golden(name):
+    """CUDA path vs trajectories produced by the reference's own headers (tests/golden/make_golden.py)."""
+    import os
+
+    from golden.make_golden import CASES, mesh_of
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "vbd_golden.npz"))
+    spec, kw, dt, iters, sub, steps = CASES[name]
+    X, T, dbc = mesh_of(spec)
+    d, vbd, _ = make(X, T, dbc=dbc, cheb=kw.get("rho") if kw.get("accel") else None, kD=kw.get("kD", 0.0),
+                     omega_mode=kw.get("omega_mode", 0),
+                     strategy=pbat.sim.vbd.InitializationStrategy(kw["strategy"]) if "strategy" in kw else None)
+    assert np.array_equal(d.colors, gold[name + "/colors"])
+    for _ in range(steps):
+        vbd.step(dt, iters, sub)
+    g = gold[name + "/x"]
+    err = rel_l2(vbd.x, g)
+    print(f"{name}: rel L2 vs reference golden = {err:.3e}")
+    assert err < TOL
+
+
+@pytest.mark.parametrize("cheb", [None, 0.9])
+@pytest.mark.parametrize("ring_slots", [0, 3, 16])
+def test_kernel_variants_bitwise_identical(cheb, ring_slots):
+    """The direct and the TMA-ring kernels do the same arithmetic in the same order: identical bits.
+    Small rings force many wrap-arounds of the producer/consumer pipeline."""
+    X, T = meshes.tet_grid(12, 6, 5, 0.1)
+    dbc = np.flatnonzero(X[0] == 0)
+    out = []
+    for variant in (1, 2):
+        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kD=1e-4, kernel_variant=variant, ring_slots=ring_slots, tile_iters=2)
+        for _ in range(3):
+            vbd.step(0.01, 7, 2)
+        out.append((vbd.x, vbd.v))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    for _ in range(3):
+        ref.step(0.01, 7, 2)
+    assert rel_l2(out[1][0], ref.x) < TOL
+
+
+def test_direct_variant_config1():
+    X, T = meshes.tet_grid(25, 9, 9, 0.04)
+    dbc = np.flatnonzero(X[0] == 0)
+    d, vbd, ref = make(X, T, dbc=dbc, cheb=0.9, kernel_variant=1)
+    for s in range(20):
+        vbd.step(0.01, 20, 1)
+        ref.step(0.01, 20, 1)
+    assert rel_l2(vbd.x, ref.x) < TOL

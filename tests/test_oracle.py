@@ -1,0 +1,105 @@
+"""CPU tests of the oracle (test infrastructure): the restated port against the reference's own
+known-answer tests and against golden trajectories generated from the reference-header build."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from physicsbasedanimationtoolkit_b200 import meshes
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "vbd_golden.npz"))
+from golden.make_golden import CASES, run  # noqa: E402
+
+KINDS = ["port"] + (["reference"] if oracle.have_ref() else [])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cube_free_fall_known_answer(kind):
+    """sim/vbd/Integrator.cpp:245-293: dz < 0, |dxy| < 1e-4, |grad f| < 1e-4, f < f0 (analytic dz = -9.81e-4)."""
+    o = oracle.Oracle(meshes.CUBE_P, meshes.CUBE_T, kind=kind)
+    assert list(o.get("colors")) == [0, 3, 2, 1, 1, 2, 3, 0]
+    dt = 1e-2
+    x0 = o.x
+    xtilde = x0 + dt * o.v + dt * dt * o.get("aext")
+    f0 = o.objective(x0, xtilde, dt)
+    o.step(dt, 10, 1)
+    dx = o.x - meshes.CUBE_P
+    assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+    assert np.allclose(dx[2], -9.81e-4, atol=1e-8)
+    assert np.linalg.norm(o.objective_gradient(o.x, xtilde, dt)) < 1e-4
+    assert o.objective(o.x, xtilde, dt) < f0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cube_chebyshev_known_answer(kind):
+    """sim/vbd/ChebyshevIntegrator.cpp:40-85 (rho = 0.9)"""
+    o = oracle.Oracle(meshes.CUBE_P, meshes.CUBE_T, accel=oracle.ACCEL_CHEBYSHEV, rho=0.9, kind=kind)
+    o.step(1e-2, 10, 1)
+    dx = o.x - meshes.CUBE_P
+    assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_snh_energy_at_identity(kind):
+    """physics/StableNeoHookeanEnergy.cpp:10-43: psi(I) = 0.5 mu (I2 - 3) + 0.5 lambda (I3 - gamma)^2 >= 0"""
+    mu, lam = 3.4e5, 3.1e6
+    psi = oracle.snh_eval(np.eye(3), mu, lam, kind=kind)
+    gamma = 1 + mu / lam
+    assert psi >= 0 and abs(psi - 0.5 * lam * (1 - gamma) ** 2) < 1e-9 * max(1.0, psi)
+
+
+def test_coloring_is_proper_for_all_strategies():
+    """graph/Color.cpp:9-49"""
+    X, T = meshes.tet_grid(4, 3, 3)
+    for ordering in range(3):
+        for selection in range(2):
+            o = oracle.Oracle(X, T, ordering=ordering, selection=selection)
+            c = o.get("colors")
+            for a in range(4):
+                for b in range(a + 1, 4):
+                    assert (c[T[a]] != c[T[b]]).all()
+
+
+def test_setup_quantities():
+    X, T = meshes.tet_grid(3, 2, 2, 0.5)
+    o = oracle.Oracle(X, T)
+    assert np.allclose(o.get("wg"), meshes.tet_volumes(X, T))
+    assert np.isclose(o.get("m").sum(), 1e3 * 3 * 2 * 2 * 0.125)
+    GP = o.get("GP")
+    assert np.allclose(GP.sum(axis=0), 0, atol=1e-12)  # gradients of a partition of unity
+    p, e, il = o.get("GVGp"), o.get("GVGe"), o.get("GVGilocal")
+    for i in range(X.shape[1]):
+        row = e[p[i]:p[i + 1]]
+        assert (np.diff(row) > 0).all() and (T[il[p[i]:p[i + 1]], row] == i).all()
+
+
+def test_invalid_inputs():
+    X, T = meshes.tet_grid(2, 2, 2)
+    with pytest.raises(ValueError):
+        oracle.Oracle(X, T[[1, 0, 2, 3]])  # inverted tets
+    with pytest.raises(ValueError):
+        oracle.Oracle(X, T, accel=oracle.ACCEL_CHEBYSHEV, rho=1.5)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if not n.startswith("config1")])
+def test_port_matches_reference_golden(name):
+    """The restated arithmetic (closed-form SNH block) against trajectories produced by the reference's
+    own headers (9x9 Hessian route): agreement to round-off."""
+    x, v, c = run(name, "port")
+    assert np.array_equal(c, GOLD[name + "/colors"])
+    assert np.allclose(x, GOLD[name + "/x"], rtol=0, atol=1e-10)
+    assert np.allclose(v, GOLD[name + "/v"], rtol=0, atol=1e-8)
+
+
+def test_port_matches_reference_golden_config1():
+    """BASELINE.json configs[0] (100 steps x 20 iterations, ~10k tets)."""
+    x, v, c = run("config1_base", "port")
+    g = GOLD["config1_base/x"]
+    assert np.linalg.norm(x - g) / np.linalg.norm(g) < 1e-9
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="needs oracle/_ref (reference tree)")
+def test_live_reference_matches_golden():
+    x, _, _ = run("beam_small_cheb", "reference")
+    assert np.array_equal(x, GOLD["beam_small_cheb/x"])
