@@ -115,7 +115,7 @@ typedef struct vbdx_data_desc {
     int32_t device;        /* CUDA device ordinal, -1 = current device */
     int32_t tile_iters;    /* tuning: target incident tets per lane (0 = default) */
     int32_t flags;         /* VBDX_FLAG_* */
-    int32_t kernel_variant;/* tuning: vbdx_kernel_variant (0 = default) */
+    int32_t kernel_variant;/* tuning: enum vbdx_kernel_variant; 0 = default */
     int32_t ring_slots;    /* tuning: shared-memory ring capacity in 2 KB record blocks (0 = default) */
 } vbdx_data_desc;
 
@@ -202,8 +202,8 @@ vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, do
 vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
 
 /* Diagnostics: with out == NULL, arm phase tracing of sweep `iteration` for the following steps (direct kernel
- * variant); with out != NULL, read back nColors x gridBlocks x 4 %globaltimer stamps (phase start, warp 0 done,
- * CTA done, barrier released) and disarm. */
+ * variant); with out != NULL, read back nColors x gridBlocks x 8 %globaltimer stamps (phase start, warp 0 done,
+ * CTA done, barrier released; warp 0's first tile: descriptor loaded, 1-rings staged, tets accumulated, solved) and disarm. */
 vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned long long* out, int64_t capacity);
 
 /* Host-only helpers (no device needed): the reference's greedy colouring of the mesh primal

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <stdexcept>
 
 namespace vbdx {
 
@@ -145,12 +146,13 @@ void GreedyColorMesh(
 
 void BuildPlan(
     int64_t nV,
-    const int32_t* deg,
+    const int32_t* E,
+    const uint32_t* vtPtr,
+    const uint32_t* vtAdj,
     const int64_t* colors,
     const uint8_t* isDbc,
     const double* X,
     int tileIters,
-    int gridBlocks,
     bool naturalOrder,
     Plan& plan)
 {
@@ -170,6 +172,34 @@ void BuildPlan(
         ext = std::max(ext, hi[d] - lo[d]);
     if (!(ext > 0))
         ext = 1;
+    // 1-ring (distinct other vertices of the incident tets) of every vertex, caller numbering
+    std::vector<uint32_t> ringPtr(nV + 1, 0);
+    std::vector<int32_t> ring;
+    {
+        std::vector<int64_t> stamp(nV, -1);
+        ring.reserve(static_cast<size_t>(nV) * 14);
+        for (int64_t u = 0; u < nV; ++u)
+        {
+            if (!isDbc[u])
+            {
+                stamp[u] = u;
+                for (uint32_t k = vtPtr[u]; k < vtPtr[u + 1]; ++k)
+                {
+                    int64_t const e = vtAdj[k] >> 2;
+                    for (int a = 0; a < 4; ++a)
+                    {
+                        int32_t const w = E[4 * e + a];
+                        if (stamp[w] != u)
+                        {
+                            stamp[w] = u;
+                            ring.push_back(w);
+                        }
+                    }
+                }
+            }
+            ringPtr[u + 1] = static_cast<uint32_t>(ring.size());
+        }
+    }
     struct Item {
         uint64_t key;
         int32_t v;
@@ -184,7 +214,7 @@ void BuildPlan(
         nColors = std::max<int64_t>(nColors, colors[i] + 1);
         if (isDbc[i])
             continue;
-        int const d = deg[i];
+        int const d = static_cast<int>(vtPtr[i + 1] - vtPtr[i]);
         int lw      = 0;
         while (lw < 5 && (int64_t(1) << lw) * tileIters < d)
             ++lw;
@@ -213,6 +243,8 @@ void BuildPlan(
     plan.old2new.resize(nV);
     plan.colorTileBegin.assign(nColors + 1, 0);
     // tiles
+    plan.ringOff.assign(plan.nActive + 1, 0);
+    plan.ringCnt.assign(plan.nActive, 0);
     int64_t pos = 0, block = 0;
     int64_t curColor = 0;
     while (pos < plan.nActive)
@@ -223,24 +255,42 @@ void BuildPlan(
         int const lw = items[pos].lw;
         int const G  = 32 >> lw;
         int n = 0, iters = 0;
+        int64_t ringLen = 0;
         while (n < G && pos + n < plan.nActive && colors[items[pos + n].v] == c &&
                items[pos + n].lw == lw)
         {
+            int32_t const v  = items[pos + n].v;
+            int64_t const rl = ringPtr[v + 1] - ringPtr[v];
+            if (n > 0 && ringLen + rl > kMaxRingPerTile)
+                break;  // keep the tile's ring list addressable with 10-bit local indices
+            ringLen += rl;
             iters = std::max<int>(iters, items[pos + n].iters);
             ++n;
         }
+        if (ringLen > kMaxRingPerTile)
+            throw std::length_error("a vertex has more than 1024 distinct neighbours");
+        uint32_t const ringStart  = static_cast<uint32_t>(plan.ringIds.size());
+        uint32_t const ringChunks = static_cast<uint32_t>((ringLen + 31) / 32);
         TileDesc t;
         t.blockStart = static_cast<uint32_t>(block);
         t.vbase      = static_cast<uint32_t>(pos);
-        t.meta       = static_cast<uint32_t>(lw) | (static_cast<uint32_t>(iters) << 8) |
-                 (static_cast<uint32_t>(n) << 24);
-        t.pad = 0;
+        t.meta       = static_cast<uint32_t>(lw) | (static_cast<uint32_t>(n) << 3) | (ringChunks << 9) |
+                 (static_cast<uint32_t>(iters) << 16);
+        t.ringStart = ringStart;
         plan.tiles.push_back(t);
         for (int k = 0; k < n; ++k)
         {
-            plan.new2old[pos + k]             = items[pos + k].v;
-            plan.old2new[items[pos + k].v]    = static_cast<int32_t>(pos + k);
+            int32_t const v                = items[pos + k].v;
+            plan.new2old[pos + k]          = v;
+            plan.old2new[v]                = static_cast<int32_t>(pos + k);
+            plan.ringOff[pos + k]          = static_cast<uint32_t>(plan.ringIds.size());
+            plan.ringCnt[pos + k]          = static_cast<uint16_t>(ringPtr[v + 1] - ringPtr[v]);
+            for (uint32_t r = ringPtr[v]; r < ringPtr[v + 1]; ++r)
+                plan.ringIds.push_back(static_cast<uint32_t>(ring[r]));  // caller ids for now
         }
+        plan.nRingEntries += ringLen;
+        plan.ringIds.resize(ringStart + static_cast<size_t>(ringChunks) * 32, 0xffffffffu);  // pad
+        plan.maxRingPerTile = std::max<int32_t>(plan.maxRingPerTile, static_cast<int32_t>(ringChunks * 32));
         pos += n;
         block += iters;
     }
@@ -256,7 +306,37 @@ void BuildPlan(
             plan.old2new[i]      = static_cast<int32_t>(tail);
             ++tail;
         }
-    // per colour, split the tile range between CTAs by equal record-block counts
+    plan.ringOff[plan.nActive] = static_cast<uint32_t>(plan.ringIds.size());
+    // ring lists: caller ids -> internal ids, flag = neighbour has a higher colour than the lister
+    for (size_t t = 0; t < plan.tiles.size(); ++t)
+    {
+        TileDesc const& td  = plan.tiles[t];
+        uint32_t const nv   = (td.meta >> 3) & 63u;
+        uint32_t const pad0 = td.vbase;  // padding entries point at the tile's first vertex
+        uint32_t const end  = td.ringStart + ((td.meta >> 9) & 127u) * 32u;
+        for (uint32_t k = 0; k < nv; ++k)
+        {
+            int32_t const vo = plan.new2old[td.vbase + k];
+            uint32_t const b = plan.ringOff[td.vbase + k];
+            for (uint32_t r = 0; r < plan.ringCnt[td.vbase + k]; ++r)
+            {
+                int32_t const jo = static_cast<int32_t>(plan.ringIds[b + r]);
+                uint32_t id      = static_cast<uint32_t>(plan.old2new[jo]);
+                if (colors[jo] > colors[vo])
+                    id |= kPrevFlag;
+                plan.ringIds[b + r] = id;
+            }
+        }
+        for (uint32_t r = td.ringStart; r < end; ++r)
+            if (plan.ringIds[r] == 0xffffffffu)
+                plan.ringIds[r] = pad0;
+    }
+}
+
+// Per colour, split the tile range between the CTAs of the persistent grid by equal record-block counts.
+void PartitionTiles(Plan& plan, int gridBlocks)
+{
+    int64_t const nColors = plan.nColors;
     gridBlocks = std::max(1, gridBlocks);
     plan.ctaTileRange.assign(static_cast<size_t>(nColors) * (gridBlocks + 1), 0);
     plan.ctaBlockBegin.assign(static_cast<size_t>(nColors) * (gridBlocks + 1), 0);

@@ -230,7 +230,7 @@ __global__ void VertexMass(const uint32_t* ptr, const uint32_t* adj, const doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// incidence records: one warp per tile
+// incidence records: one warp per tile (layout: vbdx_internal.h)
 // ------------------------------------------------------------------------------------------
 __global__ void FillRecords(
     const TileDesc* tiles,
@@ -245,17 +245,20 @@ __global__ void FillRecords(
     const double* lame,  // 2 x nT or null
     double muDefault,
     double lamDefault,
-    const int32_t* color,
-    float4* records)
+    const uint32_t* ringIds,
+    const uint32_t* ringOff,
+    const uint16_t* ringCnt,
+    float4* records,
+    uint32_t* errFlag)
 {
     int const T = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (T >= nTiles)
         return;
     uint32_t const lane   = threadIdx.x & 31u;
     TileDesc const td     = tiles[T];
-    uint32_t const lw     = td.meta & 0xffu;
-    uint32_t const iters  = (td.meta >> 8) & 0xffffu;
-    uint32_t const nverts = td.meta >> 24;
+    uint32_t const lw     = td.meta & 7u;
+    uint32_t const nverts = (td.meta >> 3) & 63u;
+    uint32_t const iters  = td.meta >> 16;
     uint32_t const w      = 1u << lw;
     uint32_t const grp    = lane >> lw;
     uint32_t const sub    = lane & (w - 1u);
@@ -263,22 +266,24 @@ __global__ void FillRecords(
     uint32_t const vi     = td.vbase + (valid ? grp : 0u);
     int32_t const vo      = new2old[vi];
     uint32_t const rowB = ptr[vo], degv = ptr[vo + 1] - rowB;
+    uint32_t const rB = ringOff[vi], rN = ringCnt[vi];
     for (uint32_t t = 0; t < iters; ++t)
     {
         uint32_t const k = t * w + sub;
-        uint32_t ids[3]  = {vi, vi, vi};
+        uint32_t idx     = 0;
         float G[9]       = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        float wmu = 0.f, wlam = 0.f, alpha = 1.f, gh2 = 0.f;
+        float wmu = 0.f, wlam = 0.f;
         if (valid && k < degv)
         {
             uint32_t const packed = adj[rowB + k];
             int64_t const e       = packed >> 2;
             int const il          = packed & 3u;
             double const* Ji      = Jinv + 9 * e;
-            double own[3]         = {0, 0, 0};
             int n                 = 0;
             for (int a = 0; a < 4; ++a)
             {
+                if (a == il)
+                    continue;
                 double g[3];
                 if (a == 0)
                     for (int d = 0; d < 3; ++d)
@@ -286,32 +291,33 @@ __global__ void FillRecords(
                 else
                     for (int d = 0; d < 3; ++d)
                         g[d] = Ji[3 * (a - 1) + d];
-                if (a == il)
+                // local index of this neighbour in the tile's staged ring list
+                uint32_t const jn = static_cast<uint32_t>(old2new[E[4 * e + a]]);
+                uint32_t loc      = 0xffffffffu;
+                for (uint32_t r = 0; r < rN; ++r)
+                    if ((ringIds[rB + r] & ~kPrevFlag) == jn)
+                    {
+                        loc = rB + r - td.ringStart;
+                        break;
+                    }
+                if (loc > 1023u)
                 {
-                    for (int d = 0; d < 3; ++d)
-                        own[d] = g[d];
-                    continue;
+                    atomicOr(errFlag, 4u);
+                    loc = 0;
                 }
-                int32_t const jo = E[4 * e + a];
-                uint32_t id      = static_cast<uint32_t>(old2new[jo]);
-                if (color[jo] > color[vo])
-                    id |= kPrevFlag;
-                ids[n] = id;
+                idx |= loc << (10 * n);
                 for (int d = 0; d < 3; ++d)
                     G[3 * n + d] = static_cast<float>(g[d]);
                 ++n;
             }
             double const mu = lame ? lame[2 * e] : muDefault, lam = lame ? lame[2 * e + 1] : lamDefault;
-            wmu   = static_cast<float>(vol[e] * mu);
-            wlam  = static_cast<float>(vol[e] * lam);
-            alpha = static_cast<float>(1.0 + mu / lam);
-            gh2   = static_cast<float>(own[0] * own[0] + own[1] * own[1] + own[2] * own[2]);
+            wmu  = static_cast<float>(vol[e] * mu);
+            wlam = static_cast<float>(vol[e] * lam);
         }
         float4* out = records + static_cast<size_t>(td.blockStart + t) * kBlockFloat4 + lane;
-        out[0]  = make_float4(__uint_as_float(ids[0]), __uint_as_float(ids[1]), __uint_as_float(ids[2]), G[0]);
-        out[32] = make_float4(G[1], G[2], G[3], G[4]);
-        out[64] = make_float4(G[5], G[6], G[7], G[8]);
-        out[96] = make_float4(wmu, wlam, alpha, gh2);
+        out[0]  = make_float4(__uint_as_float(idx), G[0], G[1], G[2]);
+        out[32] = make_float4(G[3], G[4], G[5], G[6]);
+        out[64] = make_float4(G[7], G[8], wmu, wlam);
     }
 }
 

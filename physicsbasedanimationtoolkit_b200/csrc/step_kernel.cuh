@@ -21,9 +21,11 @@ namespace vbdx {
 
 struct StepParams {
     // static topology
-    const float4* __restrict__ records;        // [nBlocks][4][32] float4
+    const float4* __restrict__ records;        // [nBlocks][3][32] float4
     const uint4* __restrict__ tiles;           // TileDesc
     const uint32_t* __restrict__ ctaTileRange; // [nColors][gridDim.x + 1]
+    const uint32_t* __restrict__ ringIds;      // ring lists of all tiles
+    uint32_t stageEntries;                     // per-warp shared-memory staging capacity (float4 entries)
     int nColors;
     int nVerts;   // all internal vertices (swept first, Dirichlet last)
     // state (internal vertex order, float4 per vertex)
@@ -43,9 +45,16 @@ struct StepParams {
     int strategy;
     int iterations, substeps;
     unsigned int* barrier;  // zeroed before launch
-    unsigned long long* trace;  // optional [nColors][gridDim.x][4] timestamps of one iteration (diagnostics)
+    unsigned long long* trace;  // optional [nColors][gridDim.x][8] timestamps of one iteration (diagnostics)
     int traceIteration;
 };
+
+__device__ __forceinline__ unsigned long long GlobalTimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p)
 {
@@ -62,13 +71,6 @@ __device__ __forceinline__ void AddRelease(unsigned int* p, unsigned int v)
 // All CTAs of the (cooperatively launched, fully resident) grid meet here.  The release/acquire
 // pair at gpu scope orders every position written before the barrier against every weak load
 // after it, and invalidates this SM's L1 so those loads may use the default cached path.
-__device__ __forceinline__ unsigned long long GlobalTimer()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 __device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr)
 {
     __syncthreads();
@@ -132,174 +134,229 @@ __device__ __forceinline__ float3 InitialPosition(
     return make_float3(x.x + s * a.x, x.y + s * a.y, x.z + s * a.z);
 }
 
+// Record source of the direct kernel: each warp reads its blocks straight from global memory
+// (streaming loads, evict-first).
+struct DirectRecords {
+    float4 const* rec;
+    __device__ __forceinline__ void Fetch(float4& c0, float4& c1, float4& c2)
+    {
+        c0 = __ldcs(rec);
+        c1 = __ldcs(rec + 32);
+        c2 = __ldcs(rec + 64);
+        rec += kBlockFloat4;
+    }
+};
+
+// One warp tile: stage the 1-rings in shared memory, accumulate the elastic blocks of all
+// incident tets, reduce over the lanes that share a vertex, solve, write back.
+//   RecordSource::Fetch(c0,c1,c2) yields this lane's 48-byte record of the next block.
+template <bool kChebyshev, bool kDamping, class RecordSource>
+__device__ __forceinline__ void ProcessTile(
+    StepParams const& p,
+    uint4 const td,
+    float4* __restrict__ stage,
+    RecordSource& src,
+    int k,
+    float omega,
+    uint32_t lane,
+    unsigned long long* trace = nullptr)
+{
+    float4 const* __restrict__ posQ = p.pos;
+    uint32_t const lw         = td.z & 7u;
+    uint32_t const nverts     = (td.z >> 3) & 63u;
+    uint32_t const ringChunks = (td.z >> 9) & 127u;
+    uint32_t const iters      = td.z >> 16;
+    uint32_t const grp        = lane >> lw;
+    bool const valid          = grp < nverts;
+    uint32_t const vi         = td.y + (valid ? grp : 0u);
+
+    // first record block: issue its loads before anything else so they overlap the ring gather
+    float4 n0, n1, n2;
+    src.Fetch(n0, n1, n2);
+    // own position: the previous iterate (P); nobody writes vertex vi during this colour
+    float4 const xi = LoadPos(posQ + p.pOff + vi);
+    // gather the tile's 1-rings once: ringChunks independent scattered loads per lane
+    {
+        uint32_t const* ids = p.ringIds + td.w + lane;
+        __syncwarp();  // the previous tile's readers are done with the staging area
+        for (uint32_t j = 0; j < ringChunks; ++j)
+        {
+            uint32_t const id = __ldg(ids + 32 * j);
+            stage[32 * j + lane] = LoadPos(posQ + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
+        }
+        __syncwarp();
+    }
+    if (trace && lane == 0)
+        trace[5] = GlobalTimer();  // 1-rings staged
+
+    float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 1
+    for (uint32_t t = 0; t < iters; ++t)
+    {
+        float4 const c0 = n0, c1 = n1, c2 = n2;
+        if (t + 1 < iters)
+            src.Fetch(n0, n1, n2);  // next block in flight while this one is computed
+        uint32_t const idx = __float_as_uint(c0.x);
+        float4 const p1 = stage[idx & 1023u];
+        float4 const p2 = stage[(idx >> 10) & 1023u];
+        float4 const p3 = stage[(idx >> 20) & 1023u];
+        // gradients of the three other vertices
+        float const a0 = c0.y, a1 = c0.z, a2 = c0.w;
+        float const b0 = c1.x, b1 = c1.y, b2 = c1.z;
+        float const e0 = c1.w, e1 = c2.x, e2 = c2.y;
+        float const wmu = c2.z, wlam = c2.w;
+        // edge vectors relative to this vertex:  F = sum_a (x_a - x_i) (x) grad_a
+        float const d1x = p1.x - xi.x, d1y = p1.y - xi.y, d1z = p1.z - xi.z;
+        float const d2x = p2.x - xi.x, d2y = p2.y - xi.y, d2z = p2.z - xi.z;
+        float const d3x = p3.x - xi.x, d3y = p3.y - xi.y, d3z = p3.z - xi.z;
+        float const F00 = d1x * a0 + d2x * b0 + d3x * e0;
+        float const F01 = d1x * a1 + d2x * b1 + d3x * e1;
+        float const F02 = d1x * a2 + d2x * b2 + d3x * e2;
+        float const F10 = d1y * a0 + d2y * b0 + d3y * e0;
+        float const F11 = d1y * a1 + d2y * b1 + d3y * e1;
+        float const F12 = d1y * a2 + d2y * b2 + d3y * e2;
+        float const F20 = d1z * a0 + d2z * b0 + d3z * e0;
+        float const F21 = d1z * a1 + d2z * b1 + d3z * e1;
+        float const F22 = d1z * a2 + d2z * b2 + d3z * e2;
+        // cofactors
+        float const C00 = F11 * F22 - F12 * F21;
+        float const C01 = F12 * F20 - F10 * F22;
+        float const C02 = F10 * F21 - F11 * F20;
+        float const C10 = F02 * F21 - F01 * F22;
+        float const C11 = F00 * F22 - F02 * F20;
+        float const C12 = F01 * F20 - F00 * F21;
+        float const C20 = F01 * F12 - F02 * F11;
+        float const C21 = F02 * F10 - F00 * F12;
+        float const C22 = F00 * F11 - F01 * F10;
+        float const J   = F00 * C00 + F01 * C01 + F02 * C02;
+        // gradient of this vertex' shape function
+        float const q0 = -(a0 + b0 + e0), q1 = -(a1 + b1 + e1), q2 = -(a2 + b2 + e2);
+        float const Fq0 = F00 * q0 + F01 * q1 + F02 * q2;
+        float const Fq1 = F10 * q0 + F11 * q1 + F12 * q2;
+        float const Fq2 = F20 * q0 + F21 * q1 + F22 * q2;
+        float const Cq0 = C00 * q0 + C01 * q1 + C02 * q2;
+        float const Cq1 = C10 * q0 + C11 * q1 + C12 * q2;
+        float const Cq2 = C20 * q0 + C21 * q1 + C22 * q2;
+        // alpha = 1 + mu/lambda; padding slots have wmu = wlam = 0 and must contribute 0, not NaN
+        float const alpha = 1.f + __fdividef(wmu, (wlam != 0.f) ? wlam : 1.f);
+        float const s     = wlam * (J - alpha);
+        g0 += wmu * Fq0 + s * Cq0;
+        g1 += wmu * Fq1 + s * Cq1;
+        g2 += wmu * Fq2 + s * Cq2;
+        float const t0 = wlam * Cq0, t1 = wlam * Cq1, t2 = wlam * Cq2;
+        h00 += t0 * Cq0;
+        h01 += t0 * Cq1;
+        h02 += t0 * Cq2;
+        h11 += t1 * Cq1;
+        h12 += t1 * Cq2;
+        h22 += t2 * Cq2;
+        hd += wmu * (q0 * q0 + q1 * q1 + q2 * q2);
+    }
+    if (trace && lane == 0)
+        trace[6] = GlobalTimer();  // incident tets accumulated
+    // butterfly over the w lanes that share a vertex (fixed order => deterministic)
+    for (uint32_t o = (1u << lw) >> 1; o > 0; o >>= 1)
+    {
+        h00 += __shfl_xor_sync(0xffffffffu, h00, o);
+        h01 += __shfl_xor_sync(0xffffffffu, h01, o);
+        h02 += __shfl_xor_sync(0xffffffffu, h02, o);
+        h11 += __shfl_xor_sync(0xffffffffu, h11, o);
+        h12 += __shfl_xor_sync(0xffffffffu, h12, o);
+        h22 += __shfl_xor_sync(0xffffffffu, h22, o);
+        hd += __shfl_xor_sync(0xffffffffu, hd, o);
+        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+        g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    }
+    if (valid && (lane & ((1u << lw) - 1u)) == 0u)
+    {
+        h00 += hd;
+        h11 += hd;
+        h22 += hd;
+        float x = xi.x, y = xi.y, z = xi.z;
+        if constexpr (kDamping)
+        {
+            float4 const xt = __ldcg(p.xt + vi);
+            float const D   = p.dampD;
+            float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
+            g0 += D * (h00 * ex + h01 * ey + h02 * ez);
+            g1 += D * (h01 * ex + h11 * ey + h12 * ez);
+            g2 += D * (h02 * ex + h12 * ey + h22 * ez);
+            float const sc = 1.f + D;
+            h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
+        }
+        float4 const xm = __ldcg(p.xtildeM + vi);
+        float const K   = xm.w / p.sdt2;
+        h00 += K, h11 += K, h22 += K;
+        g0 += K * (x - xm.x);
+        g1 += K * (y - xm.y);
+        g2 += K * (z - xm.z);
+        // Newton step with the explicit cofactor inverse of the symmetric 3x3
+        float const i00 = h11 * h22 - h12 * h12;
+        float const i01 = h02 * h12 - h01 * h22;
+        float const i02 = h01 * h12 - h02 * h11;
+        float const det = h00 * i00 + h01 * i01 + h02 * i02;
+        if (fabsf(det) > p.detHZero)
+        {
+            float const i11 = h00 * h22 - h02 * h02;
+            float const i12 = h01 * h02 - h00 * h12;
+            float const i22 = h00 * h11 - h01 * h01;
+            float const r   = 1.f / det;
+            x -= r * (i00 * g0 + i01 * g1 + i02 * g2);
+            y -= r * (i01 * g0 + i11 * g1 + i12 * g2);
+            z -= r * (i02 * g0 + i12 * g1 + i22 * g2);
+        }
+        float4 const raw = make_float4(x, y, z, 0.f);
+        if constexpr (kChebyshev)
+        {
+            // Q <- raw sweep result (read by higher colours in this iteration);
+            // P <- blended iterate (read by lower colours in the next iteration and as this
+            // vertex' own start); hist <- previous blended iterate.
+            float4 out = raw;
+            if (k > 1)
+            {
+                float4 const h2 = __ldcg(p.hist + vi);
+                out.x = omega * (x - h2.x) + h2.x;
+                out.y = omega * (y - h2.y) + h2.y;
+                out.z = omega * (z - h2.z) + h2.z;
+            }
+            p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
+            p.pos[vi]          = raw;
+            p.pos[p.pOff + vi] = out;
+        }
+        else
+        {
+            p.pos[vi] = raw;
+        }
+    }
+}
+
 // Sweep of one colour: every warp walks its share of the colour's tiles.
 template <bool kChebyshev, bool kDamping>
-__device__ __forceinline__ void SweepColor(StepParams const& p, int color, int k, float omega)
+__device__ __forceinline__ void SweepColor(StepParams const& p, int color, int k, float omega, float4* stage, unsigned long long* trace)
 {
     uint32_t const* range = p.ctaTileRange + static_cast<size_t>(color) * (gridDim.x + 1);
-    uint32_t const tBegin = range[blockIdx.x], tEnd = range[blockIdx.x + 1];
+    uint32_t const tBegin = __ldg(range + blockIdx.x), tEnd = __ldg(range + blockIdx.x + 1);
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-    float4 const* __restrict__ posQ = p.pos;
-    float4 const* __restrict__ posP = p.pos + p.pOff;
-
     for (uint32_t T = tBegin + warp; T < tEnd; T += nWarps)
     {
-        uint4 const td        = __ldg(p.tiles + T);
-        uint32_t const lw     = td.z & 0xffu;
-        uint32_t const iters  = (td.z >> 8) & 0xffffu;
-        uint32_t const nverts = td.z >> 24;
-        uint32_t const grp    = lane >> lw;
-        bool const valid      = grp < nverts;
-        uint32_t const vi     = td.y + (valid ? grp : 0u);
-        // own position: the previous iterate (P); nobody has written vertex vi in this sweep
-        float4 const xi = LoadPos(posP + vi);
-
-        float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        float4 const* rec = p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane;
-#pragma unroll 1
-        for (uint32_t t = 0; t < iters; ++t, rec += kBlockFloat4)
-        {
-            float4 const c0 = __ldcs(rec);
-            float4 const c1 = __ldcs(rec + 32);
-            float4 const c2 = __ldcs(rec + 64);
-            float4 const c3 = __ldcs(rec + 96);
-            uint32_t const j1 = __float_as_uint(c0.x), j2 = __float_as_uint(c0.y),
-                           j3 = __float_as_uint(c0.z);
-            float4 const p1 = LoadPos(posQ + (j1 & ~kPrevFlag) + ((j1 & kPrevFlag) ? p.pOff : 0u));
-            float4 const p2 = LoadPos(posQ + (j2 & ~kPrevFlag) + ((j2 & kPrevFlag) ? p.pOff : 0u));
-            float4 const p3 = LoadPos(posQ + (j3 & ~kPrevFlag) + ((j3 & kPrevFlag) ? p.pOff : 0u));
-            // gradients of the three other vertices
-            float const a0 = c0.w, a1 = c1.x, a2 = c1.y;
-            float const b0 = c1.z, b1 = c1.w, b2 = c2.x;
-            float const e0 = c2.y, e1 = c2.z, e2 = c2.w;
-            float const wmu = c3.x, wlam = c3.y, alpha = c3.z, gh2 = c3.w;
-            // edge vectors relative to this vertex:  F = sum_a (x_a - x_i) (x) grad_a
-            float const d1x = p1.x - xi.x, d1y = p1.y - xi.y, d1z = p1.z - xi.z;
-            float const d2x = p2.x - xi.x, d2y = p2.y - xi.y, d2z = p2.z - xi.z;
-            float const d3x = p3.x - xi.x, d3y = p3.y - xi.y, d3z = p3.z - xi.z;
-            float const F00 = d1x * a0 + d2x * b0 + d3x * e0;
-            float const F01 = d1x * a1 + d2x * b1 + d3x * e1;
-            float const F02 = d1x * a2 + d2x * b2 + d3x * e2;
-            float const F10 = d1y * a0 + d2y * b0 + d3y * e0;
-            float const F11 = d1y * a1 + d2y * b1 + d3y * e1;
-            float const F12 = d1y * a2 + d2y * b2 + d3y * e2;
-            float const F20 = d1z * a0 + d2z * b0 + d3z * e0;
-            float const F21 = d1z * a1 + d2z * b1 + d3z * e1;
-            float const F22 = d1z * a2 + d2z * b2 + d3z * e2;
-            // cofactors
-            float const C00 = F11 * F22 - F12 * F21;
-            float const C01 = F12 * F20 - F10 * F22;
-            float const C02 = F10 * F21 - F11 * F20;
-            float const C10 = F02 * F21 - F01 * F22;
-            float const C11 = F00 * F22 - F02 * F20;
-            float const C12 = F01 * F20 - F00 * F21;
-            float const C20 = F01 * F12 - F02 * F11;
-            float const C21 = F02 * F10 - F00 * F12;
-            float const C22 = F00 * F11 - F01 * F10;
-            float const J   = F00 * C00 + F01 * C01 + F02 * C02;
-            // gradient of this vertex' shape function
-            float const q0 = -(a0 + b0 + e0), q1 = -(a1 + b1 + e1), q2 = -(a2 + b2 + e2);
-            float const Fq0 = F00 * q0 + F01 * q1 + F02 * q2;
-            float const Fq1 = F10 * q0 + F11 * q1 + F12 * q2;
-            float const Fq2 = F20 * q0 + F21 * q1 + F22 * q2;
-            float const Cq0 = C00 * q0 + C01 * q1 + C02 * q2;
-            float const Cq1 = C10 * q0 + C11 * q1 + C12 * q2;
-            float const Cq2 = C20 * q0 + C21 * q1 + C22 * q2;
-            float const s   = wlam * (J - alpha);
-            g0 += wmu * Fq0 + s * Cq0;
-            g1 += wmu * Fq1 + s * Cq1;
-            g2 += wmu * Fq2 + s * Cq2;
-            float const t0 = wlam * Cq0, t1 = wlam * Cq1, t2 = wlam * Cq2;
-            h00 += t0 * Cq0;
-            h01 += t0 * Cq1;
-            h02 += t0 * Cq2;
-            h11 += t1 * Cq1;
-            h12 += t1 * Cq2;
-            h22 += t2 * Cq2;
-            hd += wmu * gh2;
-        }
-        // butterfly over the w lanes that share a vertex (fixed order => deterministic)
-        for (uint32_t o = (1u << lw) >> 1; o > 0; o >>= 1)
-        {
-            h00 += __shfl_xor_sync(0xffffffffu, h00, o);
-            h01 += __shfl_xor_sync(0xffffffffu, h01, o);
-            h02 += __shfl_xor_sync(0xffffffffu, h02, o);
-            h11 += __shfl_xor_sync(0xffffffffu, h11, o);
-            h12 += __shfl_xor_sync(0xffffffffu, h12, o);
-            h22 += __shfl_xor_sync(0xffffffffu, h22, o);
-            hd += __shfl_xor_sync(0xffffffffu, hd, o);
-            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-            g2 += __shfl_xor_sync(0xffffffffu, g2, o);
-        }
-        if (valid && (lane & ((1u << lw) - 1u)) == 0u)
-        {
-            h00 += hd;
-            h11 += hd;
-            h22 += hd;
-            float x = xi.x, y = xi.y, z = xi.z;
-            if constexpr (kDamping)
-            {
-                float4 const xt = __ldcg(p.xt + vi);
-                float const D   = p.dampD;
-                float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
-                g0 += D * (h00 * ex + h01 * ey + h02 * ez);
-                g1 += D * (h01 * ex + h11 * ey + h12 * ez);
-                g2 += D * (h02 * ex + h12 * ey + h22 * ez);
-                float const sc = 1.f + D;
-                h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
-            }
-            float4 const xm = __ldcg(p.xtildeM + vi);
-            float const K   = xm.w / p.sdt2;
-            h00 += K, h11 += K, h22 += K;
-            g0 += K * (x - xm.x);
-            g1 += K * (y - xm.y);
-            g2 += K * (z - xm.z);
-            // Newton step with the explicit cofactor inverse of the symmetric 3x3
-            float const i00 = h11 * h22 - h12 * h12;
-            float const i01 = h02 * h12 - h01 * h22;
-            float const i02 = h01 * h12 - h02 * h11;
-            float const det = h00 * i00 + h01 * i01 + h02 * i02;
-            if (fabsf(det) > p.detHZero)
-            {
-                float const i11 = h00 * h22 - h02 * h02;
-                float const i12 = h01 * h02 - h00 * h12;
-                float const i22 = h00 * h11 - h01 * h01;
-                float const r   = 1.f / det;
-                x -= r * (i00 * g0 + i01 * g1 + i02 * g2);
-                y -= r * (i01 * g0 + i11 * g1 + i12 * g2);
-                z -= r * (i02 * g0 + i12 * g1 + i22 * g2);
-            }
-            float4 const raw = make_float4(x, y, z, 0.f);
-            if constexpr (kChebyshev)
-            {
-                // Q <- raw sweep result (read by higher colours in this iteration);
-                // P <- blended iterate (read by lower colours in the next iteration and as this
-                // vertex' own start); hist <- previous blended iterate.
-                float4 out = raw;
-                if (k > 1)
-                {
-                    float4 const h2 = __ldcg(p.hist + vi);
-                    out.x = omega * (x - h2.x) + h2.x;
-                    out.y = omega * (y - h2.y) + h2.y;
-                    out.z = omega * (z - h2.z) + h2.z;
-                }
-                p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
-                p.pos[vi]          = raw;
-                p.pos[p.pOff + vi] = out;
-            }
-            else
-            {
-                p.pos[vi] = raw;
-            }
-        }
+        uint4 const td = __ldg(p.tiles + T);
+        unsigned long long* tr = (trace && warp == 0 && T == tBegin) ? trace : nullptr;
+        if (tr && lane == 0)
+            tr[4] = GlobalTimer() + (td.x & 0u);  // tile descriptor arrived
+        DirectRecords src{p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane};
+        ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane, tr);
+        if (tr && lane == 0)
+            tr[7] = GlobalTimer();  // first tile of warp 0 finished
     }
 }
 
 template <bool kChebyshev, bool kDamping>
 __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ StepParams p)
 {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float4* const stage = reinterpret_cast<float4*>(smemRaw) + (threadIdx.x >> 5) * p.stageEntries;
     unsigned int target = 0;
     uint32_t const gtid    = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t const gstride = gridDim.x * blockDim.x;
@@ -362,11 +419,11 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
                 unsigned long long* tr = nullptr;
                 if (p.trace != nullptr && k == p.traceIteration)
                 {
-                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 4;
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
                     if (threadIdx.x == 0)
                         tr[0] = GlobalTimer();
                 }
-                SweepColor<kChebyshev, kDamping>(p, c, k, omega);
+                SweepColor<kChebyshev, kDamping>(p, c, k, omega, stage, tr);
                 if (tr != nullptr && threadIdx.x == 0)
                     tr[1] = GlobalTimer();  // warp 0 done
                 GridBarrier(p.barrier, target, tr);

@@ -1,7 +1,7 @@
 // Warp-specialised variant of the persistent VBD step kernel (sm_100a).
 //
 // One CTA per SM.  The last warp is a *producer*: a single elected lane streams the CTA's
-// incidence-record blocks (2 KB each, static rest data) from HBM into a shared-memory ring with
+// incidence-record blocks (1.5 KB each, static rest data) from HBM into a shared-memory ring with
 // 1-D bulk asynchronous copies (cp.async.bulk, i.e. the TMA engine; SASS UBLKCP) that signal
 // per-slot "full" mbarriers.  Because the records never change, the producer runs ahead of the
 // colour barriers: while the consumers wait for the other SMs at the end of colour c, the
@@ -19,7 +19,6 @@ namespace vbdx {
 
 constexpr int kTmaThreads       = 768;                     // 23 consumer warps + 1 producer warp
 constexpr int kTmaConsumerWarps = kTmaThreads / 32 - 1;
-constexpr int kBlockBytes       = kBlockFloat4 * 16;        // 2048
 
 struct TmaParams {
     StepParams base;
@@ -70,6 +69,29 @@ __device__ __forceinline__ void BulkLoad(uint32_t dstSmem, const void* srcGmem, 
         : "memory");
 }
 
+// Record source of the consumers: this lane's 48-byte record out of the shared-memory ring slot that the
+// producer filled; the slot is handed back as soon as the warp has copied its records to registers.
+struct RingRecords {
+    unsigned char const* smem;
+    uint32_t full, empty, R, slot, fill, lane;
+    __device__ __forceinline__ void Fetch(float4& c0, float4& c1, float4& c2)
+    {
+        MbarWait(full + 8 * slot, fill & 1u);
+        unsigned char const* blk = smem + slot * kBlockBytes + lane * 16;
+        c0 = *reinterpret_cast<float4 const*>(blk);
+        c1 = *reinterpret_cast<float4 const*>(blk + 512);
+        c2 = *reinterpret_cast<float4 const*>(blk + 1024);
+        __syncwarp();
+        if (lane == 0)
+            MbarArrive(empty + 8 * slot);
+        if (++slot == R)
+        {
+            slot = 0;
+            ++fill;
+        }
+    }
+};
+
 // grid barrier among the consumer threads of all CTAs (the producer warp never joins)
 __device__ __forceinline__ void ConsumerGridBarrier(unsigned int* counter, unsigned int& target)
 {
@@ -95,6 +117,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_con
     uint32_t const ring  = SmemAddr(smem);
     uint32_t const full  = ring + R * kBlockBytes;
     uint32_t const empty = full + R * 8;
+    float4* const stage  = reinterpret_cast<float4*>(smem + R * (kBlockBytes + 16)) + (threadIdx.x >> 5) * p.stageEntries;
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0)
@@ -148,8 +171,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_con
     uint32_t const ctid      = blockIdx.x * (kTmaConsumerWarps * 32) + threadIdx.x;
     uint32_t const cstride   = gridDim.x * (kTmaConsumerWarps * 32);
     uint32_t streamBase      = 0;  // blocks of this CTA's stream before the current colour
-    float4 const* __restrict__ posQ = p.pos;
-    float4 const* __restrict__ posP = p.pos + p.pOff;
 
     for (int s = 0; s < p.substeps; ++s)
     {
@@ -204,172 +225,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_con
                 uint32_t const b0 = __ldg(blkBegin + c * stride), b1 = __ldg(blkBegin + c * stride + 1);
                 for (uint32_t T = tBegin + warp; T < tEnd; T += kTmaConsumerWarps)
                 {
-                    uint4 const td        = __ldg(p.tiles + T);
-                    uint32_t const lw     = td.z & 0xffu;
-                    uint32_t const iters  = (td.z >> 8) & 0xffffu;
-                    uint32_t const nverts = td.z >> 24;
-                    uint32_t const grp    = lane >> lw;
-                    bool const valid      = grp < nverts;
-                    uint32_t const vi     = td.y + (valid ? grp : 0u);
-                    float4 const xi       = LoadPos(posP + vi);
-                    uint32_t const n0     = streamBase + (td.x - b0);
-                    uint32_t slot         = n0 % R;
-                    uint32_t fill         = n0 / R;
-
-                    float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
-                    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-                    // software pipeline: the neighbour gathers of block t+1 are in flight while block t is computed
-                    MbarWait(full + 8 * slot, fill & 1u);
-                    float4 c0 = *reinterpret_cast<float4 const*>(smem + slot * kBlockBytes + lane * 16);
-                    float4 q1, q2, q3;
-                    {
-                        uint32_t const j1 = __float_as_uint(c0.x), j2 = __float_as_uint(c0.y), j3 = __float_as_uint(c0.z);
-                        q1 = LoadPos(posQ + (j1 & ~kPrevFlag) + ((j1 & kPrevFlag) ? p.pOff : 0u));
-                        q2 = LoadPos(posQ + (j2 & ~kPrevFlag) + ((j2 & kPrevFlag) ? p.pOff : 0u));
-                        q3 = LoadPos(posQ + (j3 & ~kPrevFlag) + ((j3 & kPrevFlag) ? p.pOff : 0u));
-                    }
-#pragma unroll 1
-                    for (uint32_t t = 0; t < iters; ++t)
-                    {
-                        unsigned char const* blk = smem + slot * kBlockBytes + lane * 16;
-                        float4 const c1 = *reinterpret_cast<float4 const*>(blk + 512);
-                        float4 const c2 = *reinterpret_cast<float4 const*>(blk + 1024);
-                        float4 const c3 = *reinterpret_cast<float4 const*>(blk + 1536);
-                        float const a0  = c0.w;
-                        float4 const p1 = q1, p2 = q2, p3 = q3;
-                        __syncwarp();
-                        if (lane == 0)
-                            MbarArrive(empty + 8 * slot);  // slot may be refilled
-                        if (++slot == R)
-                        {
-                            slot = 0;
-                            ++fill;
-                        }
-                        if (t + 1 < iters)
-                        {
-                            MbarWait(full + 8 * slot, fill & 1u);
-                            c0 = *reinterpret_cast<float4 const*>(smem + slot * kBlockBytes + lane * 16);
-                            uint32_t const j1 = __float_as_uint(c0.x), j2 = __float_as_uint(c0.y), j3 = __float_as_uint(c0.z);
-                            q1 = LoadPos(posQ + (j1 & ~kPrevFlag) + ((j1 & kPrevFlag) ? p.pOff : 0u));
-                            q2 = LoadPos(posQ + (j2 & ~kPrevFlag) + ((j2 & kPrevFlag) ? p.pOff : 0u));
-                            q3 = LoadPos(posQ + (j3 & ~kPrevFlag) + ((j3 & kPrevFlag) ? p.pOff : 0u));
-                        }
-                        float const a1 = c1.x, a2 = c1.y;
-                        float const bb0 = c1.z, bb1 = c1.w, bb2 = c2.x;
-                        float const e0 = c2.y, e1 = c2.z, e2 = c2.w;
-                        float const wmu = c3.x, wlam = c3.y, alpha = c3.z, gh2 = c3.w;
-                        float const d1x = p1.x - xi.x, d1y = p1.y - xi.y, d1z = p1.z - xi.z;
-                        float const d2x = p2.x - xi.x, d2y = p2.y - xi.y, d2z = p2.z - xi.z;
-                        float const d3x = p3.x - xi.x, d3y = p3.y - xi.y, d3z = p3.z - xi.z;
-                        float const F00 = d1x * a0 + d2x * bb0 + d3x * e0;
-                        float const F01 = d1x * a1 + d2x * bb1 + d3x * e1;
-                        float const F02 = d1x * a2 + d2x * bb2 + d3x * e2;
-                        float const F10 = d1y * a0 + d2y * bb0 + d3y * e0;
-                        float const F11 = d1y * a1 + d2y * bb1 + d3y * e1;
-                        float const F12 = d1y * a2 + d2y * bb2 + d3y * e2;
-                        float const F20 = d1z * a0 + d2z * bb0 + d3z * e0;
-                        float const F21 = d1z * a1 + d2z * bb1 + d3z * e1;
-                        float const F22 = d1z * a2 + d2z * bb2 + d3z * e2;
-                        float const C00 = F11 * F22 - F12 * F21;
-                        float const C01 = F12 * F20 - F10 * F22;
-                        float const C02 = F10 * F21 - F11 * F20;
-                        float const C10 = F02 * F21 - F01 * F22;
-                        float const C11 = F00 * F22 - F02 * F20;
-                        float const C12 = F01 * F20 - F00 * F21;
-                        float const C20 = F01 * F12 - F02 * F11;
-                        float const C21 = F02 * F10 - F00 * F12;
-                        float const C22 = F00 * F11 - F01 * F10;
-                        float const J   = F00 * C00 + F01 * C01 + F02 * C02;
-                        float const u0 = -(a0 + bb0 + e0), u1 = -(a1 + bb1 + e1), u2 = -(a2 + bb2 + e2);
-                        float const Fq0 = F00 * u0 + F01 * u1 + F02 * u2;
-                        float const Fq1 = F10 * u0 + F11 * u1 + F12 * u2;
-                        float const Fq2 = F20 * u0 + F21 * u1 + F22 * u2;
-                        float const Cq0 = C00 * u0 + C01 * u1 + C02 * u2;
-                        float const Cq1 = C10 * u0 + C11 * u1 + C12 * u2;
-                        float const Cq2 = C20 * u0 + C21 * u1 + C22 * u2;
-                        float const sJ  = wlam * (J - alpha);
-                        g0 += wmu * Fq0 + sJ * Cq0;
-                        g1 += wmu * Fq1 + sJ * Cq1;
-                        g2 += wmu * Fq2 + sJ * Cq2;
-                        float const t0 = wlam * Cq0, t1 = wlam * Cq1, t2 = wlam * Cq2;
-                        h00 += t0 * Cq0;
-                        h01 += t0 * Cq1;
-                        h02 += t0 * Cq2;
-                        h11 += t1 * Cq1;
-                        h12 += t1 * Cq2;
-                        h22 += t2 * Cq2;
-                        hd += wmu * gh2;
-                    }
-                    for (uint32_t o = (1u << lw) >> 1; o > 0; o >>= 1)
-                    {
-                        h00 += __shfl_xor_sync(0xffffffffu, h00, o);
-                        h01 += __shfl_xor_sync(0xffffffffu, h01, o);
-                        h02 += __shfl_xor_sync(0xffffffffu, h02, o);
-                        h11 += __shfl_xor_sync(0xffffffffu, h11, o);
-                        h12 += __shfl_xor_sync(0xffffffffu, h12, o);
-                        h22 += __shfl_xor_sync(0xffffffffu, h22, o);
-                        hd += __shfl_xor_sync(0xffffffffu, hd, o);
-                        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-                        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-                        g2 += __shfl_xor_sync(0xffffffffu, g2, o);
-                    }
-                    if (valid && (lane & ((1u << lw) - 1u)) == 0u)
-                    {
-                        h00 += hd;
-                        h11 += hd;
-                        h22 += hd;
-                        float x = xi.x, y = xi.y, z = xi.z;
-                        if constexpr (kDamping)
-                        {
-                            float4 const xt = __ldcg(p.xt + vi);
-                            float const D   = p.dampD;
-                            float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
-                            g0 += D * (h00 * ex + h01 * ey + h02 * ez);
-                            g1 += D * (h01 * ex + h11 * ey + h12 * ez);
-                            g2 += D * (h02 * ex + h12 * ey + h22 * ez);
-                            float const sc = 1.f + D;
-                            h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
-                        }
-                        float4 const xm = __ldcg(p.xtildeM + vi);
-                        float const K   = xm.w / p.sdt2;
-                        h00 += K, h11 += K, h22 += K;
-                        g0 += K * (x - xm.x);
-                        g1 += K * (y - xm.y);
-                        g2 += K * (z - xm.z);
-                        float const i00 = h11 * h22 - h12 * h12;
-                        float const i01 = h02 * h12 - h01 * h22;
-                        float const i02 = h01 * h12 - h02 * h11;
-                        float const det = h00 * i00 + h01 * i01 + h02 * i02;
-                        if (fabsf(det) > p.detHZero)
-                        {
-                            float const i11 = h00 * h22 - h02 * h02;
-                            float const i12 = h01 * h02 - h00 * h12;
-                            float const i22 = h00 * h11 - h01 * h01;
-                            float const r   = 1.f / det;
-                            x -= r * (i00 * g0 + i01 * g1 + i02 * g2);
-                            y -= r * (i01 * g0 + i11 * g1 + i12 * g2);
-                            z -= r * (i02 * g0 + i12 * g1 + i22 * g2);
-                        }
-                        float4 const raw = make_float4(x, y, z, 0.f);
-                        if constexpr (kChebyshev)
-                        {
-                            float4 out = raw;
-                            if (k > 1)
-                            {
-                                float4 const h2 = __ldcg(p.hist + vi);
-                                out.x = omega * (x - h2.x) + h2.x;
-                                out.y = omega * (y - h2.y) + h2.y;
-                                out.z = omega * (z - h2.z) + h2.z;
-                            }
-                            p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
-                            p.pos[vi]          = raw;
-                            p.pos[p.pOff + vi] = out;
-                        }
-                        else
-                        {
-                            p.pos[vi] = raw;
-                        }
-                    }
+                    uint4 const td    = __ldg(p.tiles + T);
+                    uint32_t const n0 = streamBase + (td.x - b0);
+                    RingRecords src{smem, full, empty, R, n0 % R, n0 / R, lane};
+                    ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane);
                 }
                 streamBase += b1 - b0;
                 ConsumerGridBarrier(p.barrier, target);

@@ -114,7 +114,8 @@ struct Integrator {
     // static sweep data
     DevBuf<float4> dRecords;
     DevBuf<TileDesc> dTiles;
-    DevBuf<uint32_t> dCtaRange, dCtaBlockBegin;
+    DevBuf<uint32_t> dCtaRange, dCtaBlockBegin, dRingIds;
+    uint32_t stageEntries = 32;
     DevBuf<int32_t> dNew2Old, dOld2New;
 
     // state
@@ -280,9 +281,10 @@ void Integrator::Create(vbdx_data_desc const& d)
         ++kernelLaunches;
     }
 
-    std::vector<uint32_t> ptrHost(static_cast<size_t>(nV + 1));
+    std::vector<uint32_t> ptrHost(static_cast<size_t>(nV + 1)), adjHost(static_cast<size_t>(4 * nT));
     uint32_t err = 0;
     dPtr.Download(ptrHost.data(), nV + 1, stream);
+    dAdj.Download(adjHost.data(), 4 * nT, stream);
     dErr.Download(&err, 1, stream);
     VBDX_CUDA(cudaStreamSynchronize(stream));
     if (err & 1u)
@@ -290,22 +292,37 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (err & 2u)
         throw Error(VBDX_INVALID_ARGUMENT, "invalid colouring: two swept vertices of one tetrahedron share a colour");
 
-    // ---- launch shape, then the host plan
-    bool const cheb0 = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    // ---- host plan (tiles, ring lists), then the launch shape, then the tile -> CTA partition
+    bool const cheb0    = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    int const tileIters = d.tile_iters > 0 ? d.tile_iters : 4;
+    try
+    {
+        BuildPlan(nV, E32.data(), ptrHost.data(), adjHost.data(), colors.data(), isDbc.data(), d.X, tileIters,
+                  (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, plan);
+    }
+    catch (std::length_error const& e)
+    {
+        throw Error(VBDX_UNSUPPORTED, e.what());
+    }
+    nRecordSlots = plan.nBlocks * 32;
+    stageEntries = static_cast<uint32_t>(std::max(32, plan.maxRingPerTile));
     // the damping variant can be switched on later (SetRayleighDampingCoefficient), so size the
     // persistent grid for the least-resident variant of this acceleration mode
-    variant = d.kernel_variant == VBDX_KERNEL_DEFAULT ? VBDX_KERNEL_TMA : d.kernel_variant;
+    variant = d.kernel_variant == VBDX_KERNEL_DEFAULT ? VBDX_KERNEL_DIRECT : d.kernel_variant;
     Require(variant == VBDX_KERNEL_DIRECT || variant == VBDX_KERNEL_TMA, "unknown kernel variant");
+    int maxOptin = 0;
+    VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     int perSm = 1 << 30;
     if (variant == VBDX_KERNEL_TMA)
     {
-        blockThreads = kTmaThreads;
-        int maxOptin = 0;
-        VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - 1024) / (kBlockBytes + 16));
-        ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : 104u;
+        blockThreads            = kTmaThreads;
+        size_t const stageBytes = static_cast<size_t>(kTmaConsumerWarps) * stageEntries * sizeof(float4);
+        if (stageBytes + 2 * (kBlockBytes + 16) > static_cast<size_t>(maxOptin))
+            throw Error(VBDX_UNSUPPORTED, "1-ring staging does not fit in shared memory (vertex valence too high)");
+        uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - stageBytes) / (kBlockBytes + 16));
+        ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : 96u;
         ringSlots = std::max(2u, std::min(ringSlots, maxSlots));
-        smemBytes = static_cast<size_t>(ringSlots) * (kBlockBytes + 16);
+        smemBytes = static_cast<size_t>(ringSlots) * (kBlockBytes + 16) + stageBytes;
         for (TmaKernelFn fn : {cheb0 ? StepKernelTma<true, false> : StepKernelTma<false, false>,
                                cheb0 ? StepKernelTma<true, true> : StepKernelTma<false, true>})
         {
@@ -319,25 +336,22 @@ void Integrator::Create(vbdx_data_desc const& d)
     else
     {
         blockThreads = 256;
+        smemBytes    = static_cast<size_t>(blockThreads / 32) * stageEntries * sizeof(float4);
+        if (smemBytes > static_cast<size_t>(maxOptin))
+            throw Error(VBDX_UNSUPPORTED, "1-ring staging does not fit in shared memory (vertex valence too high)");
         for (StepKernelFn fn : {cheb0 ? StepKernel<true, false> : StepKernel<false, false>,
                                 cheb0 ? StepKernel<true, true> : StepKernel<false, true>})
         {
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
             int n = 0;
-            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, 0));
+            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
             perSm = std::min(perSm, n);
         }
     }
     if (perSm < 1)
         throw Error(VBDX_CUDA_ERROR, "step kernel does not fit on an SM");
     gridBlocks = perSm * smCount;
-
-    std::vector<int32_t> deg(static_cast<size_t>(nV));
-    for (int64_t i = 0; i < nV; ++i)
-        deg[i] = static_cast<int32_t>(ptrHost[i + 1] - ptrHost[i]);
-    int const tileIters = d.tile_iters > 0 ? d.tile_iters : 4;
-    BuildPlan(nV, deg.data(), colors.data(), isDbc.data(), d.X, tileIters, gridBlocks,
-              (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, plan);
-    nRecordSlots = plan.nBlocks * 32;
+    PartitionTiles(plan, gridBlocks);
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
     dTiles.Upload(plan.tiles.data(), plan.tiles.size(), stream);
@@ -349,14 +363,26 @@ void Integrator::Create(vbdx_data_desc const& d)
     dNew2Old.Upload(plan.new2old.data(), nV, stream);
     dOld2New.Alloc(nV, &deviceBytes);
     dOld2New.Upload(plan.old2new.data(), nV, stream);
+    dRingIds.Alloc(plan.ringIds.size() + 32, &deviceBytes);
+    dRingIds.Upload(plan.ringIds.data(), plan.ringIds.size(), stream);
     dRecords.Alloc(static_cast<size_t>(plan.nBlocks) * kBlockFloat4 + 1, &deviceBytes);
     if (!plan.tiles.empty())
     {
+        DevBuf<uint32_t> dRingOff;
+        DevBuf<uint16_t> dRingCnt;
+        dRingOff.Alloc(plan.ringOff.size());
+        dRingOff.Upload(plan.ringOff.data(), plan.ringOff.size(), stream);
+        dRingCnt.Alloc(plan.ringCnt.size() + 1);
+        dRingCnt.Upload(plan.ringCnt.data(), plan.ringCnt.size(), stream);
         int const nTiles = static_cast<int>(plan.tiles.size());
         FillRecords<<<Blocks(static_cast<int64_t>(nTiles) * 32, 256), 256, 0, stream>>>(
             dTiles.p, nTiles, dNew2Old.p, dOld2New.p, dPtr.p, dAdj.p, dE.p, dJinv.p, dVol.p, dLame.p,
-            muDefault, lamDefault, dColor.p, dRecords.p);
+            muDefault, lamDefault, dRingIds.p, dRingOff.p, dRingCnt.p, dRecords.p, dErr.p);
         ++kernelLaunches;
+        dErr.Download(&err, 1, stream);
+        VBDX_CUDA(cudaStreamSynchronize(stream));
+        if (err & 4u)
+            throw Error(VBDX_CUDA_ERROR, "internal error: neighbour missing from a staged ring list");
     }
 
     // ---- state
@@ -423,6 +449,8 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.records      = dRecords.p;
     p.tiles        = reinterpret_cast<uint4 const*>(dTiles.p);
     p.ctaTileRange = dCtaRange.p;
+    p.ringIds      = dRingIds.p;
+    p.stageEntries = stageEntries;
     p.nColors      = plan.nColors;
     p.nVerts       = static_cast<int>(nV);
     p.pos          = dPos.p;
@@ -460,7 +488,7 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     {
         void* args[] = {&p};
         VBDX_CUDA(cudaLaunchCooperativeKernel(
-            reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, 0, stream));
+            reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
     }
     VBDX_CUDA(cudaEventRecord(evEnd, stream));
     ++kernelLaunches;
@@ -727,7 +755,7 @@ vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned lon
     return Guard([&] {
         auto& I = h->impl;
         VBDX_CUDA(cudaSetDevice(I.device));
-        size_t const n = static_cast<size_t>(I.plan.nColors) * I.gridBlocks * 4;
+        size_t const n = static_cast<size_t>(I.plan.nColors) * I.gridBlocks * 8;
         if (out == nullptr)
         {
             // arm: the next steps record the timestamps of `iteration` (direct kernel only)

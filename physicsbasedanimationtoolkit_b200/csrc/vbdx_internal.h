@@ -13,31 +13,37 @@ namespace vbdx {
 //
 // Vertices are renumbered ("internal ids"): swept vertices first, colour-major, inside a colour
 // grouped into warp tiles; Dirichlet vertices last.  A *tile* is the unit of work of one warp:
-// 32/w vertices, each owned by w adjacent lanes (w = 1,2,4,...,32 chosen from the vertex
-// valence so that every lane visits ~tile_iters incident tets).  The incident-tet data of a tile
-// is stored as `iters` consecutive *blocks* of 2 KB: block = 4 chunk rows x 32 lanes x 16 B,
-// i.e. lane l's 64-byte incidence record is the l-th float4 of each chunk row, so every warp
-// load instruction is one fully coalesced 512-byte request.
+// up to 32/w vertices, each owned by w adjacent lanes (w = 1,2,4,...,32 chosen from the vertex
+// valence so that every lane visits ~tile_iters incident tets).
 //
-// Incidence record (vertex i, incident tet e), 16 words:
-//   word 0..2   internal ids of the three *other* vertices of e (bit 31 set when that vertex has
-//               a higher colour than i: it is then read from the previous-iterate buffer, which is
-//               what fuses the Chebyshev blend into the sweep)
-//   word 3..11  shape-function gradients (rows of GP, fem/ShapeFunctions.h:267-297) of those three
+// Per tile two static streams exist:
+//  * the *ring list*: the distinct neighbour vertices (1-rings) of the tile's vertices, as
+//    internal ids (bit 31 set when the neighbour has a higher colour than the vertex that lists
+//    it: it is then read from the previous-iterate buffer, which is what fuses the Chebyshev
+//    blend into the sweep).  The warp gathers these positions ONCE per tile into shared memory;
+//    every incident tet then addresses its three other vertices by 10-bit local indices.
+//  * the *incidence records*, `iters` consecutive blocks of 1.5 KB: block = 3 chunk rows x 32
+//    lanes x 16 B, i.e. lane l's 48-byte record is the l-th float4 of each chunk row, so every
+//    warp load instruction is one fully coalesced 512-byte request.
+//
+// Incidence record (vertex i, incident tet e), 12 words:
+//   word 0      local ring indices of the three other vertices of e, 10 bits each
+//   word 1..9   shape-function gradients (rows of GP, fem/ShapeFunctions.h:267-297) of those three
 //               vertices, 3 floats each; the gradient of i itself is minus their sum
-//   word 12     wg * mu      word 13  wg * lambda      word 14  alpha = 1 + mu/lambda
-//   word 15     |grad_i|^2 (precomputed)
-// Padding slots have ids = the owning vertex and zero weights, so they contribute exactly 0.
+//   word 10     wg * mu      word 11  wg * lambda     (alpha = 1 + mu/lambda is recomputed)
+// Padding slots have index 0 and zero weights, so they contribute exactly 0.
 // -----------------------------------------------------------------------------------------
-constexpr int kRecordWords      = 16;
-constexpr int kBlockFloat4      = 128;  // float4 per block (4 chunk rows x 32 lanes)
+constexpr int kRecordWords      = 12;
+constexpr int kBlockFloat4      = 96;   // float4 per block (3 chunk rows x 32 lanes)
+constexpr int kBlockBytes       = kBlockFloat4 * 16;
 constexpr uint32_t kPrevFlag    = 0x80000000u;
+constexpr int kMaxRingPerTile   = 1024; // 10-bit local indices
 
 struct TileDesc {
-    uint32_t blockStart;  // first block of the tile
+    uint32_t blockStart;  // first record block of the tile
     uint32_t vbase;       // first internal vertex id
-    uint32_t meta;        // log2(w) | iters << 8 | nverts << 24
-    uint32_t pad;
+    uint32_t meta;        // log2(w) [0:3) | nverts [3:9) | ring chunks of 32 [9:16) | iters [16:32)
+    uint32_t ringStart;   // first entry of the tile's ring list (multiple of 32)
 };
 
 struct Plan {
@@ -48,22 +54,32 @@ struct Plan {
     std::vector<uint32_t> colorTileBegin;    // nColors + 1
     std::vector<uint32_t> ctaTileRange;      // nColors x (gridBlocks + 1): tiles of colour c for CTA b
     std::vector<uint32_t> ctaBlockBegin;     // nColors x (gridBlocks + 1): first record block of CTA b in colour c
+    std::vector<uint32_t> ringIds;           // ring lists of all tiles (internal ids | kPrevFlag)
+    std::vector<uint32_t> ringOff;           // nActive + 1: start of each swept vertex' own list in ringIds
+    std::vector<uint16_t> ringCnt;           // nActive: length of that list
+    int32_t maxRingPerTile = 0;              // longest (padded) tile ring list: sizes the per-warp staging
     int64_t nBlocks = 0;
     int64_t nIncidences = 0;                 // over swept vertices
+    int64_t nRingEntries = 0;                // sum of 1-ring sizes over swept vertices (unpadded)
 };
 
-// Host planner (plan.cpp).  deg = incident tets per vertex (caller numbering), colors = vertex
+// Host planner (plan.cpp).  E / vtPtr / vtAdj = connectivity (caller numbering), colors = vertex
 // colours, isDbc = Dirichlet mask, X = 3 x nV rest positions (for the Morton order).
 void BuildPlan(
     int64_t nV,
-    const int32_t* deg,
+    const int32_t* E,        // 4 x nT
+    const uint32_t* vtPtr,   // vertex -> tet CSR built on the device (nV + 1)
+    const uint32_t* vtAdj,   // entries 4*e + ilocal
     const int64_t* colors,
     const uint8_t* isDbc,
     const double* X,
     int tileIters,
-    int gridBlocks,
     bool naturalOrder,
     Plan& plan);
+
+// Second planning step, once the persistent grid size is known: which tiles / record blocks of each
+// colour belong to which CTA.
+void PartitionTiles(Plan& plan, int gridBlocks);
 
 // Reference colouring on the host (plan.cpp): graph/Color.h:45-135 over graph/Mesh.h:116-123.
 void GreedyColorMesh(

@@ -8,7 +8,7 @@ n = 58
 X, T = meshes.tet_grid(n, n, n, 1.0 / n)
 dbc = np.flatnonzero(X[2] == 0)
 data = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.9).construct()
-for ti in (4, 2):
+for ti in (4, 8):
     vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=1)
     for _ in range(3):
         vbd.step(0.01, 30, 1)
@@ -18,5 +18,8 @@ for ti in (4, 2):
     print(f"tile_iters={ti} step {vbd.info['lastStepMs']:.3f} ms; iteration span {(tr[...,3].max())/1e3:.1f} us")
     for c in range(tr.shape[0]):
         s, w0, cta, rel = (tr[c, :, i] for i in range(4))
+        has = tr[c, :, 4] > 0
+        td_, st_, ac_, so_ = (np.median((tr[c, has, i] - tr[c, has, 0])) / 1e3 for i in (4, 5, 6, 7))
+        print(f"      warp0 first tile (median over CTAs, us since phase start): desc {td_:.2f} staged {st_:.2f} accumulated {ac_:.2f} solved {so_:.2f}")
         print(f" colour {c}: start {s.min()/1e3:7.2f}..{s.max()/1e3:7.2f}  cta work med {np.median(cta-s)/1e3:5.2f} max {(cta-s).max()/1e3:5.2f} us | "
               f"last cta done {cta.max()/1e3:7.2f} | release first {rel.min()/1e3:7.2f} last {rel.max()/1e3:7.2f} | release-after-last-arrival {(rel.min()-cta.max())/1e3:5.2f}..{(rel.max()-cta.max())/1e3:5.2f}")
