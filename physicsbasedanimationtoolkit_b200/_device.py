@@ -20,7 +20,7 @@ def _interleaved(a, dtype, nV, name):
 class DeviceIntegrator:
     _dtype = np.float32
 
-    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0):
+    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0):
         L = _lib.lib()
         if data.x.size == 0:
             raise ValueError("Data.construct() must be called before creating an integrator")
@@ -64,6 +64,7 @@ class DeviceIntegrator:
         d.active_set_update_frequency = int(data.active_set_update_frequency)
         d.device, d.tile_iters, d.flags = int(device), int(tile_iters), int(flags)
         d.kernel_variant, d.ring_slots = int(kernel_variant), int(ring_slots)
+        d.consumer_warps = int(consumer_warps)
         # rest positions differ from x only if the caller edited data.x after construct(); the
         # element rest data must come from X (sim/vbd/Data.cpp:220-221)
         self._rest_differs = not np.array_equal(data.x, data.X)

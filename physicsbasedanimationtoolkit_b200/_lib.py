@@ -34,6 +34,7 @@ class DataDesc(C.Structure):
         ("active_set_update_frequency", C.c_int32),
         ("device", C.c_int32), ("tile_iters", C.c_int32), ("flags", C.c_int32),
         ("kernel_variant", C.c_int32), ("ring_slots", C.c_int32),
+        ("consumer_warps", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -159,7 +159,8 @@ __device__ __forceinline__ void ProcessTile(
     int k,
     float omega,
     uint32_t lane,
-    unsigned long long* trace = nullptr)
+    unsigned long long* trace = nullptr,
+    uint32_t const* idsStaged = nullptr)  // the tile's ring ids already in shared memory (else read from global)
 {
     float4 const* __restrict__ posQ = p.pos;
     uint32_t const lw         = td.z & 7u;
@@ -177,15 +178,21 @@ __device__ __forceinline__ void ProcessTile(
     float4 const xi = LoadPos(posQ + p.pOff + vi);
     // gather the tile's 1-rings once: ringChunks independent scattered loads per lane
     {
-        uint32_t const* ids = p.ringIds + td.w + lane;
+        uint32_t const* ids = (idsStaged ? idsStaged : p.ringIds + td.w) + lane;
         __syncwarp();  // the previous tile's readers are done with the staging area
         for (uint32_t j = 0; j < ringChunks; ++j)
         {
-            uint32_t const id = __ldg(ids + 32 * j);
+            uint32_t const id = idsStaged ? ids[32 * j] : __ldg(ids + 32 * j);
             stage[32 * j + lane] = LoadPos(posQ + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
         }
         __syncwarp();
     }
+    // epilogue operands, requested now so that they are in registers when the solve needs them
+    float4 const xm = __ldcg(p.xtildeM + vi);
+    float4 h2       = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kChebyshev)
+        if (k > 1)
+            h2 = __ldcg(p.hist + vi);
     if (trace && lane == 0)
         trace[5] = GlobalTimer();  // 1-rings staged
 
@@ -286,7 +293,6 @@ __device__ __forceinline__ void ProcessTile(
             float const sc = 1.f + D;
             h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
         }
-        float4 const xm = __ldcg(p.xtildeM + vi);
         float const K   = xm.w / p.sdt2;
         h00 += K, h11 += K, h22 += K;
         g0 += K * (x - xm.x);
@@ -316,7 +322,6 @@ __device__ __forceinline__ void ProcessTile(
             float4 out = raw;
             if (k > 1)
             {
-                float4 const h2 = __ldcg(p.hist + vi);
                 out.x = omega * (x - h2.x) + h2.x;
                 out.y = omega * (y - h2.y) + h2.y;
                 out.z = omega * (z - h2.z) + h2.z;

@@ -6,19 +6,22 @@
 // per-slot "full" mbarriers.  Because the records never change, the producer runs ahead of the
 // colour barriers: while the consumers wait for the other SMs at the end of colour c, the
 // records of colour c+1 are already landing in shared memory, so the HBM stream is continuous.
-// The remaining warps are *consumers*: each owns a static subset of the CTA's warp tiles, waits
-// on the slot's mbarrier, gathers the (mutable) neighbour positions from L2, accumulates the
-// closed-form Stable Neo-Hookean block, reduces over the lanes that share a vertex, and does the
-// fused damping / inertia / Newton / Chebyshev epilogue exactly as step_kernel.cuh (same
-// arithmetic, same summation order).
+//
+// The remaining warps are *consumers*.  Each owns a static subset of the CTA's warp tiles and
+// runs a two-deep software pipeline over its own tile sequence (which crosses colour and
+// iteration boundaries): the descriptor of tile i+2 and the ring ids of tile i+1 are fetched with
+// cp.async (LDGSTS) into per-warp shared memory while tile i is processed.  When a colour barrier
+// releases, everything static a warp needs is therefore already on chip and the only exposed
+// latency is the gather of the (mutable) neighbour positions from L2.
+// Arithmetic and summation order are those of step_kernel.cuh (shared ProcessTile).
 #pragma once
 
 #include "step_kernel.cuh"
 
 namespace vbdx {
 
-constexpr int kTmaThreads       = 768;                     // 23 consumer warps + 1 producer warp
-constexpr int kTmaConsumerWarps = kTmaThreads / 32 - 1;
+constexpr int kTmaMaxThreads   = 640;  // <= 102 registers per thread
+constexpr int kProducerWarps   = 4;    // power of two: record block n of a CTA's stream is issued by producer n % 4
 
 struct TmaParams {
     StepParams base;
@@ -69,13 +72,46 @@ __device__ __forceinline__ void BulkLoad(uint32_t dstSmem, const void* srcGmem, 
         : "memory");
 }
 
-// Record source of the consumers: this lane's 48-byte record out of the shared-memory ring slot that the
-// producer filled; the slot is handed back as soon as the warp has copied its records to registers.
+__device__ __forceinline__ void CpAsync4(uint32_t dstSmem, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dstSmem), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void CpAsync16(uint32_t dstSmem, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void CpAsyncWaitAll()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t LoadAcquireShared(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void StoreReleaseShared(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Record source of the consumers: this lane's 48-byte record out of the shared-memory ring slot
+// that the producer filled; the slot is handed back as soon as the warp has copied its records to
+// registers.  mbarrier phases only tell adjacent fills of a slot apart, and consumers do not
+// consume in stream order, so a consumer first makes sure the producer has *issued* block n
+// (monotonic per-producer `produced` counters) before it waits on the slot's parity.
 struct RingRecords {
     unsigned char const* smem;
-    uint32_t full, empty, R, slot, fill, lane;
+    uint32_t full, empty, produced, R, slot, fill, n, lane;
     __device__ __forceinline__ void Fetch(float4& c0, float4& c1, float4& c2)
     {
+        while (LoadAcquireShared(produced + 4 * (n & (kProducerWarps - 1))) <= n / kProducerWarps)
+        {
+        }
         MbarWait(full + 8 * slot, fill & 1u);
         unsigned char const* blk = smem + slot * kBlockBytes + lane * 16;
         c0 = *reinterpret_cast<float4 const*>(blk);
@@ -84,6 +120,7 @@ struct RingRecords {
         __syncwarp();
         if (lane == 0)
             MbarArrive(empty + 8 * slot);
+        ++n;
         if (++slot == R)
         {
             slot = 0;
@@ -93,32 +130,71 @@ struct RingRecords {
 };
 
 // grid barrier among the consumer threads of all CTAs (the producer warp never joins)
-__device__ __forceinline__ void ConsumerGridBarrier(unsigned int* counter, unsigned int& target)
+__device__ __forceinline__ void ConsumerGridBarrier(unsigned int* counter, unsigned int& target, uint32_t nConsumerThreads,
+                                                    unsigned long long* trace = nullptr)
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumerWarps * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(nConsumerThreads) : "memory");
     if (threadIdx.x == 0)
     {
+        if (trace)
+            trace[2] = GlobalTimer();
         target += gridDim.x;
         AddRelease(counter, 1u);
         while (LoadAcquire(counter) < target)
         {
         }
         __threadfence();
+        if (trace)
+            trace[3] = GlobalTimer();
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumerWarps * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(nConsumerThreads) : "memory");
+}
+
+// position of a consumer warp in its own tile sequence
+struct TileCursor {
+    int k, c;       // iteration within the substep sequence (s * iterations + k), colour
+    uint32_t T;     // tile index
+    bool valid;
+};
+
+// shared-memory footprint of the TMA kernel (host and device must agree)
+__host__ __device__ inline size_t TmaSmemBytes(uint32_t R, uint32_t nColors, uint32_t nConsumerWarps, uint32_t stageEntries)
+{
+    size_t b = static_cast<size_t>(R) * (kBlockBytes + 16);          // ring + full/empty barriers
+    b += 16;                                                          // produced counter (+pad)
+    b += static_cast<size_t>(nColors + 1) * 16;                       // range table
+    b += static_cast<size_t>(nConsumerWarps) * (4 * 16);              // tile-descriptor ring per warp
+    b += static_cast<size_t>(nConsumerWarps) * stageEntries * (2 * 4 + 16);  // ids double buffer + positions
+    return b;
 }
 
 template <bool kChebyshev, bool kDamping>
-__global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_constant__ TmaParams tp)
+__global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_constant__ TmaParams tp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     StepParams const& p  = tp.base;
     uint32_t const R     = tp.ringSlots;
-    uint32_t const ring  = SmemAddr(smem);
-    uint32_t const full  = ring + R * kBlockBytes;
-    uint32_t const empty = full + R * 8;
-    float4* const stage  = reinterpret_cast<float4*>(smem + R * (kBlockBytes + 16)) + (threadIdx.x >> 5) * p.stageEntries;
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t const NC   = (blockDim.x >> 5) - kProducerWarps;  // consumer warps
+    uint32_t const SE   = p.stageEntries;
+    uint32_t const nC   = static_cast<uint32_t>(p.nColors);
+
+    // carve shared memory
+    uint32_t const ring     = SmemAddr(smem);
+    uint32_t const full     = ring + R * kBlockBytes;
+    uint32_t const empty    = full + R * 8;
+    uint32_t const produced = empty + R * 8;
+    unsigned char* cur      = smem + static_cast<size_t>(R) * (kBlockBytes + 16) + 16;
+    uint4* const rangeTab   = reinterpret_cast<uint4*>(cur);  // per colour: {tBegin, tEnd, b0, blocks before this colour in one sweep}
+    cur += static_cast<size_t>(nC + 1) * 16;
+    uint4* const tdBuf = reinterpret_cast<uint4*>(cur) + warp * 4;
+    cur += static_cast<size_t>(NC) * 64;
+    float4* const stage = reinterpret_cast<float4*>(cur) + static_cast<size_t>(warp) * SE;
+    cur += static_cast<size_t>(NC) * SE * 16;
+    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(cur) + static_cast<size_t>(warp) * 2 * SE;
+
+    uint32_t const stride    = gridDim.x + 1;
+    uint32_t const* blkBegin = tp.ctaBlockBegin + blockIdx.x;
 
     if (threadIdx.x == 0)
     {
@@ -127,50 +203,142 @@ __global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_con
             MbarInit(full + 8 * s, 1);
             MbarInit(empty + 8 * s, 1);
         }
+        for (int j = 0; j < kProducerWarps; ++j)
+            reinterpret_cast<volatile uint32_t*>(smem + static_cast<size_t>(R) * (kBlockBytes + 16))[j] = 0u;
+        uint32_t before = 0;
+        for (uint32_t c = 0; c < nC; ++c)
+        {
+            uint32_t const* range = p.ctaTileRange + static_cast<size_t>(c) * stride + blockIdx.x;
+            uint32_t const b0 = blkBegin[c * stride], b1 = blkBegin[c * stride + 1];
+            rangeTab[c] = make_uint4(range[0], range[1], b0, before);
+            before += b1 - b0;
+        }
+        rangeTab[nC] = make_uint4(0, 0, 0, before);  // .w = record blocks of this CTA per sweep
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    uint32_t const blocksPerSweep = rangeTab[nC].w;
+    int const totalSweeps         = p.substeps * p.iterations;
 
-    uint32_t const* blkBegin = tp.ctaBlockBegin + blockIdx.x;
-    uint32_t const stride    = gridDim.x + 1;
-
-    if (warp == kTmaConsumerWarps)
+    if (warp >= NC)
     {
-        // ------------------------------ producer ------------------------------
-        if (lane == 0)
+        // ------------------------------ producers ------------------------------
+        // producer j issues blocks j, j+4, j+8, ... of this CTA's stream; one elected lane each
+        if (lane == 0 && blocksPerSweep > 0)
         {
+            uint32_t const j = warp - NC;
             uint64_t policy;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            uint32_t slot = 0, fill = 0;
-            for (int s = 0; s < p.substeps; ++s)
-                for (int k = 0; k < p.iterations; ++k)
-                    for (int c = 0; c < p.nColors; ++c)
-                    {
-                        uint32_t const b0 = __ldg(blkBegin + c * stride), b1 = __ldg(blkBegin + c * stride + 1);
-                        for (uint32_t b = b0; b < b1; ++b)
-                        {
-                            if (fill > 0)
-                                MbarWait(empty + 8 * slot, (fill & 1u) ^ 1u);
-                            MbarArriveExpectTx(full + 8 * slot, kBlockBytes);
-                            BulkLoad(ring + slot * kBlockBytes, p.records + static_cast<size_t>(b) * kBlockFloat4,
-                                     kBlockBytes, full + 8 * slot, policy);
-                            if (++slot == R)
-                            {
-                                slot = 0;
-                                ++fill;
-                            }
-                        }
-                    }
+            uint32_t const total = static_cast<uint32_t>(totalSweeps) * blocksPerSweep;
+            uint32_t c = 0, off = j;      // position inside the sweep: colour and block offset within it
+            uint32_t slot = j % R, fill = j / R, issued = 0;
+            for (uint32_t n = j; n < total; n += kProducerWarps)
+            {
+                for (;;)
+                {
+                    uint32_t const inColour = (c + 1 < nC ? rangeTab[c + 1].w : blocksPerSweep) - rangeTab[c].w;
+                    if (off < inColour)
+                        break;
+                    off -= inColour;
+                    if (++c == nC)
+                        c = 0;
+                }
+                if (fill > 0)
+                    MbarWait(empty + 8 * slot, (fill & 1u) ^ 1u);
+                MbarArriveExpectTx(full + 8 * slot, kBlockBytes);
+                BulkLoad(ring + slot * kBlockBytes, p.records + static_cast<size_t>(rangeTab[c].z + off) * kBlockFloat4,
+                         kBlockBytes, full + 8 * slot, policy);
+                StoreReleaseShared(produced + 4 * j, ++issued);
+                off += kProducerWarps;
+                slot += kProducerWarps;
+                while (slot >= R)
+                {
+                    slot -= R;
+                    ++fill;
+                }
+            }
         }
         return;
     }
 
     // ------------------------------ consumers ------------------------------
-    unsigned int target      = 0;
-    uint32_t const ctid      = blockIdx.x * (kTmaConsumerWarps * 32) + threadIdx.x;
-    uint32_t const cstride   = gridDim.x * (kTmaConsumerWarps * 32);
-    uint32_t streamBase      = 0;  // blocks of this CTA's stream before the current colour
+    uint32_t const nConsumerThreads = NC * 32;
+    unsigned int target    = 0;
+    uint32_t const ctid    = blockIdx.x * nConsumerThreads + threadIdx.x;
+    uint32_t const cstride = gridDim.x * nConsumerThreads;
+
+    // this warp's tile sequence over all sweeps; `Advance` steps to its next tile
+    auto First = [&](TileCursor& t) {
+        t.k = 0;
+        t.c = -1;
+        t.T = 0;
+        t.valid = totalSweeps > 0;
+    };
+    auto Advance = [&](TileCursor& t) {
+        if (!t.valid)
+            return;
+        if (t.c >= 0)
+        {
+            t.T += NC;
+            if (t.T < rangeTab[t.c].y)
+                return;
+        }
+        for (;;)
+        {
+            if (++t.c == static_cast<int>(nC))
+            {
+                t.c = 0;
+                if (++t.k == totalSweeps)
+                {
+                    t.valid = false;
+                    return;
+                }
+            }
+            t.T = rangeTab[t.c].x + warp;
+            if (t.T < rangeTab[t.c].y)
+                return;
+            if (blocksPerSweep == 0 && t.c == static_cast<int>(nC) - 1)
+            {
+                t.valid = false;  // this CTA owns no tiles at all
+                return;
+            }
+        }
+    };
+    // a warp with no tiles in any colour must not spin forever in Advance
+    bool warpHasTiles = false;
+    for (uint32_t c = 0; c < nC; ++c)
+        warpHasTiles |= rangeTab[c].x + warp < rangeTab[c].y;
+
+    TileCursor t1, t2;  // tiles i+1 and i+2 relative to the tile being processed
+    First(t1);
+    t1.valid &= warpHasTiles;
+    Advance(t1);  // tile 0
+    t2 = t1;
+    Advance(t2);  // tile 1
+    uint32_t seq = 0;  // index of the tile being processed in this warp's sequence
+    auto IssueTd = [&](TileCursor const& t, uint32_t s) {
+        if (t.valid && lane == 0)
+            CpAsync16(SmemAddr(tdBuf + (s & 3u)), p.tiles + t.T);
+    };
+    auto IssueIds = [&](uint32_t s) {
+        // ring ids of sequence tile s, whose descriptor is already in tdBuf
+        uint4 const td        = tdBuf[s & 3u];
+        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const dst    = SmemAddr(idsBuf + (s & 1u) * SE + lane);
+        for (uint32_t j = 0; j < chunks; ++j)
+            CpAsync4(dst + 128 * j, p.ringIds + td.w + 32 * j + lane);
+    };
+    // prologue: descriptors of tiles 0 and 1, then the ids of tile 0
+    IssueTd(t1, 0);
+    IssueTd(t2, 1);
+    CpAsyncWaitAll();
+    __syncwarp();
+    if (t1.valid)
+        IssueIds(0);
+    bool nextValid = t2.valid;  // does tile seq+1 exist
+    t1 = t2;
+    Advance(t2);                // t2 -> tile 2
 
     for (int s = 0; s < p.substeps; ++s)
     {
@@ -213,25 +381,47 @@ __global__ void __launch_bounds__(kTmaThreads, 1) StepKernelTma(const __grid_con
             if constexpr (kChebyshev)
                 p.pos[p.pOff + i] = o;
         }
-        ConsumerGridBarrier(p.barrier, target);
+        ConsumerGridBarrier(p.barrier, target, nConsumerThreads);
 
         for (int k = 0; k < p.iterations; ++k)
         {
-            float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
-            for (int c = 0; c < p.nColors; ++c)
+            float const omega        = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            uint32_t const sweepBase = static_cast<uint32_t>(s * p.iterations + k) * blocksPerSweep;
+            for (uint32_t c = 0; c < nC; ++c)
             {
-                uint32_t const* range = p.ctaTileRange + static_cast<size_t>(c) * stride + blockIdx.x;
-                uint32_t const tBegin = __ldg(range), tEnd = __ldg(range + 1);
-                uint32_t const b0 = __ldg(blkBegin + c * stride), b1 = __ldg(blkBegin + c * stride + 1);
-                for (uint32_t T = tBegin + warp; T < tEnd; T += kTmaConsumerWarps)
+                uint4 const rt = rangeTab[c];
+                unsigned long long* tr = nullptr;
+                if (p.trace != nullptr && k == p.traceIteration)
                 {
-                    uint4 const td    = __ldg(p.tiles + T);
-                    uint32_t const n0 = streamBase + (td.x - b0);
-                    RingRecords src{smem, full, empty, R, n0 % R, n0 / R, lane};
-                    ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane);
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
+                    if (threadIdx.x == 0)
+                        tr[0] = GlobalTimer();
                 }
-                streamBase += b1 - b0;
-                ConsumerGridBarrier(p.barrier, target);
+                for (uint32_t T = rt.x + warp; T < rt.y; T += NC)
+                {
+                    unsigned long long* tr0 = (tr && warp == 0 && T == rt.x) ? tr : nullptr;
+                    // descriptor + ids of this tile and the descriptor of the next one were requested at
+                    // least one tile ago
+                    CpAsyncWaitAll();
+                    __syncwarp();
+                    uint4 const td = tdBuf[seq & 3u];
+                    if (tr0 && lane == 0)
+                        tr0[4] = GlobalTimer();
+                    if (nextValid)
+                        IssueIds(seq + 1);
+                    IssueTd(t2, seq + 2);
+                    nextValid = t2.valid;
+                    Advance(t2);
+                    uint32_t const n0 = sweepBase + rt.w + (td.x - rt.z);
+                    RingRecords src{smem, full, empty, produced, R, n0 % R, n0 / R, n0, lane};
+                    ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane, tr0, idsBuf + (seq & 1u) * SE);
+                    if (tr0 && lane == 0)
+                        tr0[7] = GlobalTimer();
+                    ++seq;
+                }
+                if (tr && threadIdx.x == 0)
+                    tr[1] = GlobalTimer();
+                ConsumerGridBarrier(p.barrier, target, nConsumerThreads, tr);
             }
         }
     }

@@ -315,14 +315,18 @@ void Integrator::Create(vbdx_data_desc const& d)
     int perSm = 1 << 30;
     if (variant == VBDX_KERNEL_TMA)
     {
-        blockThreads            = kTmaThreads;
-        size_t const stageBytes = static_cast<size_t>(kTmaConsumerWarps) * stageEntries * sizeof(float4);
-        if (stageBytes + 2 * (kBlockBytes + 16) > static_cast<size_t>(maxOptin))
+        int const consumers = d.consumer_warps > 0 ? std::min(d.consumer_warps, kTmaMaxThreads / 32 - kProducerWarps) : 15;
+        blockThreads        = (consumers + kProducerWarps) * 32;
+        size_t const fixed  = TmaSmemBytes(0, plan.nColors, consumers, stageEntries);
+        if (fixed + 2 * (kBlockBytes + 16) > static_cast<size_t>(maxOptin))
             throw Error(VBDX_UNSUPPORTED, "1-ring staging does not fit in shared memory (vertex valence too high)");
-        uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - stageBytes) / (kBlockBytes + 16));
-        ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : 96u;
-        ringSlots = std::max(2u, std::min(ringSlots, maxSlots));
-        smemBytes = static_cast<size_t>(ringSlots) * (kBlockBytes + 16) + stageBytes;
+        uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - fixed) / (kBlockBytes + 16));
+        ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : maxSlots;
+        // every slot must always be served by the same producer warp: R a multiple of kProducerWarps
+        ringSlots = std::min(ringSlots, maxSlots) / kProducerWarps * kProducerWarps;
+        if (ringSlots < static_cast<uint32_t>(kProducerWarps))
+            throw Error(VBDX_UNSUPPORTED, "not enough shared memory for the record ring");
+        smemBytes = TmaSmemBytes(ringSlots, plan.nColors, consumers, stageEntries);
         for (TmaKernelFn fn : {cheb0 ? StepKernelTma<true, false> : StepKernelTma<false, false>,
                                cheb0 ? StepKernelTma<true, true> : StepKernelTma<false, true>})
         {

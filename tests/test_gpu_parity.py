@@ -20,7 +20,7 @@ def rel_l2(a, b):
 
 
 def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile_iters=0, klass=None, flags=0, v=None,
-         kernel_variant=0, ring_slots=0):
+         kernel_variant=0, ring_slots=0, consumer_warps=0):
     d = pbat.sim.vbd.Data().with_volume_mesh(X, T)
     if dbc is not None:
         d = d.with_dirichlet_vertices(dbc)
@@ -33,7 +33,8 @@ def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile
     d.omega_mode = omega_mode
     d = d.with_rayleigh_damping(kD).construct()
     klass = klass or pbat.gpu.vbd.Integrator
-    vbd = klass(d, tile_iters=tile_iters, flags=flags, kernel_variant=kernel_variant, ring_slots=ring_slots)
+    vbd = klass(d, tile_iters=tile_iters, flags=flags, kernel_variant=kernel_variant, ring_slots=ring_slots,
+                consumer_warps=consumer_warps)
     ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, v=v,
                         accel=oracle.ACCEL_CHEBYSHEV if cheb else oracle.ACCEL_NONE, rho=cheb or 1.0,
                         omega_mode=omega_mode, kD=kD,
@@ -203,15 +204,16 @@ def test_against_reference_golden(name):
 
 
 @pytest.mark.parametrize("cheb", [None, 0.9])
-@pytest.mark.parametrize("ring_slots", [0, 3, 16])
-def test_kernel_variants_bitwise_identical(cheb, ring_slots):
+@pytest.mark.parametrize("ring_slots,consumer_warps", [(0, 0), (4, 0), (16, 16), (2, 3), (8, 7)])
+def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
     """The direct and the TMA-ring kernels do the same arithmetic in the same order: identical bits.
     Small rings force many wrap-arounds of the producer/consumer pipeline."""
     X, T = meshes.tet_grid(12, 6, 5, 0.1)
     dbc = np.flatnonzero(X[0] == 0)
     out = []
     for variant in (1, 2):
-        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kD=1e-4, kernel_variant=variant, ring_slots=ring_slots, tile_iters=2)
+        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kD=1e-4, kernel_variant=variant, ring_slots=ring_slots,
+                           consumer_warps=consumer_warps, tile_iters=2)
         for _ in range(3):
             vbd.step(0.01, 7, 2)
         out.append((vbd.x, vbd.v))

@@ -8,14 +8,14 @@ n = 58
 X, T = meshes.tet_grid(n, n, n, 1.0 / n)
 dbc = np.flatnonzero(X[2] == 0)
 data = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.9).construct()
-for ti in (4, 8):
-    vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=1)
+for ti, variant, cw in ((4, 2, 16), (8, 2, 12), (8, 1, 0)):
+    vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=variant, consumer_warps=cw)
     for _ in range(3):
         vbd.step(0.01, 30, 1)
     tr = vbd.trace_phases(10, 0.01, 30, 1).astype(np.int64)
     t0 = tr[..., 0].min()
     tr = tr - t0
-    print(f"tile_iters={ti} step {vbd.info['lastStepMs']:.3f} ms; iteration span {(tr[...,3].max())/1e3:.1f} us")
+    print(f"variant={variant} cw={cw} tile_iters={ti} step {vbd.info['lastStepMs']:.3f} ms; iteration span {(tr[...,3].max())/1e3:.1f} us")
     for c in range(tr.shape[0]):
         s, w0, cta, rel = (tr[c, :, i] for i in range(4))
         has = tr[c, :, 4] > 0
