@@ -293,7 +293,7 @@ def main():
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "bytes_per_vertex_iteration": B, "kbar": kbar, "nbar": nbar,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
-                         "streamed_record_bytes_per_launch": int(info["nRecordSlots"] * 64 * ITERS)},
+                         "streamed_record_bytes_per_launch": int(info["nRecordSlots"] * 32 * ITERS)},
         }
         if world == 1 and not args.no_cpu_baseline:
             _, _, cpu = cpu_reference(X, T, dbc, x0, steps=args.cpu_steps)

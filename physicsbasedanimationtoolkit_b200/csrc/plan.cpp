@@ -12,6 +12,8 @@ namespace vbdx {
 
 namespace {
 
+constexpr uint32_t kSelfMarker = 0xfffffffeu;
+
 inline uint32_t ExpandBits10(uint32_t v)
 {
     v = (v * 0x00010001u) & 0xFF0000FFu;
@@ -255,22 +257,22 @@ void BuildPlan(
         int const lw = items[pos].lw;
         int const G  = 32 >> lw;
         int n = 0, iters = 0;
-        int64_t ringLen = 0;
+        int64_t ringLen = 0;  // neighbour entries; the tile's own vertices come first in its list
         while (n < G && pos + n < plan.nActive && colors[items[pos + n].v] == c &&
                items[pos + n].lw == lw)
         {
             int32_t const v  = items[pos + n].v;
             int64_t const rl = ringPtr[v + 1] - ringPtr[v];
-            if (n > 0 && ringLen + rl > kMaxRingPerTile)
+            if (n > 0 && (n + 1) + ringLen + rl > kMaxRingPerTile)
                 break;  // keep the tile's ring list addressable with 10-bit local indices
             ringLen += rl;
             iters = std::max<int>(iters, items[pos + n].iters);
             ++n;
         }
-        if (ringLen > kMaxRingPerTile)
-            throw std::length_error("a vertex has more than 1024 distinct neighbours");
+        if (n + ringLen > kMaxRingPerTile)
+            throw std::length_error("a vertex has more than 1023 distinct neighbours");
         uint32_t const ringStart  = static_cast<uint32_t>(plan.ringIds.size());
-        uint32_t const ringChunks = static_cast<uint32_t>((ringLen + 31) / 32);
+        uint32_t const ringChunks = static_cast<uint32_t>((n + ringLen + 31) / 32);
         TileDesc t;
         t.blockStart = static_cast<uint32_t>(block);
         t.vbase      = static_cast<uint32_t>(pos);
@@ -278,6 +280,8 @@ void BuildPlan(
                  (static_cast<uint32_t>(iters) << 16);
         t.ringStart = ringStart;
         plan.tiles.push_back(t);
+        for (int k = 0; k < n; ++k)
+            plan.ringIds.push_back(kSelfMarker);  // entry k of the list = the tile's k-th own vertex
         for (int k = 0; k < n; ++k)
         {
             int32_t const v                = items[pos + k].v;
@@ -327,6 +331,9 @@ void BuildPlan(
                 plan.ringIds[b + r] = id;
             }
         }
+        // own vertices: read from the previous-iterate buffer (their start value for this sweep)
+        for (uint32_t k = 0; k < nv; ++k)
+            plan.ringIds[td.ringStart + k] = (td.vbase + k) | kPrevFlag;
         for (uint32_t r = td.ringStart; r < end; ++r)
             if (plan.ringIds[r] == 0xffffffffu)
                 plan.ringIds[r] = pad0;

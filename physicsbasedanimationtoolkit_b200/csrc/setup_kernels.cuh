@@ -271,26 +271,28 @@ __global__ void FillRecords(
     {
         uint32_t const k = t * w + sub;
         uint32_t idx     = 0;
-        float G[9]       = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        float wmu = 0.f, wlam = 0.f;
+        float rec[6]     = {0, 0, 0, 0, 0, 0};
         if (valid && k < degv)
         {
             uint32_t const packed = adj[rowB + k];
             int64_t const e       = packed >> 2;
             int const il          = packed & 3u;
             double const* Ji      = Jinv + 9 * e;
-            int n                 = 0;
+            double g[4][3];  // shape-function gradients of the four local vertices
+            for (int d = 0; d < 3; ++d)
+            {
+                g[0][d] = -(Ji[d] + Ji[3 + d] + Ji[6 + d]);
+                for (int a = 1; a < 4; ++a)
+                    g[a][d] = Ji[3 * (a - 1) + d];
+            }
+            double const* q = g[il];
+            double u[3];
+            double const* o[3];
+            int n = 0;
             for (int a = 0; a < 4; ++a)
             {
                 if (a == il)
                     continue;
-                double g[3];
-                if (a == 0)
-                    for (int d = 0; d < 3; ++d)
-                        g[d] = -(Ji[d] + Ji[3 + d] + Ji[6 + d]);
-                else
-                    for (int d = 0; d < 3; ++d)
-                        g[d] = Ji[3 * (a - 1) + d];
                 // local index of this neighbour in the tile's staged ring list
                 uint32_t const jn = static_cast<uint32_t>(old2new[E[4 * e + a]]);
                 uint32_t loc      = 0xffffffffu;
@@ -306,18 +308,25 @@ __global__ void FillRecords(
                     loc = 0;
                 }
                 idx |= loc << (10 * n);
-                for (int d = 0; d < 3; ++d)
-                    G[3 * n + d] = static_cast<float>(g[d]);
+                o[n] = g[a];
+                u[n] = g[a][0] * q[0] + g[a][1] * q[1] + g[a][2] * q[2];
                 ++n;
             }
+            double const detG = o[0][0] * (o[1][1] * o[2][2] - o[1][2] * o[2][1]) -
+                                o[0][1] * (o[1][0] * o[2][2] - o[1][2] * o[2][0]) +
+                                o[0][2] * (o[1][0] * o[2][1] - o[1][1] * o[2][0]);
             double const mu = lame ? lame[2 * e] : muDefault, lam = lame ? lame[2 * e + 1] : lamDefault;
-            wmu  = static_cast<float>(vol[e] * mu);
-            wlam = static_cast<float>(vol[e] * lam);
+            double const wmu = vol[e] * mu, wlam = vol[e] * lam, alpha = 1.0 + mu / lam;
+            rec[0] = static_cast<float>(wmu * (u[0] + u[1] + u[2]));
+            rec[1] = static_cast<float>(wmu * u[1]);
+            rec[2] = static_cast<float>(wmu * u[2]);
+            rec[3] = static_cast<float>(wlam * detG * detG);
+            rec[4] = static_cast<float>(wlam * detG * alpha);
+            rec[5] = static_cast<float>(wmu * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]));
         }
         float4* out = records + static_cast<size_t>(td.blockStart + t) * kBlockFloat4 + lane;
-        out[0]  = make_float4(__uint_as_float(idx), G[0], G[1], G[2]);
-        out[32] = make_float4(G[3], G[4], G[5], G[6]);
-        out[64] = make_float4(G[7], G[8], wmu, wlam);
+        out[0]  = make_float4(__uint_as_float(idx), rec[0], rec[1], rec[2]);
+        out[32] = make_float4(rec[3], rec[4], rec[5], 0.f);
     }
 }
 

@@ -10,7 +10,8 @@
 //   SolveVertex                                 sim/vbd/Integrator.cpp:98-136
 //   AddDamping / AddInertiaDerivatives / IntegratePositions   sim/vbd/Kernels.h:179-191,310-339
 //   ChebyshevUpdate                             sim/vbd/Kernels.h:104-119, ChebyshevIntegrator.cpp:15-32
-// with the Stable Neo-Hookean vertex block in closed form (DESIGN.md "Math").
+// with the Stable Neo-Hookean vertex block in closed form (DESIGN.md "Math"): no deformation
+// gradient is ever formed, only the edge vector to one neighbour and the opposite face's normal.
 #pragma once
 
 #include "vbdx_internal.h"
@@ -21,9 +22,10 @@ namespace vbdx {
 
 struct StepParams {
     // static topology
-    const float4* __restrict__ records;        // [nBlocks][3][32] float4
+    const float4* __restrict__ records;        // [nBlocks][2][32] float4
     const uint4* __restrict__ tiles;           // TileDesc
-    const uint32_t* __restrict__ ctaTileRange; // [nColors][gridDim.x + 1]
+    const uint32_t* __restrict__ ctaTileRange; // [nColors][gridDim.x + 1] (TMA kernel)
+    const uint32_t* __restrict__ colorTileBegin; // [nColors + 1] (direct kernel)
     const uint32_t* __restrict__ ringIds;      // ring lists of all tiles
     uint32_t stageEntries;                     // per-warp shared-memory staging capacity (float4 entries)
     int nColors;
@@ -138,19 +140,18 @@ __device__ __forceinline__ float3 InitialPosition(
 // (streaming loads, evict-first).
 struct DirectRecords {
     float4 const* rec;
-    __device__ __forceinline__ void Fetch(float4& c0, float4& c1, float4& c2)
+    __device__ __forceinline__ void Fetch(float4& c0, float4& c1)
     {
         c0 = __ldcs(rec);
         c1 = __ldcs(rec + 32);
-        c2 = __ldcs(rec + 64);
         rec += kBlockFloat4;
     }
 };
 
 // One warp tile: stage the 1-rings in shared memory, accumulate the elastic blocks of all
 // incident tets, reduce over the lanes that share a vertex, solve, write back.
-//   RecordSource::Fetch(c0,c1,c2) yields this lane's 48-byte record of the next block.
-template <bool kChebyshev, bool kDamping, class RecordSource>
+//   RecordSource::Fetch(c0,c1) yields this lane's 32-byte record of the next block.
+template <bool kChebyshev, bool kDamping, bool kStageInside, class RecordSource>
 __device__ __forceinline__ void ProcessTile(
     StepParams const& p,
     uint4 const td,
@@ -159,8 +160,7 @@ __device__ __forceinline__ void ProcessTile(
     int k,
     float omega,
     uint32_t lane,
-    unsigned long long* trace = nullptr,
-    uint32_t const* idsStaged = nullptr)  // the tile's ring ids already in shared memory (else read from global)
+    unsigned long long* trace = nullptr)
 {
     float4 const* __restrict__ posQ = p.pos;
     uint32_t const lw         = td.z & 7u;
@@ -172,93 +172,69 @@ __device__ __forceinline__ void ProcessTile(
     uint32_t const vi         = td.y + (valid ? grp : 0u);
 
     // first record block: issue its loads before anything else so they overlap the ring gather
-    float4 n0, n1, n2;
-    src.Fetch(n0, n1, n2);
-    // own position: the previous iterate (P); nobody writes vertex vi during this colour
-    float4 const xi = LoadPos(posQ + p.pOff + vi);
-    // gather the tile's 1-rings once: ringChunks independent scattered loads per lane
+    float4 n0, n1;
+    src.Fetch(n0, n1);
+    // The tile's list = its own vertices (start values, from the previous-iterate buffer P) followed
+    // by their 1-rings.  Gather it once: ringChunks independent scattered loads per lane.
+    if constexpr (kStageInside)
     {
-        uint32_t const* ids = (idsStaged ? idsStaged : p.ringIds + td.w) + lane;
+        uint32_t const* ids = p.ringIds + td.w + lane;
         __syncwarp();  // the previous tile's readers are done with the staging area
         for (uint32_t j = 0; j < ringChunks; ++j)
         {
-            uint32_t const id = idsStaged ? ids[32 * j] : __ldg(ids + 32 * j);
+            uint32_t const id = __ldg(ids + 32 * j);
             stage[32 * j + lane] = LoadPos(posQ + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
         }
         __syncwarp();
     }
+    float4 const xi = stage[valid ? grp : 0u];  // own position; nobody writes vertex vi during this colour
+    if (trace && lane == 0)
+        trace[5] = GlobalTimer();  // 1-rings staged
     // epilogue operands, requested now so that they are in registers when the solve needs them
     float4 const xm = __ldcg(p.xtildeM + vi);
     float4 h2       = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (kChebyshev)
         if (k > 1)
             h2 = __ldcg(p.hist + vi);
-    if (trace && lane == 0)
-        trace[5] = GlobalTimer();  // 1-rings staged
 
     float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
     for (uint32_t t = 0; t < iters; ++t)
     {
-        float4 const c0 = n0, c1 = n1, c2 = n2;
+        float4 const c0 = n0, c1 = n1;
         if (t + 1 < iters)
-            src.Fetch(n0, n1, n2);  // next block in flight while this one is computed
+            src.Fetch(n0, n1);  // next block in flight while this one is computed
         uint32_t const idx = __float_as_uint(c0.x);
         float4 const p1 = stage[idx & 1023u];
         float4 const p2 = stage[(idx >> 10) & 1023u];
         float4 const p3 = stage[(idx >> 20) & 1023u];
-        // gradients of the three other vertices
-        float const a0 = c0.y, a1 = c0.z, a2 = c0.w;
-        float const b0 = c1.x, b1 = c1.y, b2 = c1.z;
-        float const e0 = c1.w, e1 = c2.x, e2 = c2.y;
-        float const wmu = c2.z, wlam = c2.w;
-        // edge vectors relative to this vertex:  F = sum_a (x_a - x_i) (x) grad_a
-        float const d1x = p1.x - xi.x, d1y = p1.y - xi.y, d1z = p1.z - xi.z;
-        float const d2x = p2.x - xi.x, d2y = p2.y - xi.y, d2z = p2.z - xi.z;
-        float const d3x = p3.x - xi.x, d3y = p3.y - xi.y, d3z = p3.z - xi.z;
-        float const F00 = d1x * a0 + d2x * b0 + d3x * e0;
-        float const F01 = d1x * a1 + d2x * b1 + d3x * e1;
-        float const F02 = d1x * a2 + d2x * b2 + d3x * e2;
-        float const F10 = d1y * a0 + d2y * b0 + d3y * e0;
-        float const F11 = d1y * a1 + d2y * b1 + d3y * e1;
-        float const F12 = d1y * a2 + d2y * b2 + d3y * e2;
-        float const F20 = d1z * a0 + d2z * b0 + d3z * e0;
-        float const F21 = d1z * a1 + d2z * b1 + d3z * e1;
-        float const F22 = d1z * a2 + d2z * b2 + d3z * e2;
-        // cofactors
-        float const C00 = F11 * F22 - F12 * F21;
-        float const C01 = F12 * F20 - F10 * F22;
-        float const C02 = F10 * F21 - F11 * F20;
-        float const C10 = F02 * F21 - F01 * F22;
-        float const C11 = F00 * F22 - F02 * F20;
-        float const C12 = F01 * F20 - F00 * F21;
-        float const C20 = F01 * F12 - F02 * F11;
-        float const C21 = F02 * F10 - F00 * F12;
-        float const C22 = F00 * F11 - F01 * F10;
-        float const J   = F00 * C00 + F01 * C01 + F02 * C02;
-        // gradient of this vertex' shape function
-        float const q0 = -(a0 + b0 + e0), q1 = -(a1 + b1 + e1), q2 = -(a2 + b2 + e2);
-        float const Fq0 = F00 * q0 + F01 * q1 + F02 * q2;
-        float const Fq1 = F10 * q0 + F11 * q1 + F12 * q2;
-        float const Fq2 = F20 * q0 + F21 * q1 + F22 * q2;
-        float const Cq0 = C00 * q0 + C01 * q1 + C02 * q2;
-        float const Cq1 = C10 * q0 + C11 * q1 + C12 * q2;
-        float const Cq2 = C20 * q0 + C21 * q1 + C22 * q2;
-        // alpha = 1 + mu/lambda; padding slots have wmu = wlam = 0 and must contribute 0, not NaN
-        float const alpha = 1.f + __fdividef(wmu, (wlam != 0.f) ? wlam : 1.f);
-        float const s     = wlam * (J - alpha);
-        g0 += wmu * Fq0 + s * Cq0;
-        g1 += wmu * Fq1 + s * Cq1;
-        g2 += wmu * Fq2 + s * Cq2;
-        float const t0 = wlam * Cq0, t1 = wlam * Cq1, t2 = wlam * Cq2;
-        h00 += t0 * Cq0;
-        h01 += t0 * Cq1;
-        h02 += t0 * Cq2;
-        h11 += t1 * Cq1;
-        h12 += t1 * Cq2;
-        h22 += t2 * Cq2;
-        hd += wmu * (q0 * q0 + q1 * q1 + q2 * q2);
+        // With a, b, c the other vertices of the tet:  d = x_a - x_i,  e1 = x_b - x_a,  e2 = x_c - x_a.
+        //   F grad N_i           = d (u_a+u_b+u_c) + e1 u_b + e2 u_c
+        //   dJ/dx_i = cof(F) grad N_i = -detG S,   S = e1 x e2   (the opposite face's area normal)
+        //   J = det F            = detG (d . S)
+        float const dx = p1.x - xi.x, dy = p1.y - xi.y, dz = p1.z - xi.z;
+        float const e1x = p2.x - p1.x, e1y = p2.y - p1.y, e1z = p2.z - p1.z;
+        float const e2x = p3.x - p1.x, e2y = p3.y - p1.y, e2z = p3.z - p1.z;
+        float const Sx = e1y * e2z - e1z * e2y;
+        float const Sy = e1z * e2x - e1x * e2z;
+        float const Sz = e1x * e2y - e1y * e2x;
+        float const detD = dx * Sx + dy * Sy + dz * Sz;
+        float const beta = c1.x;
+        float const cS   = c1.y - beta * detD;  // = -wg lambda detG (J - alpha)
+        // gradient: wg mu F grad N_i + wg lambda (J - alpha) dJ/dx_i
+        g0 += dx * c0.y + e1x * c0.z + e2x * c0.w + cS * Sx;
+        g1 += dy * c0.y + e1y * c0.z + e2y * c0.w + cS * Sy;
+        g2 += dz * c0.y + e1z * c0.z + e2z * c0.w + cS * Sz;
+        // Hessian: wg mu |grad N_i|^2 I + wg lambda (dJ/dx_i)(dJ/dx_i)^T
+        float const t0 = beta * Sx, t1 = beta * Sy, t2 = beta * Sz;
+        h00 += t0 * Sx;
+        h01 += t0 * Sy;
+        h02 += t0 * Sz;
+        h11 += t1 * Sy;
+        h12 += t1 * Sz;
+        h22 += t2 * Sz;
+        hd += c1.z;
     }
     if (trace && lane == 0)
         trace[6] = GlobalTimer();  // incident tets accumulated
@@ -341,17 +317,19 @@ __device__ __forceinline__ void ProcessTile(
 template <bool kChebyshev, bool kDamping>
 __device__ __forceinline__ void SweepColor(StepParams const& p, int color, int k, float omega, float4* stage, unsigned long long* trace)
 {
-    uint32_t const* range = p.ctaTileRange + static_cast<size_t>(color) * (gridDim.x + 1);
-    uint32_t const tBegin = __ldg(range + blockIdx.x), tEnd = __ldg(range + blockIdx.x + 1);
+    // Tiles of a colour are sorted heaviest first and dealt round-robin over every warp of the
+    // persistent grid, so each warp gets one heavy tile before anyone gets a second, lighter one.
+    uint32_t const tBegin = __ldg(p.colorTileBegin + color), tEnd = __ldg(p.colorTileBegin + color + 1);
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-    for (uint32_t T = tBegin + warp; T < tEnd; T += nWarps)
+    uint32_t const gwarp = warp * gridDim.x + blockIdx.x, gWarps = nWarps * gridDim.x;
+    for (uint32_t T = tBegin + gwarp; T < tEnd; T += gWarps)
     {
         uint4 const td = __ldg(p.tiles + T);
-        unsigned long long* tr = (trace && warp == 0 && T == tBegin) ? trace : nullptr;
+        unsigned long long* tr = (trace && warp == 0 && T == tBegin + gwarp) ? trace : nullptr;
         if (tr && lane == 0)
             tr[4] = GlobalTimer() + (td.x & 0u);  // tile descriptor arrived
         DirectRecords src{p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane};
-        ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane, tr);
+        ProcessTile<kChebyshev, kDamping, true>(p, td, stage, src, k, omega, lane, tr);
         if (tr && lane == 0)
             tr[7] = GlobalTimer();  // first tile of warp 0 finished
     }

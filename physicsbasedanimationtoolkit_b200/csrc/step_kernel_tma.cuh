@@ -1,7 +1,7 @@
 // Warp-specialised variant of the persistent VBD step kernel (sm_100a).
 //
-// One CTA per SM.  The last warp is a *producer*: a single elected lane streams the CTA's
-// incidence-record blocks (1.5 KB each, static rest data) from HBM into a shared-memory ring with
+// One CTA per SM.  The last warp is a *producer*: its lanes stream the CTA's
+// incidence-record blocks (1 KB each, static rest data) from HBM into a shared-memory ring with
 // 1-D bulk asynchronous copies (cp.async.bulk, i.e. the TMA engine; SASS UBLKCP) that signal
 // per-slot "full" mbarriers.  Because the records never change, the producer runs ahead of the
 // colour barriers: while the consumers wait for the other SMs at the end of colour c, the
@@ -9,10 +9,11 @@
 //
 // The remaining warps are *consumers*.  Each owns a static subset of the CTA's warp tiles and
 // runs a two-deep software pipeline over its own tile sequence (which crosses colour and
-// iteration boundaries): the descriptor of tile i+2 and the ring ids of tile i+1 are fetched with
-// cp.async (LDGSTS) into per-warp shared memory while tile i is processed.  When a colour barrier
-// releases, everything static a warp needs is therefore already on chip and the only exposed
-// latency is the gather of the (mutable) neighbour positions from L2.
+// iteration boundaries): the descriptor of tile i+3 and the ring ids of tile i+2 are fetched with
+// cp.async (LDGSTS) into per-warp shared memory while tile i is processed, and so are the positions
+// of tile i+1 when it belongs to the same colour.  When a colour barrier releases, everything static
+// a warp needs is therefore already on chip and the only exposed latency is the gather of the
+// (mutable) positions of its first tile from L2.
 // Arithmetic and summation order are those of step_kernel.cuh (shared ProcessTile).
 #pragma once
 
@@ -21,7 +22,7 @@
 namespace vbdx {
 
 constexpr int kTmaMaxThreads   = 640;  // <= 102 registers per thread
-constexpr int kProducerWarps   = 4;    // power of two: record block n of a CTA's stream is issued by producer n % 4
+constexpr int kProducerWarps   = 1;    // one producer warp; each of its lanes issues every 32nd block of the stream
 
 struct TmaParams {
     StepParams base;
@@ -49,6 +50,20 @@ __device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity)
         "@p bra.uni WAIT_DONE;\n"
         "bra.uni WAIT_LOOP;\n"
         "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// same, for lanes of one warp that wait on *different* barriers (divergent exit)
+__device__ __forceinline__ void MbarWaitDivergent(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_D:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP_D;\n"
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
@@ -99,24 +114,23 @@ __device__ __forceinline__ void StoreReleaseShared(uint32_t addr, uint32_t v)
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// Record source of the consumers: this lane's 48-byte record out of the shared-memory ring slot
+// Record source of the consumers: this lane's 32-byte record out of the shared-memory ring slot
 // that the producer filled; the slot is handed back as soon as the warp has copied its records to
 // registers.  mbarrier phases only tell adjacent fills of a slot apart, and consumers do not
 // consume in stream order, so a consumer first makes sure the producer has *issued* block n
-// (monotonic per-producer `produced` counters) before it waits on the slot's parity.
+// (monotonic `produced` counter) before it waits on the slot's parity.
 struct RingRecords {
     unsigned char const* smem;
     uint32_t full, empty, produced, R, slot, fill, n, lane;
-    __device__ __forceinline__ void Fetch(float4& c0, float4& c1, float4& c2)
+    __device__ __forceinline__ void Fetch(float4& c0, float4& c1)
     {
-        while (LoadAcquireShared(produced + 4 * (n & (kProducerWarps - 1))) <= n / kProducerWarps)
+        while (LoadAcquireShared(produced) <= n)
         {
         }
         MbarWait(full + 8 * slot, fill & 1u);
         unsigned char const* blk = smem + slot * kBlockBytes + lane * 16;
         c0 = *reinterpret_cast<float4 const*>(blk);
         c1 = *reinterpret_cast<float4 const*>(blk + 512);
-        c2 = *reinterpret_cast<float4 const*>(blk + 1024);
         __syncwarp();
         if (lane == 0)
             MbarArrive(empty + 8 * slot);
@@ -164,7 +178,7 @@ __host__ __device__ inline size_t TmaSmemBytes(uint32_t R, uint32_t nColors, uin
     b += 16;                                                          // produced counter (+pad)
     b += static_cast<size_t>(nColors + 1) * 16;                       // range table
     b += static_cast<size_t>(nConsumerWarps) * (4 * 16);              // tile-descriptor ring per warp
-    b += static_cast<size_t>(nConsumerWarps) * stageEntries * (2 * 4 + 16);  // ids double buffer + positions
+    b += static_cast<size_t>(nConsumerWarps) * stageEntries * (4 * 4 + 2 * 16);  // ring of 4 id lists + 2 position buffers
     return b;
 }
 
@@ -189,9 +203,9 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
     cur += static_cast<size_t>(nC + 1) * 16;
     uint4* const tdBuf = reinterpret_cast<uint4*>(cur) + warp * 4;
     cur += static_cast<size_t>(NC) * 64;
-    float4* const stage = reinterpret_cast<float4*>(cur) + static_cast<size_t>(warp) * SE;
-    cur += static_cast<size_t>(NC) * SE * 16;
-    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(cur) + static_cast<size_t>(warp) * 2 * SE;
+    float4* const stage = reinterpret_cast<float4*>(cur) + static_cast<size_t>(warp) * 2 * SE;
+    cur += static_cast<size_t>(NC) * 2 * SE * 16;
+    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(cur) + static_cast<size_t>(warp) * 4 * SE;
 
     uint32_t const stride    = gridDim.x + 1;
     uint32_t const* blkBegin = tp.ctaBlockBegin + blockIdx.x;
@@ -203,8 +217,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
             MbarInit(full + 8 * s, 1);
             MbarInit(empty + 8 * s, 1);
         }
-        for (int j = 0; j < kProducerWarps; ++j)
-            reinterpret_cast<volatile uint32_t*>(smem + static_cast<size_t>(R) * (kBlockBytes + 16))[j] = 0u;
+        *reinterpret_cast<volatile uint32_t*>(smem + static_cast<size_t>(R) * (kBlockBytes + 16)) = 0u;
         uint32_t before = 0;
         for (uint32_t c = 0; c < nC; ++c)
         {
@@ -223,17 +236,20 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
 
     if (warp >= NC)
     {
-        // ------------------------------ producers ------------------------------
-        // producer j issues blocks j, j+4, j+8, ... of this CTA's stream; one elected lane each
-        if (lane == 0 && blocksPerSweep > 0)
+        // ------------------------------ producer warp ------------------------------
+        // Lane l issues blocks l, l+L, l+2L, ... of this CTA's stream (L = min(32, R) lanes), so L bulk
+        // copies are in flight per pass of the loop and the per-block cost of the mbarrier handshake is
+        // amortised over the warp.  Fills of one slot are issued in stream order by construction.
+        uint32_t const L     = R < 32u ? R : 32u;
+        uint32_t const total = static_cast<uint32_t>(totalSweeps) * blocksPerSweep;
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        uint32_t c = 0, off = lane;  // position inside the sweep: colour and block offset within it
+        uint32_t slot = lane % R, fill = lane / R;
+        for (uint32_t base = 0; base < total; base += L)
         {
-            uint32_t const j = warp - NC;
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            uint32_t const total = static_cast<uint32_t>(totalSweeps) * blocksPerSweep;
-            uint32_t c = 0, off = j;      // position inside the sweep: colour and block offset within it
-            uint32_t slot = j % R, fill = j / R, issued = 0;
-            for (uint32_t n = j; n < total; n += kProducerWarps)
+            uint32_t const n = base + lane;
+            if (lane < L && n < total)
             {
                 for (;;)
                 {
@@ -245,19 +261,21 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
                         c = 0;
                 }
                 if (fill > 0)
-                    MbarWait(empty + 8 * slot, (fill & 1u) ^ 1u);
+                    MbarWaitDivergent(empty + 8 * slot, (fill & 1u) ^ 1u);
                 MbarArriveExpectTx(full + 8 * slot, kBlockBytes);
                 BulkLoad(ring + slot * kBlockBytes, p.records + static_cast<size_t>(rangeTab[c].z + off) * kBlockFloat4,
                          kBlockBytes, full + 8 * slot, policy);
-                StoreReleaseShared(produced + 4 * j, ++issued);
-                off += kProducerWarps;
-                slot += kProducerWarps;
+                off += L;
+                slot += L;
                 while (slot >= R)
                 {
                     slot -= R;
                     ++fill;
                 }
             }
+            __syncwarp();
+            if (lane == 0)
+                StoreReleaseShared(produced, base + L < total ? base + L : total);
         }
         return;
     }
@@ -310,12 +328,19 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
     for (uint32_t c = 0; c < nC; ++c)
         warpHasTiles |= rangeTab[c].x + warp < rangeTab[c].y;
 
-    TileCursor t1, t2;  // tiles i+1 and i+2 relative to the tile being processed
-    First(t1);
-    t1.valid &= warpHasTiles;
-    Advance(t1);  // tile 0
-    t2 = t1;
-    Advance(t2);  // tile 1
+    // Software pipeline over this warp's tile sequence (tile i = the one being processed):
+    //   descriptor of tile i+3, ring ids of tile i+2 and -- when no colour barrier lies in between --
+    //   the position gather of tile i+1 are in flight (cp.async) while tile i is computed.
+    TileCursor c1, c2, c3;
+    First(c1);
+    c1.valid &= warpHasTiles;
+    Advance(c1);  // tile 0
+    TileCursor const c0 = c1;
+    Advance(c1);  // tile 1
+    c2 = c1;
+    Advance(c2);  // tile 2
+    c3 = c2;
+    Advance(c3);  // tile 3
     uint32_t seq = 0;  // index of the tile being processed in this warp's sequence
     auto IssueTd = [&](TileCursor const& t, uint32_t s) {
         if (t.valid && lane == 0)
@@ -325,20 +350,33 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
         // ring ids of sequence tile s, whose descriptor is already in tdBuf
         uint4 const td        = tdBuf[s & 3u];
         uint32_t const chunks = (td.z >> 9) & 127u;
-        uint32_t const dst    = SmemAddr(idsBuf + (s & 1u) * SE + lane);
+        uint32_t const dst    = SmemAddr(idsBuf + (s & 3u) * SE + lane);
         for (uint32_t j = 0; j < chunks; ++j)
             CpAsync4(dst + 128 * j, p.ringIds + td.w + 32 * j + lane);
     };
-    // prologue: descriptors of tiles 0 and 1, then the ids of tile 0
-    IssueTd(t1, 0);
-    IssueTd(t2, 1);
+    auto IssueGather = [&](uint32_t s) {
+        // positions of sequence tile s (own vertices + 1-rings): descriptor and ids already in shared memory
+        uint4 const td        = tdBuf[s & 3u];
+        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const* ids   = idsBuf + (s & 3u) * SE + lane;
+        uint32_t const dst    = SmemAddr(stage + (s & 1u) * SE + lane);
+        for (uint32_t j = 0; j < chunks; ++j)
+        {
+            uint32_t const id = ids[32 * j];
+            CpAsync16(dst + 512 * j, p.pos + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
+        }
+    };
+    // prologue: descriptors of tiles 0..2, then the ids of tiles 0 and 1
+    IssueTd(c0, 0);
+    IssueTd(c1, 1);
+    IssueTd(c2, 2);
     CpAsyncWaitAll();
     __syncwarp();
-    if (t1.valid)
+    if (c0.valid)
         IssueIds(0);
-    bool nextValid = t2.valid;  // does tile seq+1 exist
-    t1 = t2;
-    Advance(t2);                // t2 -> tile 2
+    if (c1.valid)
+        IssueIds(1);
+    bool gathered = false;  // has the gather of tile `seq` been issued already
 
     for (int s = 0; s < p.substeps; ++s)
     {
@@ -400,21 +438,37 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
                 for (uint32_t T = rt.x + warp; T < rt.y; T += NC)
                 {
                     unsigned long long* tr0 = (tr && warp == 0 && T == rt.x) ? tr : nullptr;
-                    // descriptor + ids of this tile and the descriptor of the next one were requested at
-                    // least one tile ago
+                    // everything requested one tile ago has landed: descriptor i+2, ids i+1, gather i (if issued)
                     CpAsyncWaitAll();
                     __syncwarp();
                     uint4 const td = tdBuf[seq & 3u];
                     if (tr0 && lane == 0)
                         tr0[4] = GlobalTimer();
-                    if (nextValid)
-                        IssueIds(seq + 1);
-                    IssueTd(t2, seq + 2);
-                    nextValid = t2.valid;
-                    Advance(t2);
+                    bool const wasGathered = gathered;
+                    if (!wasGathered)
+                    {
+                        IssueGather(seq);  // first tile after a barrier: cannot be requested earlier
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                    if (c2.valid)
+                        IssueIds(seq + 2);
+                    IssueTd(c3, seq + 3);
+                    // the next tile's positions may be gathered now iff it belongs to this same colour sweep
+                    gathered = c1.valid && c1.k == s * p.iterations + k && c1.c == static_cast<int>(c);
+                    if (gathered)
+                        IssueGather(seq + 1);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    c1 = c2;
+                    c2 = c3;
+                    Advance(c3);
+                    if (!wasGathered)
+                    {
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        __syncwarp();
+                    }
                     uint32_t const n0 = sweepBase + rt.w + (td.x - rt.z);
                     RingRecords src{smem, full, empty, produced, R, n0 % R, n0 / R, n0, lane};
-                    ProcessTile<kChebyshev, kDamping>(p, td, stage, src, k, omega, lane, tr0, idsBuf + (seq & 1u) * SE);
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage + (seq & 1u) * SE, src, k, omega, lane, tr0);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     ++seq;

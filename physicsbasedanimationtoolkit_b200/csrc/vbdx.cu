@@ -114,7 +114,7 @@ struct Integrator {
     // static sweep data
     DevBuf<float4> dRecords;
     DevBuf<TileDesc> dTiles;
-    DevBuf<uint32_t> dCtaRange, dCtaBlockBegin, dRingIds;
+    DevBuf<uint32_t> dCtaRange, dCtaBlockBegin, dRingIds, dColorTileBegin;
     uint32_t stageEntries = 32;
     DevBuf<int32_t> dNew2Old, dOld2New;
 
@@ -322,9 +322,8 @@ void Integrator::Create(vbdx_data_desc const& d)
             throw Error(VBDX_UNSUPPORTED, "1-ring staging does not fit in shared memory (vertex valence too high)");
         uint32_t const maxSlots = static_cast<uint32_t>((maxOptin - fixed) / (kBlockBytes + 16));
         ringSlots = d.ring_slots > 0 ? static_cast<uint32_t>(d.ring_slots) : maxSlots;
-        // every slot must always be served by the same producer warp: R a multiple of kProducerWarps
-        ringSlots = std::min(ringSlots, maxSlots) / kProducerWarps * kProducerWarps;
-        if (ringSlots < static_cast<uint32_t>(kProducerWarps))
+        ringSlots = std::min(ringSlots, maxSlots);
+        if (ringSlots < 2u)
             throw Error(VBDX_UNSUPPORTED, "not enough shared memory for the record ring");
         smemBytes = TmaSmemBytes(ringSlots, plan.nColors, consumers, stageEntries);
         for (TmaKernelFn fn : {cheb0 ? StepKernelTma<true, false> : StepKernelTma<false, false>,
@@ -361,6 +360,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     dTiles.Upload(plan.tiles.data(), plan.tiles.size(), stream);
     dCtaRange.Alloc(plan.ctaTileRange.size() + 1, &deviceBytes);
     dCtaRange.Upload(plan.ctaTileRange.data(), plan.ctaTileRange.size(), stream);
+    dColorTileBegin.Alloc(plan.colorTileBegin.size() + 1, &deviceBytes);
+    dColorTileBegin.Upload(plan.colorTileBegin.data(), plan.colorTileBegin.size(), stream);
     dCtaBlockBegin.Alloc(plan.ctaBlockBegin.size() + 1, &deviceBytes);
     dCtaBlockBegin.Upload(plan.ctaBlockBegin.data(), plan.ctaBlockBegin.size(), stream);
     dNew2Old.Alloc(nV, &deviceBytes);
@@ -453,6 +454,7 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.records      = dRecords.p;
     p.tiles        = reinterpret_cast<uint4 const*>(dTiles.p);
     p.ctaTileRange = dCtaRange.p;
+    p.colorTileBegin = dColorTileBegin.p;
     p.ringIds      = dRingIds.p;
     p.stageEntries = stageEntries;
     p.nColors      = plan.nColors;

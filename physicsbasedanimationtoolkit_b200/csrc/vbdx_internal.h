@@ -22,19 +22,21 @@ namespace vbdx {
 //    it: it is then read from the previous-iterate buffer, which is what fuses the Chebyshev
 //    blend into the sweep).  The warp gathers these positions ONCE per tile into shared memory;
 //    every incident tet then addresses its three other vertices by 10-bit local indices.
-//  * the *incidence records*, `iters` consecutive blocks of 1.5 KB: block = 3 chunk rows x 32
-//    lanes x 16 B, i.e. lane l's 48-byte record is the l-th float4 of each chunk row, so every
+//  * the *incidence records*, `iters` consecutive blocks of 1 KB: block = 2 chunk rows x 32
+//    lanes x 16 B, i.e. lane l's 32-byte record is the l-th float4 of each chunk row, so every
 //    warp load instruction is one fully coalesced 512-byte request.
 //
-// Incidence record (vertex i, incident tet e), 12 words:
-//   word 0      local ring indices of the three other vertices of e, 10 bits each
-//   word 1..9   shape-function gradients (rows of GP, fem/ShapeFunctions.h:267-297) of those three
-//               vertices, 3 floats each; the gradient of i itself is minus their sum
-//   word 10     wg * mu      word 11  wg * lambda     (alpha = 1 + mu/lambda is recomputed)
-// Padding slots have index 0 and zero weights, so they contribute exactly 0.
+// Incidence record (vertex i, incident tet e with other vertices a, b, c), 8 words -- everything
+// the closed-form Stable Neo-Hookean vertex block needs (DESIGN.md "Math"):
+//   word 0   local ring indices of a, b, c, 10 bits each
+//   word 1-3 wg*mu*(u_a+u_b+u_c), wg*mu*u_b, wg*mu*u_c   with u_n = grad N_n . grad N_i
+//   word 4   beta  = wg*lambda*detG^2        (detG = det of the rows grad N_a, grad N_b, grad N_c)
+//   word 5   gamma = wg*lambda*detG*alpha    (alpha = 1 + mu/lambda)
+//   word 6   wg*mu*|grad N_i|^2              word 7  unused (0)
+// Padding slots are all-zero and therefore contribute exactly 0.
 // -----------------------------------------------------------------------------------------
-constexpr int kRecordWords      = 12;
-constexpr int kBlockFloat4      = 96;   // float4 per block (3 chunk rows x 32 lanes)
+constexpr int kRecordWords      = 8;
+constexpr int kBlockFloat4      = 64;   // float4 per block (2 chunk rows x 32 lanes)
 constexpr int kBlockBytes       = kBlockFloat4 * 16;
 constexpr uint32_t kPrevFlag    = 0x80000000u;
 constexpr int kMaxRingPerTile   = 1024; // 10-bit local indices

@@ -204,7 +204,7 @@ def test_against_reference_golden(name):
 
 
 @pytest.mark.parametrize("cheb", [None, 0.9])
-@pytest.mark.parametrize("ring_slots,consumer_warps", [(0, 0), (4, 0), (16, 16), (2, 3), (8, 7)])
+@pytest.mark.parametrize("ring_slots,consumer_warps", [(0, 0), (3, 0), (16, 16), (2, 3), (37, 7)])
 def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
     """The direct and the TMA-ring kernels do the same arithmetic in the same order: identical bits.
     Small rings force many wrap-arounds of the producer/consumer pipeline."""

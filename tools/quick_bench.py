@@ -14,7 +14,7 @@ dbc = np.flatnonzero(X[2] == 0)
 t = time.time()
 data = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.9).construct()
 print(f"mesh {n}^3: nV={X.shape[1]} nT={T.shape[1]} construct {time.time()-t:.2f}s", flush=True)
-configs = [(True, 1, 8, 0)] + [(True, 2, ti, 0, cw) for ti in (4, 8) for cw in (12, 16)] + [(True, 2, 4, 64, 16), (False, 2, 4, 0, 16)]
+configs = [(True, 1, ti, 0) for ti in (2, 3, 4, 6, 8, 12)] + [(False, 1, 8, 0), (False, 1, 4, 0)]
 if len(sys.argv) > 2:
     configs = eval(sys.argv[2])
 for cheb, variant, ti, rs, *rest in configs:
@@ -22,7 +22,10 @@ for cheb, variant, ti, rs, *rest in configs:
     data.accelerator = pbat.sim.vbd.AccelerationStrategy.Chebyshev if cheb else pbat.sim.vbd.AccelerationStrategy.Base
     if True:
         t = time.time()
-        vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=variant, ring_slots=rs, consumer_warps=cw)
+        try:
+            vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=variant, ring_slots=rs, consumer_warps=cw)
+        except Exception as e:
+            print('skip', cheb, variant, ti, rs, cw, e); continue
         tc = time.time() - t
         info = vbd.info
         xp = (X0 + 0.05 / n * rng.uniform(-1, 1, X.shape)).astype(np.float32)
@@ -42,6 +45,6 @@ for cheb, variant, ti, rs, *rest in configs:
         print(f"cheb={cheb} variant={variant} ring={rs} cw={cw} tile_iters={ti}: create {tc:.2f}s grid={info['gridBlocks']}x{info['blockThreads']} tiles={info['nTiles']} "
               f"slots/inc={info['nRecordSlots']/info['nIncidences']:.3f} step ms min/med={ms.min():.3f}/{np.median(ms):.3f} "
               f"-> {vips/1e9:.3f} Gvert-it/s, {vips*B/1e9:.0f} GB/s algorithmic ({vips*B/6552e9:.2f} of 6552), "
-              f"record stream {info['nRecordSlots']*48*iters/(ms.min()*1e-3)/1e9:.0f} GB/s", flush=True)
+              f"record stream {info['nRecordSlots']*32*iters/(ms.min()*1e-3)/1e9:.0f} GB/s", flush=True)
         assert np.isfinite(vbd.x).all()
         del vbd
