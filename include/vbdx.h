@@ -125,8 +125,10 @@ typedef struct vbdx_data_desc {
 typedef enum vbdx_kernel_variant {
     VBDX_KERNEL_DEFAULT = 0,
     VBDX_KERNEL_DIRECT  = 1, /* every warp loads its records straight from global memory */
-    VBDX_KERNEL_TMA     = 2  /* warp-specialised: a producer warp streams records into a shared-memory ring with
+    VBDX_KERNEL_TMA     = 2, /* warp-specialised: a producer warp streams records into a shared-memory ring with
                                 bulk asynchronous copies (TMA) across the colour barriers */
+    VBDX_KERNEL_PIPELINED = 3 /* every warp prefetches its next tile's static data with cp.async while it computes
+                                 the current one (the default when the per-warp buffers fit in shared memory) */
 } vbdx_kernel_variant;
 
 #define VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY 1 /* AdaptiveVbd uses the stored v(t-1) like the reference's GPU

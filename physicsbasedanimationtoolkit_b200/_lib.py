@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvbdx.so")
 VBDX_OK, VBDX_INVALID_ARGUMENT, VBDX_NO_DEVICE, VBDX_CUDA_ERROR, VBDX_OUT_OF_MEMORY, VBDX_UNSUPPORTED = range(6)
 FLAG_ADAPTIVE_VBD_GPU_HISTORY = 1
 FLAG_NATURAL_VERTEX_ORDER = 2
-KERNEL_DEFAULT, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+KERNEL_DEFAULT, KERNEL_DIRECT, KERNEL_TMA, KERNEL_PIPELINED = 0, 1, 2, 3
 
 
 class DataDesc(C.Structure):

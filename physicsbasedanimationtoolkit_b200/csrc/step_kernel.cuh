@@ -151,7 +151,11 @@ struct DirectRecords {
 // One warp tile: stage the 1-rings in shared memory, accumulate the elastic blocks of all
 // incident tets, reduce over the lanes that share a vertex, solve, write back.
 //   RecordSource::Fetch(c0,c1) yields this lane's 32-byte record of the next block.
-template <bool kChebyshev, bool kDamping, bool kStageInside, class RecordSource>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+template <bool kChebyshev, bool kDamping, bool kStageInside, class RecordSource, class AfterAccumulate = NoHook>
 __device__ __forceinline__ void ProcessTile(
     StepParams const& p,
     uint4 const td,
@@ -160,7 +164,8 @@ __device__ __forceinline__ void ProcessTile(
     int k,
     float omega,
     uint32_t lane,
-    unsigned long long* trace = nullptr)
+    unsigned long long* trace = nullptr,
+    AfterAccumulate afterAccumulate = AfterAccumulate{})  // runs once the tile's records have been consumed
 {
     float4 const* __restrict__ posQ = p.pos;
     uint32_t const lw         = td.z & 7u;
@@ -236,6 +241,7 @@ __device__ __forceinline__ void ProcessTile(
         h22 += t2 * Sz;
         hd += c1.z;
     }
+    afterAccumulate();
     if (trace && lane == 0)
         trace[6] = GlobalTimer();  // incident tets accumulated
     // butterfly over the w lanes that share a vertex (fixed order => deterministic)

@@ -1,0 +1,260 @@
+// Pipelined variant of the persistent VBD step kernel (sm_100a): every warp runs a private
+// software pipeline over its own tile sequence with asynchronous copies (cp.async / LDGSTS).
+//
+// All data a tile needs except the vertex positions is static, so it is requested long before it
+// is used -- across colour barriers, iterations and substeps:
+//   * the descriptor of tile i+2 and
+//   * the ring ids and the incidence records (the HBM stream) of tile i+1
+// travel into per-warp shared memory while tile i is computed and while the warp waits at the
+// grid barrier.  After a barrier the only exposed memory latency is the gather of the tile's
+// positions (own vertices + 1-rings) from L2, which also lands directly in shared memory.
+// Tiles are dealt round-robin over all warps of the grid (heaviest first), exactly like the direct
+// kernel; arithmetic and summation order are the shared ProcessTile.
+#pragma once
+
+#include "async_copy.cuh"
+#include "step_kernel.cuh"
+
+namespace vbdx {
+
+struct PipeParams {
+    StepParams base;
+    uint32_t maxIters;  // record buffer capacity per warp, in blocks
+};
+
+constexpr int kPipeThreads = 256;
+
+// shared-memory footprint (host and device must agree)
+__host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
+{
+    size_t b = ((static_cast<size_t>(nColors) + 1 + 3) / 4) * 16;  // colour -> first tile table
+    b += static_cast<size_t>(warps) * (4 * 16 + 2 * stageEntries * 4 + stageEntries * 16 + static_cast<size_t>(maxIters) * kBlockBytes);
+    return b;
+}
+
+// records of the current tile, already in this warp's shared-memory buffer
+struct SmemRecords {
+    float4 const* rec;
+    __device__ __forceinline__ void Fetch(float4& c0, float4& c1)
+    {
+        c0 = rec[0];
+        c1 = rec[32];
+        rec += kBlockFloat4;
+    }
+};
+
+template <bool kChebyshev, bool kDamping>
+__global__ void __launch_bounds__(kPipeThreads, 2) StepKernelPipe(const __grid_constant__ PipeParams pp)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    StepParams const& p = pp.base;
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    uint32_t const SE   = p.stageEntries;
+    uint32_t const nC   = static_cast<uint32_t>(p.nColors);
+    uint32_t const gwarp = warp * gridDim.x + blockIdx.x, gWarps = nWarps * gridDim.x;
+
+    uint32_t* const colorTab = reinterpret_cast<uint32_t*>(smem);
+    unsigned char* mine      = smem + ((static_cast<size_t>(nC) + 1 + 3) / 4) * 16 +
+                          static_cast<size_t>(warp) * (64 + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
+    float4* const recBuf   = reinterpret_cast<float4*>(mine);
+    float4* const stage    = recBuf + static_cast<size_t>(pp.maxIters) * kBlockFloat4;
+    uint4* const tdBuf     = reinterpret_cast<uint4*>(stage + SE);
+    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(tdBuf + 4);
+
+    for (uint32_t c = threadIdx.x; c <= nC; c += blockDim.x)
+        colorTab[c] = p.colorTileBegin[c];
+    __syncthreads();
+    int const totalSweeps = p.substeps * p.iterations;
+
+    // this warp's tile sequence over all sweeps
+    struct Cursor {
+        int k, c;
+        uint32_t T;
+        bool valid;
+    };
+    bool warpHasTiles = false;
+    for (uint32_t c = 0; c < nC; ++c)
+        warpHasTiles |= colorTab[c] + gwarp < colorTab[c + 1];
+    auto Advance = [&](Cursor& t) {
+        if (!t.valid)
+            return;
+        if (t.c >= 0)
+        {
+            t.T += gWarps;
+            if (t.T < colorTab[t.c + 1])
+                return;
+        }
+        for (;;)
+        {
+            if (++t.c == static_cast<int>(nC))
+            {
+                t.c = 0;
+                if (++t.k == totalSweeps)
+                {
+                    t.valid = false;
+                    return;
+                }
+            }
+            t.T = colorTab[t.c] + gwarp;
+            if (t.T < colorTab[t.c + 1])
+                return;
+        }
+    };
+    auto IssueTd = [&](Cursor const& t, uint32_t s) {
+        if (t.valid && lane == 0)
+            CpAsync16(SmemAddr(tdBuf + (s & 3u)), p.tiles + t.T);
+    };
+    // ring ids and incidence records of sequence tile s, whose descriptor is already in tdBuf
+    auto IssueStatic = [&](uint32_t s) {
+        uint4 const td        = tdBuf[s & 3u];
+        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const iters  = td.z >> 16;
+        uint32_t const dstIds = SmemAddr(idsBuf + (s & 1u) * SE + lane);
+        for (uint32_t j = 0; j < chunks; ++j)
+            CpAsync4(dstIds + 128 * j, p.ringIds + td.w + 32 * j + lane);
+        uint32_t const dstRec = SmemAddr(recBuf + lane);
+        float4 const* src     = p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane;
+        for (uint32_t t = 0; t < 2 * iters; ++t)
+            CpAsync16(dstRec + 512 * t, src + 32 * t);
+    };
+    auto IssueGather = [&](uint32_t s) {
+        uint4 const td        = tdBuf[s & 3u];
+        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const* ids   = idsBuf + (s & 1u) * SE + lane;
+        uint32_t const dst    = SmemAddr(stage + lane);
+        for (uint32_t j = 0; j < chunks; ++j)
+        {
+            uint32_t const id = ids[32 * j];
+            CpAsync16(dst + 512 * j, p.pos + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
+        }
+    };
+
+    Cursor c1{0, -1, 0, totalSweeps > 0 && warpHasTiles}, c2;
+    Advance(c1);  // tile 0
+    Cursor const c0 = c1;
+    Advance(c1);  // tile 1
+    c2 = c1;
+    Advance(c2);  // tile 2
+    IssueTd(c0, 0);
+    IssueTd(c1, 1);
+    CpAsyncWaitAll();
+    __syncwarp();
+    if (c0.valid)
+        IssueStatic(0);
+    CpAsyncCommit();
+    uint32_t seq = 0;
+
+    unsigned int target    = 0;
+    uint32_t const gtid    = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t const gstride = gridDim.x * blockDim.x;
+    for (int s = 0; s < p.substeps; ++s)
+    {
+        for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+        {
+            float4 const x4 = __ldcg(p.pos + p.pOff + i);
+            float4 v4       = __ldcg(p.vel + i);
+            float3 const vprev = make_float3(v4.x, v4.y, v4.z);
+            if (s > 0)
+            {
+                float4 const xt4 = __ldcg(p.xt + i);
+                v4.x = (x4.x - xt4.x) / p.sdt;
+                v4.y = (x4.y - xt4.y) / p.sdt;
+                v4.z = (x4.z - xt4.z) / p.sdt;
+                p.vel[i] = v4;
+            }
+            float3 vtm1 = make_float3(v4.x, v4.y, v4.z);
+            if (p.vtm1 != nullptr)
+            {
+                if (s > 0)
+                    vtm1 = vprev;
+                else
+                {
+                    float4 const q = __ldcg(p.vtm1 + i);
+                    vtm1           = make_float3(q.x, q.y, q.z);
+                }
+            }
+            float4 const a4 = __ldg(p.aext + i);
+            float4 xm       = __ldcg(p.xtildeM + i);
+            xm.x            = x4.x + p.sdt * v4.x + p.sdt2 * a4.x;
+            xm.y            = x4.y + p.sdt * v4.y + p.sdt2 * a4.y;
+            xm.z            = x4.z + p.sdt * v4.z + p.sdt2 * a4.z;
+            p.xtildeM[i]    = xm;
+            p.xt[i]         = x4;
+            float3 const x0 = InitialPosition(
+                make_float3(x4.x, x4.y, x4.z), vtm1, make_float3(v4.x, v4.y, v4.z),
+                make_float3(a4.x, a4.y, a4.z), p.sdt, p.sdt2, p.strategy);
+            float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
+            p.pos[i]       = o;
+            if constexpr (kChebyshev)
+                p.pos[p.pOff + i] = o;
+        }
+        GridBarrier(p.barrier, target);
+
+        for (int k = 0; k < p.iterations; ++k)
+        {
+            float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            for (uint32_t c = 0; c < nC; ++c)
+            {
+                unsigned long long* tr = nullptr;
+                if (p.trace != nullptr && k == p.traceIteration)
+                {
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
+                    if (threadIdx.x == 0)
+                        tr[0] = GlobalTimer();
+                }
+                uint32_t const tBegin = colorTab[c], tEnd = colorTab[c + 1];
+                for (uint32_t T = tBegin + gwarp; T < tEnd; T += gWarps)
+                {
+                    unsigned long long* tr0 = (tr && warp == 0 && T == tBegin + gwarp) ? tr : nullptr;
+                    // requested one tile ago: descriptor i+1, and ids + records of this tile
+                    CpAsyncWaitAll();
+                    __syncwarp();
+                    uint4 const td = tdBuf[seq & 3u];
+                    if (tr0 && lane == 0)
+                        tr0[4] = GlobalTimer();
+                    IssueGather(seq);
+                    CpAsyncCommit();
+                    IssueTd(c2, seq + 2);
+                    CpAsyncCommit();
+                    CpAsyncWaitGroup<1>();  // positions have landed; the descriptor may still be in flight
+                    __syncwarp();
+                    bool const nextValid = c1.valid;
+                    uint32_t const seqNext = seq + 1;
+                    auto prefetchNext = [&]() {
+                        // this tile's records and ids are consumed: request the next tile's
+                        __syncwarp();
+                        CpAsyncWaitAll();  // descriptor i+1 (requested a tile ago) and i+2
+                        __syncwarp();
+                        if (nextValid)
+                            IssueStatic(seqNext);
+                        CpAsyncCommit();
+                    };
+                    SmemRecords src{recBuf + lane};
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, k, omega, lane, tr0, prefetchNext);
+                    if (tr0 && lane == 0)
+                        tr0[7] = GlobalTimer();
+                    c1 = c2;
+                    Advance(c2);
+                    ++seq;
+                }
+                if (tr && threadIdx.x == 0)
+                    tr[1] = GlobalTimer();
+                GridBarrier(p.barrier, target, tr);
+            }
+        }
+    }
+    for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+    {
+        float4 const x4  = __ldcg(p.pos + p.pOff + i);
+        float4 const xt4 = __ldcg(p.xt + i);
+        float4 v4        = __ldcg(p.vel + i);
+        if (p.vtm1 != nullptr)
+            p.vtm1[i] = v4;
+        v4.x     = (x4.x - xt4.x) / p.sdt;
+        v4.y     = (x4.y - xt4.y) / p.sdt;
+        v4.z     = (x4.z - xt4.z) / p.sdt;
+        p.vel[i] = v4;
+    }
+}
+
+}  // namespace vbdx

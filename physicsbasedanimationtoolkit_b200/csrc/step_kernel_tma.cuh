@@ -17,6 +17,7 @@
 // Arithmetic and summation order are those of step_kernel.cuh (shared ProcessTile).
 #pragma once
 
+#include "async_copy.cuh"
 #include "step_kernel.cuh"
 
 namespace vbdx {
@@ -29,11 +30,6 @@ struct TmaParams {
     const uint32_t* __restrict__ ctaBlockBegin;  // [nColors][gridDim.x + 1] first record block per CTA
     uint32_t ringSlots;                          // R: ring capacity in blocks
 };
-
-__device__ __forceinline__ uint32_t SmemAddr(const void* p)
-{
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 
 __device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count)
 {
@@ -85,21 +81,6 @@ __device__ __forceinline__ void BulkLoad(uint32_t dstSmem, const void* srcGmem, 
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dstSmem),
         "l"(srcGmem), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
-}
-
-__device__ __forceinline__ void CpAsync4(uint32_t dstSmem, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dstSmem), "l"(src) : "memory");
-}
-
-__device__ __forceinline__ void CpAsync16(uint32_t dstSmem, const void* src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
-}
-
-__device__ __forceinline__ void CpAsyncWaitAll()
-{
-    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 __device__ __forceinline__ uint32_t LoadAcquireShared(uint32_t addr)

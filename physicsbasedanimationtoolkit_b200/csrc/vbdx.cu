@@ -5,6 +5,7 @@
 
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
+#include "step_kernel_pipe.cuh"
 #include "step_kernel_tma.cuh"
 #include "vbdx_internal.h"
 
@@ -79,6 +80,7 @@ static inline int Blocks(int64_t n, int threads) { return static_cast<int>((n + 
 
 using StepKernelFn = void (*)(StepParams);
 using TmaKernelFn  = void (*)(TmaParams);
+using PipeKernelFn = void (*)(PipeParams);
 
 struct Integrator {
     int device = 0, smCount = 0;
@@ -92,7 +94,7 @@ struct Integrator {
     Plan plan;
     int gridBlocks = 0, blockThreads = 256;
     int variant = VBDX_KERNEL_DIRECT;
-    uint32_t ringSlots = 0;
+    uint32_t ringSlots = 0, maxTileIters = 1;
     size_t smemBytes   = 0;
     int64_t nRecordSlots = 0;
 
@@ -143,6 +145,15 @@ struct Integrator {
         if (cheb)
             return damp ? StepKernel<true, true> : StepKernel<true, false>;
         return damp ? StepKernel<false, true> : StepKernel<false, false>;
+    }
+
+    PipeKernelFn KernelPipe() const
+    {
+        bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+        bool const damp = kD != 0.0;
+        if (cheb)
+            return damp ? StepKernelPipe<true, true> : StepKernelPipe<true, false>;
+        return damp ? StepKernelPipe<false, true> : StepKernelPipe<false, false>;
     }
 
     TmaKernelFn KernelTma() const
@@ -308,11 +319,33 @@ void Integrator::Create(vbdx_data_desc const& d)
     stageEntries = static_cast<uint32_t>(std::max(32, plan.maxRingPerTile));
     // the damping variant can be switched on later (SetRayleighDampingCoefficient), so size the
     // persistent grid for the least-resident variant of this acceleration mode
-    variant = d.kernel_variant == VBDX_KERNEL_DEFAULT ? VBDX_KERNEL_DIRECT : d.kernel_variant;
-    Require(variant == VBDX_KERNEL_DIRECT || variant == VBDX_KERNEL_TMA, "unknown kernel variant");
+    variant = d.kernel_variant;
+    Require(variant >= VBDX_KERNEL_DEFAULT && variant <= VBDX_KERNEL_PIPELINED, "unknown kernel variant");
     int maxOptin = 0;
     VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    maxTileIters = 1;
+    for (TileDesc const& t : plan.tiles)
+        maxTileIters = std::max(maxTileIters, t.meta >> 16);
+    size_t const pipeSmem = PipeSmemBytes(plan.nColors, kPipeThreads / 32, stageEntries, maxTileIters);
+    if (variant == VBDX_KERNEL_DEFAULT)
+        variant = pipeSmem <= static_cast<size_t>(maxOptin) ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
     int perSm = 1 << 30;
+    if (variant == VBDX_KERNEL_PIPELINED)
+    {
+        blockThreads = kPipeThreads;
+        smemBytes    = pipeSmem;
+        if (smemBytes > static_cast<size_t>(maxOptin))
+            throw Error(VBDX_UNSUPPORTED, "per-warp tile buffers do not fit in shared memory (lower tile_iters)");
+        for (PipeKernelFn fn : {cheb0 ? StepKernelPipe<true, false> : StepKernelPipe<false, false>,
+                                cheb0 ? StepKernelPipe<true, true> : StepKernelPipe<false, true>})
+        {
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            int n = 0;
+            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
+            perSm = std::min(perSm, n);
+        }
+    }
+    else
     if (variant == VBDX_KERNEL_TMA)
     {
         int const consumers = d.consumer_warps > 0 ? std::min(d.consumer_warps, kTmaMaxThreads / 32 - kProducerWarps) : 15;
@@ -480,7 +513,16 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.traceIteration = traceIteration;
     VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
-    if (variant == VBDX_KERNEL_TMA)
+    if (variant == VBDX_KERNEL_PIPELINED)
+    {
+        PipeParams pp{};
+        pp.base      = p;
+        pp.maxIters  = maxTileIters;
+        void* args[] = {&pp};
+        VBDX_CUDA(cudaLaunchCooperativeKernel(
+            reinterpret_cast<void const*>(KernelPipe()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+    }
+    else if (variant == VBDX_KERNEL_TMA)
     {
         TmaParams tp{};
         tp.base          = p;

@@ -206,18 +206,19 @@ def test_against_reference_golden(name):
 @pytest.mark.parametrize("cheb", [None, 0.9])
 @pytest.mark.parametrize("ring_slots,consumer_warps", [(0, 0), (3, 0), (16, 16), (2, 3), (37, 7)])
 def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
-    """The direct and the TMA-ring kernels do the same arithmetic in the same order: identical bits.
+    """The direct, TMA-ring and pipelined kernels do the same arithmetic in the same order: identical bits.
     Small rings force many wrap-arounds of the producer/consumer pipeline."""
     X, T = meshes.tet_grid(12, 6, 5, 0.1)
     dbc = np.flatnonzero(X[0] == 0)
     out = []
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kD=1e-4, kernel_variant=variant, ring_slots=ring_slots,
                            consumer_warps=consumer_warps, tile_iters=2)
         for _ in range(3):
             vbd.step(0.01, 7, 2)
         out.append((vbd.x, vbd.v))
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0]) and np.array_equal(out[0][1], o[1])
     for _ in range(3):
         ref.step(0.01, 7, 2)
     assert rel_l2(out[1][0], ref.x) < TOL
