@@ -117,7 +117,7 @@ typedef struct vbdx_data_desc {
     int32_t flags;         /* VBDX_FLAG_* */
     int32_t kernel_variant;/* tuning: enum vbdx_kernel_variant; 0 = default */
     int32_t ring_slots;    /* tuning: shared-memory ring capacity in 1 KB record blocks (0 = as many as fit) */
-    int32_t consumer_warps;/* tuning: consumer warps per CTA of the TMA kernel (0 = default) */
+    int32_t consumer_warps;/* tuning: (consumer) warps per CTA of the pipelined / TMA kernels (0 = default) */
     int32_t reserved;
 } vbdx_data_desc;
 

@@ -13,6 +13,7 @@ namespace vbdx {
 namespace {
 
 constexpr uint32_t kSelfMarker = 0xfffffffeu;
+constexpr uint32_t kPadMarker  = 0xffffffffu;
 
 inline uint32_t ExpandBits10(uint32_t v)
 {
@@ -245,8 +246,9 @@ void BuildPlan(
     plan.old2new.resize(nV);
     plan.colorTileBegin.assign(nColors + 1, 0);
     // tiles
-    plan.ringOff.assign(plan.nActive + 1, 0);
-    plan.ringCnt.assign(plan.nActive, 0);
+    std::vector<int64_t> seenInTile(nV, -1);  // neighbour -> tile that already lists it
+    std::vector<uint32_t> localIndex(nV, 0);
+    std::vector<int32_t> early, late;
     int64_t pos = 0, block = 0;
     int64_t curColor = 0;
     while (pos < plan.nActive)
@@ -254,47 +256,101 @@ void BuildPlan(
         int64_t const c = colors[items[pos].v];
         while (curColor < c)
             plan.colorTileBegin[++curColor] = static_cast<uint32_t>(plan.tiles.size());
+        int64_t const prevColor = (c + nColors - 1) % nColors;  // the colour swept right before c
+        int64_t const tileId    = static_cast<int64_t>(plan.tiles.size());
         int const lw = items[pos].lw;
         int const G  = 32 >> lw;
         int n = 0, iters = 0;
-        int64_t ringLen = 0;  // neighbour entries; the tile's own vertices come first in its list
+        early.clear();
+        late.clear();
         while (n < G && pos + n < plan.nActive && colors[items[pos + n].v] == c &&
                items[pos + n].lw == lw)
         {
-            int32_t const v  = items[pos + n].v;
-            int64_t const rl = ringPtr[v + 1] - ringPtr[v];
-            if (n > 0 && (n + 1) + ringLen + rl > kMaxRingPerTile)
-                break;  // keep the tile's ring list addressable with 10-bit local indices
-            ringLen += rl;
+            int32_t const v = items[pos + n].v;
+            // distinct neighbours this vertex adds to the tile's list
+            size_t const e0 = early.size(), l0 = late.size();
+            for (uint32_t r = ringPtr[v]; r < ringPtr[v + 1]; ++r)
+            {
+                int32_t const j = ring[r];
+                if (seenInTile[j] == tileId)
+                    continue;
+                seenInTile[j] = tileId;
+                (nColors > 1 && colors[j] == prevColor && !isDbc[j] ? late : early).push_back(j);
+            }
+            size_t const padded = ((n + 1 + early.size() + 31) / 32 + (late.size() + 31) / 32) * 32;
+            if (n > 0 && padded > static_cast<size_t>(kMaxRingPerTile))
+            {
+                // keep the tile's list addressable with 10-bit local indices: undo and close the tile
+                for (size_t k = e0; k < early.size(); ++k)
+                    seenInTile[early[k]] = -1;
+                for (size_t k = l0; k < late.size(); ++k)
+                    seenInTile[late[k]] = -1;
+                early.resize(e0);
+                late.resize(l0);
+                break;
+            }
             iters = std::max<int>(iters, items[pos + n].iters);
             ++n;
         }
-        if (n + ringLen > kMaxRingPerTile)
-            throw std::length_error("a vertex has more than 1023 distinct neighbours");
-        uint32_t const ringStart  = static_cast<uint32_t>(plan.ringIds.size());
-        uint32_t const ringChunks = static_cast<uint32_t>((n + ringLen + 31) / 32);
+        uint32_t const earlyChunks = static_cast<uint32_t>((n + early.size() + 31) / 32);
+        uint32_t const lateChunks  = static_cast<uint32_t>((late.size() + 31) / 32);
+        if ((earlyChunks + lateChunks) * 32 > static_cast<uint32_t>(kMaxRingPerTile))
+            throw std::length_error("a vertex has more than ~1000 distinct neighbours");
+        if (iters > static_cast<int>(kMaxTileIters))
+            throw std::length_error("a vertex has too many incident tetrahedra for one warp tile");
+        uint32_t const ringStart = static_cast<uint32_t>(plan.ringIds.size());
         TileDesc t;
         t.blockStart = static_cast<uint32_t>(block);
         t.vbase      = static_cast<uint32_t>(pos);
-        t.meta       = static_cast<uint32_t>(lw) | (static_cast<uint32_t>(n) << 3) | (ringChunks << 9) |
-                 (static_cast<uint32_t>(iters) << 16);
+        t.meta       = TileMeta(static_cast<uint32_t>(lw), static_cast<uint32_t>(n), earlyChunks + lateChunks, earlyChunks,
+                          static_cast<uint32_t>(iters));
         t.ringStart = ringStart;
         plan.tiles.push_back(t);
         for (int k = 0; k < n; ++k)
-            plan.ringIds.push_back(kSelfMarker);  // entry k of the list = the tile's k-th own vertex
-        for (int k = 0; k < n; ++k)
         {
-            int32_t const v                = items[pos + k].v;
-            plan.new2old[pos + k]          = v;
-            plan.old2new[v]                = static_cast<int32_t>(pos + k);
-            plan.ringOff[pos + k]          = static_cast<uint32_t>(plan.ringIds.size());
-            plan.ringCnt[pos + k]          = static_cast<uint16_t>(ringPtr[v + 1] - ringPtr[v]);
-            for (uint32_t r = ringPtr[v]; r < ringPtr[v + 1]; ++r)
-                plan.ringIds.push_back(static_cast<uint32_t>(ring[r]));  // caller ids for now
+            int32_t const v       = items[pos + k].v;
+            plan.new2old[pos + k] = v;
+            plan.old2new[v]       = static_cast<int32_t>(pos + k);
         }
-        plan.nRingEntries += ringLen;
-        plan.ringIds.resize(ringStart + static_cast<size_t>(ringChunks) * 32, 0xffffffffu);  // pad
-        plan.maxRingPerTile = std::max<int32_t>(plan.maxRingPerTile, static_cast<int32_t>(ringChunks * 32));
+        // list layout: [own vertices | early neighbours | pad] [late neighbours | pad]; caller ids for now
+        plan.ringIds.resize(ringStart + static_cast<size_t>(earlyChunks + lateChunks) * 32, kPadMarker);
+        for (int k = 0; k < n; ++k)
+            plan.ringIds[ringStart + k] = kSelfMarker;
+        for (size_t k = 0; k < early.size(); ++k)
+        {
+            plan.ringIds[ringStart + n + k] = static_cast<uint32_t>(early[k]);
+            localIndex[early[k]]            = static_cast<uint32_t>(n + k);
+        }
+        for (size_t k = 0; k < late.size(); ++k)
+        {
+            plan.ringIds[ringStart + earlyChunks * 32 + k] = static_cast<uint32_t>(late[k]);
+            localIndex[late[k]]                             = static_cast<uint32_t>(earlyChunks * 32 + k);
+        }
+        plan.nRingEntries += static_cast<int64_t>(n + early.size() + late.size());
+        plan.maxRingPerTile = std::max<int32_t>(plan.maxRingPerTile, static_cast<int32_t>((earlyChunks + lateChunks) * 32));
+        // packed local indices of every record slot of the tile (same slot enumeration as FillRecords)
+        plan.recIdx.resize(static_cast<size_t>(block + iters) * 32, 0u);
+        uint32_t const w = 1u << lw;
+        for (int t2 = 0; t2 < iters; ++t2)
+            for (uint32_t lane = 0; lane < 32; ++lane)
+            {
+                uint32_t const grp = lane >> lw, sub = lane & (w - 1u);
+                if (grp >= static_cast<uint32_t>(n))
+                    continue;
+                int32_t const v  = items[pos + grp].v;
+                uint32_t const k = static_cast<uint32_t>(t2) * w + sub;
+                if (k >= vtPtr[v + 1] - vtPtr[v])
+                    continue;
+                uint32_t const packed = vtAdj[vtPtr[v] + k];
+                int64_t const e       = packed >> 2;
+                uint32_t const il     = packed & 3u;
+                uint32_t idx = 0;
+                int m        = 0;
+                for (uint32_t a = 0; a < 4; ++a)
+                    if (a != il)
+                        idx |= localIndex[E[4 * e + a]] << (10 * m++);
+                plan.recIdx[static_cast<size_t>(block + t2) * 32 + lane] = idx;
+            }
         pos += n;
         block += iters;
     }
@@ -310,33 +366,30 @@ void BuildPlan(
             plan.old2new[i]      = static_cast<int32_t>(tail);
             ++tail;
         }
-    plan.ringOff[plan.nActive] = static_cast<uint32_t>(plan.ringIds.size());
-    // ring lists: caller ids -> internal ids, flag = neighbour has a higher colour than the lister
+    // ring lists: caller ids -> internal ids; flag = read from the previous-iterate buffer (own vertices, and
+    // neighbours with a higher colour than the tile's)
     for (size_t t = 0; t < plan.tiles.size(); ++t)
     {
-        TileDesc const& td  = plan.tiles[t];
-        uint32_t const nv   = (td.meta >> 3) & 63u;
-        uint32_t const pad0 = td.vbase;  // padding entries point at the tile's first vertex
-        uint32_t const end  = td.ringStart + ((td.meta >> 9) & 127u) * 32u;
-        for (uint32_t k = 0; k < nv; ++k)
+        TileDesc const& td = plan.tiles[t];
+        uint32_t const nv  = TileVerts(td.meta);
+        uint32_t const end = td.ringStart + TileChunks(td.meta) * 32u;
+        int64_t const c    = colors[plan.new2old[td.vbase]];
+        for (uint32_t r = td.ringStart; r < end; ++r)
         {
-            int32_t const vo = plan.new2old[td.vbase + k];
-            uint32_t const b = plan.ringOff[td.vbase + k];
-            for (uint32_t r = 0; r < plan.ringCnt[td.vbase + k]; ++r)
+            uint32_t const raw = plan.ringIds[r];
+            if (raw == kSelfMarker)
+                plan.ringIds[r] = (td.vbase + (r - td.ringStart)) | kPrevFlag;
+            else if (raw == kPadMarker)
+                plan.ringIds[r] = td.vbase;  // harmless load
+            else
             {
-                int32_t const jo = static_cast<int32_t>(plan.ringIds[b + r]);
-                uint32_t id      = static_cast<uint32_t>(plan.old2new[jo]);
-                if (colors[jo] > colors[vo])
+                uint32_t id = static_cast<uint32_t>(plan.old2new[raw]);
+                if (colors[raw] > c)
                     id |= kPrevFlag;
-                plan.ringIds[b + r] = id;
+                plan.ringIds[r] = id;
             }
         }
-        // own vertices: read from the previous-iterate buffer (their start value for this sweep)
-        for (uint32_t k = 0; k < nv; ++k)
-            plan.ringIds[td.ringStart + k] = (td.vbase + k) | kPrevFlag;
-        for (uint32_t r = td.ringStart; r < end; ++r)
-            if (plan.ringIds[r] == 0xffffffffu)
-                plan.ringIds[r] = pad0;
+        (void)nv;
     }
 }
 

@@ -245,20 +245,17 @@ __global__ void FillRecords(
     const double* lame,  // 2 x nT or null
     double muDefault,
     double lamDefault,
-    const uint32_t* ringIds,
-    const uint32_t* ringOff,
-    const uint16_t* ringCnt,
-    float4* records,
-    uint32_t* errFlag)
+    const uint32_t* recIdx,  // packed local ring indices per record slot (host planner)
+    float4* records)
 {
     int const T = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (T >= nTiles)
         return;
     uint32_t const lane   = threadIdx.x & 31u;
     TileDesc const td     = tiles[T];
-    uint32_t const lw     = td.meta & 7u;
-    uint32_t const nverts = (td.meta >> 3) & 63u;
-    uint32_t const iters  = td.meta >> 16;
+    uint32_t const lw     = TileLog2W(td.meta);
+    uint32_t const nverts = TileVerts(td.meta);
+    uint32_t const iters  = TileIters(td.meta);
     uint32_t const w      = 1u << lw;
     uint32_t const grp    = lane >> lw;
     uint32_t const sub    = lane & (w - 1u);
@@ -266,11 +263,10 @@ __global__ void FillRecords(
     uint32_t const vi     = td.vbase + (valid ? grp : 0u);
     int32_t const vo      = new2old[vi];
     uint32_t const rowB = ptr[vo], degv = ptr[vo + 1] - rowB;
-    uint32_t const rB = ringOff[vi], rN = ringCnt[vi];
     for (uint32_t t = 0; t < iters; ++t)
     {
         uint32_t const k = t * w + sub;
-        uint32_t idx     = 0;
+        uint32_t const idx = recIdx[static_cast<size_t>(td.blockStart + t) * 32 + lane];
         float rec[6]     = {0, 0, 0, 0, 0, 0};
         if (valid && k < degv)
         {
@@ -293,21 +289,6 @@ __global__ void FillRecords(
             {
                 if (a == il)
                     continue;
-                // local index of this neighbour in the tile's staged ring list
-                uint32_t const jn = static_cast<uint32_t>(old2new[E[4 * e + a]]);
-                uint32_t loc      = 0xffffffffu;
-                for (uint32_t r = 0; r < rN; ++r)
-                    if ((ringIds[rB + r] & ~kPrevFlag) == jn)
-                    {
-                        loc = rB + r - td.ringStart;
-                        break;
-                    }
-                if (loc > 1023u)
-                {
-                    atomicOr(errFlag, 4u);
-                    loc = 0;
-                }
-                idx |= loc << (10 * n);
                 o[n] = g[a];
                 u[n] = g[a][0] * q[0] + g[a][1] * q[1] + g[a][2] * q[2];
                 ++n;

@@ -91,6 +91,33 @@ __device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int&
     __syncthreads();
 }
 
+// Split form of the grid barrier: between GridArrive and GridWait a warp may do any work that
+// neither writes positions nor reads positions the colour just swept could still change.
+__device__ __forceinline__ void GridArrive(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (trace)
+            trace[2] = GlobalTimer();
+        target += gridDim.x;
+        AddRelease(counter, 1u);
+    }
+}
+
+__device__ __forceinline__ void GridWait(unsigned int* counter, unsigned int const& target, unsigned long long* trace = nullptr)
+{
+    if (threadIdx.x == 0)
+    {
+        while (LoadAcquire(counter) < target)
+        {
+        }
+        if (trace)
+            trace[3] = GlobalTimer();
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ float4 LoadPos(const float4* p)
 {
     return __ldcg(p);  // L2-coherent load: positions change between colours
@@ -168,10 +195,10 @@ __device__ __forceinline__ void ProcessTile(
     AfterAccumulate afterAccumulate = AfterAccumulate{})  // runs once the tile's records have been consumed
 {
     float4 const* __restrict__ posQ = p.pos;
-    uint32_t const lw         = td.z & 7u;
-    uint32_t const nverts     = (td.z >> 3) & 63u;
-    uint32_t const ringChunks = (td.z >> 9) & 127u;
-    uint32_t const iters      = td.z >> 16;
+    uint32_t const lw         = TileLog2W(td.z);
+    uint32_t const nverts     = TileVerts(td.z);
+    uint32_t const ringChunks = TileChunks(td.z);
+    uint32_t const iters      = TileIters(td.z);
     uint32_t const grp        = lane >> lw;
     bool const valid          = grp < nverts;
     uint32_t const vi         = td.y + (valid ? grp : 0u);

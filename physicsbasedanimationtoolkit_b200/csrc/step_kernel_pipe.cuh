@@ -4,10 +4,12 @@
 // All data a tile needs except the vertex positions is static, so it is requested long before it
 // is used -- across colour barriers, iterations and substeps:
 //   * the descriptor of tile i+2 and
-//   * the ring ids and the incidence records (the HBM stream) of tile i+1
+//   * the ring ids of tile i+2 and the incidence records (the HBM stream) of tile i+1
 // travel into per-warp shared memory while tile i is computed and while the warp waits at the
-// grid barrier.  After a barrier the only exposed memory latency is the gather of the tile's
-// positions (own vertices + 1-rings) from L2, which also lands directly in shared memory.
+// grid barrier.  Positions are mutable, but only the colour being swept changes: the positions of
+// tile i+1 that cannot change any more (all of them if it is in the same colour, all but its
+// "late" chunks if it is in the next colour) are gathered ahead as well.  After a barrier the only
+// exposed memory latency is the L2 gather of the few neighbours of the colour just swept.
 // Tiles are dealt round-robin over all warps of the grid (heaviest first), exactly like the direct
 // kernel; arithmetic and summation order are the shared ProcessTile.
 #pragma once
@@ -22,7 +24,7 @@ struct PipeParams {
     uint32_t maxIters;  // record buffer capacity per warp, in blocks
 };
 
-constexpr int kPipeThreads = 256;
+constexpr int kPipeMaxThreads = 512;  // compiled for up to 16 warps per CTA (<= 128 registers)
 
 // shared-memory footprint (host and device must agree)
 __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
@@ -44,7 +46,7 @@ struct SmemRecords {
 };
 
 template <bool kChebyshev, bool kDamping>
-__global__ void __launch_bounds__(kPipeThreads, 2) StepKernelPipe(const __grid_constant__ PipeParams pp)
+__global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __grid_constant__ PipeParams pp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     StepParams const& p = pp.base;
@@ -104,25 +106,28 @@ __global__ void __launch_bounds__(kPipeThreads, 2) StepKernelPipe(const __grid_c
         if (t.valid && lane == 0)
             CpAsync16(SmemAddr(tdBuf + (s & 3u)), p.tiles + t.T);
     };
-    // ring ids and incidence records of sequence tile s, whose descriptor is already in tdBuf
-    auto IssueStatic = [&](uint32_t s) {
+    // ring ids of sequence tile s, whose descriptor is already in tdBuf
+    auto IssueIds = [&](uint32_t s) {
         uint4 const td        = tdBuf[s & 3u];
-        uint32_t const chunks = (td.z >> 9) & 127u;
-        uint32_t const iters  = td.z >> 16;
+        uint32_t const chunks = TileChunks(td.z);
         uint32_t const dstIds = SmemAddr(idsBuf + (s & 1u) * SE + lane);
         for (uint32_t j = 0; j < chunks; ++j)
             CpAsync4(dstIds + 128 * j, p.ringIds + td.w + 32 * j + lane);
+    };
+    // incidence records (the HBM stream) of sequence tile s into this warp's record buffer
+    auto IssueRecords = [&](uint32_t s) {
+        uint4 const td        = tdBuf[s & 3u];
+        uint32_t const iters  = TileIters(td.z);
         uint32_t const dstRec = SmemAddr(recBuf + lane);
         float4 const* src     = p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane;
         for (uint32_t t = 0; t < 2 * iters; ++t)
             CpAsync16(dstRec + 512 * t, src + 32 * t);
     };
-    auto IssueGather = [&](uint32_t s) {
-        uint4 const td        = tdBuf[s & 3u];
-        uint32_t const chunks = (td.z >> 9) & 127u;
-        uint32_t const* ids   = idsBuf + (s & 1u) * SE + lane;
-        uint32_t const dst    = SmemAddr(stage + lane);
-        for (uint32_t j = 0; j < chunks; ++j)
+    // positions of ring chunks [from, to) of sequence tile s (descriptor and ids already in shared memory)
+    auto IssueGather = [&](uint32_t s, uint32_t from, uint32_t to) {
+        uint32_t const* ids = idsBuf + (s & 1u) * SE + lane;
+        uint32_t const dst  = SmemAddr(stage + lane);
+        for (uint32_t j = from; j < to; ++j)
         {
             uint32_t const id = ids[32 * j];
             CpAsync16(dst + 512 * j, p.pos + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
@@ -140,9 +145,17 @@ __global__ void __launch_bounds__(kPipeThreads, 2) StepKernelPipe(const __grid_c
     CpAsyncWaitAll();
     __syncwarp();
     if (c0.valid)
-        IssueStatic(0);
+    {
+        IssueIds(0);
+        IssueRecords(0);
+    }
+    if (c1.valid)
+        IssueIds(1);
     CpAsyncCommit();
-    uint32_t seq = 0;
+    uint32_t seq      = 0;
+    uint32_t gathered = 0;  // ring chunks of tile `seq` whose positions have already been requested
+    bool deferred     = false;  // static data of tile `seq` still has to be requested
+    Cursor cUp        = c0;     // cursor of tile `seq`
 
     unsigned int target    = 0;
     uint32_t const gtid    = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,34 +225,68 @@ __global__ void __launch_bounds__(kPipeThreads, 2) StepKernelPipe(const __grid_c
                     uint4 const td = tdBuf[seq & 3u];
                     if (tr0 && lane == 0)
                         tr0[4] = GlobalTimer();
-                    IssueGather(seq);
+                    uint32_t const chunks = TileChunks(td.z);
+                    if (gathered < chunks)
+                        IssueGather(seq, gathered, chunks);  // what could not be requested before the barrier
                     CpAsyncCommit();
                     IssueTd(c2, seq + 2);
                     CpAsyncCommit();
                     CpAsyncWaitGroup<1>();  // positions have landed; the descriptor may still be in flight
                     __syncwarp();
+                    // Next tile in this same colour sweep (multi-round colours): all its positions are final, so
+                    // everything it needs is requested as soon as this tile's buffers are free.  Otherwise the
+                    // requests are issued in the shadow of the grid barrier (after GridArrive below).
                     bool const nextValid = c1.valid;
+                    bool const sameSweep = nextValid && c1.k == s * p.iterations + k && c1.c == static_cast<int>(c);
                     uint32_t const seqNext = seq + 1;
+                    uint32_t nextGathered  = 0;
                     auto prefetchNext = [&]() {
-                        // this tile's records and ids are consumed: request the next tile's
+                        if (!sameSweep)
+                            return;
+                        __syncwarp();  // this tile's records, ids and staged positions are consumed
+                        CpAsyncWaitAll();  // descriptors i+1 (requested a tile ago) and i+2
                         __syncwarp();
-                        CpAsyncWaitAll();  // descriptor i+1 (requested a tile ago) and i+2
-                        __syncwarp();
-                        if (nextValid)
-                            IssueStatic(seqNext);
+                        IssueRecords(seqNext);
+                        nextGathered = TileChunks(tdBuf[seqNext & 3u].z);
+                        IssueGather(seqNext, 0, nextGathered);
+                        if (c2.valid)
+                            IssueIds(seq + 2);
                         CpAsyncCommit();
                     };
+                    deferred = nextValid && !sameSweep;
                     SmemRecords src{recBuf + lane};
                     ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, k, omega, lane, tr0, prefetchNext);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
+                    gathered = nextGathered;
+                    cUp = c1;  // cursor of the upcoming tile
                     c1 = c2;
                     Advance(c2);
                     ++seq;
                 }
                 if (tr && threadIdx.x == 0)
                     tr[1] = GlobalTimer();
-                GridBarrier(p.barrier, target, tr);
+                GridArrive(p.barrier, target, tr);
+                if (deferred)
+                {
+                    // In the shadow of the barrier: records and ids of the upcoming tile, plus the positions
+                    // that cannot change any more.  If that tile belongs to the immediately following colour
+                    // of this substep these are its "early" chunks (everything but neighbours of the colour
+                    // just swept); if it lies further ahead, nothing.
+                    int const sweep = s * p.iterations + k;
+                    bool const nextPhase = (cUp.k == sweep && cUp.c == static_cast<int>(c) + 1) ||
+                                           (cUp.k == sweep + 1 && cUp.c == 0 && c + 1 == nC && (sweep + 1) % p.iterations != 0);
+                    CpAsyncWaitAll();  // descriptors of tiles seq and seq+1
+                    __syncwarp();
+                    IssueRecords(seq);
+                    gathered = nextPhase ? TileEarlyChunks(tdBuf[seq & 3u].z) : 0u;
+                    IssueGather(seq, 0, gathered);
+                    if (c1.valid)
+                        IssueIds(seq + 1);
+                    CpAsyncCommit();
+                    deferred = false;
+                }
+                GridWait(p.barrier, target, tr);
             }
         }
     }

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
     auto IssueIds = [&](uint32_t s) {
         // ring ids of sequence tile s, whose descriptor is already in tdBuf
         uint4 const td        = tdBuf[s & 3u];
-        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const chunks = TileChunks(td.z);
         uint32_t const dst    = SmemAddr(idsBuf + (s & 3u) * SE + lane);
         for (uint32_t j = 0; j < chunks; ++j)
             CpAsync4(dst + 128 * j, p.ringIds + td.w + 32 * j + lane);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
     auto IssueGather = [&](uint32_t s) {
         // positions of sequence tile s (own vertices + 1-rings): descriptor and ids already in shared memory
         uint4 const td        = tdBuf[s & 3u];
-        uint32_t const chunks = (td.z >> 9) & 127u;
+        uint32_t const chunks = TileChunks(td.z);
         uint32_t const* ids   = idsBuf + (s & 3u) * SE + lane;
         uint32_t const dst    = SmemAddr(stage + (s & 1u) * SE + lane);
         for (uint32_t j = 0; j < chunks; ++j)

@@ -325,14 +325,15 @@ void Integrator::Create(vbdx_data_desc const& d)
     VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     maxTileIters = 1;
     for (TileDesc const& t : plan.tiles)
-        maxTileIters = std::max(maxTileIters, t.meta >> 16);
-    size_t const pipeSmem = PipeSmemBytes(plan.nColors, kPipeThreads / 32, stageEntries, maxTileIters);
+        maxTileIters = std::max(maxTileIters, TileIters(t.meta));
+    int const pipeThreads = d.consumer_warps > 0 ? std::min(d.consumer_warps * 32, kPipeMaxThreads) : 256;
+    size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeThreads / 32, stageEntries, maxTileIters);
     if (variant == VBDX_KERNEL_DEFAULT)
         variant = pipeSmem <= static_cast<size_t>(maxOptin) ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
     int perSm = 1 << 30;
     if (variant == VBDX_KERNEL_PIPELINED)
     {
-        blockThreads = kPipeThreads;
+        blockThreads = pipeThreads;
         smemBytes    = pipeSmem;
         if (smemBytes > static_cast<size_t>(maxOptin))
             throw Error(VBDX_UNSUPPORTED, "per-warp tile buffers do not fit in shared memory (lower tile_iters)");
@@ -406,21 +407,15 @@ void Integrator::Create(vbdx_data_desc const& d)
     dRecords.Alloc(static_cast<size_t>(plan.nBlocks) * kBlockFloat4 + 1, &deviceBytes);
     if (!plan.tiles.empty())
     {
-        DevBuf<uint32_t> dRingOff;
-        DevBuf<uint16_t> dRingCnt;
-        dRingOff.Alloc(plan.ringOff.size());
-        dRingOff.Upload(plan.ringOff.data(), plan.ringOff.size(), stream);
-        dRingCnt.Alloc(plan.ringCnt.size() + 1);
-        dRingCnt.Upload(plan.ringCnt.data(), plan.ringCnt.size(), stream);
+        DevBuf<uint32_t> dRecIdx;
+        dRecIdx.Alloc(plan.recIdx.size() + 1);
+        dRecIdx.Upload(plan.recIdx.data(), plan.recIdx.size(), stream);
         int const nTiles = static_cast<int>(plan.tiles.size());
         FillRecords<<<Blocks(static_cast<int64_t>(nTiles) * 32, 256), 256, 0, stream>>>(
             dTiles.p, nTiles, dNew2Old.p, dOld2New.p, dPtr.p, dAdj.p, dE.p, dJinv.p, dVol.p, dLame.p,
-            muDefault, lamDefault, dRingIds.p, dRingOff.p, dRingCnt.p, dRecords.p, dErr.p);
+            muDefault, lamDefault, dRecIdx.p, dRecords.p);
         ++kernelLaunches;
-        dErr.Download(&err, 1, stream);
-        VBDX_CUDA(cudaStreamSynchronize(stream));
-        if (err & 4u)
-            throw Error(VBDX_CUDA_ERROR, "internal error: neighbour missing from a staged ring list");
+        VBDX_CUDA(cudaStreamSynchronize(stream));  // dRecIdx is released at the end of this scope
     }
 
     // ---- state

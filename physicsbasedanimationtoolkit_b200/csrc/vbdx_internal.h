@@ -17,11 +17,14 @@ namespace vbdx {
 // valence so that every lane visits ~tile_iters incident tets).
 //
 // Per tile two static streams exist:
-//  * the *ring list*: the distinct neighbour vertices (1-rings) of the tile's vertices, as
-//    internal ids (bit 31 set when the neighbour has a higher colour than the vertex that lists
-//    it: it is then read from the previous-iterate buffer, which is what fuses the Chebyshev
-//    blend into the sweep).  The warp gathers these positions ONCE per tile into shared memory;
-//    every incident tet then addresses its three other vertices by 10-bit local indices.
+//  * the *ring list*: the tile's own vertices followed by the distinct vertices of their 1-rings,
+//    as internal ids (bit 31 set when the entry is read from the previous-iterate buffer: own
+//    vertices and neighbours of a higher colour -- which is what fuses the Chebyshev blend into
+//    the sweep).  The warp gathers these positions ONCE per tile into shared memory; every
+//    incident tet then addresses its three other vertices by 10-bit local indices.  Neighbours
+//    whose colour is the one swept immediately before the tile's colour come last ("late"
+//    chunks): everything else is stable during the preceding colour and can be gathered before
+//    the barrier.
 //  * the *incidence records*, `iters` consecutive blocks of 1 KB: block = 2 chunk rows x 32
 //    lanes x 16 B, i.e. lane l's 32-byte record is the l-th float4 of each chunk row, so every
 //    warp load instruction is one fully coalesced 512-byte request.
@@ -44,9 +47,25 @@ constexpr int kMaxRingPerTile   = 1024; // 10-bit local indices
 struct TileDesc {
     uint32_t blockStart;  // first record block of the tile
     uint32_t vbase;       // first internal vertex id
-    uint32_t meta;        // log2(w) [0:3) | nverts [3:9) | ring chunks of 32 [9:16) | iters [16:32)
+    uint32_t meta;        // log2(w) [0:3) | nverts [3:9) | ring chunks [9:15) | early ring chunks [15:21) | iters [21:32)
     uint32_t ringStart;   // first entry of the tile's ring list (multiple of 32)
 };
+
+#if defined(__CUDACC__)
+#define VBDX_HD __host__ __device__
+#else
+#define VBDX_HD
+#endif
+VBDX_HD constexpr uint32_t TileLog2W(uint32_t meta) { return meta & 7u; }
+VBDX_HD constexpr uint32_t TileVerts(uint32_t meta) { return (meta >> 3) & 63u; }
+VBDX_HD constexpr uint32_t TileChunks(uint32_t meta) { return (meta >> 9) & 63u; }       // all ring chunks of 32 entries
+VBDX_HD constexpr uint32_t TileEarlyChunks(uint32_t meta) { return (meta >> 15) & 63u; } // chunks that do not depend on the previous colour
+VBDX_HD constexpr uint32_t TileIters(uint32_t meta) { return meta >> 21; }
+VBDX_HD constexpr uint32_t TileMeta(uint32_t lw, uint32_t nverts, uint32_t chunks, uint32_t early, uint32_t iters)
+{
+    return lw | (nverts << 3) | (chunks << 9) | (early << 15) | (iters << 21);
+}
+constexpr uint32_t kMaxTileIters = 2047;
 
 struct Plan {
     int64_t nV = 0, nActive = 0;
@@ -57,8 +76,7 @@ struct Plan {
     std::vector<uint32_t> ctaTileRange;      // nColors x (gridBlocks + 1): tiles of colour c for CTA b
     std::vector<uint32_t> ctaBlockBegin;     // nColors x (gridBlocks + 1): first record block of CTA b in colour c
     std::vector<uint32_t> ringIds;           // ring lists of all tiles (internal ids | kPrevFlag)
-    std::vector<uint32_t> ringOff;           // nActive + 1: start of each swept vertex' own list in ringIds
-    std::vector<uint16_t> ringCnt;           // nActive: length of that list
+    std::vector<uint32_t> recIdx;            // per record slot: packed local ring indices of the three other vertices
     int32_t maxRingPerTile = 0;              // longest (padded) tile ring list: sizes the per-warp staging
     int64_t nBlocks = 0;
     int64_t nIncidences = 0;                 // over swept vertices

@@ -14,7 +14,7 @@ dbc = np.flatnonzero(X[2] == 0)
 t = time.time()
 data = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.9).construct()
 print(f"mesh {n}^3: nV={X.shape[1]} nT={T.shape[1]} construct {time.time()-t:.2f}s", flush=True)
-configs = [(True, 1, 8, 0)] + [(True, 3, ti, 0) for ti in (4, 8, 16)] + [(False, 3, 8, 0)]
+configs = [(True, 1, 8, 0), (True, 2, 4, 0, 16)] + [(True, 3, ti, 0) for ti in (4, 8)] + [(False, 3, 8, 0)]
 if len(sys.argv) > 2:
     configs = eval(sys.argv[2])
 for cheb, variant, ti, rs, *rest in configs:

@@ -8,7 +8,7 @@ n = 58
 X, T = meshes.tet_grid(n, n, n, 1.0 / n)
 dbc = np.flatnonzero(X[2] == 0)
 data = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.9).construct()
-for ti, variant, cw in ((8, 3, 0), (4, 3, 0)):
+for ti, variant, cw in ((8, 3, 0),):
     vbd = pbat.gpu.vbd.Integrator(data, tile_iters=ti, kernel_variant=variant, consumer_warps=cw)
     for _ in range(3):
         vbd.step(0.01, 30, 1)
