@@ -167,9 +167,9 @@ class DeviceIntegrator:
     def trace_phases(self, iteration, dt, iterations, substeps=1):
         """Diagnostics (direct kernel): %globaltimer stamps [colour, CTA, 4] of one sweep iteration."""
         info = self.info
-        n = info["nColors"] * info["gridBlocks"] * 8
+        n = info["nColors"] * info["gridBlocks"] * 12
         _lib.check(self._L.vbdx_debug_trace(self._h, int(iteration), None, 0))
         self._step(dt, iterations, substeps)
         out = np.zeros(n, dtype=np.uint64)
         _lib.check(self._L.vbdx_debug_trace(self._h, int(iteration), out.ctypes.data, n))
-        return out.reshape(info["nColors"], info["gridBlocks"], 8)
+        return out.reshape(info["nColors"], info["gridBlocks"], 12)

@@ -20,6 +20,8 @@
 
 namespace vbdx {
 
+constexpr int kTraceStamps = 12;  // %globaltimer stamps per (colour, CTA) of the diagnostics trace
+
 struct StepParams {
     // static topology
     const float4* __restrict__ records;        // [nBlocks][2][32] float4
@@ -47,7 +49,7 @@ struct StepParams {
     int strategy;
     int iterations, substeps;
     unsigned int* barrier;  // zeroed before launch
-    unsigned long long* trace;  // optional [nColors][gridDim.x][8] timestamps of one iteration (diagnostics)
+    unsigned long long* trace;  // optional [nColors][gridDim.x][kTraceStamps] timestamps of one iteration (diagnostics)
     int traceIteration;
 };
 
@@ -102,7 +104,12 @@ __device__ __forceinline__ void GridArrive(unsigned int* counter, unsigned int& 
             trace[2] = GlobalTimer();
         target += gridDim.x;
         AddRelease(counter, 1u);
+        if (trace)
+            trace[1] = GlobalTimer();  // fence + arrival issued
     }
+    // the fence of the signalling thread travels through the same load/store path as everybody's requests:
+    // hold the other warps' shadow work back until it is through
+    __syncthreads();
 }
 
 __device__ __forceinline__ void GridWait(unsigned int* counter, unsigned int const& target, unsigned long long* trace = nullptr)
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
                 unsigned long long* tr = nullptr;
                 if (p.trace != nullptr && k == p.traceIteration)
                 {
-                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
                     if (threadIdx.x == 0)
                         tr[0] = GlobalTimer();
                 }

@@ -30,7 +30,7 @@ constexpr int kPipeMaxThreads = 512;  // compiled for up to 16 warps per CTA (<=
 __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
 {
     size_t b = ((static_cast<size_t>(nColors) + 1 + 3) / 4) * 16;  // colour -> first tile table
-    b += static_cast<size_t>(warps) * (4 * 16 + 2 * stageEntries * 4 + stageEntries * 16 + static_cast<size_t>(maxIters) * kBlockBytes);
+    b += static_cast<size_t>(warps) * (4 * 16 + 16 + 2 * stageEntries * 4 + stageEntries * 16 + static_cast<size_t>(maxIters) * kBlockBytes);
     return b;
 }
 
@@ -57,15 +57,28 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
 
     uint32_t* const colorTab = reinterpret_cast<uint32_t*>(smem);
     unsigned char* mine      = smem + ((static_cast<size_t>(nC) + 1 + 3) / 4) * 16 +
-                          static_cast<size_t>(warp) * (64 + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
+                          static_cast<size_t>(warp) * (64 + 16 + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
     float4* const recBuf   = reinterpret_cast<float4*>(mine);
     float4* const stage    = recBuf + static_cast<size_t>(pp.maxIters) * kBlockFloat4;
     uint4* const tdBuf     = reinterpret_cast<uint4*>(stage + SE);
-    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(tdBuf + 4);
+    uint32_t const barRec  = SmemAddr(tdBuf + 4);      // completion of the bulk copy of a tile's records
+    uint32_t const barIds  = barRec + 8;                // ... of a tile's ring ids
+    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(tdBuf + 5);
 
     for (uint32_t c = threadIdx.x; c <= nC; c += blockDim.x)
         colorTab[c] = p.colorTileBegin[c];
+    if (lane == 0)
+    {
+        MbarInit(barRec, 1);
+        MbarInit(barIds, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
+    uint64_t streamPolicy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(streamPolicy));
+    uint32_t recFills = 0, idsFills = 0;    // bulk copies issued so far on each barrier
+    uint32_t recWaits = 0, idsWaits = 0;    // ... and waited for
     int const totalSweeps = p.substeps * p.iterations;
 
     // this warp's tile sequence over all sweeps
@@ -106,25 +119,43 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         if (t.valid && lane == 0)
             CpAsync16(SmemAddr(tdBuf + (s & 3u)), p.tiles + t.T);
     };
-    // ring ids of sequence tile s, whose descriptor is already in tdBuf
-    auto IssueIds = [&](uint32_t s) {
-        uint4 const td        = tdBuf[s & 3u];
-        uint32_t const chunks = TileChunks(td.z);
-        uint32_t const dstIds = SmemAddr(idsBuf + (s & 1u) * SE + lane);
-        for (uint32_t j = 0; j < chunks; ++j)
-            CpAsync4(dstIds + 128 * j, p.ringIds + td.w + 32 * j + lane);
+    // ring ids of sequence tile s (descriptor already in tdBuf): one bulk copy by the TMA engine
+    auto WaitIds = [&]() {
+        while (idsWaits < idsFills)
+            MbarWait(barIds, idsWaits++ & 1u);
     };
-    // incidence records (the HBM stream) of sequence tile s into this warp's record buffer
+    auto IssueIds = [&](uint32_t s) {
+        WaitIds();  // at most one copy in flight per barrier
+        uint4 const td       = tdBuf[s & 3u];
+        uint32_t const bytes = TileChunks(td.z) * 128u;
+        if (lane == 0)
+        {
+            MbarArriveExpectTx(barIds, bytes);
+            BulkLoad(SmemAddr(idsBuf + (s & 1u) * SE), p.ringIds + td.w, bytes, barIds, streamPolicy);
+        }
+        ++idsFills;
+    };
+    // incidence records (the HBM stream) of sequence tile s into this warp's record buffer, likewise
+    auto WaitRecords = [&]() {
+        while (recWaits < recFills)
+            MbarWait(barRec, recWaits++ & 1u);
+    };
     auto IssueRecords = [&](uint32_t s) {
-        uint4 const td        = tdBuf[s & 3u];
-        uint32_t const iters  = TileIters(td.z);
-        uint32_t const dstRec = SmemAddr(recBuf + lane);
-        float4 const* src     = p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane;
-        for (uint32_t t = 0; t < 2 * iters; ++t)
-            CpAsync16(dstRec + 512 * t, src + 32 * t);
+        WaitRecords();
+        uint4 const td       = tdBuf[s & 3u];
+        uint32_t const bytes = TileIters(td.z) * kBlockBytes;
+        if (lane == 0)
+        {
+            MbarArriveExpectTx(barRec, bytes);
+            BulkLoad(SmemAddr(recBuf), p.records + static_cast<size_t>(td.x) * kBlockFloat4, bytes, barRec, streamPolicy);
+        }
+        ++recFills;
     };
     // positions of ring chunks [from, to) of sequence tile s (descriptor and ids already in shared memory)
     auto IssueGather = [&](uint32_t s, uint32_t from, uint32_t to) {
+        if (from >= to)
+            return;
+        WaitIds();
         uint32_t const* ids = idsBuf + (s & 1u) * SE + lane;
         uint32_t const dst  = SmemAddr(stage + lane);
         for (uint32_t j = from; j < to; ++j)
@@ -151,7 +182,6 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     }
     if (c1.valid)
         IssueIds(1);
-    CpAsyncCommit();
     uint32_t seq      = 0;
     uint32_t gathered = 0;  // ring chunks of tile `seq` whose positions have already been requested
     bool deferred     = false;  // static data of tile `seq` still has to be requested
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                 unsigned long long* tr = nullptr;
                 if (p.trace != nullptr && k == p.traceIteration)
                 {
-                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
                     if (threadIdx.x == 0)
                         tr[0] = GlobalTimer();
                 }
@@ -254,6 +284,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                         CpAsyncCommit();
                     };
                     deferred = nextValid && !sameSweep;
+                    WaitRecords();
                     SmemRecords src{recBuf + lane};
                     ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, k, omega, lane, tr0, prefetchNext);
                     if (tr0 && lane == 0)
@@ -264,8 +295,6 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     Advance(c2);
                     ++seq;
                 }
-                if (tr && threadIdx.x == 0)
-                    tr[1] = GlobalTimer();
                 GridArrive(p.barrier, target, tr);
                 if (deferred)
                 {
@@ -278,12 +307,21 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                                            (cUp.k == sweep + 1 && cUp.c == 0 && c + 1 == nC && (sweep + 1) % p.iterations != 0);
                     CpAsyncWaitAll();  // descriptors of tiles seq and seq+1
                     __syncwarp();
+                    bool const stamp = tr && threadIdx.x == 0;
+                    if (stamp)
+                        tr[8] = GlobalTimer();
                     IssueRecords(seq);
+                    if (stamp)
+                        tr[9] = GlobalTimer();
                     gathered = nextPhase ? TileEarlyChunks(tdBuf[seq & 3u].z) : 0u;
                     IssueGather(seq, 0, gathered);
+                    if (stamp)
+                        tr[10] = GlobalTimer();
                     if (c1.valid)
                         IssueIds(seq + 1);
                     CpAsyncCommit();
+                    if (stamp)
+                        tr[11] = GlobalTimer();
                     deferred = false;
                 }
                 GridWait(p.barrier, target, tr);

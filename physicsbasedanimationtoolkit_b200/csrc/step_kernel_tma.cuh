@@ -31,58 +31,6 @@ struct TmaParams {
     uint32_t ringSlots;                          // R: ring capacity in blocks
 };
 
-__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-
-// same, for lanes of one warp that wait on *different* barriers (divergent exit)
-__device__ __forceinline__ void MbarWaitDivergent(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP_D:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra WAIT_LOOP_D;\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ void MbarArrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void MbarArriveExpectTx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void BulkLoad(uint32_t dstSmem, const void* srcGmem, uint32_t bytes, uint32_t bar, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dstSmem),
-        "l"(srcGmem), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
-
 __device__ __forceinline__ uint32_t LoadAcquireShared(uint32_t addr)
 {
     uint32_t v;
@@ -412,7 +360,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
                 unsigned long long* tr = nullptr;
                 if (p.trace != nullptr && k == p.traceIteration)
                 {
-                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * 8;
+                    tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
                     if (threadIdx.x == 0)
                         tr[0] = GlobalTimer();
                 }

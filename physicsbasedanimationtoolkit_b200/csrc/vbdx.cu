@@ -798,7 +798,7 @@ vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned lon
     return Guard([&] {
         auto& I = h->impl;
         VBDX_CUDA(cudaSetDevice(I.device));
-        size_t const n = static_cast<size_t>(I.plan.nColors) * I.gridBlocks * 8;
+        size_t const n = static_cast<size_t>(I.plan.nColors) * I.gridBlocks * vbdx::kTraceStamps;
         if (out == nullptr)
         {
             // arm: the next steps record the timestamps of `iteration` (direct kernel only)
