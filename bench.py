@@ -289,7 +289,7 @@ def main():
                     "d2h_bytes_per_step": int(nV * 12), "ms_per_step": e2e_ms / steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vbdx::StepKernel<true,false> (one persistent launch per step)",
+                         "traffic": traffic, "kernel": "vbdx::StepKernelPipe<true,false> (one persistent cooperative launch per step)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "bytes_per_vertex_iteration": B, "kbar": kbar, "nbar": nbar,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",

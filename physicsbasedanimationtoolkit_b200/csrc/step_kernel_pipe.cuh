@@ -24,7 +24,7 @@ struct PipeParams {
     uint32_t maxIters;  // record buffer capacity per warp, in blocks
 };
 
-constexpr int kPipeMaxThreads = 512;  // compiled for up to 16 warps per CTA (<= 128 registers)
+constexpr int kPipeMaxThreads = 544;  // compiled for up to 16 compute warps + 1 barrier warp per CTA (<= 120 registers)
 
 // shared-memory footprint (host and device must agree)
 __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
@@ -45,12 +45,53 @@ struct SmemRecords {
     }
 };
 
+// Warp-specialised grid barrier.  The compute warps *arrive* (non-blocking), wait only until the
+// barrier warp's fence has gone through the load/store path (a fence queued behind a burst of gather
+// requests takes microseconds), do their prefetch work in the barrier's shadow, and then wait for the
+// release.  The barrier warp does the fence + atomic arrival and polls, undisturbed by that work.
+__device__ __forceinline__ void NamedArrive(int id, uint32_t count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void NamedSync(int id, uint32_t count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int kBarArrived = 1, kBarReleased = 2, kBarFenced = 3;
+
+__device__ __forceinline__ void BarrierWarpStep(unsigned int* counter, unsigned int& target, uint32_t lane, unsigned long long* trace)
+{
+    NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
+    if (lane == 0)
+    {
+        if (trace)
+            trace[2] = GlobalTimer();
+        target += gridDim.x;
+        AddRelease(counter, 1u);
+        if (trace)
+            trace[1] = GlobalTimer();
+    }
+    __syncwarp();
+    NamedArrive(kBarFenced, blockDim.x);
+    if (lane == 0)
+    {
+        while (LoadAcquire(counter) < target)
+        {
+        }
+        if (trace)
+            trace[3] = GlobalTimer();
+    }
+    __syncwarp();
+    NamedArrive(kBarReleased, blockDim.x);
+}
+
 template <bool kChebyshev, bool kDamping>
 __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __grid_constant__ PipeParams pp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     StepParams const& p = pp.base;
-    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t const nWarps = (blockDim.x >> 5) - 1;  // compute warps; the last warp only runs the grid barrier
     uint32_t const SE   = p.stageEntries;
     uint32_t const nC   = static_cast<uint32_t>(p.nColors);
     uint32_t const gwarp = warp * gridDim.x + blockIdx.x, gWarps = nWarps * gridDim.x;
@@ -67,7 +108,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
 
     for (uint32_t c = threadIdx.x; c <= nC; c += blockDim.x)
         colorTab[c] = p.colorTileBegin[c];
-    if (lane == 0)
+    if (lane == 0 && warp < nWarps)
     {
         MbarInit(barRec, 1);
         MbarInit(barIds, 1);
@@ -80,6 +121,25 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     uint32_t recFills = 0, idsFills = 0;    // bulk copies issued so far on each barrier
     uint32_t recWaits = 0, idsWaits = 0;    // ... and waited for
     int const totalSweeps = p.substeps * p.iterations;
+
+    if (warp == nWarps)
+    {
+        // ------------------------------ barrier warp ------------------------------
+        unsigned int target = 0;
+        for (int s = 0; s < p.substeps; ++s)
+        {
+            BarrierWarpStep(p.barrier, target, lane, nullptr);  // after the pre-step pass
+            for (int k = 0; k < p.iterations; ++k)
+                for (uint32_t c = 0; c < nC; ++c)
+                {
+                    unsigned long long* tr = nullptr;
+                    if (p.trace != nullptr && k == p.traceIteration)
+                        tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
+                    BarrierWarpStep(p.barrier, target, lane, tr);
+                }
+        }
+        return;
+    }
 
     // this warp's tile sequence over all sweeps
     struct Cursor {
@@ -187,9 +247,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     bool deferred     = false;  // static data of tile `seq` still has to be requested
     Cursor cUp        = c0;     // cursor of tile `seq`
 
-    unsigned int target    = 0;
-    uint32_t const gtid    = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t const gstride = gridDim.x * blockDim.x;
+    uint32_t const gtid    = blockIdx.x * (nWarps * 32) + threadIdx.x;
+    uint32_t const gstride = gridDim.x * (nWarps * 32);
     for (int s = 0; s < p.substeps; ++s)
     {
         for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
@@ -231,7 +290,9 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             if constexpr (kChebyshev)
                 p.pos[p.pOff + i] = o;
         }
-        GridBarrier(p.barrier, target);
+        NamedArrive(kBarArrived, blockDim.x);
+        NamedSync(kBarFenced, blockDim.x);
+        NamedSync(kBarReleased, blockDim.x);
 
         for (int k = 0; k < p.iterations; ++k)
         {
@@ -295,7 +356,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     Advance(c2);
                     ++seq;
                 }
-                GridArrive(p.barrier, target, tr);
+                NamedArrive(kBarArrived, blockDim.x);
+                NamedSync(kBarFenced, blockDim.x);  // the barrier warp's fence is through
                 if (deferred)
                 {
                     // In the shadow of the barrier: records and ids of the upcoming tile, plus the positions
@@ -324,7 +386,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                         tr[11] = GlobalTimer();
                     deferred = false;
                 }
-                GridWait(p.barrier, target, tr);
+                NamedSync(kBarReleased, blockDim.x);
             }
         }
     }

@@ -305,7 +305,7 @@ void Integrator::Create(vbdx_data_desc const& d)
 
     // ---- host plan (tiles, ring lists), then the launch shape, then the tile -> CTA partition
     bool const cheb0    = acceleration == VBDX_ACCEL_CHEBYSHEV;
-    int const tileIters = d.tile_iters > 0 ? d.tile_iters : 4;
+    int const tileIters = d.tile_iters > 0 ? d.tile_iters : 8;
     try
     {
         BuildPlan(nV, E32.data(), ptrHost.data(), adjHost.data(), colors.data(), isDbc.data(), d.X, tileIters,
@@ -326,8 +326,13 @@ void Integrator::Create(vbdx_data_desc const& d)
     maxTileIters = 1;
     for (TileDesc const& t : plan.tiles)
         maxTileIters = std::max(maxTileIters, TileIters(t.meta));
-    int const pipeThreads = d.consumer_warps > 0 ? std::min(d.consumer_warps * 32, kPipeMaxThreads) : 256;
-    size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeThreads / 32, stageEntries, maxTileIters);
+    // pipelined kernel: compute warps + one barrier warp per CTA.  Default: one CTA of 16 compute warps per SM
+    // (fewer arrivals at the grid barrier) when its tile buffers fit in shared memory, else 8 compute warps.
+    int pipeWarps = d.consumer_warps > 0 ? std::min(d.consumer_warps, kPipeMaxThreads / 32 - 1) : 16;
+    if (d.consumer_warps <= 0 && PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters) > static_cast<size_t>(maxOptin))
+        pipeWarps = 8;
+    int const pipeThreads = pipeWarps * 32 + 32;
+    size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters);
     if (variant == VBDX_KERNEL_DEFAULT)
         variant = pipeSmem <= static_cast<size_t>(maxOptin) ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
     int perSm = 1 << 30;
