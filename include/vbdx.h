@@ -205,6 +205,18 @@ vbdx_status vbdx_get_adjacency(vbdx_integrator* h, int64_t* GVGp, int64_t* GVGe,
 vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, double* m);
 vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
 
+/* Contact state after the last step, per collision vertex in the order of desc->V
+ * (gpu/impl/contact/VertexTriangleMixedCcdDcd.cuh: active, nn): active[nCV] (0/1), nn[8 * nCV] nearest triangles
+ * (indices into desc->F, -1 terminated), *nActive.  Any pointer may be NULL. */
+vbdx_status vbdx_get_contact_state(vbdx_integrator* h, int32_t* active, int32_t* nn, int64_t* nActive);
+
+/* Stand-alone LBVH build over n boxes (lo, hi: 3 x n column-major) inside the world box [wmin, wmax], as
+ * pbat::gpu::impl::geometry::Bvh::Build does (gpu/impl/geometry/Bvh.cu:130-137).  Outputs use the reference's
+ * conventions: child 2 x (n-1) and rightmost 2 x (n-1) stored as [left row | right row], parent 2n-1, nodes
+ * 0..n-2 internal (root 0) and n-1..2n-2 leaves in sorted order, inds = leaf -> box.  Any output may be NULL. */
+vbdx_status vbdx_debug_bvh_build(int64_t n, const float* lo, const float* hi, const float wmin[3], const float wmax[3], int32_t* child,
+                                 int32_t* parent, int32_t* rightmost, int32_t* inds, uint32_t* codes, float* nodeLo, float* nodeHi);
+
 /* Diagnostics: with out == NULL, arm phase tracing of sweep `iteration` for the following steps (direct kernel
  * variant); with out != NULL, read back nColors x gridBlocks x 8 %globaltimer stamps (phase start, warp 0 done,
  * CTA done, barrier released; warp 0's first tile: descriptor loaded, 1-rings staged, tets accumulated, solved) and disarm. */

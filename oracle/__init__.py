@@ -41,6 +41,8 @@ class _Desc(C.Structure):
         ("ordering", C.c_int), ("selection", C.c_int),
         ("strategy", C.c_int), ("accel", C.c_int), ("omegaMode", C.c_int),
         ("kD", C.c_double), ("detHZero", C.c_double), ("rho", C.c_double),
+        ("B", C.c_void_p), ("V", C.c_void_p), ("nCV", C.c_int64), ("F", C.c_void_p), ("nF", C.c_int64),
+        ("muC", C.c_double), ("muF", C.c_double), ("epsv", C.c_double), ("activeSetUpdateFrequency", C.c_int64),
     ]
 
 
@@ -90,7 +92,7 @@ def _ptr(a):
 
 
 _F64 = ("x", "v", "aext", "xt", "xtilde", "vt", "X", "m", "GP", "wg", "lame")
-_I64 = ("GVGp", "GVGe", "GVGilocal", "colors", "Pptr", "Padj")
+_I64 = ("GVGp", "GVGe", "GVGilocal", "colors", "Pptr", "Padj", "nn", "fc", "active")
 
 
 class Oracle:
@@ -103,7 +105,8 @@ class Oracle:
     def __init__(self, X, E, *, v=None, aext=None, rhoe=None, mue=None, lambdae=None, dbc=None,
                  colors=None, ordering=ORDER_LARGEST_DEGREE, selection=SELECT_LEAST_USED,
                  strategy=ADAPTIVE_PBAT, accel=ACCEL_NONE, rho=1.0, omega_mode=0, kD=0.0,
-                 detH_zero=1e-7, kind="port"):
+                 detH_zero=1e-7, kind="port", B=None, V=None, F=None, muC=1e6, muF=0.3, epsv=1e-3,
+                 active_set_update_frequency=1):
         self.lib = _load("port" if kind == "port" else "ref")
         X = np.asarray(X, dtype=np.float64)
         E = np.asarray(E, dtype=np.int64)
@@ -127,9 +130,15 @@ class Oracle:
         rhoe = None if rhoe is None else np.ascontiguousarray(rhoe, dtype=np.float64)
         dbc = None if dbc is None else np.ascontiguousarray(dbc, dtype=np.int64)
         colors = None if colors is None else np.ascontiguousarray(colors, dtype=np.int64)
+        B = None if B is None else np.ascontiguousarray(B, dtype=np.int64)
+        V = None if V is None else np.ascontiguousarray(V, dtype=np.int64)
+        Fc = None if F is None else np.ascontiguousarray(np.asarray(F, dtype=np.int64).T)
         d = _Desc(self.nV, self.nT, _ptr(Xc), _ptr(Ec), _ptr(vc), _ptr(ac), _ptr(rhoe), _ptr(lame),
                   _ptr(dbc), 0 if dbc is None else dbc.size, _ptr(colors), ordering, selection,
-                  strategy, accel, omega_mode, kD, detH_zero, rho)
+                  strategy, accel, omega_mode, kD, detH_zero, rho,
+                  _ptr(B), _ptr(V), 0 if V is None else V.size, _ptr(Fc), 0 if Fc is None else Fc.shape[0],
+                  muC, muF, epsv, active_set_update_frequency)
+        self.nCV = 0 if V is None else V.size
         self.h = self.lib.vbdo_create(C.byref(d))
         if not self.h:
             raise ValueError(self.lib.vbdo_last_error().decode())
@@ -164,6 +173,10 @@ class Oracle:
             return out.reshape(3 * self.nT, 4).T.copy()
         if name == "lame":
             return out.reshape(self.nT, 2).T.copy()
+        if name == "nn":
+            return out.reshape(-1, 8)
+        if name == "fc":
+            return out.reshape(-1, 8)
         return out
 
     def set(self, name, a):

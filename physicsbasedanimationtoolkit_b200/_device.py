@@ -74,6 +74,7 @@ class DeviceIntegrator:
         self._L = L
         _lib.check(L.vbdx_create(C.byref(d), C.byref(self._h)))
         self.nV, self.nT = nV, nT
+        self._ncv = int(d.nCV)
         self._strategy, self._kD, self._detH = int(data.strategy), float(data.kD), float(data.detH_zero)
         if self._rest_differs:
             self.x = data.x
@@ -173,3 +174,12 @@ class DeviceIntegrator:
         out = np.zeros(n, dtype=np.uint64)
         _lib.check(self._L.vbdx_debug_trace(self._h, int(iteration), out.ctypes.data, n))
         return out.reshape(info["nColors"], info["gridBlocks"], 12)
+
+    def contact_state(self):
+        """Extension: (active[nCV], nn[nCV, 8], nActive) of the vertex-triangle active set."""
+        ncv = self._ncv
+        active = np.zeros(ncv, np.int32)
+        nn = np.zeros((ncv, 8), np.int32)
+        na = C.c_int64(0)
+        _lib.check(self._L.vbdx_get_contact_state(self._h, active.ctypes.data, nn.ctypes.data, C.byref(na)))
+        return active.astype(bool), nn, na.value

@@ -75,6 +75,8 @@ SYMBOLS = {
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),
     "vbdx_set_scene_bounding_box": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_get_contact_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbdx_debug_bvh_build": (C.c_int, [C.c_int64] + [C.c_void_p] * 11),
     "vbdx_debug_trace": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_get_info": (C.c_int, [_H, C.POINTER(Info)]),
     "vbdx_get_adjacency": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),

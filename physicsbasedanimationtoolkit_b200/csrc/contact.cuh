@@ -1,0 +1,326 @@
+// Vertex-triangle contact for the B200 VBD integrator: active-set management over a linear BVH and
+// the per-vertex contact energy.  Written from scratch; the behaviour it reproduces is the reference's
+// GPU path (the reference's CPU integrator has no contact):
+//   gpu/impl/contact/VertexTriangleMixedCcdDcd.cu:51-223   InitializeActiveSet / UpdateActiveSet / FinalizeActiveSet
+//   gpu/impl/vbd/Integrator.cu:82-103,163-188,250-273      where Step calls them and fills the contact lists fc
+//   gpu/impl/vbd/Kernels.cuh:80-114,203-223                area-scaled penalty, loop over <= 8 contacts
+//   sim/vbd/Kernels.h:223-302                              normal penalty + IPC-style smoothed friction
+// Deliberate, documented deviations (DESIGN.md "Contact"): the warm-start radius `dupper` of a vertex is
+// the maximum over the triangles whose swept box it overlaps (the reference keeps whichever its traversal
+// visited last), and vertices are sorted by a stable sort (the reference's sort of the query points is
+// unstable): both only affect implementation-defined orderings in the reference.
+#pragma once
+
+#include "lbvh.cuh"
+
+namespace vbdx {
+
+constexpr int kMaxContacts = 8;  // gpu/impl/contact/VertexTriangleMixedCcdDcd.cuh kMaxNeighbours
+
+// ------------------------------------------------------------------------------------------
+// geometry helpers (fp32 restatements)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 F3(float4 a) { return make_float3(a.x, a.y, a.z); }
+__device__ __forceinline__ float3 Sub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 Add(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 Mul(float s, float3 a) { return make_float3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float Dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 Cross(float3 a, float3 b)
+{
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+// squared distance point <-> triangle, Ericson's region walk (geometry/ClosestPointQueries.h:299-393,
+// geometry/DistanceQueries.h:212-221)
+__device__ __forceinline__ float PointTriangleDistance2(float3 P, float3 A, float3 B, float3 C)
+{
+    float3 const AB = Sub(B, A), AC = Sub(C, A), AP = Sub(P, A);
+    float const d1 = Dot(AB, AP), d2 = Dot(AC, AP);
+    float u, v, w;
+    float3 const BP = Sub(P, B);
+    float const d3 = Dot(AB, BP), d4 = Dot(AC, BP);
+    float3 const CP = Sub(P, C);
+    float const d5 = Dot(AB, CP), d6 = Dot(AC, CP);
+    float const vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+    if (d1 <= 0.f && d2 <= 0.f)
+        u = 1.f, v = 0.f, w = 0.f;
+    else if (d3 >= 0.f && d4 <= d3)
+        u = 0.f, v = 1.f, w = 0.f;
+    else if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f)
+    {
+        v = d1 / (d1 - d3);
+        u = 1.f - v, w = 0.f;
+    }
+    else if (d6 >= 0.f && d5 <= d6)
+        u = 0.f, v = 0.f, w = 1.f;
+    else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f)
+    {
+        w = d2 / (d2 - d6);
+        u = 1.f - w, v = 0.f;
+    }
+    else if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f)
+    {
+        w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        u = 0.f, v = 1.f - w;
+    }
+    else
+    {
+        float const denom = 1.f / (va + vb + vc);
+        v = vb * denom, w = vc * denom;
+        u = 1.f - v - w;
+    }
+    float3 const Q = Add(Add(Mul(u, A), Mul(v, B)), Mul(w, C));
+    float3 const D = Sub(P, Q);
+    return Dot(D, D);
+}
+
+// Contact energy derivatives of one (vertex, triangle) pair (sim/vbd/Kernels.h:223-302).
+// g += dE/dx_v, H (symmetric, 6 entries h00 h01 h02 h11 h12 h22) += d2E/dx_v2
+__device__ __forceinline__ void AccumulateVertexTriangleContact(
+    float3 xtv, float3 xv, float3 const xtf[3], float3 const xf[3], float dt, float k, float muF, float epsv,
+    float g[3], float H[6])
+{
+    float3 T0 = Sub(xf[1], xf[0]), T1 = Sub(xf[2], xf[0]);
+    float3 n             = Cross(T0, T1);
+    float const dblarea  = sqrtf(Dot(n, n));
+    if (dblarea <= 1e-8f)
+        return;
+    n               = Mul(1.f / dblarea, n);
+    float3 const xc = Sub(xv, Mul(Dot(n, Sub(xv, xf[0])), n));
+    // barycentric coordinates of the projection (geometry/IntersectionQueries.h:45-67)
+    float3 const AP = Sub(xc, xf[0]);
+    float const d00 = Dot(T0, T0), d01 = Dot(T0, T1), d11 = Dot(T1, T1), d20 = Dot(AP, T0), d21 = Dot(AP, T1);
+    float const denom = d00 * d11 - d01 * d01;
+    float const bv = (d11 * d20 - d01 * d21) / denom, bw = (d00 * d21 - d01 * d20) / denom, bu = 1.f - bv - bw;
+    bool const inside = bu >= 0.f && bu <= 1.f && bv >= 0.f && bv <= 1.f && bw >= 0.f && bw <= 1.f;
+    if (!inside)
+        return;
+    float3 const xb    = Add(Add(Mul(bu, xf[0]), Mul(bv, xf[1])), Mul(bw, xf[2]));
+    float const d      = fminf(0.f, Dot(Sub(xv, xb), n));
+    float const lambda = k * d;
+    g[0] += lambda * n.x, g[1] += lambda * n.y, g[2] += lambda * n.z;
+    H[0] += k * n.x * n.x, H[1] += k * n.x * n.y, H[2] += k * n.x * n.z;
+    H[3] += k * n.y * n.y, H[4] += k * n.y * n.z, H[5] += k * n.z * n.z;
+    // IPC smooth friction: tangent basis = (unnormalised edge, n x edge) as the reference has it
+    T1                  = Cross(n, T0);
+    float3 const xtb    = Add(Add(Mul(bu, xtf[0]), Mul(bv, xtf[1])), Mul(bw, xtf[2]));
+    float3 const dx     = Sub(Sub(xv, xtv), Sub(xb, xtb));
+    float const u0 = Dot(T0, dx), u1 = Dot(T1, dx);
+    float const unorm   = sqrtf(u0 * u0 + u1 * u1) + FLT_EPSILON;
+    float const epsvh   = epsv * dt;
+    float const muFl    = muF * fabsf(lambda);
+    float const y       = unorm / epsvh;
+    float const f1      = (y < 1.f) ? 2.f * y - y * y : 1.f;
+    float const c       = muFl * f1 / unorm;
+    float3 const Tu     = Add(Mul(u0, T0), Mul(u1, T1));
+    g[0] += c * Tu.x, g[1] += c * Tu.y, g[2] += c * Tu.z;
+    H[0] += c * (T0.x * T0.x + T1.x * T1.x), H[1] += c * (T0.x * T0.y + T1.x * T1.y), H[2] += c * (T0.x * T0.z + T1.x * T1.z);
+    H[3] += c * (T0.y * T0.y + T1.y * T1.y), H[4] += c * (T0.y * T0.z + T1.y * T1.z), H[5] += c * (T0.z * T0.z + T1.z * T1.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// active-set kernels.  Vertex and triangle ids are *internal* ids; q indexes the sorted query order.
+// ------------------------------------------------------------------------------------------
+struct ContactMesh {
+    const int32_t* B;  // body of every internal vertex
+    const int32_t* V;  // collision vertices (internal ids)
+    const int4* F;     // collision triangles (internal vertex ids)
+    uint32_t nCV, nF;
+};
+
+// scene bounds when the caller supplied none: min/max over positions (float atomics via ordered ints)
+__device__ __forceinline__ int FloatToOrdered(float f)
+{
+    int const i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float OrderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void SceneBoundsReset(int* bounds)
+{
+    if (threadIdx.x < 3)
+    {
+        bounds[threadIdx.x]     = FloatToOrdered(FLT_MAX);
+        bounds[3 + threadIdx.x] = FloatToOrdered(-FLT_MAX);
+    }
+}
+
+__global__ void SceneBoundsReduce(const float4* pos, uint32_t n, int* bounds)
+{
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 const p = pos[i];
+        lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+    }
+    for (int d = 0; d < 3; ++d)
+    {
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            atomicMin(&bounds[d], FloatToOrdered(lo[d]));
+            atomicMax(&bounds[3 + d], FloatToOrdered(hi[d]));
+        }
+    }
+}
+
+__global__ void SceneBoundsFinish(const int* bounds, WorldBox* w)
+{
+    if (threadIdx.x < 3)
+    {
+        float const lo = OrderedToFloat(bounds[threadIdx.x]), hi = OrderedToFloat(bounds[3 + threadIdx.x]);
+        w->lo[threadIdx.x]  = lo;
+        w->ext[threadIdx.x] = hi > lo ? hi - lo : 1.f;
+    }
+}
+
+// predictor of the full step (gpu/impl/vbd/Integrator.cu:163-188): x1 = xt + dt v + dt^2 aext
+__device__ __forceinline__ float3 Predict(float4 x, float4 v, float4 a, float dt)
+{
+    return make_float3(x.x + dt * v.x + dt * dt * a.x, x.y + dt * v.y + dt * dt * a.y, x.z + dt * v.z + dt * dt * a.z);
+}
+
+// swept boxes of the collision vertices, in the order given by ids (VertexTriangleMixedCcdDcd.cu:62-75)
+__global__ void SweptPointBoxes(ContactMesh m, const uint32_t* ids, const float4* x, const float4* vel, const float4* aext, float dt,
+                                float4* lo, float4* hi)
+{
+    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m.nCV)
+        return;
+    int const i     = m.V[ids[q]];
+    float4 const p0 = x[i];
+    float3 const p1 = Predict(p0, vel[i], aext[i], dt);
+    lo[q] = make_float4(fminf(p0.x, p1.x), fminf(p0.y, p1.y), fminf(p0.z, p1.z), 0.f);
+    hi[q] = make_float4(fmaxf(p0.x, p1.x), fmaxf(p0.y, p1.y), fmaxf(p0.z, p1.z), 0.f);
+}
+
+// swept boxes of the triangles by triangle id (VertexTriangleMixedCcdDcd.cu:89-103); dt = 0: current boxes
+__global__ void TriangleBoxes(ContactMesh m, const float4* x, const float4* vel, const float4* aext, float dt, float4* lo, float4* hi)
+{
+    uint32_t const f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.nF)
+        return;
+    int4 const t = m.F[f];
+    int const id[3] = {t.x, t.y, t.z};
+    float l[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, h[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < 3; ++k)
+    {
+        float4 const p0 = x[id[k]];
+        l[0] = fminf(l[0], p0.x), l[1] = fminf(l[1], p0.y), l[2] = fminf(l[2], p0.z);
+        h[0] = fmaxf(h[0], p0.x), h[1] = fmaxf(h[1], p0.y), h[2] = fmaxf(h[2], p0.z);
+        if (dt != 0.f)
+        {
+            float3 const p1 = Predict(p0, vel[id[k]], aext[id[k]], dt);
+            l[0] = fminf(l[0], p1.x), l[1] = fminf(l[1], p1.y), l[2] = fminf(l[2], p1.z);
+            h[0] = fmaxf(h[0], p1.x), h[1] = fmaxf(h[1], p1.y), h[2] = fmaxf(h[2], p1.z);
+        }
+    }
+    lo[f] = make_float4(l[0], l[1], l[2], 0.f);
+    hi[f] = make_float4(h[0], h[1], h[2], 0.f);
+}
+
+// VertexTriangleMixedCcdDcd.cu:107-140: a vertex becomes active when its swept box overlaps the swept box
+// of a triangle of another body; dupper = squared diagonal of the joint box (max over such triangles)
+__global__ void MarkActive(ContactMesh m, BvhView t, const uint32_t* ids, const float4* qlo, const float4* qhi,
+                           const float4* triLo, const float4* triHi, uint8_t* active, float* dupper)
+{
+    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m.nCV)
+        return;
+    uint32_t const v = ids[q];
+    int const i      = m.V[v];
+    int const body   = m.B[i];
+    float4 const lo = qlo[q], hi = qhi[q];
+    float best = -1.f;
+    BvhForEachOverlap(t, lo, hi, [&](int, uint32_t f) {
+        if (m.B[m.F[f].x] == body)
+            return;  // no self collision
+        float4 const tl = triLo[f], th = triHi[f];
+        float const dx = fmaxf(hi.x, th.x) - fminf(lo.x, tl.x), dy = fmaxf(hi.y, th.y) - fminf(lo.y, tl.y),
+                    dz = fmaxf(hi.z, th.z) - fminf(lo.z, tl.z);
+        best = fmaxf(best, dx * dx + dy * dy + dz * dz);
+    });
+    if (best >= 0.f)
+    {
+        active[v] = 1;
+        dupper[v] = best;
+    }
+}
+
+__global__ void ActiveFlags(const uint32_t* ids, const uint8_t* active, uint32_t n, uint32_t* flags)
+{
+    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q <= n)
+        flags[q] = (q < n && active[ids[q]]) ? 1u : 0u;
+}
+
+// av = active vertices in sorted order, -1 elsewhere (VertexTriangleMixedCcdDcd.cu:141-146)
+__global__ void CompactActive(const uint32_t* ids, const uint32_t* flags, const uint32_t* offsets, uint32_t n, int32_t* av, uint32_t* nActive)
+{
+    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n)
+    {
+        if (flags[q])
+            av[offsets[q]] = static_cast<int32_t>(ids[q]);
+        if (q >= offsets[n])
+            av[q] = -1;
+    }
+    if (q == 0)
+        *nActive = offsets[n];
+}
+
+// k-nearest triangles of the active vertices (VertexTriangleMixedCcdDcd.cuh:108-162).
+// mode 0: UpdateActiveSet -> nn rows, and the contact lists fc of the vertices (gpu/impl/vbd/Integrator.cu:250-273)
+// mode 1: FinalizeActiveSet -> active[v] = vertex is on the negative side of (the last of) its nearest triangles
+__global__ void NearestTriangles(ContactMesh m, BvhView t, const int32_t* av, const uint32_t* nActive, const float4* x, const float* dupper,
+                                 float eps, int mode, int32_t* nn, int32_t* fc, uint8_t* active)
+{
+    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= *nActive)
+        return;
+    int const v    = av[q];
+    int const i    = m.V[v];
+    int const body = m.B[i];
+    float3 const p = F3(x[i]);
+    int found[kMaxContacts];
+    float dmin;
+    int const count = BvhNearest<kMaxContacts>(
+        t, p, dupper[v], eps,
+        [&](int f) {
+            int4 const tri = m.F[f];
+            if (m.B[tri.x] == body)
+                return FLT_MAX;
+            return PointTriangleDistance2(p, F3(x[tri.x]), F3(x[tri.y]), F3(x[tri.z]));
+        },
+        found, dmin);
+    if (mode == 0)
+    {
+        for (int k = 0; k < kMaxContacts; ++k)
+        {
+            int const f               = k < count ? found[k] : -1;
+            nn[v * kMaxContacts + k]  = f;
+            fc[i * kMaxContacts + k]  = f;
+        }
+    }
+    else if (count > 0)
+    {
+        int4 const tri  = m.F[found[count - 1]];
+        float3 const A = F3(x[tri.x]), Bq = F3(x[tri.y]), C = F3(x[tri.z]);
+        float3 const n  = Cross(Sub(Bq, A), Sub(C, A));
+        active[v]       = Dot(Sub(p, A), n) < 0.f ? 1 : 0;  // sign of geometry/DistanceQueries.h PointPlane
+    }
+}
+
+__global__ void FillI32(int32_t* a, int32_t v, size_t n)
+{
+    size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        a[i] = v;
+}
+
+}  // namespace vbdx

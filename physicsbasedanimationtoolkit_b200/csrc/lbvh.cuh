@@ -1,0 +1,368 @@
+// Linear BVH (Karras 2012) for sm_100a: 30-bit Morton codes, a hand-written stable LSD radix sort,
+// hierarchy generation, bottom-up boxes, and the two traversals the VBD contact path needs (box overlap
+// and k-nearest-neighbour branch and bound).  Written from scratch; behaviourally it follows the
+// reference's
+//   geometry/Morton.h:35-80, gpu/impl/geometry/Morton.cu:23-44      (codes of box centroids)
+//   gpu/impl/geometry/Bvh.cu:139-157                                 (stable sort by code, then by index)
+//   gpu/impl/geometry/Bvh.cu:24-116                                  (range / split / children / rightmost)
+//   gpu/impl/geometry/Bvh.cu:175-233                                 (internal boxes, atomic visit counters)
+//   gpu/impl/geometry/Bvh.cuh:347-474,476-581                        (nearest neighbours, range search)
+// so that the tree topology equals the reference's golden arrays (gpu/impl/geometry/Bvh.cu:367-410).
+// Node numbering is the reference's: internal nodes 0..n-2 (root 0), leaves n-1..2n-2 in sorted order.
+#pragma once
+
+#include "setup_kernels.cuh"
+
+#include <cfloat>
+#include <cuda_runtime.h>
+
+namespace vbdx {
+
+// ------------------------------------------------------------------------------------------
+// stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass
+//   one warp owns a contiguous segment of kSortSegment items and walks it in chunks of 32, so that
+//   ranks within a digit follow item order (stability) without any cross-warp bookkeeping
+// ------------------------------------------------------------------------------------------
+constexpr int kSortSegment     = 2048;
+constexpr int kSortWarpsPerCta = 4;
+
+__global__ void RadixCount(const uint32_t* keys, uint32_t n, int shift, uint32_t nSeg, uint32_t* counts)
+{
+    __shared__ uint32_t hist[kSortWarpsPerCta][256];
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t const seg  = blockIdx.x * kSortWarpsPerCta + warp;
+    for (uint32_t d = lane; d < 256; d += 32)
+        hist[warp][d] = 0;
+    __syncwarp();
+    if (seg < nSeg)
+    {
+        uint32_t const begin = seg * kSortSegment;
+        uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
+        for (uint32_t base = begin; base < end; base += 32)
+        {
+            uint32_t const i    = base + lane;
+            bool const in       = i < end;
+            uint32_t const mask = __ballot_sync(0xffffffffu, in);
+            if (in)
+            {
+                uint32_t const d     = (keys[i] >> shift) & 255u;
+                uint32_t const peers = __match_any_sync(mask, d);
+                if (lane == static_cast<uint32_t>(__ffs(peers) - 1))
+                    hist[warp][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        for (uint32_t d = lane; d < 256; d += 32)
+            counts[d * nSeg + seg] = hist[warp][d];
+    }
+}
+
+__global__ void RadixScatter(
+    const uint32_t* keys,
+    const uint32_t* vals,
+    uint32_t n,
+    int shift,
+    uint32_t nSeg,
+    const uint32_t* offsets,
+    uint32_t* keysOut,
+    uint32_t* valsOut)
+{
+    __shared__ uint32_t run[kSortWarpsPerCta][256];
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t const seg  = blockIdx.x * kSortWarpsPerCta + warp;
+    if (seg >= nSeg)
+        return;
+    for (uint32_t d = lane; d < 256; d += 32)
+        run[warp][d] = offsets[d * nSeg + seg];
+    __syncwarp();
+    uint32_t const begin = seg * kSortSegment;
+    uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
+    for (uint32_t base = begin; base < end; base += 32)
+    {
+        uint32_t const i    = base + lane;
+        bool const in       = i < end;
+        uint32_t const mask = __ballot_sync(0xffffffffu, in);
+        uint32_t key = 0, val = 0, d = 0, peers = 0, dst = 0;
+        if (in)
+        {
+            key   = keys[i];
+            val   = vals[i];
+            d     = (key >> shift) & 255u;
+            peers = __match_any_sync(mask, d);
+            dst   = run[warp][d] + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncwarp();
+        if (in && lane == static_cast<uint32_t>(__ffs(peers) - 1))
+            run[warp][d] += __popc(peers);
+        __syncwarp();
+        if (in)
+        {
+            keysOut[dst] = key;
+            valsOut[dst] = val;
+        }
+    }
+}
+
+// Sorts in place (4 passes ping-pong through the temporaries).  counts: 256 * nSeg (+ scan scratch).
+inline void RadixSortPairs(
+    uint32_t* keys,
+    uint32_t* vals,
+    uint32_t* keysTmp,
+    uint32_t* valsTmp,
+    uint32_t n,
+    uint32_t* counts,
+    uint32_t* scanScratch,
+    cudaStream_t s,
+    int64_t* launches = nullptr)
+{
+    if (n < 2)
+        return;
+    uint32_t const nSeg = (n + kSortSegment - 1) / kSortSegment;
+    int const ctas      = static_cast<int>((nSeg + kSortWarpsPerCta - 1) / kSortWarpsPerCta);
+    uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
+    for (int pass = 0; pass < 4; ++pass)
+    {
+        RadixCount<<<ctas, kSortWarpsPerCta * 32, 0, s>>>(kin, n, 8 * pass, nSeg, counts);
+        ExclusiveScanU32(counts, counts, 256 * static_cast<int64_t>(nSeg), scanScratch, s);
+        RadixScatter<<<ctas, kSortWarpsPerCta * 32, 0, s>>>(kin, vin, n, 8 * pass, nSeg, counts, kout, vout);
+        uint32_t* t = kin;
+        kin         = kout;
+        kout        = t;
+        t           = vin;
+        vin         = vout;
+        vout        = t;
+        if (launches)
+            *launches += 5;
+    }
+}
+
+inline size_t RadixSortCountsSize(uint32_t n)
+{
+    return 256 * static_cast<size_t>((n + kSortSegment - 1) / kSortSegment) + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Morton codes (geometry/Morton.h:35-80)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ExpandBits10Dev(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t Morton3D(float x, float y, float z)
+{
+    uint32_t const xx = ExpandBits10Dev(static_cast<uint32_t>(fminf(fmaxf(x * 1024.f, 0.f), 1023.f)));
+    uint32_t const yy = ExpandBits10Dev(static_cast<uint32_t>(fminf(fmaxf(y * 1024.f, 0.f), 1023.f)));
+    uint32_t const zz = ExpandBits10Dev(static_cast<uint32_t>(fminf(fmaxf(z * 1024.f, 0.f), 1023.f)));
+    return xx * 4 + yy * 2 + zz;
+}
+
+struct WorldBox {
+    float lo[3], ext[3];  // minimum corner and extent (gpu/impl/geometry/Morton.cu:32-40)
+};
+
+// code of the centroid of box i; also resets ids to the identity (the reference re-sequences `inds`
+// before every BVH sort, gpu/impl/geometry/Bvh.cu:144)
+__global__ void MortonOfBoxes(const float4* lo, const float4* hi, uint32_t n, const WorldBox* world, uint32_t* codes, uint32_t* ids)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    WorldBox const w = *world;
+    float4 const a = lo[i], b = hi[i];
+    codes[i] = Morton3D((0.5f * (a.x + b.x) - w.lo[0]) / w.ext[0], (0.5f * (a.y + b.y) - w.lo[1]) / w.ext[1],
+                        (0.5f * (a.z + b.z) - w.lo[2]) / w.ext[2]);
+    if (ids)
+        ids[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// the tree
+// ------------------------------------------------------------------------------------------
+struct BvhView {
+    uint32_t n;            // leaves
+    const uint32_t* codes; // sorted Morton codes
+    const uint32_t* inds;  // leaf -> primitive
+    int32_t* child[2];     // n-1
+    int32_t* parent;       // 2n-1
+    int32_t* rightmost[2]; // n-1
+    float4* nodeLo;        // 2n-1: internal boxes then leaf boxes (sorted order)
+    float4* nodeHi;
+    uint32_t* visits;      // n-1
+};
+
+__device__ __forceinline__ int BvhDelta(const uint32_t* codes, int n, int i, int j)
+{
+    if (j < 0 || j >= n)
+        return -1;
+    uint32_t const a = codes[i], b = codes[j];
+    if (a == b)
+        return 32 + __clz(i ^ j);  // duplicate codes: fall back to the leaf index
+    return __clz(a ^ b);
+}
+
+__global__ void BvhHierarchy(BvhView t)
+{
+    int const in = blockIdx.x * blockDim.x + threadIdx.x;
+    int const n  = static_cast<int>(t.n);
+    if (in >= n - 1)
+        return;
+    // direction and extent of the node's key range
+    int const d    = (BvhDelta(t.codes, n, in, in + 1) - BvhDelta(t.codes, n, in, in - 1)) > 0 ? 1 : -1;
+    int const dmin = BvhDelta(t.codes, n, in, in - d);
+    int lmax       = 2;
+    while (BvhDelta(t.codes, n, in, in + lmax * d) > dmin)
+        lmax <<= 1;
+    int l = 0;
+    do
+    {
+        lmax >>= 1;
+        if (BvhDelta(t.codes, n, in, in + (l + lmax) * d) > dmin)
+            l += lmax;
+    } while (lmax > 1);
+    int const j = in + l * d;
+    // split position
+    int const dnode = BvhDelta(t.codes, n, in, j);
+    int s = 0, len = l;
+    do
+    {
+        len = (len + 1) >> 1;
+        if (BvhDelta(t.codes, n, in, in + (s + len) * d) > dnode)
+            s += len;
+    } while (len > 1);
+    int const gamma = in + s * d + min(d, 0);
+    int const lo = min(in, j), hi = max(in, j);
+    int const leafBegin = n - 1;
+    int const lc        = (lo == gamma) ? leafBegin + gamma : gamma;
+    int const rc        = (hi == gamma + 1) ? leafBegin + gamma + 1 : gamma + 1;
+    t.child[0][in]      = lc;
+    t.child[1][in]      = rc;
+    t.parent[lc]        = in;
+    t.parent[rc]        = in;
+    t.rightmost[0][in]  = leafBegin + gamma;
+    t.rightmost[1][in]  = leafBegin + hi;
+}
+
+// leaf boxes in sorted order from the per-primitive boxes
+__global__ void BvhGatherLeafBoxes(BvhView t, const float4* primLo, const float4* primHi)
+{
+    uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= t.n)
+        return;
+    uint32_t const f       = t.inds[k];
+    t.nodeLo[t.n - 1 + k]  = primLo[f];
+    t.nodeHi[t.n - 1 + k]  = primHi[f];
+}
+
+// internal boxes bottom-up: the second thread to reach a node merges its children and moves on
+__global__ void BvhInternalBoxes(BvhView t)
+{
+    uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= t.n)
+        return;
+    int p = t.parent[t.n - 1 + k];
+    while (p >= 0)
+    {
+        __threadfence();
+        if (atomicAdd(&t.visits[p], 1u) == 0u)
+            break;
+        __threadfence();
+        int const lc = t.child[0][p], rc = t.child[1][p];
+        float4 const al = t.nodeLo[lc], ah = t.nodeHi[lc], bl = t.nodeLo[rc], bh = t.nodeHi[rc];
+        t.nodeLo[p] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+        t.nodeHi[p] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+        p           = t.parent[p];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// traversals (per-thread explicit stack, right child first like the reference's push order)
+// ------------------------------------------------------------------------------------------
+constexpr int kBvhStack = 64;
+
+// geometry/OverlapQueries.h:608-616
+__device__ __forceinline__ bool BoxesOverlap(float4 al, float4 ah, float4 bl, float4 bh)
+{
+    return (al.x <= bh.x && ah.x >= bl.x) && (al.y <= bh.y && ah.y >= bl.y) && (al.z <= bh.z && ah.z >= bl.z);
+}
+
+// calls f(leafSlot, primitive) for every leaf whose box overlaps [qlo, qhi]  (Bvh.cuh:282-345)
+template <class F>
+__device__ __forceinline__ void BvhForEachOverlap(BvhView const& t, float4 qlo, float4 qhi, F f)
+{
+    int stack[kBvhStack];
+    int top        = 0;
+    stack[top++]   = 0;
+    int const leaf0 = static_cast<int>(t.n) - 1;
+    do
+    {
+        int const node = stack[--top];
+        if (!BoxesOverlap(t.nodeLo[node], t.nodeHi[node], qlo, qhi))
+            continue;
+        if (node >= leaf0)
+            f(node - leaf0, t.inds[node - leaf0]);
+        else if (top + 2 <= kBvhStack)
+        {
+            stack[top++] = t.child[0][node];
+            stack[top++] = t.child[1][node];
+        }
+    } while (top > 0);
+}
+
+// squared distance point <-> box (geometry/DistanceQueries.h:199-210)
+__device__ __forceinline__ float PointBoxDistance2(float3 p, float4 lo, float4 hi)
+{
+    float const cx = fminf(fmaxf(p.x, lo.x), hi.x), cy = fminf(fmaxf(p.y, lo.y), hi.y), cz = fminf(fmaxf(p.z, lo.z), hi.z);
+    float const dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Depth-first branch and bound (Bvh.cuh:347-474): keeps the nearest primitive and the ones whose squared
+// distance lies within +-eps of the running minimum, at most kMaxNN of them, in discovery order.
+// dist(primitive) returns the squared distance (FLT_MAX to reject).  Returns the number found.
+template <int kMaxNN, class FDist>
+__device__ __forceinline__ int BvhNearest(BvhView const& t, float3 q, float dmin, float eps, FDist dist, int* out, float& dminOut)
+{
+    int stack[kBvhStack];
+    int top         = 0;
+    stack[top++]    = 0;
+    int count       = 0;
+    int const leaf0 = static_cast<int>(t.n) - 1;
+    do
+    {
+        int const node  = stack[--top];
+        float const lo  = dmin - eps, hi = dmin + eps;
+        float const db  = PointBoxDistance2(q, t.nodeLo[node], t.nodeHi[node]);
+        if (!(db <= hi))
+            continue;
+        if (node < leaf0)
+        {
+            if (top + 2 <= kBvhStack)
+            {
+                stack[top++] = t.child[0][node];
+                stack[top++] = t.child[1][node];
+            }
+        }
+        else
+        {
+            int const prim = static_cast<int>(t.inds[node - leaf0]);
+            float const d  = dist(prim);
+            if (d < lo)
+            {
+                count  = 0;
+                out[count++] = prim;
+                dmin   = d;
+            }
+            else if (d <= hi && count < kMaxNN)
+                out[count++] = prim;
+        }
+    } while (top > 0);
+    dminOut = dmin;
+    return count;
+}
+
+}  // namespace vbdx

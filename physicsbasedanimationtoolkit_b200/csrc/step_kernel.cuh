@@ -14,6 +14,7 @@
 // gradient is ever formed, only the edge vector to one neighbour and the opposite face's normal.
 #pragma once
 
+#include "contact.cuh"
 #include "vbdx_internal.h"
 
 #include <cuda_runtime.h>
@@ -49,6 +50,15 @@ struct StepParams {
     int strategy;
     int iterations, substeps;
     unsigned int* barrier;  // zeroed before launch
+    // vertex-triangle contact (fc == nullptr: disabled)
+    const int32_t* __restrict__ fc;      // 8 triangle ids per internal vertex, -1 terminated
+    const int4* __restrict__ triF;       // collision triangles (internal vertex ids)
+    const float* __restrict__ XVA;       // vertex areas (internal order)
+    const float* __restrict__ FA;        // triangle areas
+    float4* snap;                        // 2 x nVerts: positions as they were when the iteration started
+    const uint32_t* __restrict__ colorVertexBegin;  // nColors + 1: internal id range of every colour
+    float muC, muF, epsv;
+    int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path)
     unsigned long long* trace;  // optional [nColors][gridDim.x][kTraceStamps] timestamps of one iteration (diagnostics)
     int traceIteration;
 };
@@ -130,7 +140,8 @@ __device__ __forceinline__ float4 LoadPos(const float4* p)
     return __ldcg(p);  // L2-coherent load: positions change between colours
 }
 
-// InitialPositionsForSolve (sim/vbd/Kernels.h:45-94)
+// InitialPositionsForSolve (sim/vbd/Kernels.h:45-94).  Roundings are spelled out (no implicit
+// multiply-add contraction) so that every kernel that inlines this code produces the same bits.
 __device__ __forceinline__ float3 InitialPosition(
     float3 xt,
     float3 vtm1,
@@ -142,32 +153,105 @@ __device__ __forceinline__ float3 InitialPosition(
 {
     if (strategy == 0)
         return xt;
-    float3 x = make_float3(xt.x + dt * vt.x, xt.y + dt * vt.y, xt.z + dt * vt.z);
+    float3 x = make_float3(fmaf(dt, vt.x, xt.x), fmaf(dt, vt.y, xt.y), fmaf(dt, vt.z, xt.z));
     if (strategy == 1)
         return x;
     float atilde = 1.f;
     if (strategy >= 3)
     {
-        float const an2 = a.x * a.x + a.y * a.y + a.z * a.z;
+        float const an2 = fmaf(a.z, a.z, fmaf(a.y, a.y, __fmul_rn(a.x, a.x)));
         atilde          = 0.f;
         if (an2 != 0.f)
         {
             if (strategy == 3)
             {
-                float const d = ((vt.x - vtm1.x) / dt) * a.x + ((vt.y - vtm1.y) / dt) * a.y +
-                                ((vt.z - vtm1.z) / dt) * a.z;
-                atilde = fminf(fmaxf(d / an2, 0.f), 1.f);
+                float const d = fmaf(__fdiv_rn(__fsub_rn(vt.z, vtm1.z), dt), a.z,
+                                     fmaf(__fdiv_rn(__fsub_rn(vt.y, vtm1.y), dt), a.y,
+                                          __fmul_rn(__fdiv_rn(__fsub_rn(vt.x, vtm1.x), dt), a.x)));
+                atilde = fminf(fmaxf(__fdiv_rn(d, an2), 0.f), 1.f);
             }
             else
             {
-                float const nrm = sqrtf(vt.x * vt.x + vt.y * vt.y + vt.z * vt.z) + 1.17549435e-38f;
-                float const d   = (vt.x / nrm) * a.x + (vt.y / nrm) * a.y + (vt.z / nrm) * a.z;
-                atilde          = fminf(fabsf(d / an2), 1.f);
+                float const nrm =
+                    __fadd_rn(__fsqrt_rn(fmaf(vt.z, vt.z, fmaf(vt.y, vt.y, __fmul_rn(vt.x, vt.x)))), 1.17549435e-38f);
+                float const d = fmaf(__fdiv_rn(vt.z, nrm), a.z, fmaf(__fdiv_rn(vt.y, nrm), a.y, __fmul_rn(__fdiv_rn(vt.x, nrm), a.x)));
+                atilde        = fminf(fabsf(__fdiv_rn(d, an2)), 1.f);
             }
         }
     }
-    float const s = dt2 * atilde;
-    return make_float3(x.x + s * a.x, x.y + s * a.y, x.z + s * a.z);
+    float const s = __fmul_rn(dt2, atilde);
+    return make_float3(fmaf(s, a.x, x.x), fmaf(s, a.y, x.y), fmaf(s, a.z, x.z));
+}
+
+// Per-vertex pre-step, fused with the velocity update of the previous substep
+// (sim/vbd/Integrator.cpp:31-35,39; sim/vbd/Kernels.h:29-94):
+//   v = (x - xt)/h [s > 0];  xt = x;  xtilde = xt + h v + h^2 a;  x = initial guess
+template <bool kChebyshev>
+__device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, int s)
+{
+    float4 const x4    = __ldcg(p.pos + p.pOff + i);
+    float4 v4          = __ldcg(p.vel + i);
+    float3 const vprev = make_float3(v4.x, v4.y, v4.z);
+    if (s > 0)
+    {
+        float4 const xt4 = __ldcg(p.xt + i);
+        v4.x = __fdiv_rn(__fsub_rn(x4.x, xt4.x), p.sdt);
+        v4.y = __fdiv_rn(__fsub_rn(x4.y, xt4.y), p.sdt);
+        v4.z = __fdiv_rn(__fsub_rn(x4.z, xt4.z), p.sdt);
+        p.vel[i] = v4;
+    }
+    // "previous velocity" of InitialPositionsForSolve: the CPU reference passes vt == v
+    // (sim/vbd/Integrator.cpp:32,61-68); the GPU reference keeps a real v(t-1)
+    float3 vtm1 = make_float3(v4.x, v4.y, v4.z);
+    if (p.vtm1 != nullptr)
+    {
+        if (s > 0)
+            vtm1 = vprev;
+        else
+        {
+            float4 const q = __ldcg(p.vtm1 + i);
+            vtm1           = make_float3(q.x, q.y, q.z);
+        }
+    }
+    float4 const a4 = __ldg(p.aext + i);
+    float4 xm       = __ldcg(p.xtildeM + i);
+    xm.x            = fmaf(p.sdt2, a4.x, fmaf(p.sdt, v4.x, x4.x));
+    xm.y            = fmaf(p.sdt2, a4.y, fmaf(p.sdt, v4.y, x4.y));
+    xm.z            = fmaf(p.sdt2, a4.z, fmaf(p.sdt, v4.z, x4.z));
+    p.xtildeM[i]    = xm;
+    p.xt[i]         = x4;
+    float3 const x0 = InitialPosition(
+        make_float3(x4.x, x4.y, x4.z), vtm1, make_float3(v4.x, v4.y, v4.z), make_float3(a4.x, a4.y, a4.z), p.sdt,
+        p.sdt2, p.strategy);
+    float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
+    p.pos[i]       = o;
+    if constexpr (kChebyshev)
+        p.pos[p.pOff + i] = o;
+    if (p.snap != nullptr)
+        p.snap[i] = o;
+}
+
+// velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
+// v(t-1) <- v like the reference's UpdateBdfState (gpu/impl/vbd/Integrator.cu:329-347)
+__device__ __forceinline__ void PostStepVertex(StepParams const& p, uint32_t i)
+{
+    float4 const x4  = __ldcg(p.pos + p.pOff + i);
+    float4 const xt4 = __ldcg(p.xt + i);
+    float4 v4        = __ldcg(p.vel + i);
+    if (p.vtm1 != nullptr)
+        p.vtm1[i] = v4;
+    v4.x     = __fdiv_rn(__fsub_rn(x4.x, xt4.x), p.sdt);
+    v4.y     = __fdiv_rn(__fsub_rn(x4.y, xt4.y), p.sdt);
+    v4.z     = __fdiv_rn(__fsub_rn(x4.z, xt4.z), p.sdt);
+    p.vel[i] = v4;
+}
+
+template <bool kChebyshev>
+__global__ void PreStepKernel(const __grid_constant__ StepParams p)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < static_cast<uint32_t>(p.nVerts))
+        PreStepVertex<kChebyshev>(p, i, 0);
 }
 
 // Record source of the direct kernel: each warp reads its blocks straight from global memory
@@ -195,6 +279,7 @@ __device__ __forceinline__ void ProcessTile(
     uint4 const td,
     float4* __restrict__ stage,
     RecordSource& src,
+    int color,
     int k,
     float omega,
     uint32_t lane,
@@ -294,26 +379,78 @@ __device__ __forceinline__ void ProcessTile(
     }
     if (valid && (lane & ((1u << lw) - 1u)) == 0u)
     {
-        h00 += hd;
-        h11 += hd;
-        h22 += hd;
+        h00 = __fadd_rn(h00, hd);
+        h11 = __fadd_rn(h11, hd);
+        h22 = __fadd_rn(h22, hd);
         float x = xi.x, y = xi.y, z = xi.z;
         if constexpr (kDamping)
         {
             float4 const xt = __ldcg(p.xt + vi);
             float const D   = p.dampD;
             float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
-            g0 += D * (h00 * ex + h01 * ey + h02 * ez);
-            g1 += D * (h01 * ex + h11 * ey + h12 * ez);
-            g2 += D * (h02 * ex + h12 * ey + h22 * ez);
+            g0 = fmaf(D, fmaf(h02, ez, fmaf(h01, ey, __fmul_rn(h00, ex))), g0);
+            g1 = fmaf(D, fmaf(h12, ez, fmaf(h11, ey, __fmul_rn(h01, ex))), g1);
+            g2 = fmaf(D, fmaf(h22, ez, fmaf(h12, ey, __fmul_rn(h02, ex))), g2);
+            // explicit roundings from here to the Newton step: the statements around the (runtime-optional)
+            // contact block must not be contracted differently in the different kernels that inline this code
             float const sc = 1.f + D;
-            h00 *= sc, h01 *= sc, h02 *= sc, h11 *= sc, h12 *= sc, h22 *= sc;
+            h00 = __fmul_rn(h00, sc), h01 = __fmul_rn(h01, sc), h02 = __fmul_rn(h02, sc);
+            h11 = __fmul_rn(h11, sc), h12 = __fmul_rn(h12, sc), h22 = __fmul_rn(h22, sc);
+        }
+        if constexpr (kDamping)
+        {
+            // vertex-triangle contact (gpu/impl/vbd/Kernels.cuh:203-223): area-scaled penalty over <= 8 triangles.
+            // Triangle vertices are read as the reference's per-colour write buffer makes them visible: colours
+            // already swept in this iteration -> current values, later colours -> previous iterate, the colour
+            // being swept -> the values it had when the iteration started (snapshot).
+            if (p.fc != nullptr)
+            {
+                int const* fcv = p.fc + static_cast<size_t>(vi) * kMaxContacts;
+                int f[kMaxContacts];
+                int nContacts = 0;
+                float sumfa   = 0.f;
+#pragma unroll
+                for (int c = 0; c < kMaxContacts; ++c)
+                {
+                    f[c] = __ldcg(fcv + c);
+                    if (f[c] >= 0)
+                        ++nContacts;
+                }
+                for (int c = 0; c < nContacts; ++c)
+                    sumfa += __ldg(p.FA + f[c]);
+                if (nContacts > 0)
+                {
+                    float const kC      = __ldg(p.XVA + vi) * p.muC / sumfa;
+                    uint32_t const cb   = __ldg(p.colorVertexBegin + color), ce = __ldg(p.colorVertexBegin + color + 1);
+                    float4 const* snapK = p.snap + static_cast<size_t>(k & 1) * p.nVerts;
+                    float3 const xtv    = F3(__ldcg(p.xt + vi));
+                    float gC[3] = {0.f, 0.f, 0.f}, HC[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int c = 0; c < nContacts; ++c)
+                    {
+                        int4 const tri   = __ldg(p.triF + f[c]);
+                        int const id[3]  = {tri.x, tri.y, tri.z};
+                        float3 xf[3], xtf[3];
+                        for (int a = 0; a < 3; ++a)
+                        {
+                            uint32_t const j = static_cast<uint32_t>(id[a]);
+                            float4 const q   = j < cb ? __ldcg(p.pos + j) : j >= ce ? __ldcg(p.pos + p.pOff + j) : __ldcg(snapK + j);
+                            xf[a]            = F3(q);
+                            xtf[a]           = F3(__ldcg(p.xt + j));
+                        }
+                        AccumulateVertexTriangleContact(xtv, make_float3(x, y, z), xtf, xf, p.sdt, kC * __ldg(p.FA + f[c]), p.muF,
+                                                        p.epsv, gC, HC);
+                    }
+                    g0 = __fadd_rn(g0, gC[0]), g1 = __fadd_rn(g1, gC[1]), g2 = __fadd_rn(g2, gC[2]);
+                    h00 = __fadd_rn(h00, HC[0]), h01 = __fadd_rn(h01, HC[1]), h02 = __fadd_rn(h02, HC[2]);
+                    h11 = __fadd_rn(h11, HC[3]), h12 = __fadd_rn(h12, HC[4]), h22 = __fadd_rn(h22, HC[5]);
+                }
+            }
         }
         float const K   = xm.w / p.sdt2;
-        h00 += K, h11 += K, h22 += K;
-        g0 += K * (x - xm.x);
-        g1 += K * (y - xm.y);
-        g2 += K * (z - xm.z);
+        h00 = __fadd_rn(h00, K), h11 = __fadd_rn(h11, K), h22 = __fadd_rn(h22, K);
+        g0 = fmaf(K, x - xm.x, g0);
+        g1 = fmaf(K, y - xm.y, g1);
+        g2 = fmaf(K, z - xm.z, g2);
         // Newton step with the explicit cofactor inverse of the symmetric 3x3
         float const i00 = h11 * h22 - h12 * h12;
         float const i01 = h02 * h12 - h01 * h22;
@@ -325,9 +462,9 @@ __device__ __forceinline__ void ProcessTile(
             float const i12 = h01 * h02 - h00 * h12;
             float const i22 = h00 * h11 - h01 * h01;
             float const r   = 1.f / det;
-            x -= r * (i00 * g0 + i01 * g1 + i02 * g2);
-            y -= r * (i01 * g0 + i11 * g1 + i12 * g2);
-            z -= r * (i02 * g0 + i12 * g1 + i22 * g2);
+            x = fmaf(-r, fmaf(i02, g2, fmaf(i01, g1, __fmul_rn(i00, g0))), x);
+            y = fmaf(-r, fmaf(i12, g2, fmaf(i11, g1, __fmul_rn(i01, g0))), y);
+            z = fmaf(-r, fmaf(i22, g2, fmaf(i12, g1, __fmul_rn(i02, g0))), z);
         }
         float4 const raw = make_float4(x, y, z, 0.f);
         if constexpr (kChebyshev)
@@ -338,17 +475,21 @@ __device__ __forceinline__ void ProcessTile(
             float4 out = raw;
             if (k > 1)
             {
-                out.x = omega * (x - h2.x) + h2.x;
-                out.y = omega * (y - h2.y) + h2.y;
-                out.z = omega * (z - h2.z) + h2.z;
+                out.x = fmaf(omega, x - h2.x, h2.x);
+                out.y = fmaf(omega, y - h2.y, h2.y);
+                out.z = fmaf(omega, z - h2.z, h2.z);
             }
             p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
             p.pos[vi]          = raw;
             p.pos[p.pOff + vi] = out;
+            if (p.snap != nullptr)
+                p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = out;  // what iteration k+1 starts from
         }
         else
         {
             p.pos[vi] = raw;
+            if (p.snap != nullptr)
+                p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;
         }
     }
 }
@@ -369,7 +510,7 @@ __device__ __forceinline__ void SweepColor(StepParams const& p, int color, int k
         if (tr && lane == 0)
             tr[4] = GlobalTimer() + (td.x & 0u);  // tile descriptor arrived
         DirectRecords src{p.records + static_cast<size_t>(td.x) * kBlockFloat4 + lane};
-        ProcessTile<kChebyshev, kDamping, true>(p, td, stage, src, k, omega, lane, tr);
+        ProcessTile<kChebyshev, kDamping, true>(p, td, stage, src, color, k, omega, lane, tr);
         if (tr && lane == 0)
             tr[7] = GlobalTimer();  // first tile of warp 0 finished
     }
@@ -385,54 +526,9 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
     uint32_t const gstride = gridDim.x * blockDim.x;
     for (int s = 0; s < p.substeps; ++s)
     {
-        // pre-step (fused with the velocity update of the previous substep):
-        //   v = (x - xt)/h; xt = x; xtilde = xt + h v + h^2 a; x = initial guess
-        for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
-        {
-            float4 const x4 = __ldcg(p.pos + p.pOff + i);
-            float4 v4       = __ldcg(p.vel + i);
-            float3 vprev    = make_float3(v4.x, v4.y, v4.z);
-            if (s > 0)
-            {
-                float4 const xt4 = __ldcg(p.xt + i);
-                v4.x = (x4.x - xt4.x) / p.sdt;
-                v4.y = (x4.y - xt4.y) / p.sdt;
-                v4.z = (x4.z - xt4.z) / p.sdt;
-                p.vel[i] = v4;
-            }
-            // "previous velocity" of InitialPositionsForSolve: the CPU reference passes vt == v
-            // (sim/vbd/Integrator.cpp:32,61-68); the GPU reference keeps a real v(t-1)
-            float3 vtm1 = make_float3(v4.x, v4.y, v4.z);
-            if (p.vtm1 != nullptr)
-            {
-                if (s > 0)
-                    vtm1 = vprev;
-                else
-                {
-                    float4 const q = __ldcg(p.vtm1 + i);
-                    vtm1           = make_float3(q.x, q.y, q.z);
-                }
-            }
-            float4 const a4 = __ldg(p.aext + i);
-            float4 xm       = __ldcg(p.xtildeM + i);
-            xm.x            = x4.x + p.sdt * v4.x + p.sdt2 * a4.x;
-            xm.y            = x4.y + p.sdt * v4.y + p.sdt2 * a4.y;
-            xm.z            = x4.z + p.sdt * v4.z + p.sdt2 * a4.z;
-            p.xtildeM[i]    = xm;
-            p.xt[i]         = x4;
-            float3 const x0 = InitialPosition(
-                make_float3(x4.x, x4.y, x4.z),
-                vtm1,
-                make_float3(v4.x, v4.y, v4.z),
-                make_float3(a4.x, a4.y, a4.z),
-                p.sdt,
-                p.sdt2,
-                p.strategy);
-            float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
-            p.pos[i]       = o;
-            if constexpr (kChebyshev)
-                p.pos[p.pOff + i] = o;
-        }
+        if (!p.skipPreStep)
+            for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+                PreStepVertex<kChebyshev>(p, i, s);
         GridBarrier(p.barrier, target);
         for (int k = 0; k < p.iterations; ++k)
         {
@@ -447,26 +543,12 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
                         tr[0] = GlobalTimer();
                 }
                 SweepColor<kChebyshev, kDamping>(p, c, k, omega, stage, tr);
-                if (tr != nullptr && threadIdx.x == 0)
-                    tr[1] = GlobalTimer();  // warp 0 done
                 GridBarrier(p.barrier, target, tr);
             }
         }
     }
-    // velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
-    // v(t-1) <- v like the reference's UpdateBdfState (gpu/impl/vbd/Integrator.cu:329-347)
     for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
-    {
-        float4 const x4  = __ldcg(p.pos + p.pOff + i);
-        float4 const xt4 = __ldcg(p.xt + i);
-        float4 v4        = __ldcg(p.vel + i);
-        if (p.vtm1 != nullptr)
-            p.vtm1[i] = v4;
-        v4.x     = (x4.x - xt4.x) / p.sdt;
-        v4.y     = (x4.y - xt4.y) / p.sdt;
-        v4.z     = (x4.z - xt4.z) / p.sdt;
-        p.vel[i] = v4;
-    }
+        PostStepVertex(p, i);
 }
 
 }  // namespace vbdx

@@ -251,45 +251,9 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     uint32_t const gstride = gridDim.x * (nWarps * 32);
     for (int s = 0; s < p.substeps; ++s)
     {
-        for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
-        {
-            float4 const x4 = __ldcg(p.pos + p.pOff + i);
-            float4 v4       = __ldcg(p.vel + i);
-            float3 const vprev = make_float3(v4.x, v4.y, v4.z);
-            if (s > 0)
-            {
-                float4 const xt4 = __ldcg(p.xt + i);
-                v4.x = (x4.x - xt4.x) / p.sdt;
-                v4.y = (x4.y - xt4.y) / p.sdt;
-                v4.z = (x4.z - xt4.z) / p.sdt;
-                p.vel[i] = v4;
-            }
-            float3 vtm1 = make_float3(v4.x, v4.y, v4.z);
-            if (p.vtm1 != nullptr)
-            {
-                if (s > 0)
-                    vtm1 = vprev;
-                else
-                {
-                    float4 const q = __ldcg(p.vtm1 + i);
-                    vtm1           = make_float3(q.x, q.y, q.z);
-                }
-            }
-            float4 const a4 = __ldg(p.aext + i);
-            float4 xm       = __ldcg(p.xtildeM + i);
-            xm.x            = x4.x + p.sdt * v4.x + p.sdt2 * a4.x;
-            xm.y            = x4.y + p.sdt * v4.y + p.sdt2 * a4.y;
-            xm.z            = x4.z + p.sdt * v4.z + p.sdt2 * a4.z;
-            p.xtildeM[i]    = xm;
-            p.xt[i]         = x4;
-            float3 const x0 = InitialPosition(
-                make_float3(x4.x, x4.y, x4.z), vtm1, make_float3(v4.x, v4.y, v4.z),
-                make_float3(a4.x, a4.y, a4.z), p.sdt, p.sdt2, p.strategy);
-            float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
-            p.pos[i]       = o;
-            if constexpr (kChebyshev)
-                p.pos[p.pOff + i] = o;
-        }
+        if (!p.skipPreStep)
+            for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+                PreStepVertex<kChebyshev>(p, i, s);
         NamedArrive(kBarArrived, blockDim.x);
         NamedSync(kBarFenced, blockDim.x);
         NamedSync(kBarReleased, blockDim.x);
@@ -347,7 +311,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     deferred = nextValid && !sameSweep;
                     WaitRecords();
                     SmemRecords src{recBuf + lane};
-                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, k, omega, lane, tr0, prefetchNext);
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), k, omega, lane, tr0, prefetchNext);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     gathered = nextGathered;
@@ -391,17 +355,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         }
     }
     for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
-    {
-        float4 const x4  = __ldcg(p.pos + p.pOff + i);
-        float4 const xt4 = __ldcg(p.xt + i);
-        float4 v4        = __ldcg(p.vel + i);
-        if (p.vtm1 != nullptr)
-            p.vtm1[i] = v4;
-        v4.x     = (x4.x - xt4.x) / p.sdt;
-        v4.y     = (x4.y - xt4.y) / p.sdt;
-        v4.z     = (x4.z - xt4.z) / p.sdt;
-        p.vel[i] = v4;
-    }
+        PostStepVertex(p, i);
 }
 
 }  // namespace vbdx

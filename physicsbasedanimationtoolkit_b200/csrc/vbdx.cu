@@ -3,6 +3,8 @@
 // setup_kernels.cuh / step_kernel.cuh.  No Thrust/CUB dispatch, no CPU fallback.
 #include "../../include/vbdx.h"
 
+#include "device_buffer.cuh"
+#include "contact_host.cuh"
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
 #include "step_kernel_pipe.cuh"
@@ -18,65 +20,6 @@
 #include <vector>
 
 namespace vbdx {
-
-struct Error : std::runtime_error {
-    vbdx_status status;
-    Error(vbdx_status s, std::string const& what) : std::runtime_error(what), status(s) {}
-};
-
-#define VBDX_CUDA(call)                                                                          \
-    do                                                                                           \
-    {                                                                                            \
-        cudaError_t const err__ = (call);                                                        \
-        if (err__ != cudaSuccess)                                                                \
-            throw ::vbdx::Error(                                                                 \
-                err__ == cudaErrorMemoryAllocation ? VBDX_OUT_OF_MEMORY : VBDX_CUDA_ERROR,       \
-                std::string(#call) + ": " + cudaGetErrorString(err__));                          \
-    } while (0)
-
-static void Require(bool cond, char const* what)
-{
-    if (!cond)
-        throw Error(VBDX_INVALID_ARGUMENT, what);
-}
-
-// plain device allocation with byte accounting
-template <class T>
-struct DevBuf {
-    T* p     = nullptr;
-    size_t n = 0;
-    DevBuf() = default;
-    DevBuf(DevBuf const&)            = delete;
-    DevBuf& operator=(DevBuf const&) = delete;
-    ~DevBuf() { Free(); }
-    void Alloc(size_t count, int64_t* accounting = nullptr)
-    {
-        Free();
-        n = count;
-        if (count == 0)
-            return;
-        VBDX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
-        if (accounting)
-            *accounting += static_cast<int64_t>(count * sizeof(T));
-    }
-    void Free()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-    void Upload(T const* src, size_t count, cudaStream_t s)
-    {
-        VBDX_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
-    }
-    void Download(T* dst, size_t count, cudaStream_t s) const
-    {
-        VBDX_CUDA(cudaMemcpyAsync(dst, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
-    }
-};
-
-static inline int Blocks(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
 using StepKernelFn = void (*)(StepParams);
 using TmaKernelFn  = void (*)(TmaParams);
@@ -127,6 +70,8 @@ struct Integrator {
     DevBuf<double> dStaging;  // 3 nV doubles
     DevBuf<unsigned long long> dTrace;
     int traceIteration = -1;
+    ContactState contact;
+    double muC = 1e6, muF = 0.3, epsv = 1e-3;
 
     ~Integrator()
     {
@@ -141,7 +86,7 @@ struct Integrator {
     StepKernelFn Kernel() const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-        bool const damp = kD != 0.0;
+        bool const damp = kD != 0.0 || contact.enabled;  // the "extras" variants carry damping and contact
         if (cheb)
             return damp ? StepKernel<true, true> : StepKernel<true, false>;
         return damp ? StepKernel<false, true> : StepKernel<false, false>;
@@ -150,7 +95,7 @@ struct Integrator {
     PipeKernelFn KernelPipe() const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-        bool const damp = kD != 0.0;
+        bool const damp = kD != 0.0 || contact.enabled;  // the "extras" variants carry damping and contact
         if (cheb)
             return damp ? StepKernelPipe<true, true> : StepKernelPipe<true, false>;
         return damp ? StepKernelPipe<false, true> : StepKernelPipe<false, false>;
@@ -159,7 +104,7 @@ struct Integrator {
     TmaKernelFn KernelTma() const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-        bool const damp = kD != 0.0;
+        bool const damp = kD != 0.0 || contact.enabled;  // the "extras" variants carry damping and contact
         if (cheb)
             return damp ? StepKernelTma<true, true> : StepKernelTma<true, false>;
         return damp ? StepKernelTma<false, true> : StepKernelTma<false, false>;
@@ -453,6 +398,68 @@ void Integrator::Create(vbdx_data_desc const& d)
     ++kernelLaunches;
     VBDX_CUDA(cudaStreamSynchronize(stream));
     VBDX_CUDA(cudaGetLastError());
+
+    // ---- vertex-triangle contact (Data::V, F, B; sim/vbd/Data.cpp:34-54 for the areas)
+    muC = d.muC, muF = d.muF, epsv = d.epsv;
+    if (d.nF > 0 && d.nCV > 0)
+    {
+        Require(d.F != nullptr && d.V != nullptr, "collision mesh pointers missing");
+        Require(d.active_set_update_frequency >= 1, "active set update frequency must be >= 1");
+        ContactState& cs = contact;
+        cs.nCV = static_cast<uint32_t>(d.nCV), cs.nF = static_cast<uint32_t>(d.nF);
+        cs.updateFrequency = d.active_set_update_frequency;
+        std::vector<int32_t> Bh(nV), Vh(d.nCV);
+        std::vector<int4> Fh(d.nF);
+        std::vector<float> XVAh(nV, 0.f), FAh(d.nF);
+        std::vector<double> xva(nV, 0.0);
+        for (int64_t i = 0; i < nV; ++i)
+            Bh[plan.old2new[i]] = d.B ? static_cast<int32_t>(d.B[i]) : 1;  // default body map: all ones (sim/vbd/Data.cpp:27-30)
+        for (int64_t k = 0; k < d.nCV; ++k)
+        {
+            Require(d.V[k] >= 0 && d.V[k] < nV, "collision vertex index out of range");
+            Vh[k] = plan.old2new[d.V[k]];
+        }
+        for (int64_t f = 0; f < d.nF; ++f)
+        {
+            int64_t const a = d.F[3 * f], b = d.F[3 * f + 1], c = d.F[3 * f + 2];
+            Require(a >= 0 && a < nV && b >= 0 && b < nV && c >= 0 && c < nV, "collision triangle index out of range");
+            Fh[f] = make_int4(plan.old2new[a], plan.old2new[b], plan.old2new[c], 0);
+            double ab[3], ac[3];
+            for (int k = 0; k < 3; ++k)
+            {
+                ab[k] = d.X[3 * b + k] - d.X[3 * a + k];
+                ac[k] = d.X[3 * c + k] - d.X[3 * a + k];
+            }
+            double const nx = ab[1] * ac[2] - ab[2] * ac[1], ny = ab[2] * ac[0] - ab[0] * ac[2], nz = ab[0] * ac[1] - ab[1] * ac[0];
+            double const dbl = std::sqrt(nx * nx + ny * ny + nz * nz);
+            xva[a] += dbl / 6, xva[b] += dbl / 6, xva[c] += dbl / 6;
+            FAh[f] = static_cast<float>(dbl / 2);
+        }
+        for (int64_t i = 0; i < nV; ++i)
+            XVAh[plan.old2new[i]] = static_cast<float>(xva[i]);
+        // internal id range of every colour (swept vertices are numbered colour-major)
+        std::vector<uint32_t> cvb(plan.nColors + 1, 0);
+        for (int32_t c = 0; c < plan.nColors; ++c)
+        {
+            uint32_t const t0 = plan.colorTileBegin[c];
+            cvb[c]            = t0 < plan.tiles.size() ? plan.tiles[t0].vbase : static_cast<uint32_t>(plan.nActive);
+        }
+        cvb[plan.nColors] = static_cast<uint32_t>(plan.nActive);
+        for (int32_t c = plan.nColors - 1; c >= 0; --c)  // empty colours inherit the next begin
+            if (plan.colorTileBegin[c] == plan.colorTileBegin[c + 1])
+                cvb[c] = cvb[c + 1];
+        cs.B.Alloc(nV, &deviceBytes), cs.V.Alloc(d.nCV, &deviceBytes), cs.F.Alloc(d.nF, &deviceBytes);
+        cs.XVA.Alloc(nV, &deviceBytes), cs.FA.Alloc(d.nF, &deviceBytes), cs.colorVertexBegin.Alloc(cvb.size(), &deviceBytes);
+        cs.B.Upload(Bh.data(), nV, stream), cs.V.Upload(Vh.data(), d.nCV, stream), cs.F.Upload(Fh.data(), d.nF, stream);
+        cs.XVA.Upload(XVAh.data(), nV, stream), cs.FA.Upload(FAh.data(), d.nF, stream);
+        cs.colorVertexBegin.Upload(cvb.data(), cvb.size(), stream);
+        cs.mesh = ContactMesh{cs.B.p, cs.V.p, cs.F.p, cs.nCV, cs.nF};
+        cs.Alloc(nV, &deviceBytes, stream);
+        // snapshot buffer 0 = initial positions
+        VBDX_CUDA(cudaMemcpyAsync(cs.snap.p, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        VBDX_CUDA(cudaStreamSynchronize(stream));
+        cs.enabled = true;
+    }
 }
 
 void Integrator::Step(double dt, int iterations, int substeps, bool sync)
@@ -511,35 +518,73 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.barrier      = dBarrier.p;
     p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
     p.traceIteration = traceIteration;
-    VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
+    if (contact.enabled)
+    {
+        p.fc               = contact.fc.p;
+        p.triF             = contact.F.p;
+        p.XVA              = contact.XVA.p;
+        p.FA               = contact.FA.p;
+        p.snap             = contact.snap.p;
+        p.colorVertexBegin = contact.colorVertexBegin.p;
+        p.muC = static_cast<float>(muC), p.muF = static_cast<float>(muF), p.epsv = static_cast<float>(epsv);
+    }
+    auto launchStep = [&](StepParams const& q) {
+        VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
+        if (variant == VBDX_KERNEL_PIPELINED)
+        {
+            PipeParams pp{};
+            pp.base      = q;
+            pp.maxIters  = maxTileIters;
+            void* args[] = {&pp};
+            VBDX_CUDA(cudaLaunchCooperativeKernel(
+                reinterpret_cast<void const*>(KernelPipe()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+        }
+        else if (variant == VBDX_KERNEL_TMA)
+        {
+            TmaParams tp{};
+            tp.base          = q;
+            tp.ctaBlockBegin = dCtaBlockBegin.p;
+            tp.ringSlots     = ringSlots;
+            void* args[]     = {&tp};
+            VBDX_CUDA(cudaLaunchCooperativeKernel(
+                reinterpret_cast<void const*>(KernelTma()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+        }
+        else
+        {
+            StepParams qq = q;
+            void* args[]  = {&qq};
+            VBDX_CUDA(cudaLaunchCooperativeKernel(
+                reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+        }
+        ++kernelLaunches;
+    };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
-    if (variant == VBDX_KERNEL_PIPELINED)
-    {
-        PipeParams pp{};
-        pp.base      = p;
-        pp.maxIters  = maxTileIters;
-        void* args[] = {&pp};
-        VBDX_CUDA(cudaLaunchCooperativeKernel(
-            reinterpret_cast<void const*>(KernelPipe()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
-    }
-    else if (variant == VBDX_KERNEL_TMA)
-    {
-        TmaParams tp{};
-        tp.base          = p;
-        tp.ctaBlockBegin = dCtaBlockBegin.p;
-        tp.ringSlots     = ringSlots;
-        void* args[]     = {&tp};
-        VBDX_CUDA(cudaLaunchCooperativeKernel(
-            reinterpret_cast<void const*>(KernelTma()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
-    }
+    if (!contact.enabled)
+        launchStep(p);
     else
     {
-        void* args[] = {&p};
-        VBDX_CUDA(cudaLaunchCooperativeKernel(
-            reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+        // gpu/impl/vbd/Integrator.cu:82-103: active set from the full-step predictor, then per substep
+        // inertial targets + initial guess, (every `frequency` substeps) nearest triangles from the initial
+        // guess, the solve, the velocity update; finally prune vertices that left the surface
+        float4 const* xFinal = dPos.p + p.pOff;
+        contact.InitializeActiveSet(xFinal, dVel.p, dAext.p, nV, static_cast<float>(dt), stream, &kernelLaunches);
+        StepParams q  = p;
+        q.substeps    = 1;
+        q.skipPreStep = 1;
+        for (int s = 0; s < substeps; ++s)
+        {
+            if (cheb)
+                PreStepKernel<true><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+            else
+                PreStepKernel<false><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+            ++kernelLaunches;
+            if (s % contact.updateFrequency == 0)
+                contact.NearestPass(xFinal, 0, stream, &kernelLaunches);
+            launchStep(q);
+        }
+        contact.NearestPass(xFinal, 1, stream, &kernelLaunches);
     }
     VBDX_CUDA(cudaEventRecord(evEnd, stream));
-    ++kernelLaunches;
     stepTimed = true;
     if (sync)
     {
@@ -781,9 +826,98 @@ vbdx_status vbdx_set_block_size(vbdx_integrator* h, int32_t block_size)
 
 vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3], const float max3[3])
 {
-    (void)min3;
-    (void)max3;
-    return NeedHandle(h);
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        vbdx::Require(min3 && max3 && max3[0] > min3[0] && max3[1] > min3[1] && max3[2] > min3[2], "scene bounding box must have positive extent");
+        if (h->impl.contact.enabled)
+        {
+            VBDX_CUDA(cudaSetDevice(h->impl.device));
+            h->impl.contact.SetWorldBox(min3, max3, h->impl.stream);
+        }
+    });
+}
+
+vbdx_status vbdx_get_contact_state(vbdx_integrator* h, int32_t* active, int32_t* nn, int64_t* nActive)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I  = h->impl;
+        auto& cs = I.contact;
+        vbdx::Require(cs.enabled, "the integrator was created without a collision mesh");
+        VBDX_CUDA(cudaSetDevice(I.device));
+        std::vector<uint8_t> a(cs.nCV);
+        cs.active.Download(a.data(), cs.nCV, I.stream);
+        if (nn)
+            cs.nn.Download(nn, static_cast<size_t>(cs.nCV) * vbdx::kMaxContacts, I.stream);
+        uint32_t na = 0;
+        cs.nActive.Download(&na, 1, I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        if (active)
+            for (uint32_t k = 0; k < cs.nCV; ++k)
+                active[k] = a[k];
+        if (nActive)
+            *nActive = na;
+    });
+}
+
+vbdx_status vbdx_debug_bvh_build(int64_t n, const float* lo, const float* hi, const float wmin[3], const float wmax[3], int32_t* child,
+                                 int32_t* parent, int32_t* rightmost, int32_t* inds, uint32_t* codes, float* nodeLo, float* nodeHi)
+{
+    return Guard([&] {
+        vbdx::Require(n >= 1 && lo && hi && wmin && wmax, "vbdx_debug_bvh_build: bad arguments");
+        if (vbdx_device_count() == 0)
+            throw vbdx::Error(VBDX_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+        cudaStream_t s = nullptr;
+        int64_t bytes = 0, launches = 0;
+        vbdx::DeviceBvh bvh;
+        bvh.Alloc(static_cast<uint32_t>(n), &bytes);
+        std::vector<float4> l(n), u(n);
+        for (int64_t i = 0; i < n; ++i)
+        {
+            l[i] = make_float4(lo[3 * i], lo[3 * i + 1], lo[3 * i + 2], 0.f);
+            u[i] = make_float4(hi[3 * i], hi[3 * i + 1], hi[3 * i + 2], 0.f);
+        }
+        vbdx::DevBuf<float4> dl, du;
+        vbdx::DevBuf<vbdx::WorldBox> dw;
+        dl.Alloc(n), du.Alloc(n), dw.Alloc(1);
+        dl.Upload(l.data(), n, s), du.Upload(u.data(), n, s);
+        vbdx::WorldBox w;
+        for (int d = 0; d < 3; ++d)
+            w.lo[d] = wmin[d], w.ext[d] = wmax[d] - wmin[d];
+        dw.Upload(&w, 1, s);
+        bvh.Build(dl.p, du.p, dw.p, s, &launches);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        size_t const ni = static_cast<size_t>(n - 1);
+        if (child && ni)
+        {
+            bvh.child0.Download(child, ni, s);
+            bvh.child1.Download(child + ni, ni, s);
+        }
+        if (rightmost && ni)
+        {
+            bvh.right0.Download(rightmost, ni, s);
+            bvh.right1.Download(rightmost + ni, ni, s);
+        }
+        if (parent)
+            bvh.parent.Download(parent, 2 * n - 1, s);
+        if (inds)
+            bvh.inds.Download(reinterpret_cast<uint32_t*>(inds), n, s);
+        if (codes)
+            bvh.codes.Download(codes, n, s);
+        std::vector<float4> nl(2 * n - 1), nh(2 * n - 1);
+        bvh.nodeLo.Download(nl.data(), 2 * n - 1, s);
+        bvh.nodeHi.Download(nh.data(), 2 * n - 1, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        for (int64_t k = 0; k < 2 * n - 1; ++k)
+        {
+            if (nodeLo)
+                nodeLo[3 * k] = nl[k].x, nodeLo[3 * k + 1] = nl[k].y, nodeLo[3 * k + 2] = nl[k].z;
+            if (nodeHi)
+                nodeHi[3 * k] = nh[k].x, nodeHi[3 * k + 1] = nh[k].y, nodeHi[3 * k + 2] = nh[k].z;
+        }
+    });
 }
 
 vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream)

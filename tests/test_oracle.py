@@ -103,3 +103,26 @@ def test_port_matches_reference_golden_config1():
 def test_live_reference_matches_golden():
     x, _, _ = run("beam_small_cheb", "reference")
     assert np.array_equal(x, GOLD["beam_small_cheb/x"])
+
+
+def _stacked():
+    Xb, Tb = meshes.tet_grid(2, 2, 1, 0.5)
+    Xt, Tt = meshes.tet_grid(1, 1, 1, 0.5, origin=(0.2, 0.3, 0.53))
+    X = np.concatenate([Xb, Xt], axis=1)
+    T = np.concatenate([Tb, Tt + Xb.shape[1]], axis=1)
+    B = np.concatenate([np.zeros(Xb.shape[1], np.int64), np.ones(Xt.shape[1], np.int64)])
+    F = meshes.boundary_facets(T)
+    return X, T, B, F, np.unique(F), np.flatnonzero(X[2] == 0)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_contact_oracle_supports_a_resting_body(kind):
+    """Contact oracle sanity: a cube dropped on a fixed slab comes to rest on it."""
+    X, T, B, F, V, dbc = _stacked()
+    o = oracle.Oracle(X, T, dbc=dbc, B=B, V=V, F=F, muC=1e5, kind=kind)
+    for _ in range(60):
+        o.step(0.01, 10, 1)
+    z = o.x[2, B == 1]
+    assert z.min() > 0.45 and (o.get("nn") >= 0).any()
+
+
