@@ -117,6 +117,9 @@ typedef struct vbdx_data_desc {
     int32_t flags;         /* VBDX_FLAG_* */
     int32_t kernel_variant;/* tuning: enum vbdx_kernel_variant; 0 = default */
     int32_t ring_slots;    /* tuning: shared-memory ring capacity in 1 KB record blocks (0 = as many as fit) */
+    const int64_t* ghosts; /* nGhosts vertices owned by another GPU (domain decomposition): never swept, never touched by
+                              the pre-step; their positions are written by the owner.  NULL for a single-GPU problem */
+    int64_t nGhosts;
     int32_t consumer_warps;/* tuning: (consumer) warps per CTA of the pipelined / TMA kernels (0 = default) */
     int32_t reserved;
 } vbdx_data_desc;
@@ -204,6 +207,22 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out);
 vbdx_status vbdx_get_adjacency(vbdx_integrator* h, int64_t* GVGp, int64_t* GVGe, int64_t* GVGilocal);
 vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, double* m);
 vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
+
+/* ---- multi-GPU domain decomposition (new: the reference is single-GPU) --------------------
+ * One handle per GPU/process.  Each handle simulates the vertices it owns plus a ghost layer (desc->ghosts).  After
+ * a colour is swept, the owner stores the new positions directly into the ghost slots of its peers over NVLink
+ * (peer-to-peer stores inside the persistent step kernel) and the colour barrier spans all GPUs.
+ *   1. vbdx_get_internal_ids: caller-order vertex -> device-internal slot (peers need the slots of their ghosts)
+ *   2. vbdx_dist_ipc_handles: 128 opaque bytes to all-gather between the processes (CUDA IPC handles)
+ *   3. vbdx_dist_connect: open the peers' buffers and install the send lists:
+ *        send_local[k]  caller-order id of an owned vertex,
+ *        send_peer[k]   rank that holds it as a ghost,
+ *        send_remote[k] that rank's internal slot of the ghost;  peer_nverts[r] = rank r's local vertex count.
+ * All ranks must then call vbdx_step with identical arguments. */
+vbdx_status vbdx_get_internal_ids(vbdx_integrator* h, int64_t* old2new);
+vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128);
+vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
+                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote);
 
 /* Contact state after the last step, per collision vertex in the order of desc->V
  * (gpu/impl/contact/VertexTriangleMixedCcdDcd.cuh: active, nn): active[nCV] (0/1), nn[8 * nCV] nearest triangles

@@ -20,7 +20,7 @@ def _interleaved(a, dtype, nV, name):
 class DeviceIntegrator:
     _dtype = np.float32
 
-    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0):
+    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0, ghosts=None):
         L = _lib.lib()
         if data.x.size == 0:
             raise ValueError("Data.construct() must be called before creating an integrator")
@@ -65,6 +65,8 @@ class DeviceIntegrator:
         d.device, d.tile_iters, d.flags = int(device), int(tile_iters), int(flags)
         d.kernel_variant, d.ring_slots = int(kernel_variant), int(ring_slots)
         d.consumer_warps = int(consumer_warps)
+        d.ghosts = ptr(ghosts, np.int64)
+        d.nGhosts = 0 if ghosts is None else int(np.size(ghosts))
         # rest positions differ from x only if the caller edited data.x after construct(); the
         # element rest data must come from X (sim/vbd/Data.cpp:220-221)
         self._rest_differs = not np.array_equal(data.x, data.X)
@@ -183,3 +185,21 @@ class DeviceIntegrator:
         na = C.c_int64(0)
         _lib.check(self._L.vbdx_get_contact_state(self._h, active.ctypes.data, nn.ctypes.data, C.byref(na)))
         return active.astype(bool), nn, na.value
+
+    # ---- domain decomposition plumbing (see dist.py) -----------------------------------------
+    def internal_ids(self):
+        out = np.empty(self.nV, np.int64)
+        _lib.check(self._L.vbdx_get_internal_ids(self._h, out.ctypes.data))
+        return out
+
+    def ipc_handles(self):
+        out = np.zeros(128, np.uint8)
+        _lib.check(self._L.vbdx_dist_ipc_handles(self._h, out.ctypes.data))
+        return out
+
+    def dist_connect(self, rank, world, all_handles, peer_nverts, send_local, send_peer, send_remote):
+        all_handles = np.ascontiguousarray(all_handles, np.uint8)
+        peer_nverts = np.ascontiguousarray(peer_nverts, np.int64)
+        sl, sp, sr = (np.ascontiguousarray(a, np.int64) for a in (send_local, send_peer, send_remote))
+        _lib.check(self._L.vbdx_dist_connect(self._h, int(rank), int(world), all_handles.ctypes.data, peer_nverts.ctypes.data,
+                                             sl.size, sl.ctypes.data, sp.ctypes.data, sr.ctypes.data))

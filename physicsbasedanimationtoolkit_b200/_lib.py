@@ -34,6 +34,7 @@ class DataDesc(C.Structure):
         ("active_set_update_frequency", C.c_int32),
         ("device", C.c_int32), ("tile_iters", C.c_int32), ("flags", C.c_int32),
         ("kernel_variant", C.c_int32), ("ring_slots", C.c_int32),
+        ("ghosts", C.c_void_p), ("nGhosts", C.c_int64),
         ("consumer_warps", C.c_int32), ("reserved", C.c_int32),
     ]
 
@@ -75,6 +76,9 @@ SYMBOLS = {
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),
     "vbdx_set_scene_bounding_box": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_get_internal_ids": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_dist_ipc_handles": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_dist_connect": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_get_contact_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_debug_bvh_build": (C.c_int, [C.c_int64] + [C.c_void_p] * 11),
     "vbdx_debug_trace": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),

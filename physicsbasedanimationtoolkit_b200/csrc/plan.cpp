@@ -253,13 +253,18 @@ void BuildPlan(
     }
     {
         int64_t tail = plan.nActive;
-        for (int64_t i = 0; i < nV; ++i)
-            if (isDbc[i])
-            {
-                plan.new2old[tail] = static_cast<int32_t>(i);
-                plan.old2new[i]    = static_cast<int32_t>(tail);
-                ++tail;
-            }
+        for (int pass = 1; pass <= 2; ++pass)  // Dirichlet vertices, then ghosts
+        {
+            if (pass == 2)
+                plan.ghostBegin = tail;
+            for (int64_t i = 0; i < nV; ++i)
+                if (isDbc[i] == pass)
+                {
+                    plan.new2old[tail] = static_cast<int32_t>(i);
+                    plan.old2new[i]    = static_cast<int32_t>(tail);
+                    ++tail;
+                }
+        }
     }
     // tiles
     std::vector<int64_t> seenInTile(nV, -1);  // neighbour -> tile that already lists it

@@ -59,6 +59,17 @@ struct StepParams {
     const uint32_t* __restrict__ colorVertexBegin;  // nColors + 1: internal id range of every colour
     float muC, muF, epsv;
     int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path)
+    // multi-GPU domain decomposition (world == 1: single GPU)
+    uint32_t ghostBegin;                 // internal ids >= ghostBegin are ghosts: written by their owner GPU only
+    const uint32_t* __restrict__ sendPtr;  // per internal vertex < ghostBegin: range into sendDst (null: nothing to send)
+    const uint32_t* __restrict__ sendDst;  // peer rank << 28 | internal slot of the ghost on that peer
+    float4* peerPos[8];                  // position buffers of the peers (CUDA IPC mappings over NVLink)
+    uint32_t peerPOff[8];                // their previous-iterate offsets
+    unsigned int* peerFlags[8];          // their flag arrays: slot [rank] is written by this GPU
+    unsigned int* myFlags;               // slot r: last epoch GPU r finished;  slot 8: release epoch for this GPU's CTAs
+    unsigned int* distError;             // set when a peer did not show up in time
+    unsigned int epochBase;              // epochs used by earlier launches
+    int rank, world;
     unsigned long long* trace;  // optional [nColors][gridDim.x][kTraceStamps] timestamps of one iteration (diagnostics)
     int traceIteration;
 };
@@ -183,6 +194,23 @@ __device__ __forceinline__ float3 InitialPosition(
     return make_float3(fmaf(s, a.x, x.x), fmaf(s, a.y, x.y), fmaf(s, a.z, x.z));
 }
 
+// Domain decomposition: push the new position of an owned vertex into the ghost slots of the peers that hold
+// it (plain stores to peer memory; the colour barrier's system-scope release makes them visible).
+__device__ __forceinline__ void SendToPeers(StepParams const& p, uint32_t vi, float4 raw, float4 blended)
+{
+    if (p.sendPtr == nullptr)
+        return;
+    uint32_t const b = __ldg(p.sendPtr + vi), e = __ldg(p.sendPtr + vi + 1);
+    for (uint32_t k = b; k < e; ++k)
+    {
+        uint32_t const dst = __ldg(p.sendDst + k);
+        uint32_t const r = dst >> 28, slot = dst & 0x0fffffffu;
+        p.peerPos[r][slot] = raw;
+        if (p.peerPOff[r] != 0u)
+            p.peerPos[r][p.peerPOff[r] + slot] = blended;
+    }
+}
+
 // Per-vertex pre-step, fused with the velocity update of the previous substep
 // (sim/vbd/Integrator.cpp:31-35,39; sim/vbd/Kernels.h:29-94):
 //   v = (x - xt)/h [s > 0];  xt = x;  xtilde = xt + h v + h^2 a;  x = initial guess
@@ -229,6 +257,7 @@ __device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, i
         p.pos[p.pOff + i] = o;
     if (p.snap != nullptr)
         p.snap[i] = o;
+    SendToPeers(p, i, o, o);
 }
 
 // velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
@@ -250,7 +279,7 @@ template <bool kChebyshev>
 __global__ void PreStepKernel(const __grid_constant__ StepParams p)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < static_cast<uint32_t>(p.nVerts))
+    if (i < p.ghostBegin)
         PreStepVertex<kChebyshev>(p, i, 0);
 }
 
@@ -482,12 +511,14 @@ __device__ __forceinline__ void ProcessTile(
             p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
             p.pos[vi]          = raw;
             p.pos[p.pOff + vi] = out;
+            SendToPeers(p, vi, raw, out);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = out;  // what iteration k+1 starts from
         }
         else
         {
             p.pos[vi] = raw;
+            SendToPeers(p, vi, raw, raw);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;
         }
@@ -527,7 +558,7 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
     for (int s = 0; s < p.substeps; ++s)
     {
         if (!p.skipPreStep)
-            for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+            for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
                 PreStepVertex<kChebyshev>(p, i, s);
         GridBarrier(p.barrier, target);
         for (int k = 0; k < p.iterations; ++k)
@@ -547,7 +578,7 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
             }
         }
     }
-    for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+    for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
         PostStepVertex(p, i);
 }
 

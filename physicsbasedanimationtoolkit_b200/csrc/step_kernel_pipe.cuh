@@ -59,7 +59,29 @@ __device__ __forceinline__ void NamedSync(int id, uint32_t count)
 }
 constexpr int kBarArrived = 1, kBarReleased = 2, kBarFenced = 3;
 
-__device__ __forceinline__ void BarrierWarpStep(unsigned int* counter, unsigned int& target, uint32_t lane, unsigned long long* trace)
+__device__ __forceinline__ unsigned int LoadAcquireSys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void StoreReleaseSys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.  Domain decomposition
+// (p.world > 1): the barrier additionally spans the peers.  Every CTA fences at system scope (its warps
+// stored into peer memory) and arrives; CTA 0 waits for the local arrivals, publishes this GPU's epoch in
+// every peer's flag array (st.release.sys over NVLink), waits for every peer's epoch, and only then
+// releases the local CTAs through `myFlags[8]`.  A peer that never shows up raises distError instead of
+// hanging the GPU.
+__device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
+                                                unsigned long long* trace)
 {
     NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
     if (lane == 0)
@@ -67,16 +89,49 @@ __device__ __forceinline__ void BarrierWarpStep(unsigned int* counter, unsigned 
         if (trace)
             trace[2] = GlobalTimer();
         target += gridDim.x;
-        AddRelease(counter, 1u);
+        if (p.world > 1)
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        AddRelease(p.barrier, 1u);
         if (trace)
             trace[1] = GlobalTimer();
     }
     __syncwarp();
     NamedArrive(kBarFenced, blockDim.x);
+    ++epoch;
     if (lane == 0)
     {
-        while (LoadAcquire(counter) < target)
+        if (p.world <= 1)
         {
+            while (LoadAcquire(p.barrier) < target)
+            {
+            }
+        }
+        else if (blockIdx.x == 0)
+        {
+            while (LoadAcquire(p.barrier) < target)
+            {
+            }
+            unsigned int const e = p.epochBase + epoch;
+            for (int r = 0; r < p.world; ++r)
+                if (r != p.rank)
+                    StoreReleaseSys(p.peerFlags[r] + p.rank, e);
+            unsigned long long const t0 = GlobalTimer();
+            for (int r = 0; r < p.world; ++r)
+                if (r != p.rank)
+                    while (static_cast<int>(LoadAcquireSys(p.myFlags + r) - e) < 0)
+                        if (GlobalTimer() - t0 > 20000000000ull)  // 20 s: a peer is missing
+                        {
+                            atomicExch(p.distError, 1u);
+                            break;
+                        }
+            StoreReleaseGpu(p.myFlags + 8, e);
+        }
+        else
+        {
+            unsigned int const e = p.epochBase + epoch;
+            while (static_cast<int>(LoadAcquire(p.myFlags + 8) - e) < 0)
+            {
+            }
         }
         if (trace)
             trace[3] = GlobalTimer();
@@ -125,17 +180,17 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     if (warp == nWarps)
     {
         // ------------------------------ barrier warp ------------------------------
-        unsigned int target = 0;
+        unsigned int target = 0, epoch = 0;
         for (int s = 0; s < p.substeps; ++s)
         {
-            BarrierWarpStep(p.barrier, target, lane, nullptr);  // after the pre-step pass
+            BarrierWarpStep(p, target, epoch, lane, nullptr);  // after the pre-step pass
             for (int k = 0; k < p.iterations; ++k)
                 for (uint32_t c = 0; c < nC; ++c)
                 {
                     unsigned long long* tr = nullptr;
                     if (p.trace != nullptr && k == p.traceIteration)
                         tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
-                    BarrierWarpStep(p.barrier, target, lane, tr);
+                    BarrierWarpStep(p, target, epoch, lane, tr);
                 }
         }
         return;
@@ -252,7 +307,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     for (int s = 0; s < p.substeps; ++s)
     {
         if (!p.skipPreStep)
-            for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+            for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
                 PreStepVertex<kChebyshev>(p, i, s);
         NamedArrive(kBarArrived, blockDim.x);
         NamedSync(kBarFenced, blockDim.x);
@@ -354,7 +409,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             }
         }
     }
-    for (uint32_t i = gtid; i < static_cast<uint32_t>(p.nVerts); i += gstride)
+    for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
         PostStepVertex(p, i);
 }
 

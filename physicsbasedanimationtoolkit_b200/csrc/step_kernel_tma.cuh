@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
     for (int s = 0; s < p.substeps; ++s)
     {
         if (!p.skipPreStep)
-            for (uint32_t i = ctid; i < static_cast<uint32_t>(p.nVerts); i += cstride)
+            for (uint32_t i = ctid; i < p.ghostBegin; i += cstride)
                 PreStepVertex<kChebyshev>(p, i, s);
         ConsumerGridBarrier(p.barrier, target, nConsumerThreads);
 
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
             }
         }
     }
-    for (uint32_t i = ctid; i < static_cast<uint32_t>(p.nVerts); i += cstride)
+    for (uint32_t i = ctid; i < p.ghostBegin; i += cstride)
         PostStepVertex(p, i);
 }
 

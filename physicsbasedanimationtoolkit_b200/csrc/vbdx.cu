@@ -71,10 +71,22 @@ struct Integrator {
     DevBuf<unsigned long long> dTrace;
     int traceIteration = -1;
     ContactState contact;
+    // domain decomposition
+    int distRank = 0, distWorld = 1;
+    unsigned int distEpoch = 0;
+    DevBuf<unsigned int> dDistFlags;  // [0..7] peers' epochs, [8] local release, [9] error
+    DevBuf<uint32_t> dSendPtr, dSendDst;
+    float4* peerPos[8]        = {};
+    uint32_t peerPOff[8]      = {};
+    unsigned int* peerFlags[8] = {};
+    void* ipcOpened[16]        = {};
     double muC = 1e6, muF = 0.3, epsv = 1e-3;
 
     ~Integrator()
     {
+        for (void* q : ipcOpened)
+            if (q)
+                cudaIpcCloseMemHandle(q);
         if (evBegin)
             cudaEventDestroy(evBegin);
         if (evEnd)
@@ -172,6 +184,12 @@ void Integrator::Create(vbdx_data_desc const& d)
     {
         Require(d.dbc[k] >= 0 && d.dbc[k] < nV, "Dirichlet vertex index out of range");
         isDbc[d.dbc[k]] = 1;
+    }
+    Require(d.nGhosts >= 0 && (d.nGhosts == 0 || d.ghosts), "ghosts pointer missing");
+    for (int64_t k = 0; k < d.nGhosts; ++k)
+    {
+        Require(d.ghosts[k] >= 0 && d.ghosts[k] < nV, "ghost vertex index out of range");
+        isDbc[d.ghosts[k]] = 2;  // never swept, and never touched by the pre-step: the owner GPU writes it
     }
     if (d.colors)
     {
@@ -380,6 +398,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (flags & VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY)
         dVtm1.Alloc(nV, &deviceBytes);
     dBarrier.Alloc(1, &deviceBytes);
+    dDistFlags.Alloc(16, &deviceBytes);
+    VBDX_CUDA(cudaMemsetAsync(dDistFlags.p, 0, 16 * sizeof(unsigned int), stream));
     dStaging.Alloc(3 * nV, &deviceBytes);
     DevBuf<double> dV0, dA0;
     if (d.v)
@@ -516,6 +536,18 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     p.iterations   = iterations;
     p.substeps     = substeps;
     p.barrier      = dBarrier.p;
+    p.ghostBegin   = static_cast<uint32_t>(plan.ghostBegin);
+    p.rank = distRank, p.world = distWorld;
+    if (distWorld > 1)
+    {
+        p.sendPtr = dSendPtr.p, p.sendDst = dSendDst.p;
+        for (int r = 0; r < 8; ++r)
+            p.peerPos[r] = peerPos[r], p.peerPOff[r] = peerPOff[r], p.peerFlags[r] = peerFlags[r];
+        p.myFlags   = dDistFlags.p;
+        p.distError = dDistFlags.p + 9;
+        p.epochBase = distEpoch;
+        distEpoch += static_cast<unsigned int>(substeps) * (1u + static_cast<unsigned int>(iterations) * static_cast<unsigned int>(plan.nColors));
+    }
     p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
     p.traceIteration = traceIteration;
     if (contact.enabled)
@@ -589,6 +621,13 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
     if (sync)
     {
         VBDX_CUDA(cudaStreamSynchronize(stream));
+        if (distWorld > 1)
+        {
+            unsigned int e = 0;
+            VBDX_CUDA(cudaMemcpy(&e, dDistFlags.p + 9, sizeof(e), cudaMemcpyDeviceToHost));
+            if (e)
+                throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not reach the colour barrier within 20 s");
+        }
         float ms = 0;
         VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
         lastStepMs = ms;
@@ -835,6 +874,87 @@ vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3],
             VBDX_CUDA(cudaSetDevice(h->impl.device));
             h->impl.contact.SetWorldBox(min3, max3, h->impl.stream);
         }
+    });
+}
+
+vbdx_status vbdx_get_internal_ids(vbdx_integrator* h, int64_t* old2new)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    for (int64_t i = 0; i < h->impl.nV; ++i)
+        old2new[i] = h->impl.plan.old2new[i];
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        cudaIpcMemHandle_t hp, hf;
+        VBDX_CUDA(cudaIpcGetMemHandle(&hp, I.dPos.p));
+        VBDX_CUDA(cudaIpcGetMemHandle(&hf, I.dDistFlags.p));
+        std::memcpy(out128, &hp, 64);
+        std::memcpy(static_cast<char*>(out128) + 64, &hf, 64);
+    });
+}
+
+vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
+                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I = h->impl;
+        vbdx::Require(world >= 1 && world <= 8 && rank >= 0 && rank < world, "domain decomposition supports 1..8 GPUs of one node");
+        vbdx::Require(I.variant == VBDX_KERNEL_PIPELINED, "domain decomposition needs the pipelined kernel variant");
+        vbdx::Require(!I.contact.enabled, "contact is not supported together with domain decomposition yet");
+        VBDX_CUDA(cudaSetDevice(I.device));
+        bool const cheb = I.acceleration == VBDX_ACCEL_CHEBYSHEV;
+        for (int r = 0; r < world; ++r)
+        {
+            if (r == rank)
+                continue;
+            cudaIpcMemHandle_t hp, hf;
+            std::memcpy(&hp, static_cast<const char*>(all_handles) + 128 * r, 64);
+            std::memcpy(&hf, static_cast<const char*>(all_handles) + 128 * r + 64, 64);
+            void *pp = nullptr, *pf = nullptr;
+            VBDX_CUDA(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
+            VBDX_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+            I.ipcOpened[2 * r] = pp, I.ipcOpened[2 * r + 1] = pf;
+            I.peerPos[r]   = static_cast<float4*>(pp);
+            I.peerFlags[r] = static_cast<unsigned int*>(pf);
+            I.peerPOff[r]  = cheb ? static_cast<uint32_t>(peer_nverts[r]) : 0u;
+        }
+        // per-vertex send lists in internal order
+        std::vector<uint32_t> ptr(I.nV + 1, 0), dst(static_cast<size_t>(nSend));
+        for (int64_t k = 0; k < nSend; ++k)
+        {
+            vbdx::Require(send_local[k] >= 0 && send_local[k] < I.nV && send_peer[k] >= 0 && send_peer[k] < world && send_peer[k] != rank &&
+                              send_remote[k] >= 0 && send_remote[k] < (int64_t(1) << 28),
+                          "bad send list entry");
+            int32_t const vi = I.plan.old2new[send_local[k]];
+            vbdx::Require(vi < I.plan.ghostBegin, "a ghost vertex cannot be sent");
+            ++ptr[vi + 1];
+        }
+        for (int64_t i = 0; i < I.nV; ++i)
+            ptr[i + 1] += ptr[i];
+        std::vector<uint32_t> cur(ptr.begin(), ptr.end() - 1);
+        for (int64_t k = 0; k < nSend; ++k)
+        {
+            int32_t const vi = I.plan.old2new[send_local[k]];
+            dst[cur[vi]++]   = (static_cast<uint32_t>(send_peer[k]) << 28) | static_cast<uint32_t>(send_remote[k]);
+        }
+        I.dSendPtr.Alloc(ptr.size(), &I.deviceBytes);
+        I.dSendDst.Alloc(dst.size() + 1, &I.deviceBytes);
+        I.dSendPtr.Upload(ptr.data(), ptr.size(), I.stream);
+        if (!dst.empty())
+            I.dSendDst.Upload(dst.data(), dst.size(), I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        I.distRank = rank, I.distWorld = world;
     });
 }
 

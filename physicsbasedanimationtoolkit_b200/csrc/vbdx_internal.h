@@ -69,6 +69,7 @@ constexpr uint32_t kMaxTileIters = 2047;
 
 struct Plan {
     int64_t nV = 0, nActive = 0;
+    int64_t ghostBegin = 0;                  // internal ids >= ghostBegin are ghosts of another GPU's vertices
     int32_t nColors = 0;
     std::vector<int32_t> new2old, old2new;   // internal <-> caller vertex ids
     std::vector<TileDesc> tiles;
@@ -91,7 +92,7 @@ void BuildPlan(
     const uint32_t* vtPtr,   // vertex -> tet CSR built on the device (nV + 1)
     const uint32_t* vtAdj,   // entries 4*e + ilocal
     const int64_t* colors,
-    const uint8_t* isDbc,
+    const uint8_t* isDbc,    // 1 = Dirichlet, 2 = ghost (both are never swept)
     const double* X,
     int tileIters,
     bool naturalOrder,

@@ -1,0 +1,61 @@
+"""Runs the other BASELINE.json configurations (parity-test cases, not the judged bench line) and prints
+timings:  python tools/run_config.py {1|3|5} [scale]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import physicsbasedanimationtoolkit_b200 as pbat
+from physicsbasedanimationtoolkit_b200 import meshes
+
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+t0 = time.time()
+if cfg == 1:
+    X, T = meshes.tet_grid(25, 9, 9, 0.04)
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(np.flatnonzero(X[0] == 0)).construct()
+    iters, steps, name = 20, 100, "config 1: cantilever 25x9x9"
+elif cfg == 3:
+    n = max(2, int(round(29 * scale)))
+    Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+    X, T, B = meshes.stack_bodies(Xb, Tb, 16, axis=2, gap_frac=0.1)
+    F = meshes.boundary_facets(T)
+    V = np.unique(F)
+    zcut = X[2].min() + 0.01 * (Xb[2].max() - Xb[2].min())
+    dbc = np.flatnonzero(X[2] <= zcut)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e6, 0.3, 1e-3).construct())
+    iters, steps, name = 20, 50, f"config 3: 16 stacked bodies of {n}^3"
+else:
+    n_scenes = max(1, int(round(512 * scale)))
+    Xs, Ts = meshes.tet_grid(10, 10, 10, 0.1)
+    X, T = meshes.batch_scenes(Xs, Ts, n_scenes, perturb=0.002)
+    dbc = np.flatnonzero(np.tile(Xs[2] == 0, n_scenes))
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).construct()
+    iters, steps, name = 20, 20, f"config 5: {n_scenes} scenes of 10^3 on one GPU"
+t1 = time.time()
+vbd = pbat.gpu.vbd.Integrator(d)
+t2 = time.time()
+info = vbd.info
+for _ in range(3):
+    vbd.step(0.01, iters, 1)
+l0 = vbd.info["kernelLaunches"]
+ts = time.perf_counter()
+ms = []
+for _ in range(steps):
+    vbd.step(0.01, iters, 1)
+    ms.append(vbd.info["lastStepMs"])
+wall = time.perf_counter() - ts
+x = vbd.x
+out = {"config": name, "nV": int(info["nV"]), "nT": int(info["nT"]), "colors": int(info["nColors"]),
+       "host_construct_s": round(t1 - t0, 2), "create_s": round(t2 - t1, 2), "steps": steps, "iterations": iters,
+       "step_ms_device_median": float(np.median(ms)), "step_ms_wall": wall / steps * 1e3,
+       "vertex_iterations_per_s": info["nActiveVertices"] * iters / (np.median(ms) * 1e-3),
+       "launches_per_step": (vbd.info["kernelLaunches"] - l0) / steps, "finite": bool(np.isfinite(x).all()),
+       "device_MB": info["deviceBytes"] / 1e6}
+if cfg == 3:
+    _, nn, na = vbd.contact_state()
+    out["active_vertices"] = int(na)
+    out["vertices_with_contacts"] = int((nn >= 0).any(axis=1).sum())
+    zb = [x[2, B == b].min() for b in range(16)]
+    out["bodies_ordered_in_z"] = bool(np.all(np.diff(zb) > 0))
+    out["lowest_z_per_body_first4"] = [round(float(z), 4) for z in zb[:4]]
+print(json.dumps(out))
