@@ -13,8 +13,12 @@ Stable Neo-Hookean, 30 iterations/step, Chebyshev rho = 0.9, z = 0 face fixed.
   roofline   algorithmic bytes per launch (B = k*68 + n*12 + 36 + 48) / kernel time
   cpu_baseline  the reference's CPU arithmetic (oracle/_ref, OpenMP over each colour) on this host
 
-N > 1: independent scene replicas, one per rank (SURVEY.md 8e "independent scene batches"): no
-data-path collective, weak scaling.  --impl reference times the CPU reference on rank 0 only.
+N > 1: one mesh domain-decomposed over the GPUs: a beam of N x 58^3 cubes, one 58^3 slab
+(the N = 1 workload) per rank, so the per-GPU work is fixed ("weak" scaling).  After every colour the
+owners push the new positions of the slab interfaces into their neighbours' ghost slots with peer-to-peer
+stores over NVLink inside the step kernel, and the colour barrier spans all GPUs; NCCL (torch.distributed)
+only does the set-up exchange and the timing reduction.  --replicas runs N independent copies instead.
+--impl reference times the CPU reference on rank 0 only.
 """
 from __future__ import annotations
 
@@ -37,10 +41,10 @@ RHO = 0.9
 DT = 0.01
 
 
-def workload(seed=0):
+def workload(seed=0, slabs=1):
     from physicsbasedanimationtoolkit_b200 import meshes
 
-    X, T = meshes.tet_grid(GRID, GRID, GRID, 1.0 / GRID)
+    X, T = meshes.tet_grid(GRID * slabs, GRID, GRID, 1.0 / GRID)
     dbc = np.flatnonzero(X[2] == 0)
     rng = np.random.default_rng(seed)
     x0 = X + 0.05 / GRID * rng.uniform(-1, 1, X.shape)
@@ -141,6 +145,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-iters", type=int, default=0)
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of domain decomposition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -150,7 +155,10 @@ def main():
     config = {"workload": f"configs[1]: synthetic {GRID}^3-cube tet grid, Stable Neo-Hookean, {ITERS} iterations/step, "
                           f"Chebyshev rho={RHO}, dt={DT}, z=0 face Dirichlet",
               "tets": None, "vertices": None, "iterations": ITERS, "substeps": 1,
-              "parallelism": "single GPU" if args.gpus == 1 else f"{args.gpus} independent scene replicas (no collective)",
+              "parallelism": "single GPU" if args.gpus == 1 else (
+                  f"{args.gpus} independent scene replicas (no collective)" if args.replicas else
+                  f"domain decomposition: {args.gpus} x-slabs of {GRID}^3 cubes of one {GRID * args.gpus}x{GRID}x{GRID} beam, "
+                  "per-colour halo push over NVLink (peer-to-peer stores inside the step kernel), inter-GPU colour barrier"),
               "l2": "working set per sweep (incidence-record stream) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -183,14 +191,31 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    X, T, dbc, x0 = workload(seed=rank)
-    nV, nT = X.shape[1], T.shape[1]
-    config["tets"], config["vertices"] = int(nT), int(nV)
-    data = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
-            .with_chebyshev_acceleration(RHO).construct())
-    vbd = pbat.gpu.vbd.Integrator(data, device=local_rank, tile_iters=args.tile_iters)
-    info = vbd.info
-    n_active = info["nActiveVertices"]
+    decomposed = world > 1 and not args.replicas
+    if decomposed:
+        from physicsbasedanimationtoolkit_b200.dist import DomainDecomposedIntegrator
+
+        Xg, Tg, dbc_g, x0g = workload(seed=0, slabs=world)
+        config["tets"], config["vertices"] = int(Tg.shape[1]), int(Xg.shape[1])
+        dd = DomainDecomposedIntegrator(Xg, Tg, dbc=dbc_g, rho_chebyshev=RHO, axis=0, tile_iters=args.tile_iters)
+        vbd, lp = dd.vbd, dd.local
+        X, T, dbc = lp.X, lp.T, np.concatenate([lp.dbc, lp.ghost_local])
+        x0 = x0g[:, lp.l2g]
+        nV, nT = X.shape[1], T.shape[1]
+        info = vbd.info
+        n_active = info["nActiveVertices"]
+        n_active_job = int(Xg.shape[1] - dbc_g.size)
+        del Xg, Tg, x0g
+    else:
+        X, T, dbc, x0 = workload(seed=rank)
+        nV, nT = X.shape[1], T.shape[1]
+        config["tets"], config["vertices"] = int(nT), int(nV)
+        data = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
+                .with_chebyshev_acceleration(RHO).construct())
+        vbd = pbat.gpu.vbd.Integrator(data, device=local_rank, tile_iters=args.tile_iters)
+        info = vbd.info
+        n_active = info["nActiveVertices"]
+        n_active_job = n_active * world
     active = np.ones(nV, bool)
     active[dbc] = False
     B, kbar, nbar = algorithmic_bytes_per_vertex_iteration(T, nV, active)
@@ -260,7 +285,7 @@ def main():
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(times[0]), float(times[1])
-    work = n_active * ITERS * steps * world
+    work = n_active_job * ITERS * steps
     value = work / (total_ms * 1e-3)
     e2e_value = work / (e2e_ms * 1e-3)
 

@@ -74,6 +74,13 @@ struct StepParams {
     int traceIteration;
 };
 
+__device__ __forceinline__ unsigned int AddReleaseReturn(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ unsigned long long GlobalTimer()
 {
     unsigned long long t;

@@ -76,45 +76,45 @@ __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
 
 // One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.  Domain decomposition
 // (p.world > 1): the barrier additionally spans the peers.  Every CTA fences at system scope (its warps
-// stored into peer memory) and arrives; CTA 0 waits for the local arrivals, publishes this GPU's epoch in
-// every peer's flag array (st.release.sys over NVLink), waits for every peer's epoch, and only then
-// releases the local CTAs through `myFlags[8]`.  A peer that never shows up raises distError instead of
-// hanging the GPU.
+// stored into peer memory) and arrives; the CTA that arrives last publishes this GPU's epoch in every
+// peer's flag array (st.release.sys over NVLink); every CTA then waits for the local arrivals and for
+// every peer's epoch.  A peer that never shows up raises distError instead of hanging the GPU.
 __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
                                                 unsigned long long* trace)
 {
     NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
+    ++epoch;
+    unsigned int const e = p.epochBase + epoch;
     if (lane == 0)
     {
         if (trace)
             trace[2] = GlobalTimer();
         target += gridDim.x;
         if (p.world > 1)
+        {
+            // this CTA's warps stored into peer memory: make that visible system-wide before arriving; the CTA
+            // that arrives last then tells the peers that this GPU is done with the phase
             asm volatile("fence.acq_rel.sys;" ::: "memory");
-        AddRelease(p.barrier, 1u);
+            if (AddReleaseReturn(p.barrier, 1u) + 1u == target)
+                for (int r = 0; r < p.world; ++r)
+                    if (r != p.rank)
+                        StoreReleaseSys(p.peerFlags[r] + p.rank, e);
+        }
+        else
+            AddRelease(p.barrier, 1u);
         if (trace)
             trace[1] = GlobalTimer();
     }
     __syncwarp();
     NamedArrive(kBarFenced, blockDim.x);
-    ++epoch;
     if (lane == 0)
     {
-        if (p.world <= 1)
+        while (LoadAcquire(p.barrier) < target)
         {
-            while (LoadAcquire(p.barrier) < target)
-            {
-            }
         }
-        else if (blockIdx.x == 0)
+        if (p.world > 1)
         {
-            while (LoadAcquire(p.barrier) < target)
-            {
-            }
-            unsigned int const e = p.epochBase + epoch;
-            for (int r = 0; r < p.world; ++r)
-                if (r != p.rank)
-                    StoreReleaseSys(p.peerFlags[r] + p.rank, e);
+            // every CTA waits for the peers' epochs itself (flags live in this GPU's memory, written over NVLink)
             unsigned long long const t0 = GlobalTimer();
             for (int r = 0; r < p.world; ++r)
                 if (r != p.rank)
@@ -124,14 +124,6 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
                             atomicExch(p.distError, 1u);
                             break;
                         }
-            StoreReleaseGpu(p.myFlags + 8, e);
-        }
-        else
-        {
-            unsigned int const e = p.epochBase + epoch;
-            while (static_cast<int>(LoadAcquire(p.myFlags + 8) - e) < 0)
-            {
-            }
         }
         if (trace)
             trace[3] = GlobalTimer();
