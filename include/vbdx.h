@@ -217,12 +217,15 @@ vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
  *   3. vbdx_dist_connect: open the peers' buffers and install the send lists:
  *        send_local[k]  caller-order id of an owned vertex,
  *        send_peer[k]   rank that holds it as a ghost,
- *        send_remote[k] that rank's internal slot of the ghost;  peer_nverts[r] = rank r's local vertex count.
+ *        send_remote[k] that rank's internal slot of the ghost;  peer_nverts[r] = rank r's local vertex count;
+ *        recv_mask bit r = rank r owns some of this rank's ghosts.  A GPU synchronises only with the ranks it
+ *        sends to or receives from.
  * All ranks must then call vbdx_step with identical arguments. */
 vbdx_status vbdx_get_internal_ids(vbdx_integrator* h, int64_t* old2new);
 vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128);
 vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
-                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote);
+                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
+                              uint32_t recv_mask);
 
 /* Contact state after the last step, per collision vertex in the order of desc->V
  * (gpu/impl/contact/VertexTriangleMixedCcdDcd.cuh: active, nn): active[nCV] (0/1), nn[8 * nCV] nearest triangles

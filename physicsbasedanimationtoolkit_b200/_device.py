@@ -197,9 +197,9 @@ class DeviceIntegrator:
         _lib.check(self._L.vbdx_dist_ipc_handles(self._h, out.ctypes.data))
         return out
 
-    def dist_connect(self, rank, world, all_handles, peer_nverts, send_local, send_peer, send_remote):
+    def dist_connect(self, rank, world, all_handles, peer_nverts, send_local, send_peer, send_remote, recv_mask):
         all_handles = np.ascontiguousarray(all_handles, np.uint8)
         peer_nverts = np.ascontiguousarray(peer_nverts, np.int64)
         sl, sp, sr = (np.ascontiguousarray(a, np.int64) for a in (send_local, send_peer, send_remote))
         _lib.check(self._L.vbdx_dist_connect(self._h, int(rank), int(world), all_handles.ctypes.data, peer_nverts.ctypes.data,
-                                             sl.size, sl.ctypes.data, sp.ctypes.data, sr.ctypes.data))
+                                             sl.size, sl.ctypes.data, sp.ctypes.data, sr.ctypes.data, int(recv_mask)))

@@ -296,7 +296,7 @@ void BuildPlan(
                 if (seenInTile[j] == tileId)
                     continue;
                 seenInTile[j] = tileId;
-                (nColors > 1 && colors[j] == prevColor && !isDbc[j] ? late : early).push_back(j);
+                (nColors > 1 && colors[j] == prevColor && isDbc[j] != 1 ? late : early).push_back(j);  // ghosts (2) do change
             }
             size_t const padded = ((n + 1 + early.size() + 31) / 32 + (late.size() + 31) / 32) * 32;
             if (n > 0 && padded > static_cast<size_t>(kMaxRingPerTile))

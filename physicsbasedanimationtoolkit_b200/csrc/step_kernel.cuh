@@ -70,6 +70,7 @@ struct StepParams {
     unsigned int* distError;             // set when a peer did not show up in time
     unsigned int epochBase;              // epochs used by earlier launches
     int rank, world;
+    unsigned int peerMask;               // ranks this GPU exchanges halo data with (bit r); only they are synchronised with
     unsigned long long* trace;  // optional [nColors][gridDim.x][kTraceStamps] timestamps of one iteration (diagnostics)
     int traceIteration;
 };

@@ -77,8 +77,8 @@ __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
 // One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.  Domain decomposition
 // (p.world > 1): the barrier additionally spans the peers.  Every CTA fences at system scope (its warps
 // stored into peer memory) and arrives; the CTA that arrives last publishes this GPU's epoch in every
-// peer's flag array (st.release.sys over NVLink); every CTA then waits for the local arrivals and for
-// every peer's epoch.  A peer that never shows up raises distError instead of hanging the GPU.
+// neighbour's flag array (over NVLink); every CTA then waits for the local arrivals and for the epochs of
+// the neighbours it exchanges halo data with (non-neighbours share no data and may drift).  A peer that never shows up raises distError instead of hanging the GPU.
 __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
                                                 unsigned long long* trace)
 {
@@ -96,9 +96,13 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
             // that arrives last then tells the peers that this GPU is done with the phase
             asm volatile("fence.acq_rel.sys;" ::: "memory");
             if (AddReleaseReturn(p.barrier, 1u) + 1u == target)
+            {
+                // one system-scope fence, then plain strong stores of the epoch into the neighbours' flag arrays
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
                 for (int r = 0; r < p.world; ++r)
-                    if (r != p.rank)
-                        StoreReleaseSys(p.peerFlags[r] + p.rank, e);
+                    if ((p.peerMask >> r) & 1u)
+                        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peerFlags[r] + p.rank), "r"(e) : "memory");
+            }
         }
         else
             AddRelease(p.barrier, 1u);
@@ -117,7 +121,7 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
             // every CTA waits for the peers' epochs itself (flags live in this GPU's memory, written over NVLink)
             unsigned long long const t0 = GlobalTimer();
             for (int r = 0; r < p.world; ++r)
-                if (r != p.rank)
+                if ((p.peerMask >> r) & 1u)
                     while (static_cast<int>(LoadAcquireSys(p.myFlags + r) - e) < 0)
                         if (GlobalTimer() - t0 > 20000000000ull)  // 20 s: a peer is missing
                         {

@@ -73,7 +73,7 @@ struct Integrator {
     ContactState contact;
     // domain decomposition
     int distRank = 0, distWorld = 1;
-    unsigned int distEpoch = 0;
+    unsigned int distEpoch = 0, peerMask = 0;
     DevBuf<unsigned int> dDistFlags;  // [0..7] peers' epochs, [8] local release, [9] error
     DevBuf<uint32_t> dSendPtr, dSendDst;
     float4* peerPos[8]        = {};
@@ -546,6 +546,7 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
         p.myFlags   = dDistFlags.p;
         p.distError = dDistFlags.p + 9;
         p.epochBase = distEpoch;
+        p.peerMask  = peerMask;
         distEpoch += static_cast<unsigned int>(substeps) * (1u + static_cast<unsigned int>(iterations) * static_cast<unsigned int>(plan.nColors));
     }
     p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
@@ -903,7 +904,8 @@ vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128)
 }
 
 vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
-                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote)
+                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
+                              uint32_t recv_mask)
 {
     if (vbdx_status s = NeedHandle(h))
         return s;
@@ -955,6 +957,9 @@ vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, c
             I.dSendDst.Upload(dst.data(), dst.size(), I.stream);
         VBDX_CUDA(cudaStreamSynchronize(I.stream));
         I.distRank = rank, I.distWorld = world;
+        I.peerMask = recv_mask;
+        for (int64_t k = 0; k < nSend; ++k)
+            I.peerMask |= 1u << send_peer[k];
     });
 }
 

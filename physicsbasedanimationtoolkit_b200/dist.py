@@ -155,7 +155,8 @@ class DomainDecomposedIntegrator:
             nvs = [torch.zeros_like(nv) for _ in range(self.world)]
             dist.all_gather(nvs, nv)
             self.vbd.dist_connect(self.rank, self.world, torch.stack(handles).cpu().numpy(),
-                                  torch.cat(nvs).cpu().numpy(), sl, sp, sr)
+                                  torch.cat(nvs).cpu().numpy(), sl, sp, sr,
+                                  sum(1 << int(r) for r in np.unique(lp.ghost_owner)))
             dist.barrier()
         self.n_send = 0 if self.world == 1 else int(sl.size)
 
