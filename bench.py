@@ -220,11 +220,7 @@ def main():
     active[dbc] = False
     B, kbar, nbar = algorithmic_bytes_per_vertex_iteration(T, nV, active)
 
-    # pinned host buffers for the end-to-end leg
-    xh = torch.empty((nV, 3), dtype=torch.float32, pin_memory=True)
-    xin = xh.numpy()
-    xin[:] = x0.T.astype(np.float32)
-    x_start = np.ascontiguousarray(xin.T)
+    x_start = np.ascontiguousarray(x0, dtype=np.float32)
     v_zero = np.zeros((3, nV), np.float32)
 
     def barrier():
@@ -237,6 +233,7 @@ def main():
     # launching stream (recorded inside the library around the cooperative launch)
     vbd.x = x_start
     vbd.v = v_zero
+    barrier()  # domain decomposition: the ranks' kernels wait for each other, start them together
     for _ in range(warmup):
         vbd.step(DT, ITERS, 1)
     launches0 = vbd.info["kernelLaunches"]
@@ -264,20 +261,25 @@ def main():
     kernel_ms = float(np.mean(kms))
     assert np.isfinite(vbd.x).all(), "non-finite positions after the timed steps"
 
-    # ---- end-to-end leg through the public API with host buffers
+    # ---- end-to-end leg through the public API with HOST buffers (page-locked, pbat.host.pinned_empty):
+    # every step uploads the input positions, steps, and reads the result back
     vbd.x = x_start
     vbd.v = v_zero
-    xcur = x_start
+    xin = pbat.host.pinned_empty((3, nV), np.float32)
+    xout = pbat.host.pinned_empty((3, nV), np.float32)
+    xin[...] = x_start
     for _ in range(min(warmup, 2)):
-        vbd.x = xcur
+        vbd.x = xin
         vbd.step(DT, ITERS, 1)
-        xcur = vbd.x
+        vbd.positions(out=xout)
+        xin, xout = xout, xin
     barrier()
     te = time.perf_counter()
     for _ in range(steps):
-        vbd.x = xcur          # H2D of this step's input positions
+        vbd.x = xin                 # H2D of this step's input positions
         vbd.step(DT, ITERS, 1)
-        xcur = vbd.x          # D2H of the step's result
+        vbd.positions(out=xout)     # D2H of the step's result
+        xin, xout = xout, xin       # the result is the next step's input
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te
 

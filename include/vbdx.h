@@ -171,6 +171,20 @@ vbdx_status vbdx_get_positions_f64(vbdx_integrator* h, double* x, int64_t nV);
 vbdx_status vbdx_get_velocities_f32(vbdx_integrator* h, float* v, int64_t nV);
 vbdx_status vbdx_get_velocities_f64(vbdx_integrator* h, double* v, int64_t nV);
 
+/* The same setters/getters with an explicit element type and storage order, so that a caller holding a
+ * row-major 3 x nV array (numpy's default for the arrays bindings/pypbat hands out) needs no host-side
+ * transposition: VBDX_LAYOUT_COLUMNS = column-major 3 x nV (Eigen; xyz of a vertex adjacent),
+ * VBDX_LAYOUT_ROWS = row-major 3 x nV (all x, then all y, then all z).  Host pointers may be pageable or
+ * pinned; with pinned memory (vbdx_host_alloc) the copy is a single DMA transfer. */
+typedef enum vbdx_field { VBDX_FIELD_POSITIONS = 0, VBDX_FIELD_VELOCITIES = 1, VBDX_FIELD_EXTERNAL_ACCELERATION = 2 } vbdx_field;
+typedef enum vbdx_dtype { VBDX_F32 = 0, VBDX_F64 = 1 } vbdx_dtype;
+typedef enum vbdx_layout { VBDX_LAYOUT_COLUMNS = 0, VBDX_LAYOUT_ROWS = 1 } vbdx_layout;
+vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV);
+vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV);
+/* Page-locked host memory for the arrays above (cudaHostAlloc / cudaFreeHost). */
+vbdx_status vbdx_host_alloc(void** out, int64_t bytes);
+vbdx_status vbdx_host_free(void* p);
+
 /* Integrator::SetNumericalZeroForHessianDeterminant   gpu/vbd/Integrator.h:111 */
 vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero);
 /* Integrator::SetRayleighDampingCoefficient           gpu/vbd/Integrator.h:116 */
@@ -209,22 +223,26 @@ vbdx_status vbdx_get_element_data(vbdx_integrator* h, double* GP, double* wg, do
 vbdx_status vbdx_get_colors(vbdx_integrator* h, int64_t* colors);
 
 /* ---- multi-GPU domain decomposition (new: the reference is single-GPU) --------------------
- * One handle per GPU/process.  Each handle simulates the vertices it owns plus a ghost layer (desc->ghosts).  After
- * a colour is swept, the owner stores the new positions directly into the ghost slots of its peers over NVLink
- * (peer-to-peer stores inside the persistent step kernel) and the colour barrier spans all GPUs.
+ * One handle per GPU/process.  Each handle simulates the vertices it owns plus a ghost layer (desc->ghosts).  When
+ * a boundary vertex is swept, its owner stores the new position directly into the ghost slots of its peers over
+ * NVLink (peer-to-peer stores inside the persistent step kernel).  Every such store carries the number of the
+ * write ("tag") in the fourth component of the same 16 bytes, and a reader waits until the ghost it gathered
+ * carries the tag of the write it needs -- so the halo exchange needs no fence, flag or collective on the critical
+ * path; the GPUs only bound how far they may drift apart (two colour phases).
  *   1. vbdx_get_internal_ids: caller-order vertex -> device-internal slot (peers need the slots of their ghosts)
  *   2. vbdx_dist_ipc_handles: 128 opaque bytes to all-gather between the processes (CUDA IPC handles)
  *   3. vbdx_dist_connect: open the peers' buffers and install the send lists:
  *        send_local[k]  caller-order id of an owned vertex,
  *        send_peer[k]   rank that holds it as a ghost,
- *        send_remote[k] that rank's internal slot of the ghost;  peer_nverts[r] = rank r's local vertex count;
+ *        send_remote[k] that rank's internal slot of the ghost;
+ *        peer_nverts[r] / peer_nghosts[r] = rank r's local vertex count / how many of them are ghosts;
  *        recv_mask bit r = rank r owns some of this rank's ghosts.  A GPU synchronises only with the ranks it
  *        sends to or receives from.
  * All ranks must then call vbdx_step with identical arguments. */
 vbdx_status vbdx_get_internal_ids(vbdx_integrator* h, int64_t* old2new);
 vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128);
 vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
-                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
+                              const int64_t* peer_nghosts, int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
                               uint32_t recv_mask);
 
 /* Contact state after the last step, per collision vertex in the order of desc->V

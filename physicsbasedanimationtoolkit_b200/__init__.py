@@ -5,6 +5,6 @@
 for this path (bindings/pypbat/sim/vbd, bindings/pypbat/gpu/vbd).  Everything executes in
 hand-written sm_100a CUDA kernels behind the C-ABI of ``include/vbdx.h``.
 """
-from . import graph, meshes, sim, gpu  # noqa: F401
+from . import graph, host, meshes, sim, gpu  # noqa: F401
 
-__all__ = ["graph", "meshes", "sim", "gpu"]
+__all__ = ["graph", "host", "meshes", "sim", "gpu"]

@@ -106,14 +106,34 @@ class DeviceIntegrator:
     def _sfx(self):
         return "f32" if self._dtype == np.float32 else "f64"
 
-    def _get(self, what):
-        out = np.empty((self.nV, 3), dtype=self._dtype)
-        _lib.check(getattr(self._L, f"vbdx_get_{what}_{self._sfx()}")(self._h, out.ctypes.data, self.nV))
-        return np.ascontiguousarray(out.T)
+    _FIELDS = {"positions": 0, "velocities": 1, "external_acceleration": 2}
+
+    def _get(self, what, out=None):
+        """3 x nV array of ``what``.  ``out`` (C-contiguous 3 x nV of the integrator's dtype, ideally from
+        ``pinned_empty``) receives the device-to-host copy directly."""
+        if out is None:
+            out = np.empty((3, self.nV), dtype=self._dtype)
+        elif not (isinstance(out, np.ndarray) and out.shape == (3, self.nV) and out.dtype == self._dtype and out.flags.c_contiguous):
+            raise ValueError(f"out must be a C-contiguous 3 x {self.nV} array of {np.dtype(self._dtype).name}")
+        _lib.check(self._L.vbdx_get_vertex_field(self._h, self._FIELDS[what], int(self._dtype == np.float64), 1, out.ctypes.data, self.nV))
+        return out
 
     def _set(self, what, a):
-        a = _interleaved(a, self._dtype, self.nV, what)
-        _lib.check(getattr(self._L, f"vbdx_set_{what}_{self._sfx()}")(self._h, a.ctypes.data, self.nV))
+        a = np.asarray(a, dtype=self._dtype)
+        if a.shape != (3, self.nV):
+            raise ValueError(f"{what} must be 3 x {self.nV}, got {a.shape}")  # gpu/impl/common/Eigen.cuh:28-35
+        # row-major (numpy default) and column-major (Eigen) inputs are both consumed in place
+        rows = not a.flags.f_contiguous
+        if rows and not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        _lib.check(self._L.vbdx_set_vertex_field(self._h, self._FIELDS[what], int(self._dtype == np.float64), int(rows), a.ctypes.data, self.nV))
+
+    def positions(self, out=None):
+        """``x`` with an optional preallocated (pinned) destination."""
+        return self._get("positions", out)
+
+    def velocities(self, out=None):
+        return self._get("velocities", out)
 
     x = property(lambda s: s._get("positions"), lambda s, a: s._set("positions", a))
     v = property(lambda s: s._get("velocities"), lambda s, a: s._set("velocities", a))
@@ -197,9 +217,10 @@ class DeviceIntegrator:
         _lib.check(self._L.vbdx_dist_ipc_handles(self._h, out.ctypes.data))
         return out
 
-    def dist_connect(self, rank, world, all_handles, peer_nverts, send_local, send_peer, send_remote, recv_mask):
+    def dist_connect(self, rank, world, all_handles, peer_nverts, peer_nghosts, send_local, send_peer, send_remote, recv_mask):
         all_handles = np.ascontiguousarray(all_handles, np.uint8)
         peer_nverts = np.ascontiguousarray(peer_nverts, np.int64)
+        peer_nghosts = np.ascontiguousarray(peer_nghosts, np.int64)
         sl, sp, sr = (np.ascontiguousarray(a, np.int64) for a in (send_local, send_peer, send_remote))
-        _lib.check(self._L.vbdx_dist_connect(self._h, int(rank), int(world), all_handles.ctypes.data, peer_nverts.ctypes.data,
+        _lib.check(self._L.vbdx_dist_connect(self._h, int(rank), int(world), all_handles.ctypes.data, peer_nverts.ctypes.data, peer_nghosts.ctypes.data,
                                              sl.size, sl.ctypes.data, sp.ctypes.data, sr.ctypes.data, int(recv_mask)))

@@ -60,6 +60,10 @@ SYMBOLS = {
     "vbdx_step": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32]),
     "vbdx_step_async": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32]),
     "vbdx_synchronize": (C.c_int, [_H]),
+    "vbdx_set_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "vbdx_get_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "vbdx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "vbdx_host_free": (C.c_int, [C.c_void_p]),
     "vbdx_set_positions_f32": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "vbdx_set_positions_f64": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "vbdx_set_velocities_f32": (C.c_int, [_H, C.c_void_p, C.c_int64]),
@@ -78,7 +82,7 @@ SYMBOLS = {
     "vbdx_set_stream": (C.c_int, [_H, C.c_void_p]),
     "vbdx_get_internal_ids": (C.c_int, [_H, C.c_void_p]),
     "vbdx_dist_ipc_handles": (C.c_int, [_H, C.c_void_p]),
-    "vbdx_dist_connect": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "vbdx_dist_connect": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "vbdx_get_contact_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_debug_bvh_build": (C.c_int, [C.c_int64] + [C.c_void_p] * 11),
     "vbdx_debug_trace": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),

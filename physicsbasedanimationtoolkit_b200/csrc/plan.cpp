@@ -326,6 +326,12 @@ void BuildPlan(
         t.meta       = TileMeta(static_cast<uint32_t>(lw), static_cast<uint32_t>(n), earlyChunks + lateChunks, earlyChunks,
                           static_cast<uint32_t>(iters));
         t.ringStart = ringStart;
+        for (int32_t j : early)
+            if (isDbc[j] == 2)
+                t.meta |= 0x80000000u;
+        for (int32_t j : late)
+            if (isDbc[j] == 2)
+                t.meta |= 0x80000000u;
         plan.tiles.push_back(t);
         // neighbours in ascending internal id: lanes of one gather instruction then touch few cache lines
         auto byNewId = [&](int32_t a, int32_t b) { return plan.old2new[a] < plan.old2new[b]; };

@@ -355,14 +355,20 @@ __global__ void InitState(
     acc[i] = a4;
 }
 
+// Caller order <-> internal order.  Component d of caller vertex o sits at src[d * sd + o * si]:
+// (sd, si) = (1, 3) for a column-major 3 x nV matrix (Eigen, xyz interleaved), (nV, 1) for a row-major one.
 template <class T>
-__global__ void ScatterFromCaller(int64_t nV, const int32_t* old2new, const T* src, float4* dst0, float4* dst1)
+__global__ void ScatterFromCaller(int64_t nV, const int32_t* old2new, const T* src, int64_t sd, int64_t si, float4* dst0, float4* dst1,
+                                  int64_t ghostBegin)
 {
     int64_t const o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (o >= nV)
         return;
     int64_t const i = old2new[o];
-    float4 const q  = make_float4(static_cast<float>(src[3 * o]), static_cast<float>(src[3 * o + 1]), static_cast<float>(src[3 * o + 2]), 0.f);
+    if (i >= ghostBegin)
+        return;  // ghosts belong to the GPU that owns the vertex: it may be writing them right now
+    T const* a      = src + o * si;
+    float4 const q  = make_float4(static_cast<float>(a[0]), static_cast<float>(a[sd]), static_cast<float>(a[2 * sd]), 0.f);
     float const w   = dst0[i].w;
     dst0[i]         = make_float4(q.x, q.y, q.z, w);
     if (dst1)
@@ -370,15 +376,16 @@ __global__ void ScatterFromCaller(int64_t nV, const int32_t* old2new, const T* s
 }
 
 template <class T>
-__global__ void GatherToCaller(int64_t nV, const int32_t* old2new, const float4* src, T* dst)
+__global__ void GatherToCaller(int64_t nV, const int32_t* old2new, const float4* src, T* dst, int64_t sd, int64_t si)
 {
     int64_t const o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (o >= nV)
         return;
     float4 const q = src[old2new[o]];
-    dst[3 * o]     = static_cast<T>(q.x);
-    dst[3 * o + 1] = static_cast<T>(q.y);
-    dst[3 * o + 2] = static_cast<T>(q.z);
+    T* a           = dst + o * si;
+    a[0]           = static_cast<T>(q.x);
+    a[sd]          = static_cast<T>(q.y);
+    a[2 * sd]      = static_cast<T>(q.z);
 }
 
 }  // namespace vbdx

@@ -69,6 +69,13 @@ struct StepParams {
     unsigned int* myFlags;               // slot r: last epoch GPU r finished;  slot 8: release epoch for this GPU's CTAs
     unsigned int* distError;             // set when a peer did not show up in time
     unsigned int epochBase;              // epochs used by earlier launches
+    unsigned long long distTimeoutNs;    // how long to wait for a peer before giving up
+    // Ghost values carry the number of their write in .w ("tag": the pre-step of substep s writes tag
+    // tagBase + s (iterations + 1), iteration k writes that + k + 1), and every ghost exists twice: the copy for
+    // even tags sits in the ordinary slot, the copy for odd tags at [ghostExt + g] (Q) / [ghostExt + nGhost + g] (P).
+    unsigned int tagBase;                // tags used by earlier launches
+    uint32_t ghostExt, nGhost;
+    uint32_t peerGhostExt[8], peerGhostBegin[8], peerNGhost[8];
     int rank, world;
     unsigned int peerMask;               // ranks this GPU exchanges halo data with (bit r); only they are synchronised with
     unsigned long long* trace;  // optional [nColors][gridDim.x][kTraceStamps] timestamps of one iteration (diagnostics)
@@ -79,6 +86,13 @@ __device__ __forceinline__ unsigned int AddReleaseReturn(unsigned int* p, unsign
 {
     unsigned int old;
     asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+__device__ __forceinline__ unsigned int AddAcqRelReturn(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
 }
 
@@ -203,20 +217,30 @@ __device__ __forceinline__ float3 InitialPosition(
 }
 
 // Domain decomposition: push the new position of an owned vertex into the ghost slots of the peers that hold
-// it (plain stores to peer memory; the colour barrier's system-scope release makes them visible).
-__device__ __forceinline__ void SendToPeers(StepParams const& p, uint32_t vi, float4 raw, float4 blended)
+// it: plain 16-byte stores into peer memory over NVLink, the write's tag travelling in .w of the same store, so
+// that a reader can tell from the datum itself whether it has arrived (no fence, no flag on the critical path).
+__device__ __forceinline__ void SendToPeers(StepParams const& p, uint32_t vi, float4 raw, float4 blended, uint32_t tag)
 {
     if (p.sendPtr == nullptr)
         return;
     uint32_t const b = __ldg(p.sendPtr + vi), e = __ldg(p.sendPtr + vi + 1);
+    raw.w = blended.w = __uint_as_float(tag);
+    bool const odd = (tag & 1u) != 0u;
     for (uint32_t k = b; k < e; ++k)
     {
         uint32_t const dst = __ldg(p.sendDst + k);
         uint32_t const r = dst >> 28, slot = dst & 0x0fffffffu;
-        p.peerPos[r][slot] = raw;
+        uint32_t const q = odd ? p.peerGhostExt[r] + (slot - p.peerGhostBegin[r]) : slot;
+        p.peerPos[r][q] = raw;
         if (p.peerPOff[r] != 0u)
-            p.peerPos[r][p.peerPOff[r] + slot] = blended;
+            p.peerPos[r][q + (odd ? p.peerNGhost[r] : p.peerPOff[r])] = blended;
     }
+}
+
+// index (into pos) of the copy of ghost `base` that holds the write with tag `tag`; prev = previous-iterate buffer
+__device__ __forceinline__ uint32_t GhostIndex(StepParams const& p, uint32_t base, bool prev, uint32_t tag)
+{
+    return (tag & 1u) ? p.ghostExt + (prev && p.pOff != 0u ? p.nGhost : 0u) + (base - p.ghostBegin) : base + (prev ? p.pOff : 0u);
 }
 
 // Per-vertex pre-step, fused with the velocity update of the previous substep
@@ -265,7 +289,7 @@ __device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, i
         p.pos[p.pOff + i] = o;
     if (p.snap != nullptr)
         p.snap[i] = o;
-    SendToPeers(p, i, o, o);
+    SendToPeers(p, i, o, o, p.tagBase + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.iterations + 1));
 }
 
 // velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
@@ -321,7 +345,8 @@ __device__ __forceinline__ void ProcessTile(
     float omega,
     uint32_t lane,
     unsigned long long* trace = nullptr,
-    AfterAccumulate afterAccumulate = AfterAccumulate{})  // runs once the tile's records have been consumed
+    AfterAccumulate afterAccumulate = AfterAccumulate{},  // runs once the tile's records have been consumed
+    uint32_t sendTag = 0u)                                // domain decomposition: tag of this sweep's writes
 {
     float4 const* __restrict__ posQ = p.pos;
     uint32_t const lw         = TileLog2W(td.z);
@@ -519,14 +544,14 @@ __device__ __forceinline__ void ProcessTile(
             p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
             p.pos[vi]          = raw;
             p.pos[p.pOff + vi] = out;
-            SendToPeers(p, vi, raw, out);
+            SendToPeers(p, vi, raw, out, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = out;  // what iteration k+1 starts from
         }
         else
         {
             p.pos[vi] = raw;
-            SendToPeers(p, vi, raw, raw);
+            SendToPeers(p, vi, raw, raw, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;
         }

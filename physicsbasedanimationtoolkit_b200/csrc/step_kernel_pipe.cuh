@@ -74,13 +74,24 @@ __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.  Domain decomposition
-// (p.world > 1): the barrier additionally spans the peers.  Every CTA fences at system scope (its warps
-// stored into peer memory) and arrives; the CTA that arrives last publishes this GPU's epoch in every
-// neighbour's flag array (over NVLink); every CTA then waits for the local arrivals and for the epochs of
-// the neighbours it exchanges halo data with (non-neighbours share no data and may drift).  A peer that never shows up raises distError instead of hanging the GPU.
+__device__ __forceinline__ float4 LoadPosSys(const float4* q)
+{
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
+    return v;
+}
+
+// One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.
+// Domain decomposition (p.world > 1): halo data synchronises itself (every ghost value carries the tag of its
+// write, readers wait for the tag they need), so the colour barrier stays local.  What remains between GPUs is
+// a bound on how far a GPU may run ahead, so that it never overwrites a ghost copy a slower peer still reads:
+// the CTA that arrives last publishes this GPU's epoch in its neighbours' flag arrays (a relaxed store over
+// NVLink, nobody waits for it now), and every CTA waits until its neighbours have finished epoch e - lag
+// (lag = 2 inside a substep -- a copy is rewritten nColors + 1 phases after its last reader at the earliest --
+// and 0 at the end of a substep, whose pre-step rewrites every ghost).  A peer that never shows up raises
+// distError instead of hanging the GPU.
 __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
-                                                unsigned long long* trace)
+                                                unsigned int lag, unsigned long long* trace)
 {
     NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
     ++epoch;
@@ -92,17 +103,10 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
         target += gridDim.x;
         if (p.world > 1)
         {
-            // this CTA's warps stored into peer memory: make that visible system-wide before arriving; the CTA
-            // that arrives last then tells the peers that this GPU is done with the phase
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-            if (AddReleaseReturn(p.barrier, 1u) + 1u == target)
-            {
-                // one system-scope fence, then plain strong stores of the epoch into the neighbours' flag arrays
-                asm volatile("fence.acq_rel.sys;" ::: "memory");
+            if (AddAcqRelReturn(p.barrier, 1u) + 1u == target)
                 for (int r = 0; r < p.world; ++r)
                     if ((p.peerMask >> r) & 1u)
                         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peerFlags[r] + p.rank), "r"(e) : "memory");
-            }
         }
         else
             AddRelease(p.barrier, 1u);
@@ -118,12 +122,12 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
         }
         if (p.world > 1)
         {
-            // every CTA waits for the peers' epochs itself (flags live in this GPU's memory, written over NVLink)
+            // flags live in this GPU's memory, written over NVLink
             unsigned long long const t0 = GlobalTimer();
             for (int r = 0; r < p.world; ++r)
                 if ((p.peerMask >> r) & 1u)
-                    while (static_cast<int>(LoadAcquireSys(p.myFlags + r) - e) < 0)
-                        if (GlobalTimer() - t0 > 20000000000ull)  // 20 s: a peer is missing
+                    while (static_cast<int>(LoadAcquireSys(p.myFlags + r) - (e - lag)) < 0)
+                        if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)  // a peer is missing
                         {
                             atomicExch(p.distError, 1u);
                             break;
@@ -177,16 +181,18 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     {
         // ------------------------------ barrier warp ------------------------------
         unsigned int target = 0, epoch = 0;
+        unsigned int const lagIn = nC >= 2u ? 2u : 0u;
         for (int s = 0; s < p.substeps; ++s)
         {
-            BarrierWarpStep(p, target, epoch, lane, nullptr);  // after the pre-step pass
+            BarrierWarpStep(p, target, epoch, lane, p.iterations > 0 ? lagIn : 0u, nullptr);  // after the pre-step pass
             for (int k = 0; k < p.iterations; ++k)
                 for (uint32_t c = 0; c < nC; ++c)
                 {
                     unsigned long long* tr = nullptr;
                     if (p.trace != nullptr && k == p.traceIteration)
                         tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
-                    BarrierWarpStep(p, target, epoch, lane, tr);
+                    bool const lastOfSubstep = k + 1 == p.iterations && c + 1 == nC;
+                    BarrierWarpStep(p, target, epoch, lane, lastOfSubstep ? 0u : lagIn, tr);
                 }
         }
         return;
@@ -263,7 +269,10 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         ++recFills;
     };
     // positions of ring chunks [from, to) of sequence tile s (descriptor and ids already in shared memory)
-    auto IssueGather = [&](uint32_t s, uint32_t from, uint32_t to) {
+    uint32_t const ghostFrom = p.world > 1 ? p.ghostBegin : 0xffffffffu;  // ids from here on are written by peers
+    // tagLow = tag of the sweep before the tile's own (what its higher-colour ghosts must carry; lower-colour
+    // ghosts carry tagLow + 1): selects which copy of a ghost is read
+    auto IssueGather = [&](uint32_t s, uint32_t from, uint32_t to, uint32_t tagLow) {
         if (from >= to)
             return;
         WaitIds();
@@ -271,9 +280,43 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         uint32_t const dst  = SmemAddr(stage + lane);
         for (uint32_t j = from; j < to; ++j)
         {
-            uint32_t const id = ids[32 * j];
-            CpAsync16(dst + 512 * j, p.pos + (id & ~kPrevFlag) + ((id & kPrevFlag) ? p.pOff : 0u));
+            uint32_t const id   = ids[32 * j];
+            uint32_t const base = id & ~kPrevFlag;
+            bool const prev     = (id & kPrevFlag) != 0u;
+            uint32_t const at   = base >= ghostFrom ? GhostIndex(p, base, prev, tagLow + (prev ? 0u : 1u)) : base + (prev ? p.pOff : 0u);
+            CpAsync16(dst + 512 * j, p.pos + at);
         }
+    };
+    // Domain decomposition: the staged ghosts of tile s must carry the tags of the writes this sweep reads; one
+    // that has not crossed NVLink yet is polled until it has.
+    auto AwaitGhosts = [&](uint32_t s, uint32_t chunks, uint32_t tagLow) {
+        uint32_t const* ids = idsBuf + (s & 1u) * SE + lane;
+        for (uint32_t j = 0; j < chunks; ++j)
+        {
+            uint32_t const id   = ids[32 * j];
+            uint32_t const base = id & ~kPrevFlag;
+            if (base < ghostFrom)
+                continue;
+            bool const prev       = (id & kPrevFlag) != 0u;
+            uint32_t const expect = tagLow + (prev ? 0u : 1u);
+            float4 q              = stage[32 * j + lane];
+            if (__float_as_uint(q.w) != expect)
+            {
+                float4 const* src           = p.pos + GhostIndex(p, base, prev, expect);
+                unsigned long long const t0 = GlobalTimer();
+                do
+                {
+                    q = LoadPosSys(src);
+                    if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)  // the owner is missing
+                    {
+                        atomicExch(p.distError, 1u);
+                        break;
+                    }
+                } while (__float_as_uint(q.w) != expect);
+                stage[32 * j + lane] = q;
+            }
+        }
+        __syncwarp();
     };
 
     Cursor c1{0, -1, 0, totalSweeps > 0 && warpHasTiles}, c2;
@@ -312,6 +355,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         for (int k = 0; k < p.iterations; ++k)
         {
             float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            // tags (domain decomposition): the pre-step wrote tagBase + s (iterations + 1), iteration k writes that + k + 1
+            uint32_t const tagLow = p.tagBase + static_cast<uint32_t>(s * (p.iterations + 1) + k);
             for (uint32_t c = 0; c < nC; ++c)
             {
                 unsigned long long* tr = nullptr;
@@ -333,12 +378,14 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                         tr0[4] = GlobalTimer();
                     uint32_t const chunks = TileChunks(td.z);
                     if (gathered < chunks)
-                        IssueGather(seq, gathered, chunks);  // what could not be requested before the barrier
+                        IssueGather(seq, gathered, chunks, tagLow);  // what could not be requested before the barrier
                     CpAsyncCommit();
                     IssueTd(c2, seq + 2);
                     CpAsyncCommit();
                     CpAsyncWaitGroup<1>();  // positions have landed; the descriptor may still be in flight
                     __syncwarp();
+                    if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
+                        AwaitGhosts(seq, chunks, tagLow);
                     // Next tile in this same colour sweep (multi-round colours): all its positions are final, so
                     // everything it needs is requested as soon as this tile's buffers are free.  Otherwise the
                     // requests are issued in the shadow of the grid barrier (after GridArrive below).
@@ -354,7 +401,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                         __syncwarp();
                         IssueRecords(seqNext);
                         nextGathered = TileChunks(tdBuf[seqNext & 3u].z);
-                        IssueGather(seqNext, 0, nextGathered);
+                        IssueGather(seqNext, 0, nextGathered, tagLow);
                         if (c2.valid)
                             IssueIds(seq + 2);
                         CpAsyncCommit();
@@ -362,7 +409,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     deferred = nextValid && !sameSweep;
                     WaitRecords();
                     SmemRecords src{recBuf + lane};
-                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), k, omega, lane, tr0, prefetchNext);
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), k, omega, lane, tr0, prefetchNext, tagLow + 1u);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     gathered = nextGathered;
@@ -391,7 +438,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     if (stamp)
                         tr[9] = GlobalTimer();
                     gathered = nextPhase ? TileEarlyChunks(tdBuf[seq & 3u].z) : 0u;
-                    IssueGather(seq, 0, gathered);
+                    IssueGather(seq, 0, gathered, p.tagBase + static_cast<uint32_t>(cUp.k + cUp.k / p.iterations));
                     if (stamp)
                         tr[10] = GlobalTimer();
                     if (c1.valid)

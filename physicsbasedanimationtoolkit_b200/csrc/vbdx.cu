@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -74,6 +75,9 @@ struct Integrator {
     // domain decomposition
     int distRank = 0, distWorld = 1;
     unsigned int distEpoch = 0, peerMask = 0;
+    unsigned int distTag = 2;         // tags of ghost writes used so far (0 = never written)
+    int64_t nGhost = 0;
+    uint32_t peerGhostExt[8] = {}, peerGhostBegin[8] = {}, peerNGhost[8] = {};
     DevBuf<unsigned int> dDistFlags;  // [0..7] peers' epochs, [8] local release, [9] error
     DevBuf<uint32_t> dSendPtr, dSendDst;
     float4* peerPos[8]        = {};
@@ -125,9 +129,9 @@ struct Integrator {
     void Create(vbdx_data_desc const& d);
     void Step(double dt, int iterations, int substeps, bool sync);
     template <class T>
-    void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1);
+    void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows = false);
     template <class T>
-    void GetVertexField(float4 const* src, T* dst, int64_t n);
+    void GetVertexField(float4 const* src, T* dst, int64_t n, bool rows = false);
 };
 
 void Integrator::Create(vbdx_data_desc const& d)
@@ -189,6 +193,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     for (int64_t k = 0; k < d.nGhosts; ++k)
     {
         Require(d.ghosts[k] >= 0 && d.ghosts[k] < nV, "ghost vertex index out of range");
+        Require(isDbc[d.ghosts[k]] == 0, "a ghost vertex must not be a Dirichlet vertex or listed twice (constrained vertices never change: keep them as plain Dirichlet vertices on every rank)");
         isDbc[d.ghosts[k]] = 2;  // never swept, and never touched by the pre-step: the owner GPU writes it
     }
     if (d.colors)
@@ -388,7 +393,9 @@ void Integrator::Create(vbdx_data_desc const& d)
 
     // ---- state
     bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-    dPos.Alloc(static_cast<size_t>(nV) * (cheb ? 2 : 1), &deviceBytes);
+    // Q (and P under Chebyshev), then the odd-tag copies of the ghosts (domain decomposition, step_kernel.cuh)
+    nGhost = static_cast<int64_t>(nV) - plan.ghostBegin;
+    dPos.Alloc(static_cast<size_t>(nV) * (cheb ? 2 : 1) + 2 * static_cast<size_t>(nGhost), &deviceBytes);
     if (cheb)
         dHist.Alloc(nV, &deviceBytes);
     dXtildeM.Alloc(nV, &deviceBytes);
@@ -547,6 +554,18 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
         p.distError = dDistFlags.p + 9;
         p.epochBase = distEpoch;
         p.peerMask  = peerMask;
+        p.tagBase   = distTag;
+        {
+            // processes reach their first step at different times; VBDX_DIST_TIMEOUT_S bounds the wait for a dead peer
+            const char* t   = std::getenv("VBDX_DIST_TIMEOUT_S");
+            double const ts = t ? std::atof(t) : 30.0;
+            p.distTimeoutNs = static_cast<unsigned long long>((ts > 0 ? ts : 30.0) * 1e9);
+        }
+        p.ghostExt  = static_cast<uint32_t>(nV) * (cheb ? 2u : 1u);
+        p.nGhost    = static_cast<uint32_t>(nGhost);
+        for (int r = 0; r < 8; ++r)
+            p.peerGhostExt[r] = peerGhostExt[r], p.peerGhostBegin[r] = peerGhostBegin[r], p.peerNGhost[r] = peerNGhost[r];
+        distTag += static_cast<unsigned int>(substeps) * (static_cast<unsigned int>(iterations) + 1u);
         distEpoch += static_cast<unsigned int>(substeps) * (1u + static_cast<unsigned int>(iterations) * static_cast<unsigned int>(plan.nColors));
     }
     p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
@@ -627,7 +646,7 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
             unsigned int e = 0;
             VBDX_CUDA(cudaMemcpy(&e, dDistFlags.p + 9, sizeof(e), cudaMemcpyDeviceToHost));
             if (e)
-                throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not reach the colour barrier within 20 s");
+                throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not deliver its halo or reach the colour barrier in time (VBDX_DIST_TIMEOUT_S, default 30 s)");
         }
         float ms = 0;
         VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
@@ -636,24 +655,25 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
 }
 
 template <class T>
-void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1)
+void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows)
 {
     Require(src != nullptr && n == nV, "expected a 3 x nV array");  // gpu/impl/common/Eigen.cuh:28-35
     VBDX_CUDA(cudaSetDevice(device));
     T* staging = reinterpret_cast<T*>(dStaging.p);
     VBDX_CUDA(cudaMemcpyAsync(staging, src, 3 * nV * sizeof(T), cudaMemcpyHostToDevice, stream));
-    ScatterFromCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, staging, dst0, dst1);
+    ScatterFromCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, staging, rows ? nV : 1, rows ? 1 : 3, dst0, dst1,
+                                                                 distWorld > 1 ? plan.ghostBegin : nV);
     ++kernelLaunches;
     VBDX_CUDA(cudaStreamSynchronize(stream));
 }
 
 template <class T>
-void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n)
+void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n, bool rows)
 {
     Require(dst != nullptr && n == nV, "expected a 3 x nV array");
     VBDX_CUDA(cudaSetDevice(device));
     T* staging = reinterpret_cast<T*>(dStaging.p);
-    GatherToCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, src, staging);
+    GatherToCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, src, staging, rows ? nV : 1, rows ? 1 : 3);
     ++kernelLaunches;
     VBDX_CUDA(cudaMemcpyAsync(dst, staging, 3 * nV * sizeof(T), cudaMemcpyDeviceToHost, stream));
     VBDX_CUDA(cudaStreamSynchronize(stream));
@@ -829,6 +849,59 @@ VBDX_GETTER(vbdx_get_positions_f64, double, (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_
 VBDX_GETTER(vbdx_get_velocities_f32, float, h->impl.dVel.p)
 VBDX_GETTER(vbdx_get_velocities_f64, double, h->impl.dVel.p)
 
+vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        vbdx::Require(field >= VBDX_FIELD_POSITIONS && field <= VBDX_FIELD_EXTERNAL_ACCELERATION, "unknown vertex field");
+        vbdx::Require(dtype == VBDX_F32 || dtype == VBDX_F64, "unknown dtype");
+        vbdx::Require(layout == VBDX_LAYOUT_COLUMNS || layout == VBDX_LAYOUT_ROWS, "unknown layout");
+        float4* dst0 = field == VBDX_FIELD_POSITIONS ? VBDX_POS_Q : field == VBDX_FIELD_VELOCITIES ? h->impl.dVel.p : h->impl.dAext.p;
+        float4* dst1 = field == VBDX_FIELD_POSITIONS ? VBDX_POS_P : nullptr;
+        bool const rows = layout == VBDX_LAYOUT_ROWS;
+        if (dtype == VBDX_F32)
+            h->impl.SetVertexField<float>(static_cast<const float*>(src), nV, dst0, dst1, rows);
+        else
+            h->impl.SetVertexField<double>(static_cast<const double*>(src), nV, dst0, dst1, rows);
+    });
+}
+
+vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        vbdx::Require(field == VBDX_FIELD_POSITIONS || field == VBDX_FIELD_VELOCITIES, "only positions and velocities can be read back");
+        vbdx::Require(dtype == VBDX_F32 || dtype == VBDX_F64, "unknown dtype");
+        vbdx::Require(layout == VBDX_LAYOUT_COLUMNS || layout == VBDX_LAYOUT_ROWS, "unknown layout");
+        float4 const* src = field == VBDX_FIELD_POSITIONS ? (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_Q) : h->impl.dVel.p;
+        bool const rows   = layout == VBDX_LAYOUT_ROWS;
+        if (dtype == VBDX_F32)
+            h->impl.GetVertexField<float>(src, static_cast<float*>(dst), nV, rows);
+        else
+            h->impl.GetVertexField<double>(src, static_cast<double*>(dst), nV, rows);
+    });
+}
+
+vbdx_status vbdx_host_alloc(void** out, int64_t bytes)
+{
+    if (out == nullptr || bytes <= 0)
+    {
+        gLastError = "vbdx_host_alloc: null output or non-positive size";
+        return VBDX_INVALID_ARGUMENT;
+    }
+    return Guard([&] { VBDX_CUDA(cudaHostAlloc(out, static_cast<size_t>(bytes), cudaHostAllocPortable)); });
+}
+
+vbdx_status vbdx_host_free(void* p)
+{
+    return Guard([&] {
+        if (p)
+            VBDX_CUDA(cudaFreeHost(p));
+    });
+}
+
 vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero)
 {
     if (vbdx_status s = NeedHandle(h))
@@ -904,7 +977,7 @@ vbdx_status vbdx_dist_ipc_handles(vbdx_integrator* h, void* out128)
 }
 
 vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, const void* all_handles, const int64_t* peer_nverts,
-                              int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
+                              const int64_t* peer_nghosts, int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
                               uint32_t recv_mask)
 {
     if (vbdx_status s = NeedHandle(h))
@@ -930,14 +1003,19 @@ vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, c
             I.peerPos[r]   = static_cast<float4*>(pp);
             I.peerFlags[r] = static_cast<unsigned int*>(pf);
             I.peerPOff[r]  = cheb ? static_cast<uint32_t>(peer_nverts[r]) : 0u;
+            vbdx::Require(peer_nghosts[r] >= 0 && peer_nghosts[r] <= peer_nverts[r], "bad peer ghost count");
+            I.peerNGhost[r]     = static_cast<uint32_t>(peer_nghosts[r]);
+            I.peerGhostBegin[r] = static_cast<uint32_t>(peer_nverts[r] - peer_nghosts[r]);  // ghosts are last in internal order
+            I.peerGhostExt[r]   = static_cast<uint32_t>(peer_nverts[r]) * (cheb ? 2u : 1u);
         }
         // per-vertex send lists in internal order
         std::vector<uint32_t> ptr(I.nV + 1, 0), dst(static_cast<size_t>(nSend));
         for (int64_t k = 0; k < nSend; ++k)
         {
             vbdx::Require(send_local[k] >= 0 && send_local[k] < I.nV && send_peer[k] >= 0 && send_peer[k] < world && send_peer[k] != rank &&
-                              send_remote[k] >= 0 && send_remote[k] < (int64_t(1) << 28),
-                          "bad send list entry");
+                              send_remote[k] >= I.peerGhostBegin[send_peer[k]] &&
+                              send_remote[k] < I.peerGhostBegin[send_peer[k]] + I.peerNGhost[send_peer[k]] && send_remote[k] < (int64_t(1) << 28),
+                          "bad send list entry (the remote slot must be a ghost of that peer)");
             int32_t const vi = I.plan.old2new[send_local[k]];
             vbdx::Require(vi < I.plan.ghostBegin, "a ghost vertex cannot be sent");
             ++ptr[vi + 1];

@@ -47,7 +47,7 @@ constexpr int kMaxRingPerTile   = 1024; // 10-bit local indices
 struct TileDesc {
     uint32_t blockStart;  // first record block of the tile
     uint32_t vbase;       // first internal vertex id
-    uint32_t meta;        // log2(w) [0:3) | nverts [3:9) | ring chunks [9:15) | early ring chunks [15:21) | iters [21:32)
+    uint32_t meta;        // log2(w) [0:3) | nverts [3:9) | ring chunks [9:15) | early ring chunks [15:21) | iters [21:31) | reads ghosts [31]
     uint32_t ringStart;   // first entry of the tile's ring list (multiple of 32)
 };
 
@@ -60,12 +60,13 @@ VBDX_HD constexpr uint32_t TileLog2W(uint32_t meta) { return meta & 7u; }
 VBDX_HD constexpr uint32_t TileVerts(uint32_t meta) { return (meta >> 3) & 63u; }
 VBDX_HD constexpr uint32_t TileChunks(uint32_t meta) { return (meta >> 9) & 63u; }       // all ring chunks of 32 entries
 VBDX_HD constexpr uint32_t TileEarlyChunks(uint32_t meta) { return (meta >> 15) & 63u; } // chunks that do not depend on the previous colour
-VBDX_HD constexpr uint32_t TileIters(uint32_t meta) { return meta >> 21; }
+VBDX_HD constexpr uint32_t TileIters(uint32_t meta) { return (meta >> 21) & 1023u; }
+VBDX_HD constexpr bool TileReadsGhosts(uint32_t meta) { return (meta >> 31) != 0u; }  // its ring list holds vertices owned by another GPU
 VBDX_HD constexpr uint32_t TileMeta(uint32_t lw, uint32_t nverts, uint32_t chunks, uint32_t early, uint32_t iters)
 {
     return lw | (nverts << 3) | (chunks << 9) | (early << 15) | (iters << 21);
 }
-constexpr uint32_t kMaxTileIters = 2047;
+constexpr uint32_t kMaxTileIters = 1023;
 
 struct Plan {
     int64_t nV = 0, nActive = 0;

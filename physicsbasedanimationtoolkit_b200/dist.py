@@ -3,9 +3,10 @@
 The reference has no multi-GPU path; this is new.  Ownership is by vertex.  Every rank holds the
 vertices it owns, one layer of *ghost* vertices (every vertex that shares a tet with an owned vertex
 but is owned elsewhere) and every tet incident to an owned vertex.  Ghosts are never swept locally:
-after a colour is swept their owner pushes the new positions straight into the ghost slots of the
-peers (NVLink peer-to-peer stores inside the persistent step kernel), and the colour barrier spans all
-GPUs.  Colours are computed once on the global mesh so that colour c means the same on every rank.
+when a boundary vertex is swept its owner pushes the new position straight into the ghost slots of the
+peers (NVLink peer-to-peer stores inside the persistent step kernel, tagged with the number of the
+write so that readers can wait on the datum itself).  Colours are computed once on the global mesh so
+that colour c means the same on every rank.
 
 Everything in this module is host logic (numpy + ``torch.distributed`` collectives for the plumbing):
 partitioning, local problems, and the exchange lists.  It runs on CPU with the ``gloo`` backend, which
@@ -29,8 +30,9 @@ def partition_slabs(X, nparts: int, axis: int = 0):
 
 
 class LocalProblem:
-    """What one rank simulates: global ids of its local vertices (owned first, ascending; then ghosts,
-    ascending), the local tets in local numbering, and which local vertices are ghosts."""
+    """What one rank simulates: global ids of its local vertices (owned first, ascending; then the
+    constrained vertices of other ranks its tets touch; then ghosts, ascending), the local tets in local
+    numbering, and which local vertices are ghosts."""
 
     def __init__(self, rank, owner, X, T, colors, dbc=None, v=None):
         owner = np.asarray(owner)
@@ -39,10 +41,15 @@ class LocalProblem:
         Tl = T[:, tet_mask]
         touched = np.zeros(owner.size, dtype=bool)
         touched[Tl.reshape(-1)] = True
+        isd = np.zeros(owner.size, dtype=bool)
+        if dbc is not None and len(dbc):
+            isd[np.asarray(dbc)] = True
         owned = np.flatnonzero(mine)
-        ghosts = np.flatnonzero(touched & ~mine)
+        # constrained vertices of other ranks never move: they are plain Dirichlet vertices here, not ghosts
+        fixed = np.flatnonzero(touched & ~mine & isd)
+        ghosts = np.flatnonzero(touched & ~mine & ~isd)
         self.rank = rank
-        self.l2g = np.concatenate([owned, ghosts])
+        self.l2g = np.concatenate([owned, fixed, ghosts])
         self.n_owned = owned.size
         g2l = np.full(owner.size, -1, dtype=np.int64)
         g2l[self.l2g] = np.arange(self.l2g.size)
@@ -51,12 +58,9 @@ class LocalProblem:
         self.tet_ids = np.flatnonzero(tet_mask)
         self.X = np.ascontiguousarray(X[:, self.l2g])
         self.colors = np.ascontiguousarray(np.asarray(colors)[self.l2g])
-        self.ghost_local = np.arange(self.n_owned, self.l2g.size)
+        self.ghost_local = np.arange(self.n_owned + fixed.size, self.l2g.size)
         self.ghost_owner = owner[ghosts]
-        isd = np.zeros(owner.size, dtype=bool)
-        if dbc is not None and len(dbc):
-            isd[np.asarray(dbc)] = True
-        # local Dirichlet set = real constraints; ghosts are handled separately (never swept either)
+        # local Dirichlet set = the real constraints among the local vertices; ghosts are never swept either
         self.dbc = np.flatnonzero(isd[self.l2g])
         self.v = None if v is None else np.ascontiguousarray(v[:, self.l2g])
 
@@ -151,11 +155,12 @@ class DomainDecomposedIntegrator:
             mine = torch.as_tensor(self.vbd.ipc_handles(), device=dev)
             handles = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(handles, mine)
-            nv = torch.tensor([lp.l2g.size], dtype=torch.int64, device=dev)
+            nv = torch.tensor([lp.l2g.size, lp.ghost_local.size], dtype=torch.int64, device=dev)
             nvs = [torch.zeros_like(nv) for _ in range(self.world)]
             dist.all_gather(nvs, nv)
+            nvs = torch.stack(nvs).cpu().numpy()
             self.vbd.dist_connect(self.rank, self.world, torch.stack(handles).cpu().numpy(),
-                                  torch.cat(nvs).cpu().numpy(), sl, sp, sr,
+                                  nvs[:, 0], nvs[:, 1], sl, sp, sr,
                                   sum(1 << int(r) for r in np.unique(lp.ghost_owner)))
             dist.barrier()
         self.n_send = 0 if self.world == 1 else int(sl.size)

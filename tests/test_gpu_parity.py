@@ -232,3 +232,46 @@ def test_direct_variant_config1():
         vbd.step(0.01, 20, 1)
         ref.step(0.01, 20, 1)
     assert rel_l2(vbd.x, ref.x) < TOL
+
+
+def test_host_layouts_and_pinned_buffers():
+    """State crosses the boundary in either storage order and through page-locked arrays without change
+    (vbdx_set/get_vertex_field; the f32/f64 column-major entry points stay the reference's convention)."""
+    import ctypes as C
+    from physicsbasedanimationtoolkit_b200 import _lib
+
+    X, T = meshes.tet_grid(5, 4, 3, 0.1)
+    nV = X.shape[1]
+    d, vbd, _ = make(X, T, dbc=np.flatnonzero(X[2] == 0), cheb=0.7)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, nV)).astype(np.float32)
+    vbd.x = x                                   # row-major
+    assert np.array_equal(vbd.x, x)
+    vbd.x = np.asfortranarray(x)                # column-major (Eigen), consumed in place
+    assert np.array_equal(vbd.x, x)
+    vbd.x = x[:, ::-1][:, ::-1]                 # non-contiguous view
+    assert np.array_equal(vbd.x, x)
+    pin = pbat.host.pinned_empty((3, nV), np.float32)
+    pin[...] = x + 1
+    vbd.x = pin
+    out = pbat.host.pinned_empty((3, nV), np.float32)
+    assert vbd.positions(out=out) is out and np.array_equal(out, x + 1)
+    vbd.v = x
+    assert np.array_equal(vbd.velocities(), x)
+    # the legacy column-major C entry points agree with the generic ones
+    L = _lib.lib()
+    cols = np.empty((nV, 3), np.float32)
+    _lib.check(L.vbdx_get_positions_f32(vbd._h, cols.ctypes.data, nV))
+    assert np.array_equal(cols.T, x + 1)
+    cols64 = np.empty((nV, 3), np.float64)
+    _lib.check(L.vbdx_get_vertex_field(vbd._h, 0, 1, 0, cols64.ctypes.data, nV))
+    assert np.array_equal(cols64.T, (x + 1).astype(np.float64))
+    with pytest.raises(ValueError):
+        vbd.positions(out=np.empty((nV, 3), np.float32))
+    with pytest.raises(ValueError):
+        _lib.check(L.vbdx_get_vertex_field(vbd._h, 2, 0, 0, cols.ctypes.data, nV))
+    # double interface
+    sim = pbat.sim.vbd.Integrator(d)
+    xd = rng.standard_normal((3, nV))
+    sim.x = xd
+    assert np.array_equal(sim.x, xd.astype(np.float32).astype(np.float64))
