@@ -18,6 +18,6 @@ def test_domain_decomposition_two_gpus_bitwise():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("world=2")]
-    assert len(lines) == 2, out.stdout
+    assert len(lines) == 4, out.stdout
     for l in lines:
         assert "rel L2 vs single GPU = 0.000e+00" in l, l
