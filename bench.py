@@ -242,6 +242,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.Stream()  # events must sit on the stream the kernels are launched on
     vbd.use_stream(stream.cuda_stream)
+    if decomposed:
+        vbd.dist_stats()  # reset the halo diagnostics
     t0 = time.time()
     ev0.record(stream)
     for _ in range(steps):
@@ -252,6 +254,7 @@ def main():
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     total_ms = ev0.elapsed_time(ev1)
+    halo = vbd.dist_stats() if decomposed else None
     launches = vbd.info["kernelLaunches"] - launches0
     # per-launch kernel duration (events around a single launch)
     kms = []
@@ -322,6 +325,8 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
                          "streamed_record_bytes_per_launch": int(info["nRecordSlots"] * 32 * ITERS)},
         }
+        if halo is not None:
+            line["halo"] = dict(halo, note="rank 0, over the timed steps: ghost values that had to be polled / ns polling (summed over lanes) / barriers of CTA 0 that waited for a neighbour's epoch / ns")
         if world == 1 and not args.no_cpu_baseline:
             _, _, cpu = cpu_reference(X, T, dbc, x0, steps=args.cpu_steps)
             line["cpu_baseline"] = cpu

@@ -245,6 +245,11 @@ vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, c
                               const int64_t* peer_nghosts, int64_t nSend, const int64_t* send_local, const int64_t* send_peer, const int64_t* send_remote,
                               uint32_t recv_mask);
 
+/* Diagnostics of the halo exchange since the last reset: out4 = {ghost values that had not arrived when a tile needed
+ * them, ns spent polling them (summed over lanes), colour barriers (CTA 0) that had to wait for a neighbour's epoch,
+ * ns spent there}. */
+vbdx_status vbdx_dist_stats(vbdx_integrator* h, uint32_t out4[4], int32_t reset);
+
 /* Contact state after the last step, per collision vertex in the order of desc->V
  * (gpu/impl/contact/VertexTriangleMixedCcdDcd.cuh: active, nn): active[nCV] (0/1), nn[8 * nCV] nearest triangles
  * (indices into desc->F, -1 terminated), *nActive.  Any pointer may be NULL. */

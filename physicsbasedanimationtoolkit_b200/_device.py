@@ -217,6 +217,12 @@ class DeviceIntegrator:
         _lib.check(self._L.vbdx_dist_ipc_handles(self._h, out.ctypes.data))
         return out
 
+    def dist_stats(self, reset=True):
+        """Halo-exchange diagnostics (``vbdx_dist_stats``): late ghosts, ns polling, barriers that waited, ns."""
+        out = np.zeros(4, np.uint32)
+        _lib.check(self._L.vbdx_dist_stats(self._h, out.ctypes.data, int(reset)))
+        return dict(late_ghosts=int(out[0]), ghost_poll_ns=int(out[1]), epoch_waits=int(out[2]), epoch_wait_ns=int(out[3]))
+
     def dist_connect(self, rank, world, all_handles, peer_nverts, peer_nghosts, send_local, send_peer, send_remote, recv_mask):
         all_handles = np.ascontiguousarray(all_handles, np.uint8)
         peer_nverts = np.ascontiguousarray(peer_nverts, np.int64)

@@ -83,6 +83,7 @@ SYMBOLS = {
     "vbdx_get_internal_ids": (C.c_int, [_H, C.c_void_p]),
     "vbdx_dist_ipc_handles": (C.c_int, [_H, C.c_void_p]),
     "vbdx_dist_connect": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "vbdx_dist_stats": (C.c_int, [_H, C.c_void_p, C.c_int32]),
     "vbdx_get_contact_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_debug_bvh_build": (C.c_int, [C.c_int64] + [C.c_void_p] * 11),
     "vbdx_debug_trace": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),

@@ -4,6 +4,7 @@
 #include "vbdx_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
@@ -203,6 +204,8 @@ void BuildPlan(
             ringPtr[u + 1] = static_cast<uint32_t>(ring.size());
         }
     }
+    const char* boEnv       = std::getenv("VBDX_BOUNDARY_ORDER");
+    int const boundaryOrder = boEnv ? std::atoi(boEnv) : 0;
     struct Item {
         uint64_t key;
         int32_t v;
@@ -233,7 +236,17 @@ void BuildPlan(
             morton = (ExpandBits10(q[0]) << 2) | (ExpandBits10(q[1]) << 1) | ExpandBits10(q[2]);
         }
         uint64_t const itKey = 4095u - static_cast<uint32_t>(std::min(iters, 4095));
-        uint64_t const key   = (static_cast<uint64_t>(colors[i]) << 45) |
+        // domain decomposition tuning knob (VBDX_BOUNDARY_ORDER = 1 / 2): vertices next to another GPU's vertices first /
+        // last within their colour.  Default 0 (Morton order): both groupings measured slower.
+        uint64_t group = 0;
+        if (boundaryOrder != 0)
+        {
+            bool boundary = false;
+            for (uint32_t r = ringPtr[i]; r < ringPtr[i + 1]; ++r)
+                boundary |= isDbc[ring[r]] == 2;
+            group = (boundaryOrder == 1) ? (boundary ? 0u : 1u) : (boundary ? 1u : 0u);
+        }
+        uint64_t const key = (static_cast<uint64_t>(colors[i]) << 46) | (group << 45) |
                              (static_cast<uint64_t>(5 - lw) << 42) | (itKey << 30) | morton;
         items.push_back({key, static_cast<int32_t>(i), static_cast<uint8_t>(lw),
                          static_cast<uint16_t>(std::min(iters, 65535))});

@@ -68,6 +68,7 @@ struct StepParams {
     unsigned int* peerFlags[8];          // their flag arrays: slot [rank] is written by this GPU
     unsigned int* myFlags;               // slot r: last epoch GPU r finished;  slot 8: release epoch for this GPU's CTAs
     unsigned int* distError;             // set when a peer did not show up in time
+    unsigned int* distStats;             // [0] ghosts that had to be polled, [1] ns spent polling them, [2] barriers that waited for a peer's epoch, [3] ns
     unsigned int epochBase;              // epochs used by earlier launches
     unsigned long long distTimeoutNs;    // how long to wait for a peer before giving up
     // Ghost values carry the number of their write in .w ("tag": the pre-step of substep s writes tag

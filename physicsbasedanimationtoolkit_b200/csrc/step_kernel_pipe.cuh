@@ -65,6 +65,12 @@ __device__ __forceinline__ unsigned int LoadAcquireSys(const unsigned int* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int LoadRelaxedSys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void StoreReleaseSys(unsigned int* p, unsigned int v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -85,8 +91,8 @@ __device__ __forceinline__ float4 LoadPosSys(const float4* q)
 // Domain decomposition (p.world > 1): halo data synchronises itself (every ghost value carries the tag of its
 // write, readers wait for the tag they need), so the colour barrier stays local.  What remains between GPUs is
 // a bound on how far a GPU may run ahead, so that it never overwrites a ghost copy a slower peer still reads:
-// the CTA that arrives last publishes this GPU's epoch in its neighbours' flag arrays (a relaxed store over
-// NVLink, nobody waits for it now), and every CTA waits until its neighbours have finished epoch e - lag
+// once the local barrier is complete CTA 0 publishes this GPU's epoch in its neighbours' flag arrays (a relaxed
+// store over NVLink, nobody waits for it now), and every CTA waits until its neighbours have finished epoch e - lag
 // (lag = 2 inside a substep -- a copy is rewritten nColors + 1 phases after its last reader at the earliest --
 // and 0 at the end of a substep, whose pre-step rewrites every ghost).  A peer that never shows up raises
 // distError instead of hanging the GPU.
@@ -101,15 +107,7 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
         if (trace)
             trace[2] = GlobalTimer();
         target += gridDim.x;
-        if (p.world > 1)
-        {
-            if (AddAcqRelReturn(p.barrier, 1u) + 1u == target)
-                for (int r = 0; r < p.world; ++r)
-                    if ((p.peerMask >> r) & 1u)
-                        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peerFlags[r] + p.rank), "r"(e) : "memory");
-        }
-        else
-            AddRelease(p.barrier, 1u);
+        AddRelease(p.barrier, 1u);
         if (trace)
             trace[1] = GlobalTimer();
     }
@@ -117,21 +115,40 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
     NamedArrive(kBarFenced, blockDim.x);
     if (lane == 0)
     {
+        // The neighbours' epochs: one relaxed look before the local wait (e - lag is old news in steady state; the
+        // acquire of the local poll below orders what follows) ...
+        unsigned int pending = 0;
+        if (p.world > 1)
+            for (int r = 0; r < p.world; ++r)
+                if (((p.peerMask >> r) & 1u) && static_cast<int>(LoadRelaxedSys(p.myFlags + r) - (e - lag)) < 0)
+                    pending |= 1u << r;
         while (LoadAcquire(p.barrier) < target)
         {
         }
-        if (p.world > 1)
-        {
-            // flags live in this GPU's memory, written over NVLink
-            unsigned long long const t0 = GlobalTimer();
+        // ... every CTA of this GPU has finished the phase: CTA 0 tells the neighbours (flags live in the reader's
+        // memory, written over NVLink; nobody waits for this one now) ...
+        if (p.world > 1 && blockIdx.x == 0)
             for (int r = 0; r < p.world; ++r)
                 if ((p.peerMask >> r) & 1u)
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peerFlags[r] + p.rank), "r"(e) : "memory");
+        // ... and only then a blocking wait for the neighbours that were behind (always the case at the end of a
+        // substep, where lag = 0: publishing first is what keeps two GPUs from waiting for each other)
+        if (pending != 0u)
+        {
+            unsigned long long const t0 = GlobalTimer();
+            for (int r = 0; r < p.world; ++r)
+                if ((pending >> r) & 1u)
                     while (static_cast<int>(LoadAcquireSys(p.myFlags + r) - (e - lag)) < 0)
                         if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)  // a peer is missing
                         {
                             atomicExch(p.distError, 1u);
                             break;
                         }
+            if (blockIdx.x == 0)
+            {
+                atomicAdd(p.distStats + 2, 1u);
+                atomicAdd(p.distStats + 3, static_cast<unsigned int>(GlobalTimer() - t0));
+            }
         }
         if (trace)
             trace[3] = GlobalTimer();
@@ -304,16 +321,21 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             {
                 float4 const* src           = p.pos + GhostIndex(p, base, prev, expect);
                 unsigned long long const t0 = GlobalTimer();
-                do
+                for (uint32_t polls = 1;; ++polls)
                 {
                     q = LoadPosSys(src);
-                    if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)  // the owner is missing
+                    if (__float_as_uint(q.w) == expect)
+                        break;
+                    // the owner is missing? (looked at rarely: the poll itself must stay one load per round trip)
+                    if ((polls & 255u) == 0u && (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u))
                     {
                         atomicExch(p.distError, 1u);
                         break;
                     }
-                } while (__float_as_uint(q.w) != expect);
+                }
                 stage[32 * j + lane] = q;
+                atomicAdd(p.distStats, 1u);
+                atomicAdd(p.distStats + 1, static_cast<unsigned int>(GlobalTimer() - t0));
             }
         }
         __syncwarp();

@@ -552,6 +552,7 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
             p.peerPos[r] = peerPos[r], p.peerPOff[r] = peerPOff[r], p.peerFlags[r] = peerFlags[r];
         p.myFlags   = dDistFlags.p;
         p.distError = dDistFlags.p + 9;
+        p.distStats = dDistFlags.p + 10;
         p.epochBase = distEpoch;
         p.peerMask  = peerMask;
         p.tagBase   = distTag;
@@ -1038,6 +1039,20 @@ vbdx_status vbdx_dist_connect(vbdx_integrator* h, int32_t rank, int32_t world, c
         I.peerMask = recv_mask;
         for (int64_t k = 0; k < nSend; ++k)
             I.peerMask |= 1u << send_peer[k];
+    });
+}
+
+vbdx_status vbdx_dist_stats(vbdx_integrator* h, uint32_t out4[4], int32_t reset)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        VBDX_CUDA(cudaMemcpy(out4, I.dDistFlags.p + 10, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (reset)
+            VBDX_CUDA(cudaMemset(I.dDistFlags.p + 10, 0, 4 * sizeof(uint32_t)));
     });
 }
 
