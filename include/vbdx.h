@@ -121,7 +121,7 @@ typedef struct vbdx_data_desc {
                               the pre-step; their positions are written by the owner.  NULL for a single-GPU problem */
     int64_t nGhosts;
     int32_t consumer_warps;/* tuning: (consumer) warps per CTA of the pipelined / TMA kernels (0 = default) */
-    int32_t reserved;
+    int32_t window_size;   /* Anderson acceleration window (Data::mWindowSize, default 5) */
 } vbdx_data_desc;
 
 /* Which persistent step kernel runs the sweeps.  Both compute the same arithmetic in the same order. */
@@ -176,7 +176,11 @@ vbdx_status vbdx_get_velocities_f64(vbdx_integrator* h, double* v, int64_t nV);
  * transposition: VBDX_LAYOUT_COLUMNS = column-major 3 x nV (Eigen; xyz of a vertex adjacent),
  * VBDX_LAYOUT_ROWS = row-major 3 x nV (all x, then all y, then all z).  Host pointers may be pageable or
  * pinned; with pinned memory (vbdx_host_alloc) the copy is a single DMA transfer. */
-typedef enum vbdx_field { VBDX_FIELD_POSITIONS = 0, VBDX_FIELD_VELOCITIES = 1, VBDX_FIELD_EXTERNAL_ACCELERATION = 2 } vbdx_field;
+typedef enum vbdx_field {
+    VBDX_FIELD_POSITIONS = 0, VBDX_FIELD_VELOCITIES = 1, VBDX_FIELD_EXTERNAL_ACCELERATION = 2,
+    VBDX_FIELD_INERTIAL_TARGET = 3,   /* read-only: Data::xtilde of the current substep */
+    VBDX_FIELD_PREVIOUS_POSITIONS = 4 /* read-only: Data::xt */
+} vbdx_field;
 typedef enum vbdx_dtype { VBDX_F32 = 0, VBDX_F64 = 1 } vbdx_dtype;
 typedef enum vbdx_layout { VBDX_LAYOUT_COLUMNS = 0, VBDX_LAYOUT_ROWS = 1 } vbdx_layout;
 vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV);
@@ -184,6 +188,18 @@ vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dty
 /* Page-locked host memory for the arrays above (cudaHostAlloc / cudaFreeHost). */
 vbdx_status vbdx_host_alloc(void** out, int64_t bytes);
 vbdx_status vbdx_host_free(void* p);
+
+/* A slice of ONE substep of length sdt, for callers that look at every iterate (Integrator::TraceNextStep /
+ * ExportTrace, sim/vbd/Integrator.cpp:47-52,202-235; gpu TracedStep, gpu/impl/vbd/Integrator.cu:105-148,284-301):
+ * [pre-step: xt, xtilde, initial guess] -> iterations k_begin..k_end-1 of a solve of total_iterations ->
+ * [post-step: velocity update].  Base and Chebyshev solves; blocking. */
+#define VBDX_PARTIAL_PRE_STEP 1
+#define VBDX_PARTIAL_POST_STEP 2
+vbdx_status vbdx_step_partial(vbdx_integrator* h, double sdt, int32_t k_begin, int32_t k_end, int32_t total_iterations, int32_t flags);
+/* Integrator::ObjectiveFunction / ObjectiveFunctionGradient (sim/vbd/Integrator.h:45-58, Integrator.cpp:138-200):
+ * f = 1/2 |xk - xtilde|_M^2 + dt^2 sum_e wg_e psi_e(xk), evaluated on the device in double precision.
+ * xk, xtilde: 3 x nV column-major, caller's vertex order; f and grad (3 nV) may each be NULL. */
+vbdx_status vbdx_objective(vbdx_integrator* h, const double* xk, const double* xtilde, double dt, double* f, double* grad);
 
 /* Integrator::SetNumericalZeroForHessianDeterminant   gpu/vbd/Integrator.h:111 */
 vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero);

@@ -21,7 +21,7 @@ REF_LIB = os.path.join(_HERE, "_ref", "liboracle_ref.so")
 
 # enums shared with the product (sim/vbd/Enums.h:9-28, graph/Enums.h)
 POSITION, INERTIA, KINETIC_ENERGY_MINIMUM, ADAPTIVE_VBD, ADAPTIVE_PBAT = range(5)
-ACCEL_NONE, ACCEL_CHEBYSHEV = 0, 1
+ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV = 0, 1, 2, 3   # = vbdx_acceleration_strategy
 ORDER_NATURAL, ORDER_SMALLEST_DEGREE, ORDER_LARGEST_DEGREE = range(3)
 SELECT_LEAST_USED, SELECT_FIRST_AVAILABLE = range(2)
 
@@ -72,6 +72,8 @@ def _load(kind: str) -> C.CDLL:
     lib.vbdo_get_i64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     lib.vbdo_set_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     lib.vbdo_set_params.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.vbdo_set_acceleration.restype = C.c_int
+    lib.vbdo_set_acceleration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64]
     lib.vbdo_objective.restype = C.c_double
     lib.vbdo_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     lib.vbdo_objective_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -188,6 +190,12 @@ class Oracle:
 
     x = property(lambda s: s.get("x"), lambda s, a: s.set("x", a))
     v = property(lambda s: s.get("v"), lambda s, a: s.set("v", a))
+
+    def set_acceleration(self, accel, rho=1.0, L=1.0, start=3, window=5):
+        """Data::With{Chebyshev,Anderson,Nesterov}Acceleration; ``accel`` = ACCEL_* (the reference validates in
+        Data::Construct, sim/vbd/Data.cpp:268-296)."""
+        if self.lib.vbdo_set_acceleration(self.h, int(accel), float(rho), float(L), int(start), int(window)):
+            raise ValueError("invalid acceleration parameters")
 
     def objective(self, xk, xtilde, dt):
         a = np.ascontiguousarray(np.asarray(xk, np.float64).T)

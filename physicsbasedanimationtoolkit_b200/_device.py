@@ -65,6 +65,7 @@ class DeviceIntegrator:
         d.device, d.tile_iters, d.flags = int(device), int(tile_iters), int(flags)
         d.kernel_variant, d.ring_slots = int(kernel_variant), int(ring_slots)
         d.consumer_warps = int(consumer_warps)
+        d.window_size = int(getattr(data, "manderson", 5))
         d.ghosts = ptr(ghosts, np.int64)
         d.nGhosts = 0 if ghosts is None else int(np.size(ghosts))
         # rest positions differ from x only if the caller edited data.x after construct(); the
@@ -91,6 +92,40 @@ class DeviceIntegrator:
     def _step(self, dt, iterations, substeps):
         _lib.check(self._L.vbdx_step(self._h, float(dt), int(iterations), int(substeps)))
 
+    PRE_STEP, POST_STEP = 1, 2
+
+    def step_partial(self, sdt, k_begin, k_end, total_iterations, flags=0):
+        """One slice of a substep (``vbdx_step_partial``): optional pre-step, iterations ``k_begin..k_end-1`` of a
+        solve of ``total_iterations``, optional velocity update."""
+        _lib.check(self._L.vbdx_step_partial(self._h, float(sdt), int(k_begin), int(k_end), int(total_iterations), int(flags)))
+
+    def objective(self, xk, xtilde, dt, gradient=False):
+        """``Integrator::ObjectiveFunction`` / ``ObjectiveFunctionGradient`` (sim/vbd/Integrator.cpp:138-200) at the
+        given 3 x nV arrays, evaluated on the device in double precision.  Returns f, or (f, grad 3 x nV)."""
+        xk = np.ascontiguousarray(np.asarray(xk, np.float64).T)
+        xt = np.ascontiguousarray(np.asarray(xtilde, np.float64).T)
+        if xk.shape != (self.nV, 3) or xt.shape != (self.nV, 3):
+            raise ValueError(f"xk and xtilde must be 3 x {self.nV}")
+        f = C.c_double(0.0)
+        g = np.empty((self.nV, 3)) if gradient else None
+        _lib.check(self._L.vbdx_objective(self._h, xk.ctypes.data, xt.ctypes.data, float(dt), C.byref(f),
+                                          None if g is None else g.ctypes.data))
+        return (f.value, np.ascontiguousarray(g.T)) if gradient else f.value
+
+    def _traced_substeps(self, dt, iterations, substeps):
+        """Generator over the iterates of one step: yields (substep, k, x, xtilde, sdt) before every sweep and once
+        more (k = iterations) after the velocity update -- the points at which the reference records its trace."""
+        sdt = dt / substeps
+        f64 = np.float64
+        for s in range(substeps):
+            self.step_partial(sdt, 0, 0, iterations, self.PRE_STEP)
+            xtilde = self._get("inertial_target").astype(f64)
+            for k in range(iterations):
+                yield s, k, self._get("positions").astype(f64), xtilde, sdt
+                self.step_partial(sdt, k, k + 1, iterations, 0)
+            self.step_partial(sdt, iterations, iterations, iterations, self.POST_STEP)
+            yield s, iterations, self._get("positions").astype(f64), xtilde, sdt
+
     def step_async(self, dt, iterations, substeps=1):
         """Extension: enqueue a step on the handle's stream and return immediately."""
         _lib.check(self._L.vbdx_step_async(self._h, float(dt), int(iterations), int(substeps)))
@@ -106,7 +141,7 @@ class DeviceIntegrator:
     def _sfx(self):
         return "f32" if self._dtype == np.float32 else "f64"
 
-    _FIELDS = {"positions": 0, "velocities": 1, "external_acceleration": 2}
+    _FIELDS = {"positions": 0, "velocities": 1, "external_acceleration": 2, "inertial_target": 3, "previous_positions": 4}
 
     def _get(self, what, out=None):
         """3 x nV array of ``what``.  ``out`` (C-contiguous 3 x nV of the integrator's dtype, ideally from

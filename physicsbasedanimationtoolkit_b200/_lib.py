@@ -35,7 +35,7 @@ class DataDesc(C.Structure):
         ("device", C.c_int32), ("tile_iters", C.c_int32), ("flags", C.c_int32),
         ("kernel_variant", C.c_int32), ("ring_slots", C.c_int32),
         ("ghosts", C.c_void_p), ("nGhosts", C.c_int64),
-        ("consumer_warps", C.c_int32), ("reserved", C.c_int32),
+        ("consumer_warps", C.c_int32), ("window_size", C.c_int32),
     ]
 
 
@@ -60,6 +60,8 @@ SYMBOLS = {
     "vbdx_step": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32]),
     "vbdx_step_async": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32]),
     "vbdx_synchronize": (C.c_int, [_H]),
+    "vbdx_step_partial": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vbdx_objective": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "vbdx_set_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_get_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

@@ -58,7 +58,9 @@ struct StepParams {
     float4* snap;                        // 2 x nVerts: positions as they were when the iteration started
     const uint32_t* __restrict__ colorVertexBegin;  // nColors + 1: internal id range of every colour
     float muC, muF, epsv;
-    int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path)
+    int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path) or by an earlier partial launch
+    int skipPostStep;                    // partial launch: more iterations of this substep follow
+    int iterBegin;                       // partial launch: index (within the substep's solve) of this launch's first iteration
     // multi-GPU domain decomposition (world == 1: single GPU)
     uint32_t ghostBegin;                 // internal ids >= ghostBegin are ghosts: written by their owner GPU only
     const uint32_t* __restrict__ sendPtr;  // per internal vertex < ghostBegin: range into sendDst (null: nothing to send)
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
         GridBarrier(p.barrier, target);
         for (int k = 0; k < p.iterations; ++k)
         {
-            float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            float const omega = kChebyshev ? __ldg(p.omega + p.iterBegin + k) : 1.f;
             for (int c = 0; c < p.nColors; ++c)
             {
                 unsigned long long* tr = nullptr;
@@ -607,13 +609,14 @@ __global__ void __launch_bounds__(256, 3) StepKernel(const __grid_constant__ Ste
                     if (threadIdx.x == 0)
                         tr[0] = GlobalTimer();
                 }
-                SweepColor<kChebyshev, kDamping>(p, c, k, omega, stage, tr);
+                SweepColor<kChebyshev, kDamping>(p, c, p.iterBegin + k, omega, stage, tr);
                 GridBarrier(p.barrier, target, tr);
             }
         }
     }
-    for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
-        PostStepVertex(p, i);
+    if (!p.skipPostStep)
+        for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
+            PostStepVertex(p, i);
 }
 
 }  // namespace vbdx

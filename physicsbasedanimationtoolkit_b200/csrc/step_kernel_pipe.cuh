@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
 
         for (int k = 0; k < p.iterations; ++k)
         {
-            float const omega = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            float const omega = kChebyshev ? __ldg(p.omega + p.iterBegin + k) : 1.f;
             // tags (domain decomposition): the pre-step wrote tagBase + s (iterations + 1), iteration k writes that + k + 1
             uint32_t const tagLow = p.tagBase + static_cast<uint32_t>(s * (p.iterations + 1) + k);
             for (uint32_t c = 0; c < nC; ++c)
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     deferred = nextValid && !sameSweep;
                     WaitRecords();
                     SmemRecords src{recBuf + lane};
-                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), k, omega, lane, tr0, prefetchNext, tagLow + 1u);
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), p.iterBegin + k, omega, lane, tr0, prefetchNext, tagLow + 1u);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     gathered = nextGathered;
@@ -474,8 +474,9 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             }
         }
     }
-    for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
-        PostStepVertex(p, i);
+    if (!p.skipPostStep)
+        for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
+            PostStepVertex(p, i);
 }
 
 }  // namespace vbdx

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
 
         for (int k = 0; k < p.iterations; ++k)
         {
-            float const omega        = kChebyshev ? __ldg(p.omega + k) : 1.f;
+            float const omega        = kChebyshev ? __ldg(p.omega + p.iterBegin + k) : 1.f;
             uint32_t const sweepBase = static_cast<uint32_t>(s * p.iterations + k) * blocksPerSweep;
             for (uint32_t c = 0; c < nC; ++c)
             {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
                     }
                     uint32_t const n0 = sweepBase + rt.w + (td.x - rt.z);
                     RingRecords src{smem, full, empty, produced, R, n0 % R, n0 / R, n0, lane};
-                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage + (seq & 1u) * SE, src, static_cast<int>(c), k, omega, lane, tr0);
+                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage + (seq & 1u) * SE, src, static_cast<int>(c), p.iterBegin + k, omega, lane, tr0);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     ++seq;
@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) StepKernelTma(const __grid_
             }
         }
     }
-    for (uint32_t i = ctid; i < p.ghostBegin; i += cstride)
-        PostStepVertex(p, i);
+    if (!p.skipPostStep)
+        for (uint32_t i = ctid; i < p.ghostBegin; i += cstride)
+            PostStepVertex(p, i);
 }
 
 }  // namespace vbdx

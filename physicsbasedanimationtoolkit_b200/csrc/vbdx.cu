@@ -4,7 +4,9 @@
 #include "../../include/vbdx.h"
 
 #include "device_buffer.cuh"
+#include "anderson.cuh"
 #include "contact_host.cuh"
+#include "diagnostics.cuh"
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
 #include "step_kernel_pipe.cuh"
@@ -52,7 +54,14 @@ struct Integrator {
     // setup products kept for introspection (caller numbering)
     DevBuf<int32_t> dE;
     DevBuf<uint32_t> dPtr, dAdj;
-    DevBuf<double> dJinv, dVol, dMass;
+    DevBuf<double> dJinv, dVol, dMass, dLame;  // dLame empty = the reference's default material everywhere
+    double mu0 = 0, lambda0 = 0;
+    // Anderson acceleration (anderson.cuh)
+    int window = 5;
+    DevBuf<float4> dAndVec;   // xkm1, Gkm1, Fkm1, Fk, DF[m], DG[m]
+    DevBuf<double> dAndSmall; // gram m*m, scratch 2m, alpha m
+    // objective / gradient evaluation (diagnostics.cuh)
+    DevBuf<double> dObjX, dObjXt, dObjGrad, dObjVal;
     DevBuf<int32_t> dColor;
     DevBuf<uint8_t> dIsDbc;
     std::vector<int64_t> colors;
@@ -128,6 +137,14 @@ struct Integrator {
 
     void Create(vbdx_data_desc const& d);
     void Step(double dt, int iterations, int substeps, bool sync);
+    void PrepareOmega(int iterations);
+    StepParams MakeParams(double sdt, int iterations, int substeps);
+    void LaunchStepKernel(StepParams const& q);
+    void RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync);
+    void LaunchPreStep(StepParams const& q);
+    void AndersonStep(StepParams const& p, int iterations, int substeps);
+    void StepPartial(double sdt, int kBegin, int kEnd, int totalIterations, int flags);
+    void Objective(const double* xk, const double* xtilde, double dt, double* f, double* grad);
     template <class T>
     void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows = false);
     template <class T>
@@ -141,8 +158,17 @@ void Integrator::Create(vbdx_data_desc const& d)
     Require(d.nV > 0 && d.nT > 0 && d.X && d.E, "need a volume mesh: X (3 x nV) and E (4 x nT)");
     Require(d.nV < (int64_t(1) << 31) - 1 && d.nT < (int64_t(1) << 29), "mesh too large for 32-bit device indices");
     Require(d.acceleration >= VBDX_ACCEL_NONE && d.acceleration <= VBDX_ACCEL_TRUST_REGION, "unknown acceleration strategy");
-    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV)
-        throw Error(VBDX_UNSUPPORTED, "only the base and Chebyshev-accelerated VBD solves are implemented");
+    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV && d.acceleration != VBDX_ACCEL_ANDERSON)
+        throw Error(VBDX_UNSUPPORTED, "only the base, Chebyshev- and Anderson-accelerated VBD solves are implemented");
+    if (d.acceleration == VBDX_ACCEL_ANDERSON)
+    {
+        // sim/vbd/Data.cpp:277-283 (window >= 1); the device solver keeps the window's Gram matrix in registers
+        Require(d.window_size >= 1, "Expected window size >= 1");
+        if (d.window_size > kMaxAndersonWindow)
+            throw Error(VBDX_UNSUPPORTED, "Anderson windows larger than 16 are not supported");
+        Require(d.nF == 0 && d.nGhosts == 0, "Anderson acceleration is not combined with contact or domain decomposition yet");
+        window = d.window_size;
+    }
     if (d.material != VBDX_MATERIAL_STABLE_NEO_HOOKEAN)
         throw Error(VBDX_UNSUPPORTED, "only the Stable Neo-Hookean energy is implemented");
     if (d.acceleration == VBDX_ACCEL_CHEBYSHEV)
@@ -235,7 +261,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     ElementQuantities<<<Blocks(nT, 128), 128, 0, stream>>>(dX.p, dE.p, nT, dColor.p, dIsDbc.p, dJinv.p, dVol.p, dErr.p);
     kernelLaunches += 7;
 
-    DevBuf<double> dLame, dRho;
+    DevBuf<double> dRho;
     // default material: Y = 1e6, nu = 0.45 (sim/vbd/Data.cpp:199-205, physics/HyperElasticity.cpp:6-11)
     double const Y = 1e6, nu = 0.45;
     double const muDefault = Y / (2. * (1. + nu)), lamDefault = (Y * nu) / ((1. + nu) * (1. - 2. * nu));
@@ -243,9 +269,10 @@ void Integrator::Create(vbdx_data_desc const& d)
     {
         for (int64_t e = 0; e < nT; ++e)
             Require(d.lame[2 * e + 1] != 0.0, "lambda must be non-zero (alpha = 1 + mu/lambda)");
-        dLame.Alloc(2 * nT);
+        dLame.Alloc(2 * nT, &deviceBytes);
         dLame.Upload(d.lame, 2 * nT, stream);
     }
+    mu0 = muDefault, lambda0 = lamDefault;
     dMass.Alloc(nV, &deviceBytes);
     if (d.m)
         dMass.Upload(d.m, nV, stream);
@@ -493,6 +520,14 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
 {
     Require(dt > 0 && iterations >= 0 && substeps >= 1, "Step: need dt > 0, iterations >= 0, substeps >= 1");
     VBDX_CUDA(cudaSetDevice(device));
+    PrepareOmega(iterations);
+    StepParams p = MakeParams(dt / static_cast<double>(substeps), iterations, substeps);
+    RunStep(p, dt, iterations, substeps, sync);
+}
+
+// ChebyshevOmega for every iteration of a solve (sim/vbd/Kernels.h:96-102), uploaded once per iteration count
+void Integrator::PrepareOmega(int iterations)
+{
     bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
     if (cheb && omegaIterations != iterations)
     {
@@ -516,7 +551,12 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
         VBDX_CUDA(cudaStreamSynchronize(stream));  // omegaHost must outlive the copy
         omegaIterations = iterations;
     }
-    double const sdt = dt / static_cast<double>(substeps);
+}
+
+// Everything a step kernel launch needs, for `substeps` substeps of length sdt with `iterations` sweeps each.
+StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
+{
+    bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
     StepParams p{};
     p.records      = dRecords.p;
     p.tiles        = reinterpret_cast<uint4 const*>(dTiles.p);
@@ -581,7 +621,12 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
         p.colorVertexBegin = contact.colorVertexBegin.p;
         p.muC = static_cast<float>(muC), p.muF = static_cast<float>(muF), p.epsv = static_cast<float>(epsv);
     }
-    auto launchStep = [&](StepParams const& q) {
+    return p;
+}
+
+void Integrator::LaunchStepKernel(StepParams const& q)
+{
+    {
         VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
         if (variant == VBDX_KERNEL_PIPELINED)
         {
@@ -610,9 +655,17 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
                 reinterpret_cast<void const*>(Kernel()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
         }
         ++kernelLaunches;
-    };
+    }
+}
+
+void Integrator::RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync)
+{
+    bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    auto launchStep = [&](StepParams const& q) { LaunchStepKernel(q); };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
-    if (!contact.enabled)
+    if (acceleration == VBDX_ACCEL_ANDERSON)
+        AndersonStep(p, iterations, substeps);
+    else if (!contact.enabled)
         launchStep(p);
     else
     {
@@ -653,6 +706,111 @@ void Integrator::Step(double dt, int iterations, int substeps, bool sync)
         VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
         lastStepMs = ms;
     }
+}
+
+void Integrator::LaunchPreStep(StepParams const& q)
+{
+    if (acceleration == VBDX_ACCEL_CHEBYSHEV)
+        PreStepKernel<true><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+    else
+        PreStepKernel<false><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+    ++kernelLaunches;
+}
+
+// AndersonIntegrator::Solve inside Integrator::Step (sim/vbd/AndersonIntegrator.cpp:24-58): the sweeps are one-iteration
+// launches of the persistent step kernel, the window lives in anderson.cuh's kernels; nothing returns to the host.
+void Integrator::AndersonStep(StepParams const& p, int iterations, int substeps)
+{
+    int const m = window;
+    if (dAndVec.n == 0)
+    {
+        dAndVec.Alloc(static_cast<size_t>(nV) * (4 + 2 * m), &deviceBytes);
+        dAndSmall.Alloc(static_cast<size_t>(m) * m + 3 * m, &deviceBytes);
+    }
+    AndersonView a{};
+    a.n = nV, a.m = m, a.pos = dPos.p;
+    a.xkm1 = dAndVec.p, a.Gkm1 = a.xkm1 + nV, a.Fkm1 = a.Gkm1 + nV, a.Fk = a.Fkm1 + nV, a.DF = a.Fk + nV;
+    a.DG      = a.DF + static_cast<size_t>(m) * nV;
+    a.gram    = dAndSmall.p;
+    a.scratch = a.gram + m * m;
+    a.alpha   = a.scratch + 2 * m;
+    StepParams q   = p;
+    q.substeps     = 1;
+    q.skipPreStep  = 1;
+    q.skipPostStep = 1;
+    q.iterations   = 1;
+    int const grid = Blocks(nV, 256);
+    for (int s = 0; s < substeps; ++s)
+    {
+        LaunchPreStep(q);
+        if (iterations > 0)
+        {
+            VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, dAndSmall.n * sizeof(double), stream));
+            VBDX_CUDA(cudaMemcpyAsync(a.xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            q.iterBegin = 0;
+            LaunchStepKernel(q);
+            AndersonFirst<<<grid, 256, 0, stream>>>(a);
+            ++kernelLaunches;
+            // the first sweep's result is the second sweep's start: x^{k-1} = x
+            if (iterations > 1)
+                VBDX_CUDA(cudaMemcpyAsync(a.xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        }
+        for (int k = 1; k < iterations; ++k)
+        {
+            q.iterBegin = k;
+            LaunchStepKernel(q);
+            int const dkl = (k - 1) % m, mk = std::min(m, k);
+            AndersonWindow<kMaxAndersonWindow><<<std::min(grid, 4 * 148), 256, 0, stream>>>(a, dkl, mk);
+            AndersonSolveSmall<<<1, 32, 0, stream>>>(a, dkl, mk, 1e-10);
+            AndersonApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive);
+            kernelLaunches += 3;
+        }
+        StepParams post = q;
+        post.iterations = 0, post.skipPostStep = 0;
+        LaunchStepKernel(post);  // velocity update only
+    }
+}
+
+// A slice of one substep: [pre-step] [iterations kBegin .. kEnd of a solve of totalIterations] [velocity update].
+// What TraceNextStep / TracedStep need to look at every iterate (sim/vbd/Integrator.cpp:47-52,73-75,202-235).
+void Integrator::StepPartial(double sdt, int kBegin, int kEnd, int totalIterations, int flags)
+{
+    Require(sdt > 0 && kBegin >= 0 && kEnd >= kBegin && totalIterations >= kEnd, "StepPartial: bad iteration range");
+    Require(!contact.enabled && distWorld == 1, "partial steps are not available with contact or domain decomposition");
+    Require(acceleration == VBDX_ACCEL_NONE || acceleration == VBDX_ACCEL_CHEBYSHEV, "partial steps need the base or Chebyshev solve");
+    VBDX_CUDA(cudaSetDevice(device));
+    PrepareOmega(totalIterations);
+    StepParams q   = MakeParams(sdt, kEnd - kBegin, 1);
+    q.iterBegin    = kBegin;
+    q.skipPreStep  = (flags & VBDX_PARTIAL_PRE_STEP) ? 0 : 1;
+    q.skipPostStep = (flags & VBDX_PARTIAL_POST_STEP) ? 0 : 1;
+    LaunchStepKernel(q);
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+}
+
+// f and (optionally) grad f at caller-supplied xk, xtilde (3 x nV column-major doubles, caller order)
+void Integrator::Objective(const double* xk, const double* xtilde, double dt, double* f, double* grad)
+{
+    Require(xk && xtilde && (f || grad) && dt > 0, "Objective: need xk, xtilde, dt > 0 and an output");
+    VBDX_CUDA(cudaSetDevice(device));
+    if (dObjX.n == 0)
+    {
+        dObjX.Alloc(3 * nV, &deviceBytes), dObjXt.Alloc(3 * nV, &deviceBytes), dObjGrad.Alloc(3 * nV, &deviceBytes);
+        dObjVal.Alloc(1, &deviceBytes);
+    }
+    dObjX.Upload(xk, 3 * nV, stream);
+    dObjXt.Upload(xtilde, 3 * nV, stream);
+    VBDX_CUDA(cudaMemsetAsync(dObjVal.p, 0, sizeof(double), stream));
+    double* g = grad ? dObjGrad.p : nullptr;
+    ObjectiveKinetic<<<std::min(Blocks(nV, 256), 1184), 256, 0, stream>>>(dObjX.p, dObjXt.p, dMass.p, nV, dObjVal.p, g);
+    ObjectiveElastic<<<std::min(Blocks(nT, 256), 1184), 256, 0, stream>>>(dObjX.p, dE.p, dJinv.p, dVol.p, dLame.p, mu0, lambda0, nT, dt * dt,
+                                                                            dObjVal.p, g);
+    kernelLaunches += 2;
+    if (f)
+        dObjVal.Download(f, 1, stream);
+    if (grad)
+        dObjGrad.Download(grad, 3 * nV, stream);
+    VBDX_CUDA(cudaStreamSynchronize(stream));
 }
 
 template <class T>
@@ -747,6 +905,7 @@ void vbdx_data_desc_init(vbdx_data_desc* d)
     std::memset(d, 0, sizeof(*d));
     d->abi_version  = VBDX_ABI_VERSION;
     d->struct_size  = sizeof(vbdx_data_desc);
+    d->window_size  = 5;  // sim/vbd/Data.h:237
     d->ordering     = VBDX_ORDER_LARGEST_DEGREE;  // sim/vbd/Data.h:211-216
     d->selection    = VBDX_SELECT_LEAST_USED;
     d->strategy     = VBDX_INIT_ADAPTIVE_PBAT;    // sim/vbd/Data.h:222-223
@@ -873,10 +1032,15 @@ vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dty
     if (vbdx_status s = NeedHandle(h))
         return s;
     return Guard([&] {
-        vbdx::Require(field == VBDX_FIELD_POSITIONS || field == VBDX_FIELD_VELOCITIES, "only positions and velocities can be read back");
+        vbdx::Require(field == VBDX_FIELD_POSITIONS || field == VBDX_FIELD_VELOCITIES || field == VBDX_FIELD_INERTIAL_TARGET ||
+                          field == VBDX_FIELD_PREVIOUS_POSITIONS,
+                      "this field cannot be read back");
         vbdx::Require(dtype == VBDX_F32 || dtype == VBDX_F64, "unknown dtype");
         vbdx::Require(layout == VBDX_LAYOUT_COLUMNS || layout == VBDX_LAYOUT_ROWS, "unknown layout");
-        float4 const* src = field == VBDX_FIELD_POSITIONS ? (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_Q) : h->impl.dVel.p;
+        float4 const* src = field == VBDX_FIELD_POSITIONS            ? (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_Q)
+                            : field == VBDX_FIELD_VELOCITIES         ? h->impl.dVel.p
+                            : field == VBDX_FIELD_INERTIAL_TARGET    ? h->impl.dXtildeM.p
+                                                                     : h->impl.dXt.p;
         bool const rows   = layout == VBDX_LAYOUT_ROWS;
         if (dtype == VBDX_F32)
             h->impl.GetVertexField<float>(src, static_cast<float*>(dst), nV, rows);
@@ -901,6 +1065,20 @@ vbdx_status vbdx_host_free(void* p)
         if (p)
             VBDX_CUDA(cudaFreeHost(p));
     });
+}
+
+vbdx_status vbdx_step_partial(vbdx_integrator* h, double sdt, int32_t k_begin, int32_t k_end, int32_t total_iterations, int32_t flags)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] { h->impl.StepPartial(sdt, k_begin, k_end, total_iterations, flags); });
+}
+
+vbdx_status vbdx_objective(vbdx_integrator* h, const double* xk, const double* xtilde, double dt, double* f, double* grad)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] { h->impl.Objective(xk, xtilde, dt, f, grad); });
 }
 
 vbdx_status vbdx_set_detH_zero(vbdx_integrator* h, double zero)

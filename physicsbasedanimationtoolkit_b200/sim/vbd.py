@@ -9,6 +9,7 @@ the GPU -- there is no CPU integrator in this package.
 from __future__ import annotations
 
 import enum
+import os
 
 import numpy as np
 
@@ -281,23 +282,53 @@ class Data:
 class Integrator(DeviceIntegrator):
     """``pbat.sim.vbd.Integrator`` (bindings/pypbat/sim/vbd/Integrator.cpp:30-90): positions and
     velocities cross the boundary as float64 3 x nV arrays.  Dispatch on ``data.accelerator``
-    happens at construction like the reference's factory; strategies other than Base and
-    Chebyshev raise ``NotImplementedError``."""
+    happens at construction like the reference's factory: Base, Chebyshev and Anderson are
+    implemented, the others raise ``NotImplementedError``."""
 
     _dtype = np.float64
 
     def __init__(self, data: Data, **tuning):
         super().__init__(data, **tuning)
         self.data = data
+        self._trace = None
 
     def step(self, dt, iterations, substeps=1):
-        self._step(dt, iterations, substeps)
+        if self._trace is None:
+            self._step(dt, iterations, substeps)
+        else:
+            self._export_trace(dt, iterations, substeps)
         # keep the public `data` member in sync, like the reference whose Step mutates data.x / data.v
         self.data.x = self.x
         self.data.v = self.v
 
     def trace_next_step(self, path=".", t=-1):
-        raise NotImplementedError("iterate tracing is not implemented (SURVEY.md section 8f, rank 3)")
+        """``Integrator::TraceNextStep`` (sim/vbd/Integrator.cpp:47-52): the next ``step`` records, before every
+        sweep and after the velocity update of each substep, the objective, its gradient and the iterate, and
+        writes ``<path>/<t>.<substep>.{f,grad,x}.mtx`` (``ExportTrace``, sim/vbd/Integrator.cpp:202-224)."""
+        self._trace = (str(path), int(t))
+
+    def _export_trace(self, dt, iterations, substeps):
+        from .. import mtx
+
+        path, t = self._trace
+        self._trace = None  # the reference clears mTraceIterates at the end of Step
+        f, G, X = [], [], []
+        for s, k, x, xtilde, sdt in self._traced_substeps(dt, iterations, substeps):
+            fk, gk = self.objective(x, xtilde, sdt, gradient=True)
+            f.append(fk), G.append(gk.T.reshape(-1)), X.append(x.T.reshape(-1))
+            if k == iterations:
+                mtx.save_dense(os.path.join(path, f"{t}.{s}.f.mtx"), np.asarray(f).reshape(-1, 1))
+                mtx.save_dense(os.path.join(path, f"{t}.{s}.grad.mtx"), np.stack(G, axis=1))
+                mtx.save_dense(os.path.join(path, f"{t}.{s}.x.mtx"), np.stack(X, axis=1))
+                f, G, X = [], [], []
+
+    def objective_function(self, xk, xtilde, dt):
+        """``Integrator::ObjectiveFunction`` (sim/vbd/Integrator.h:45-51)."""
+        return self.objective(xk, xtilde, dt)
+
+    def objective_function_gradient(self, xk, xtilde, dt):
+        """``Integrator::ObjectiveFunctionGradient`` (sim/vbd/Integrator.h:52-58): 3|#verts| vector."""
+        return self.objective(xk, xtilde, dt, gradient=True)[1].T.reshape(-1)
 
     strategy = property(lambda s: InitializationStrategy(s._strategy), lambda s, v: s._set_strategy(v))
     kD = property(lambda s: s._kD, lambda s, v: s._set_kD(v))

@@ -173,7 +173,7 @@ def test_errors():
     vbd = pbat.gpu.vbd.Integrator(d)
     with pytest.raises(ValueError):
         vbd.x = np.zeros((3, 5), dtype=np.float32)
-    d2 = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_anderson_acceleration(5).construct()
+    d2 = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_nesterov_acceleration(1.0, 3).construct()
     with pytest.raises(NotImplementedError):
         pbat.gpu.vbd.Integrator(d2)
 
@@ -275,3 +275,120 @@ def test_host_layouts_and_pinned_buffers():
     xd = rng.standard_normal((3, nV))
     sim.x = xd
     assert np.array_equal(sim.x, xd.astype(np.float32).astype(np.float64))
+
+
+def test_anderson_acceleration():
+    """AndersonIntegrator (sim/vbd/AndersonIntegrator.cpp:24-58): the reference's cube known answer and parity with
+    the oracle on a cantilever where the window wraps around."""
+    d = pbat.sim.vbd.Data().with_volume_mesh(meshes.CUBE_P, meshes.CUBE_T).with_anderson_acceleration(5).construct()
+    vbd = pbat.sim.vbd.Integrator(d)
+    dt = 1e-2
+    x0 = vbd.x
+    xtilde = x0 + dt * vbd.v + dt * dt * d.aext
+    f0 = vbd.objective_function(x0, xtilde, dt)
+    vbd.step(dt, 10, 1)
+    dx = vbd.x - meshes.CUBE_P
+    assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+    assert np.linalg.norm(vbd.objective_function_gradient(vbd.x, xtilde, dt)) < 1e-4 * 50  # fp32 iterate, f in double
+    assert vbd.objective_function(vbd.x, xtilde, dt) < f0
+
+    X, T = meshes.tet_grid(12, 4, 4, 0.05)
+    dbc = np.flatnonzero(X[0] == 0)
+    for window, substeps in ((3, 1), (5, 2)):
+        d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_anderson_acceleration(window).construct()
+        vbd = pbat.gpu.vbd.Integrator(d)
+        ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors)
+        ref.set_acceleration(oracle.ACCEL_ANDERSON, window=window)
+        plain = oracle.Oracle(X, T, dbc=dbc, colors=d.colors)
+        # Tolerance: Anderson mixing amplifies the rounding of the iterates -- rounding the DOUBLE oracle's iterates
+        # to fp32 after every sweep already moves this trajectory by 7e-5 after one step and 4.5e-4 after ten
+        # (measured with the oracle alone).  Hence 2e-4 after the first step and 1.5e-3 after ten, instead of the
+        # 1e-4 of the base and Chebyshev solves.
+        for step in range(10):
+            vbd.step(0.01, 10, substeps)
+            ref.step(0.01, 10, substeps)
+            plain.step(0.01, 10, substeps)
+            if step == 0:
+                assert rel_l2(vbd.x, ref.x) < 2e-4, rel_l2(vbd.x, ref.x)
+        err = rel_l2(vbd.x, ref.x)
+        assert err < 1.5e-3, err
+        # and the acceleration really is in effect: the accelerated trajectory differs from the plain one by more
+        assert rel_l2(plain.x, ref.x) > 3 * err
+    with pytest.raises(ValueError):
+        pbat.sim.vbd.Data().with_volume_mesh(X, T).with_anderson_acceleration(0).construct()
+
+
+def test_objective_function_and_gradient():
+    """Integrator::ObjectiveFunction / ObjectiveFunctionGradient (sim/vbd/Integrator.cpp:138-200) on the device
+    (double precision) against the oracle, with per-element material parameters."""
+    X, T = meshes.tet_grid(5, 3, 4, 0.2)
+    nT = T.shape[1]
+    rng = np.random.default_rng(5)
+    mue, lame = 3e5 * (1 + rng.random(nT)), 2e6 * (1 + rng.random(nT))
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_material(np.full(nT, 1e3), mue, lame).construct()
+    vbd = pbat.sim.vbd.Integrator(d)
+    ref = oracle.Oracle(X, T, mue=mue, lambdae=lame, colors=d.colors)
+    xk = X + 0.02 * rng.standard_normal(X.shape)
+    xtilde = X + 0.01 * rng.standard_normal(X.shape)
+    for dt in (1e-2, 0.3):
+        f, g = vbd.objective_function(xk, xtilde, dt), vbd.objective_function_gradient(xk, xtilde, dt)
+        fr, gr = ref.objective(xk, xtilde, dt), ref.objective_gradient(xk, xtilde, dt)
+        assert abs(f - fr) <= 1e-12 * abs(fr)
+        assert np.linalg.norm(g - gr.T.reshape(-1)) <= 1e-11 * np.linalg.norm(gr)
+    d2 = pbat.sim.vbd.Data().with_volume_mesh(X, T).construct()          # default material path
+    v2, r2 = pbat.sim.vbd.Integrator(d2), oracle.Oracle(X, T, colors=d2.colors)
+    assert abs(v2.objective_function(xk, xtilde, 0.01) - r2.objective(xk, xtilde, 0.01)) <= 1e-12 * abs(r2.objective(xk, xtilde, 0.01))
+
+
+@pytest.mark.parametrize("cheb", [None, 0.8])
+def test_traced_steps(tmp_path, cheb):
+    """TraceNextStep / ExportTrace (sim/vbd/Integrator.cpp:47-52,202-235) and the GPU TracedStep
+    (gpu/impl/vbd/Integrator.cu:105-148,284-301): a traced step is the same step, and the files hold the iterates."""
+    from physicsbasedanimationtoolkit_b200 import mtx
+
+    X, T = meshes.tet_grid(6, 3, 3, 0.1)
+    dbc = np.flatnonzero(X[0] == 0)
+    nV, iters, substeps = X.shape[1], 6, 2
+
+    def data():
+        d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
+        return (d.with_chebyshev_acceleration(cheb) if cheb else d).construct()
+
+    a, b = pbat.sim.vbd.Integrator(data()), pbat.sim.vbd.Integrator(data())
+    a.step(0.01, iters, substeps), b.step(0.01, iters, substeps)
+    a.trace_next_step(str(tmp_path), 7)
+    a.step(0.01, iters, substeps)
+    b.step(0.01, iters, substeps)
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.v, b.v)       # tracing does not change the step
+    for s in range(substeps):
+        f = mtx.load_dense(tmp_path / f"7.{s}.f.mtx")
+        G = mtx.load_dense(tmp_path / f"7.{s}.grad.mtx")
+        Xs = mtx.load_dense(tmp_path / f"7.{s}.x.mtx")
+        assert f.shape == (iters + 1, 1) and G.shape == (3 * nV, iters + 1) and Xs.shape == (3 * nV, iters + 1)
+        assert f[-1, 0] < f[0, 0]                                           # the solve descends
+    assert np.array_equal(Xs[:, -1].reshape(nV, 3).T, a.x)
+    a.step(0.01, iters, substeps)                                           # the flag was cleared
+    assert not (tmp_path / "8.0.f.mtx").exists()
+    # trajectory of the iterates against the oracle's plain sweeps (first substep, no acceleration)
+    if not cheb:
+        ref = oracle.Oracle(X, T, dbc=dbc, colors=a.data.colors)
+        c = pbat.sim.vbd.Integrator(data())
+        c.trace_next_step(str(tmp_path), 0)
+        c.step(0.01, iters, 1)
+        Xs = mtx.load_dense(tmp_path / "0.0.x.mtx")
+        ref.step(0.01, 0, 1)
+        ref.v = np.zeros_like(X)
+        for k in range(iters):
+            assert rel_l2(Xs[:, k].reshape(nV, 3).T, ref.x) < TOL
+            ref.sweeps(0.01, 1)
+    # GPU-flavoured trace
+    g = pbat.gpu.vbd.Integrator(data())
+    g.traced_step(0.01, iters, substeps, 0, str(tmp_path))
+    h = pbat.gpu.vbd.Integrator(data())
+    h.step(0.01, iters, substeps)
+    assert np.array_equal(g.x, h.x)
+    assert mtx.load_dense(tmp_path / "T.mtx").shape == (T.shape[1], 4)
+    assert mtx.load_dense(tmp_path / "GP.mtx").shape == (4, 3 * T.shape[1])
+    last = mtx.load_dense(tmp_path / f"x.t.0.s.{substeps - 1}.k.{iters}.mtx")
+    assert last.shape == (nV, 3) and np.array_equal(last.T.astype(np.float32), g.x)
+    assert mtx.load_dense(tmp_path / "xtilde.t.0.s.1.mtx").shape == (nV, 3)
