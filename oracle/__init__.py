@@ -24,6 +24,7 @@ POSITION, INERTIA, KINETIC_ENERGY_MINIMUM, ADAPTIVE_VBD, ADAPTIVE_PBAT = range(5
 ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV = 0, 1, 2, 3   # = vbdx_acceleration_strategy
 ORDER_NATURAL, ORDER_SMALLEST_DEGREE, ORDER_LARGEST_DEGREE = range(3)
 SELECT_LEAST_USED, SELECT_FIRST_AVAILABLE = range(2)
+MATERIAL_STABLE_NEO_HOOKEAN, MATERIAL_STVK = range(2)  # = vbdx_material
 
 
 def build(ref: bool = True) -> None:
@@ -79,6 +80,9 @@ def _load(kind: str) -> C.CDLL:
     lib.vbdo_objective_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     lib.vbdo_snh_eval.restype = C.c_double
     lib.vbdo_snh_eval.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.vbdo_stvk_eval.restype = C.c_double
+    lib.vbdo_stvk_eval.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.vbdo_set_material.argtypes = [C.c_void_p, C.c_int]
     lib.vbdo_num_threads.restype = C.c_int
     lib.vbdo_set_num_threads.argtypes = [C.c_int]
     _libs[kind] = lib
@@ -108,7 +112,7 @@ class Oracle:
                  colors=None, ordering=ORDER_LARGEST_DEGREE, selection=SELECT_LEAST_USED,
                  strategy=ADAPTIVE_PBAT, accel=ACCEL_NONE, rho=1.0, omega_mode=0, kD=0.0,
                  detH_zero=1e-7, kind="port", B=None, V=None, F=None, muC=1e6, muF=0.3, epsv=1e-3,
-                 active_set_update_frequency=1):
+                 active_set_update_frequency=1, material=MATERIAL_STABLE_NEO_HOOKEAN):
         self.lib = _load("port" if kind == "port" else "ref")
         X = np.asarray(X, dtype=np.float64)
         E = np.asarray(E, dtype=np.int64)
@@ -145,6 +149,7 @@ class Oracle:
         if not self.h:
             raise ValueError(self.lib.vbdo_last_error().decode())
         self.kind = self.lib.vbdo_kind().decode()
+        self.lib.vbdo_set_material(self.h, int(material))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -221,3 +226,9 @@ def snh_eval(F, mu, lam, kind="port"):
     lib = _load("port" if kind == "port" else "ref")
     f = np.ascontiguousarray(np.asarray(F, np.float64).T).reshape(-1)  # column-major
     return lib.vbdo_snh_eval(_ptr(f), mu, lam)
+
+
+def stvk_eval(F, mu, lam, kind="port"):
+    lib = _load("port" if kind == "port" else "ref")
+    f = np.ascontiguousarray(np.asarray(F, np.float64).T).reshape(-1)  # column-major
+    return lib.vbdo_stvk_eval(_ptr(f), mu, lam)

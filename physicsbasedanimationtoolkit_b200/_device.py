@@ -54,6 +54,7 @@ class DeviceIntegrator:
         d.strategy = int(data.strategy)
         d.acceleration = int(data.accelerator)
         d.omega_mode = int(getattr(data, "omega_mode", 0))
+        d.material = int(getattr(data, "energy", 0))
         d.kD, d.detHZero, d.rho = float(data.kD), float(data.detH_zero), float(data.rho)
         d.B = ptr(data.B, np.int64)
         d.V = ptr(data.V, np.int64)

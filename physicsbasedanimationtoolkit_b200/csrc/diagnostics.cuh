@@ -2,7 +2,9 @@
 //   f(x) = 1/2 (x - xtilde)^T M (x - xtilde) + dt^2 sum_e wg_e psi(F_e(x))
 // Integrator::ObjectiveFunction / ObjectiveFunctionGradient (sim/vbd/Integrator.cpp:138-200) with the Stable
 // Neo-Hookean density of physics/StableNeoHookeanEnergy.h:738-755,
-//   psi = mu/2 (|F|^2 - 3) + lambda/2 (det F - 1 - mu/lambda)^2.
+//   psi = mu/2 (|F|^2 - 3) + lambda/2 (det F - 1 - mu/lambda)^2,
+// or the St. Venant-Kirchhoff density of physics/SaintVenantKirchhoffEnergy.h,
+//   psi = mu tr(E^2) + lambda/2 tr(E)^2,  E = (F^T F - I)/2.
 // These feed the iterate traces (TraceNextStep / ExportTrace, sim/vbd/Integrator.cpp:47-52,202-235) and the
 // convergence checks of the reference's tests; they are not on the step's hot path.
 // Inputs are 3 x nV column-major double arrays in the CALLER's vertex order.
@@ -74,6 +76,7 @@ __global__ void ObjectiveElastic(
     double lambda0,
     int64_t nT,
     double dt2,
+    int stvk,
     double* out,
     double* grad)
 {
@@ -106,17 +109,45 @@ __global__ void ObjectiveElastic(
                 I2 += F[r][c] * F[r][c];
         double const d = J - 1.0 - mu / lam;
         double const w = vol[e];
-        acc += w * (0.5 * lam * d * d + 0.5 * mu * (I2 - 3.0));
+        // first Piola-Kirchhoff stress P = dpsi/dF
+        double P[3][3];
+        if (!stvk)
+        {
+            acc += w * (0.5 * lam * d * d + 0.5 * mu * (I2 - 3.0));
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    P[r][c] = mu * F[r][c] + lam * d * C[r][c];
+        }
+        else
+        {
+            double Eg[3][3], trE = 0, E2 = 0;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                {
+                    Eg[r][c] = 0.5 * (F[0][r] * F[0][c] + F[1][r] * F[1][c] + F[2][r] * F[2][c] - (r == c ? 1.0 : 0.0));
+                    E2 += Eg[r][c] * Eg[r][c];
+                }
+            trE = Eg[0][0] + Eg[1][1] + Eg[2][2];
+            acc += w * (mu * E2 + 0.5 * lam * trE * trE);
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                {
+                    double s = 0;  // (F S)_{rc},  S = 2 mu E + lambda tr(E) I
+                    for (int k = 0; k < 3; ++k)
+                        s += F[r][k] * (2.0 * mu * Eg[k][c] + (k == c ? lam * trE : 0.0));
+                    P[r][c] = s;
+                }
+        }
         if (grad)
         {
-            // P = mu F + lambda (J - alpha) C;  g_a = P grad N_a, grad N_0 = -(grad N_1 + grad N_2 + grad N_3)
+            // g_a = P grad N_a, grad N_0 = -(grad N_1 + grad N_2 + grad N_3)
             double g0[3] = {0, 0, 0};
             for (int a = 0; a < 3; ++a)
                 for (int r = 0; r < 3; ++r)
                 {
                     double ga = 0;
                     for (int c = 0; c < 3; ++c)
-                        ga += (mu * F[r][c] + lam * d * C[r][c]) * Ji[3 * a + c];
+                        ga += P[r][c] * Ji[3 * a + c];
                     ga *= dt2 * w;
                     atomicAdd(grad + 3 * static_cast<int64_t>(t[a + 1]) + r, ga);
                     g0[r] -= ga;

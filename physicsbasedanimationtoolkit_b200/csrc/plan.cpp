@@ -158,9 +158,11 @@ void BuildPlan(
     const double* X,
     int tileIters,
     bool naturalOrder,
+    int blocksPerIncidence,
     Plan& plan)
 {
     plan      = Plan{};
+    blocksPerIncidence = std::max(1, blocksPerIncidence);
     plan.nV   = nV;
     tileIters = std::max(1, tileIters);
     // bounding box for the Morton order
@@ -330,14 +332,14 @@ void BuildPlan(
         uint32_t const lateChunks  = static_cast<uint32_t>((late.size() + 31) / 32);
         if ((earlyChunks + lateChunks) * 32 > static_cast<uint32_t>(kMaxRingPerTile))
             throw std::length_error("a vertex has more than ~1000 distinct neighbours");
-        if (iters > static_cast<int>(kMaxTileIters))
+        if (iters * blocksPerIncidence > static_cast<int>(kMaxTileIters))
             throw std::length_error("a vertex has too many incident tetrahedra for one warp tile");
         uint32_t const ringStart = static_cast<uint32_t>(plan.ringIds.size());
         TileDesc t;
         t.blockStart = static_cast<uint32_t>(block);
         t.vbase      = static_cast<uint32_t>(pos);
         t.meta       = TileMeta(static_cast<uint32_t>(lw), static_cast<uint32_t>(n), earlyChunks + lateChunks, earlyChunks,
-                          static_cast<uint32_t>(iters));
+                          static_cast<uint32_t>(iters * blocksPerIncidence));
         t.ringStart = ringStart;
         for (int32_t j : early)
             if (isDbc[j] == 2)
@@ -367,7 +369,7 @@ void BuildPlan(
         plan.nRingEntries += static_cast<int64_t>(n + early.size() + late.size());
         plan.maxRingPerTile = std::max<int32_t>(plan.maxRingPerTile, static_cast<int32_t>((earlyChunks + lateChunks) * 32));
         // packed local indices of every record slot of the tile (same slot enumeration as FillRecords)
-        plan.recIdx.resize(static_cast<size_t>(block + iters) * 32, 0u);
+        plan.recIdx.resize(static_cast<size_t>(block + iters * blocksPerIncidence) * 32, 0u);
         uint32_t const w = 1u << lw;
         for (int t2 = 0; t2 < iters; ++t2)
             for (uint32_t lane = 0; lane < 32; ++lane)
@@ -387,10 +389,10 @@ void BuildPlan(
                 for (uint32_t a = 0; a < 4; ++a)
                     if (a != il)
                         idx |= localIndex[E[4 * e + a]] << (10 * m++);
-                plan.recIdx[static_cast<size_t>(block + t2) * 32 + lane] = idx;
+                plan.recIdx[static_cast<size_t>(block + t2 * blocksPerIncidence) * 32 + lane] = idx;
             }
         pos += n;
-        block += iters;
+        block += iters * blocksPerIncidence;
     }
     while (curColor < nColors)
         plan.colorTileBegin[++curColor] = static_cast<uint32_t>(plan.tiles.size());

@@ -246,6 +246,7 @@ __global__ void FillRecords(
     double muDefault,
     double lamDefault,
     const uint32_t* recIdx,  // packed local ring indices per record slot (host planner)
+    int stvk,                // 0: Stable Neo-Hookean records, 1: St. Venant-Kirchhoff (two blocks per incident tet)
     float4* records)
 {
     int const T = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -255,7 +256,8 @@ __global__ void FillRecords(
     TileDesc const td     = tiles[T];
     uint32_t const lw     = TileLog2W(td.meta);
     uint32_t const nverts = TileVerts(td.meta);
-    uint32_t const iters  = TileIters(td.meta);
+    uint32_t const bpi    = stvk ? 2u : 1u;
+    uint32_t const iters  = TileIters(td.meta) / bpi;
     uint32_t const w      = 1u << lw;
     uint32_t const grp    = lane >> lw;
     uint32_t const sub    = lane & (w - 1u);
@@ -266,8 +268,9 @@ __global__ void FillRecords(
     for (uint32_t t = 0; t < iters; ++t)
     {
         uint32_t const k = t * w + sub;
-        uint32_t const idx = recIdx[static_cast<size_t>(td.blockStart + t) * 32 + lane];
+        uint32_t const idx = recIdx[static_cast<size_t>(td.blockStart + t * bpi) * 32 + lane];
         float rec[6]     = {0, 0, 0, 0, 0, 0};
+        float sv[11]     = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // StVK: grad N_a, grad N_b, grad N_c, wg mu, wg lambda
         if (valid && k < degv)
         {
             uint32_t const packed = adj[rowB + k];
@@ -304,10 +307,24 @@ __global__ void FillRecords(
             rec[3] = static_cast<float>(wlam * detG * detG);
             rec[4] = static_cast<float>(wlam * detG * alpha);
             rec[5] = static_cast<float>(wmu * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]));
+            for (int a = 0; a < 3; ++a)
+                for (int d = 0; d < 3; ++d)
+                    sv[3 * a + d] = static_cast<float>(o[a][d]);
+            sv[9] = static_cast<float>(wmu), sv[10] = static_cast<float>(wlam);
         }
-        float4* out = records + static_cast<size_t>(td.blockStart + t) * kBlockFloat4 + lane;
-        out[0]  = make_float4(__uint_as_float(idx), rec[0], rec[1], rec[2]);
-        out[32] = make_float4(rec[3], rec[4], rec[5], 0.f);
+        float4* out = records + static_cast<size_t>(td.blockStart + t * bpi) * kBlockFloat4 + lane;
+        if (!stvk)
+        {
+            out[0]  = make_float4(__uint_as_float(idx), rec[0], rec[1], rec[2]);
+            out[32] = make_float4(rec[3], rec[4], rec[5], 0.f);
+        }
+        else
+        {
+            out[0]                 = make_float4(__uint_as_float(idx), sv[0], sv[1], sv[2]);
+            out[32]                = make_float4(sv[3], sv[4], sv[5], sv[9]);
+            out[kBlockFloat4]      = make_float4(sv[6], sv[7], sv[8], sv[10]);
+            out[kBlockFloat4 + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 

@@ -337,7 +337,7 @@ struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
 
-template <bool kChebyshev, bool kDamping, bool kStageInside, class RecordSource, class AfterAccumulate = NoHook>
+template <bool kChebyshev, bool kDamping, bool kStageInside, class RecordSource, class AfterAccumulate = NoHook, bool kStvk = false>
 __device__ __forceinline__ void ProcessTile(
     StepParams const& p,
     uint4 const td,
@@ -388,6 +388,69 @@ __device__ __forceinline__ void ProcessTile(
 
     float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if constexpr (kStvk)
+    {
+        // St. Venant-Kirchhoff, psi = mu tr(E^2) + lambda/2 tr(E)^2, E = (F^T F - I)/2
+        // (physics/SaintVenantKirchhoffEnergy.h), contracted to the vertex block like sim/vbd/Kernels.h:137-171:
+        //   F = d_a (x) g_a + d_b (x) g_b + d_c (x) g_c        (d_n = x_n - x_i,  g_n = grad N_n,  sum_n g_n = 0)
+        //   S = 2 mu E + lambda tr(E) I,   grad_i = w F S g_i,
+        //   H_i = w [ (g_i.S g_i) I + (mu + lambda) (F g_i)(F g_i)^T + mu |g_i|^2 F F^T ]
+        // An incidence record is two blocks (vbdx_internal.h).
+#pragma unroll 1
+        for (uint32_t t = 0; t < iters; t += 2)
+        {
+            float4 const c0 = n0, c1 = n1;
+            float4 c2, c3;
+            src.Fetch(c2, c3);
+            if (t + 2 < iters)
+                src.Fetch(n0, n1);
+            uint32_t const idx = __float_as_uint(c0.x);
+            float4 const p1 = stage[idx & 1023u];
+            float4 const p2 = stage[(idx >> 10) & 1023u];
+            float4 const p3 = stage[(idx >> 20) & 1023u];
+            float const da[3] = {p1.x - xi.x, p1.y - xi.y, p1.z - xi.z};
+            float const db[3] = {p2.x - xi.x, p2.y - xi.y, p2.z - xi.z};
+            float const dc[3] = {p3.x - xi.x, p3.y - xi.y, p3.z - xi.z};
+            float const ga[3] = {c0.y, c0.z, c0.w}, gb[3] = {c1.x, c1.y, c1.z}, gc[3] = {c2.x, c2.y, c2.z};
+            float const wmu = c1.w, wlam = c2.w;
+            float const gi[3] = {-(ga[0] + gb[0] + gc[0]), -(ga[1] + gb[1] + gc[1]), -(ga[2] + gb[2] + gc[2])};
+            float F[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    F[r][c] = da[r] * ga[c] + db[r] * gb[c] + dc[r] * gc[c];
+            // E (symmetric) and S' = 2 wmu E + wlam tr(E) I
+            float const e00 = 0.5f * (F[0][0] * F[0][0] + F[1][0] * F[1][0] + F[2][0] * F[2][0] - 1.f);
+            float const e11 = 0.5f * (F[0][1] * F[0][1] + F[1][1] * F[1][1] + F[2][1] * F[2][1] - 1.f);
+            float const e22 = 0.5f * (F[0][2] * F[0][2] + F[1][2] * F[1][2] + F[2][2] * F[2][2] - 1.f);
+            float const e01 = 0.5f * (F[0][0] * F[0][1] + F[1][0] * F[1][1] + F[2][0] * F[2][1]);
+            float const e02 = 0.5f * (F[0][0] * F[0][2] + F[1][0] * F[1][2] + F[2][0] * F[2][2]);
+            float const e12 = 0.5f * (F[0][1] * F[0][2] + F[1][1] * F[1][2] + F[2][1] * F[2][2]);
+            float const ltr = wlam * (e00 + e11 + e22), m2 = 2.f * wmu;
+            float const s00 = m2 * e00 + ltr, s11 = m2 * e11 + ltr, s22 = m2 * e22 + ltr;
+            float const s01 = m2 * e01, s02 = m2 * e02, s12 = m2 * e12;
+            float const sg0 = s00 * gi[0] + s01 * gi[1] + s02 * gi[2];
+            float const sg1 = s01 * gi[0] + s11 * gi[1] + s12 * gi[2];
+            float const sg2 = s02 * gi[0] + s12 * gi[1] + s22 * gi[2];
+            g0 += F[0][0] * sg0 + F[0][1] * sg1 + F[0][2] * sg2;
+            g1 += F[1][0] * sg0 + F[1][1] * sg1 + F[1][2] * sg2;
+            g2 += F[2][0] * sg0 + F[2][1] * sg1 + F[2][2] * sg2;
+            hd += gi[0] * sg0 + gi[1] * sg1 + gi[2] * sg2;
+            float const f0 = F[0][0] * gi[0] + F[0][1] * gi[1] + F[0][2] * gi[2];
+            float const f1 = F[1][0] * gi[0] + F[1][1] * gi[1] + F[1][2] * gi[2];
+            float const f2 = F[2][0] * gi[0] + F[2][1] * gi[1] + F[2][2] * gi[2];
+            float const ml = wmu + wlam, mg = wmu * (gi[0] * gi[0] + gi[1] * gi[1] + gi[2] * gi[2]);
+            h00 += ml * f0 * f0 + mg * (F[0][0] * F[0][0] + F[0][1] * F[0][1] + F[0][2] * F[0][2]);
+            h01 += ml * f0 * f1 + mg * (F[0][0] * F[1][0] + F[0][1] * F[1][1] + F[0][2] * F[1][2]);
+            h02 += ml * f0 * f2 + mg * (F[0][0] * F[2][0] + F[0][1] * F[2][1] + F[0][2] * F[2][2]);
+            h11 += ml * f1 * f1 + mg * (F[1][0] * F[1][0] + F[1][1] * F[1][1] + F[1][2] * F[1][2]);
+            h12 += ml * f1 * f2 + mg * (F[1][0] * F[2][0] + F[1][1] * F[2][1] + F[1][2] * F[2][2]);
+            h22 += ml * f2 * f2 + mg * (F[2][0] * F[2][0] + F[2][1] * F[2][1] + F[2][2] * F[2][2]);
+            (void)c3;
+        }
+    }
+    else
 #pragma unroll 1
     for (uint32_t t = 0; t < iters; ++t)
     {

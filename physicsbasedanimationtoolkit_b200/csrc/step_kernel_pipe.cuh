@@ -157,7 +157,7 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
     NamedArrive(kBarReleased, blockDim.x);
 }
 
-template <bool kChebyshev, bool kDamping>
+template <bool kChebyshev, bool kDamping, bool kStvk = false>
 __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __grid_constant__ PipeParams pp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     deferred = nextValid && !sameSweep;
                     WaitRecords();
                     SmemRecords src{recBuf + lane};
-                    ProcessTile<kChebyshev, kDamping, false>(p, td, stage, src, static_cast<int>(c), p.iterBegin + k, omega, lane, tr0, prefetchNext, tagLow + 1u);
+                    ProcessTile<kChebyshev, kDamping, false, SmemRecords, decltype(prefetchNext), kStvk>(p, td, stage, src, static_cast<int>(c), p.iterBegin + k, omega, lane, tr0, prefetchNext,
+                                                                                                          tagLow + 1u);
                     if (tr0 && lane == 0)
                         tr0[7] = GlobalTimer();
                     gathered = nextGathered;

@@ -58,6 +58,7 @@ struct Integrator {
     double mu0 = 0, lambda0 = 0;
     // Anderson acceleration (anderson.cuh)
     int window = 5;
+    int material = VBDX_MATERIAL_STABLE_NEO_HOOKEAN;
     DevBuf<float4> dAndVec;   // xkm1, Gkm1, Fkm1, Fk, DF[m], DG[m]
     DevBuf<double> dAndSmall; // gram m*m, scratch 2m, alpha m
     // objective / gradient evaluation (diagnostics.cuh)
@@ -121,6 +122,12 @@ struct Integrator {
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
         bool const damp = kD != 0.0 || contact.enabled;  // the "extras" variants carry damping and contact
+        if (material == VBDX_MATERIAL_STVK)
+        {
+            if (cheb)
+                return damp ? StepKernelPipe<true, true, true> : StepKernelPipe<true, false, true>;
+            return damp ? StepKernelPipe<false, true, true> : StepKernelPipe<false, false, true>;
+        }
         if (cheb)
             return damp ? StepKernelPipe<true, true> : StepKernelPipe<true, false>;
         return damp ? StepKernelPipe<false, true> : StepKernelPipe<false, false>;
@@ -169,8 +176,10 @@ void Integrator::Create(vbdx_data_desc const& d)
         Require(d.nF == 0 && d.nGhosts == 0, "Anderson acceleration is not combined with contact or domain decomposition yet");
         window = d.window_size;
     }
-    if (d.material != VBDX_MATERIAL_STABLE_NEO_HOOKEAN)
-        throw Error(VBDX_UNSUPPORTED, "only the Stable Neo-Hookean energy is implemented");
+    Require(d.material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN || d.material == VBDX_MATERIAL_STVK, "unknown material");
+    if (d.material == VBDX_MATERIAL_STVK && d.kernel_variant != VBDX_KERNEL_DEFAULT && d.kernel_variant != VBDX_KERNEL_PIPELINED)
+        throw Error(VBDX_UNSUPPORTED, "St. Venant-Kirchhoff runs on the pipelined step kernel only");
+    material = d.material;
     if (d.acceleration == VBDX_ACCEL_CHEBYSHEV)
         Require(d.rho > 0 && d.rho < 1, "Expected 0 < rho < 1");  // sim/vbd/Data.cpp:272-276
     Require(d.strategy >= 0 && d.strategy <= VBDX_INIT_ADAPTIVE_PBAT, "unknown initialization strategy");
@@ -304,7 +313,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     try
     {
         BuildPlan(nV, E32.data(), ptrHost.data(), adjHost.data(), colors.data(), isDbc.data(), d.X, tileIters,
-                  (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, plan);
+                  (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, material == VBDX_MATERIAL_STVK ? 2 : 1, plan);
     }
     catch (std::length_error const& e)
     {
@@ -329,7 +338,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     int const pipeThreads = pipeWarps * 32 + 32;
     size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters);
     if (variant == VBDX_KERNEL_DEFAULT)
-        variant = pipeSmem <= static_cast<size_t>(maxOptin) ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
+        variant = pipeSmem <= static_cast<size_t>(maxOptin) || material == VBDX_MATERIAL_STVK ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
     int perSm = 1 << 30;
     if (variant == VBDX_KERNEL_PIPELINED)
     {
@@ -337,8 +346,12 @@ void Integrator::Create(vbdx_data_desc const& d)
         smemBytes    = pipeSmem;
         if (smemBytes > static_cast<size_t>(maxOptin))
             throw Error(VBDX_UNSUPPORTED, "per-warp tile buffers do not fit in shared memory (lower tile_iters)");
-        for (PipeKernelFn fn : {cheb0 ? StepKernelPipe<true, false> : StepKernelPipe<false, false>,
-                                cheb0 ? StepKernelPipe<true, true> : StepKernelPipe<false, true>})
+        bool const stvk = material == VBDX_MATERIAL_STVK;
+        for (PipeKernelFn fn :
+             {stvk ? (cheb0 ? StepKernelPipe<true, false, true> : StepKernelPipe<false, false, true>)
+                   : (cheb0 ? StepKernelPipe<true, false> : StepKernelPipe<false, false>),
+              stvk ? (cheb0 ? StepKernelPipe<true, true, true> : StepKernelPipe<false, true, true>)
+                   : (cheb0 ? StepKernelPipe<true, true> : StepKernelPipe<false, true>)})
         {
             VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
             int n = 0;
@@ -413,7 +426,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         int const nTiles = static_cast<int>(plan.tiles.size());
         FillRecords<<<Blocks(static_cast<int64_t>(nTiles) * 32, 256), 256, 0, stream>>>(
             dTiles.p, nTiles, dNew2Old.p, dOld2New.p, dPtr.p, dAdj.p, dE.p, dJinv.p, dVol.p, dLame.p,
-            muDefault, lamDefault, dRecIdx.p, dRecords.p);
+            muDefault, lamDefault, dRecIdx.p, material == VBDX_MATERIAL_STVK ? 1 : 0, dRecords.p);
         ++kernelLaunches;
         VBDX_CUDA(cudaStreamSynchronize(stream));  // dRecIdx is released at the end of this scope
     }
@@ -804,7 +817,7 @@ void Integrator::Objective(const double* xk, const double* xtilde, double dt, do
     double* g = grad ? dObjGrad.p : nullptr;
     ObjectiveKinetic<<<std::min(Blocks(nV, 256), 1184), 256, 0, stream>>>(dObjX.p, dObjXt.p, dMass.p, nV, dObjVal.p, g);
     ObjectiveElastic<<<std::min(Blocks(nT, 256), 1184), 256, 0, stream>>>(dObjX.p, dE.p, dJinv.p, dVol.p, dLame.p, mu0, lambda0, nT, dt * dt,
-                                                                            dObjVal.p, g);
+                                                                            material == VBDX_MATERIAL_STVK ? 1 : 0, dObjVal.p, g);
     kernelLaunches += 2;
     if (f)
         dObjVal.Download(f, 1, stream);

@@ -37,6 +37,12 @@ namespace vbdx {
 //   word 5   gamma = wg*lambda*detG*alpha    (alpha = 1 + mu/lambda)
 //   word 6   wg*mu*|grad N_i|^2              word 7  unused (0)
 // Padding slots are all-zero and therefore contribute exactly 0.
+//
+// St. Venant-Kirchhoff needs the deformation gradient itself, i.e. the three shape-function gradients of the other
+// vertices: its incidence record is TWO consecutive blocks (same lane), so that every copy path stays as it is:
+//   block 2t   : word 0 local ring indices | grad N_a (3) || grad N_b (3) | wg*mu
+//   block 2t+1 : grad N_c (3) | wg*lambda  || unused (0)
+// TileIters then counts blocks (2 per incident tet).
 // -----------------------------------------------------------------------------------------
 constexpr int kRecordWords      = 8;
 constexpr int kBlockFloat4      = 64;   // float4 per block (2 chunk rows x 32 lanes)
@@ -97,6 +103,7 @@ void BuildPlan(
     const double* X,
     int tileIters,
     bool naturalOrder,
+    int blocksPerIncidence,  // record blocks per incident tet: 1 (Stable Neo-Hookean), 2 (St. Venant-Kirchhoff)
     Plan& plan);
 
 // Second planning step, once the persistent grid size is known: which tiles / record blocks of each

@@ -36,6 +36,14 @@ class AccelerationStrategy(enum.IntEnum):
     TrustRegion = 5
 
 
+class HyperElasticEnergy(enum.IntEnum):
+    """Elastic energy density of the sweep (include/vbdx.h vbdx_material).  The reference's integrator
+    instantiates ``physics::StableNeoHookeanEnergy<3>`` (sim/vbd/Integrator.cpp:120); ``SaintVenantKirchhoff``
+    (physics/SaintVenantKirchhoffEnergy.h) is offered in its place as the north star asks."""
+    StableNeoHookean = 0
+    SaintVenantKirchhoff = 1
+
+
 def lame_coefficients(Y, nu):
     """physics/HyperElasticity.cpp:6-11"""
     mu = Y / (2.0 * (1.0 + nu))
@@ -102,6 +110,8 @@ class Data:
         # extension (not in the reference): which omega recurrence the Chebyshev solve uses,
         # 0 = as the reference evaluates it, 1 = textbook (include/vbdx.h vbdx_omega_mode)
         self.omega_mode = 0
+        # extension: elastic energy (HyperElasticEnergy); the reference's only choice is the default
+        self.energy = HyperElasticEnergy.StableNeoHookean
 
     # ---- fluent builder (sim/vbd/Data.cpp:20-177) ----------------------------------------
     def with_volume_mesh(self, X, T):
@@ -141,6 +151,11 @@ class Data:
         self.rhoe = np.asarray(rhoe, dtype=np.float64).reshape(-1).copy()
         self.lame = np.stack([np.asarray(mue, np.float64).reshape(-1),
                               np.asarray(lambdae, np.float64).reshape(-1)])
+        return self
+
+    def with_hyper_elastic_energy(self, energy):
+        """Extension: choose the elastic energy density (``HyperElasticEnergy``)."""
+        self.energy = HyperElasticEnergy(energy)
         return self
 
     def with_dirichlet_vertices(self, dbc, muD=1.0, input_sorted=True):

@@ -27,6 +27,9 @@ CASES = {
     "beam_small_inertia": (("grid", 6, 3, 3, 0.1), dict(strategy=1), 1e-2, 10, 1, 10),
     "beam_small_kinetic": (("grid", 6, 3, 3, 0.1), dict(strategy=2), 1e-2, 10, 1, 10),
     "beam_small_adaptive_vbd": (("grid", 6, 3, 3, 0.1), dict(strategy=3), 1e-2, 10, 1, 10),
+    # St. Venant-Kirchhoff in place of the Stable Neo-Hookean energy (reference header physics/SaintVenantKirchhoffEnergy.h)
+    "beam_small_stvk": (("grid", 6, 3, 3, 0.1), dict(material=1), 1e-2, 10, 1, 10),
+    "beam_small_stvk_cheb_damped": (("grid", 6, 3, 3, 0.1), dict(material=1, accel=1, rho=0.9, kD=1e-3), 1e-2, 10, 2, 10),
     "config1_base": (("grid", 25, 9, 9, 0.04), {}, 1e-2, 20, 1, 100),
     "config1_cheb": (("grid", 25, 9, 9, 0.04), dict(accel=1, rho=0.9), 1e-2, 20, 1, 100),
 }

@@ -20,8 +20,8 @@ def rel_l2(a, b):
 
 
 def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile_iters=0, klass=None, flags=0, v=None,
-         kernel_variant=0, ring_slots=0, consumer_warps=0):
-    d = pbat.sim.vbd.Data().with_volume_mesh(X, T)
+         kernel_variant=0, ring_slots=0, consumer_warps=0, material=0):
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_hyper_elastic_energy(material)
     if dbc is not None:
         d = d.with_dirichlet_vertices(dbc)
     if cheb:
@@ -37,7 +37,7 @@ def make(X, T, *, dbc=None, cheb=None, strategy=None, kD=0.0, omega_mode=0, tile
                 consumer_warps=consumer_warps)
     ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, v=v,
                         accel=oracle.ACCEL_CHEBYSHEV if cheb else oracle.ACCEL_NONE, rho=cheb or 1.0,
-                        omega_mode=omega_mode, kD=kD,
+                        omega_mode=omega_mode, kD=kD, material=material,
                         strategy=int(d.strategy))
     return d, vbd, ref
 
@@ -181,7 +181,7 @@ def test_errors():
 @pytest.mark.parametrize("name", ["cube_base", "cube_cheb", "beam_small_base", "beam_small_cheb",
                                   "beam_small_cheb_textbook", "beam_small_substeps_damped", "beam_small_position",
                                   "beam_small_inertia", "beam_small_kinetic", "beam_small_adaptive_vbd",
-                                  "config1_base", "config1_cheb"])
+                                  "beam_small_stvk", "beam_small_stvk_cheb_damped", "config1_base", "config1_cheb"])
 def test_against_reference_golden(name):
     """CUDA path vs trajectories produced by the reference's own headers (tests/golden/make_golden.py)."""
     import os
@@ -192,7 +192,7 @@ def test_against_reference_golden(name):
     spec, kw, dt, iters, sub, steps = CASES[name]
     X, T, dbc = mesh_of(spec)
     d, vbd, _ = make(X, T, dbc=dbc, cheb=kw.get("rho") if kw.get("accel") else None, kD=kw.get("kD", 0.0),
-                     omega_mode=kw.get("omega_mode", 0),
+                     omega_mode=kw.get("omega_mode", 0), material=kw.get("material", 0),
                      strategy=pbat.sim.vbd.InitializationStrategy(kw["strategy"]) if "strategy" in kw else None)
     assert np.array_equal(d.colors, gold[name + "/colors"])
     for _ in range(steps):
@@ -338,6 +338,38 @@ def test_objective_function_and_gradient():
     d2 = pbat.sim.vbd.Data().with_volume_mesh(X, T).construct()          # default material path
     v2, r2 = pbat.sim.vbd.Integrator(d2), oracle.Oracle(X, T, colors=d2.colors)
     assert abs(v2.objective_function(xk, xtilde, 0.01) - r2.objective(xk, xtilde, 0.01)) <= 1e-12 * abs(r2.objective(xk, xtilde, 0.01))
+
+
+@pytest.mark.parametrize("tile_iters", [0, 2])
+def test_stvk_material(tile_iters):
+    """St. Venant-Kirchhoff energy (physics/SaintVenantKirchhoffEnergy.h) in place of the Stable Neo-Hookean one:
+    perturbed config-1-like beam with per-element Lame parameters, sweep + objective + gradient against the oracle."""
+    X, T = meshes.tet_grid(12, 5, 4, 0.05)
+    rng = np.random.default_rng(11)
+    X = X + 0.004 * rng.uniform(-1, 1, X.shape)
+    nT = T.shape[1]
+    mue, lame = 3e5 * (1 + rng.random(nT)), 2e6 * (1 + rng.random(nT))
+    dbc = np.flatnonzero(X[0] < 0.01)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_material(np.full(nT, 1e3), mue, lame)
+         .with_dirichlet_vertices(dbc).with_hyper_elastic_energy(pbat.sim.vbd.HyperElasticEnergy.SaintVenantKirchhoff)
+         .with_chebyshev_acceleration(0.8).construct())
+    vbd = pbat.sim.vbd.Integrator(d, tile_iters=tile_iters)
+    ref = oracle.Oracle(X, T, mue=mue, lambdae=lame, dbc=dbc, colors=d.colors, accel=oracle.ACCEL_CHEBYSHEV, rho=0.8,
+                        material=oracle.MATERIAL_STVK)
+    for _ in range(20):
+        vbd.step(0.01, 10, 1)
+        ref.step(0.01, 10, 1)
+    err = rel_l2(vbd.x, ref.x)
+    derr = np.linalg.norm(vbd.x - ref.x) / np.linalg.norm(ref.x - X)
+    print(f"stvk: rel L2 = {err:.3e}, displacement-relative = {derr:.3e}")
+    assert err < TOL
+    xk, xtilde = ref.x, ref.get("xtilde")
+    f, g = vbd.objective_function(xk, xtilde, 0.01), vbd.objective_function_gradient(xk, xtilde, 0.01)
+    fr, gr = ref.objective(xk, xtilde, 0.01), ref.objective_gradient(xk, xtilde, 0.01)
+    assert abs(f - fr) <= 1e-12 * abs(fr)
+    assert np.linalg.norm(g - gr.T.reshape(-1)) <= 1e-11 * np.linalg.norm(gr)
+    with pytest.raises((RuntimeError, ValueError)):   # the direct / TMA variants carry Stable Neo-Hookean records only
+        pbat.sim.vbd.Integrator(d, kernel_variant=1)
 
 
 @pytest.mark.parametrize("cheb", [None, 0.8])

@@ -103,6 +103,42 @@ def test_snh_energy_at_identity(kind):
     assert psi >= 0 and abs(psi - 0.5 * lam * (1 - gamma) ** 2) < 1e-9 * max(1.0, psi)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_stvk_energy_known_answer(kind):
+    """physics/SaintVenantKirchhoffEnergy.cpp:9-39: psi(I) = 0 and psi(F) = mu |E|^2 + lambda/2 tr(E)^2."""
+    mu, lam = 3.4e5, 3.1e6
+    assert abs(oracle.stvk_eval(np.eye(3), mu, lam, kind=kind)) <= 1e-15
+    F = np.eye(3) + 0.2 * np.random.default_rng(3).standard_normal((3, 3))
+    E = 0.5 * (F.T @ F - np.eye(3))
+    expected = mu * (E * E).sum() + 0.5 * lam * np.trace(E) ** 2
+    assert abs(oracle.stvk_eval(F, mu, lam, kind=kind) - expected) <= 1e-12 * expected
+
+
+@pytest.mark.parametrize("material", [oracle.MATERIAL_STABLE_NEO_HOOKEAN, oracle.MATERIAL_STVK])
+def test_objective_gradient_is_the_derivative_of_the_objective(material):
+    """sim/vbd/Integrator.cpp:138-200 restated: central differences of f against the analytic gradient, and the
+    per-vertex Newton blocks of the sweep are consistent with it (one sweep from a perturbed state lowers f)."""
+    X, T = meshes.tet_grid(3, 2, 2, 0.3)
+    o = oracle.Oracle(X, T, material=material)
+    rng = np.random.default_rng(1)
+    xk = X + 0.02 * rng.standard_normal(X.shape)
+    xt = X + 0.01 * rng.standard_normal(X.shape)
+    g = o.objective_gradient(xk, xt, 0.05).reshape(-1, 3).T
+    for _ in range(12):
+        i, dd = rng.integers(X.shape[1]), rng.integers(3)
+        h = 1e-6
+        xp, xm = xk.copy(), xk.copy()
+        xp[dd, i] += h
+        xm[dd, i] -= h
+        fd = (o.objective(xp, xt, 0.05) - o.objective(xm, xt, 0.05)) / (2 * h)
+        assert abs(fd - g[dd, i]) <= 1e-6 * max(1.0, abs(g[dd, i]))
+    o.step(0.01, 0, 1)                      # sets xtilde, no sweeps
+    xtilde = o.get("xtilde")
+    f0 = o.objective(o.x, xtilde, 0.01)
+    o.sweeps(0.01, 5)
+    assert o.objective(o.x, xtilde, 0.01) < f0
+
+
 def test_coloring_is_proper_for_all_strategies():
     """graph/Color.cpp:9-49"""
     X, T = meshes.tet_grid(4, 3, 3)
