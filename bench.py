@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the CPU-baseline sample (about 1.1 s each on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-iters", type=int, default=0)
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of domain decomposition")
@@ -164,9 +164,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        X, T, dbc, x0 = workload()
+        # the arm's own workload: one 58^3 slab per GPU of the domain-decomposed beam (N slabs), or one replica
+        slabs = 1 if args.replicas else max(args.gpus, 1)
+        X, T, dbc, x0 = workload(slabs=slabs)
         config["tets"], config["vertices"] = int(T.shape[1]), int(X.shape[1])
-        k = min(max(steps, 1), 3)
+        # bounded sample: about 25 s of CPU work (a step of one slab takes about 1.1 s on 16 cores)
+        k = max(1, min(max(steps, 1), 24 // slabs))
         value, spstep, info = cpu_reference(X, T, dbc, x0, steps=k, warmup=min(warmup, 1))
         info["sample"] = f"bounded: {k} timed step(s) instead of {steps}; " + info["sample"]
         line = {"impl": "reference", "metric": "VBD vertex-iterations/sec", "value": value, "unit": "vertex-iterations/s",
