@@ -21,7 +21,7 @@ REF_LIB = os.path.join(_HERE, "_ref", "liboracle_ref.so")
 
 # enums shared with the product (sim/vbd/Enums.h:9-28, graph/Enums.h)
 POSITION, INERTIA, KINETIC_ENERGY_MINIMUM, ADAPTIVE_VBD, ADAPTIVE_PBAT = range(5)
-ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV = 0, 1, 2, 3   # = vbdx_acceleration_strategy
+ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV, ACCEL_BROYDEN = 0, 1, 2, 3, 4   # = vbdx_acceleration_strategy
 ORDER_NATURAL, ORDER_SMALLEST_DEGREE, ORDER_LARGEST_DEGREE = range(3)
 SELECT_LEAST_USED, SELECT_FIRST_AVAILABLE = range(2)
 MATERIAL_STABLE_NEO_HOOKEAN, MATERIAL_STVK = range(2)  # = vbdx_material

@@ -5,6 +5,7 @@
 
 #include "device_buffer.cuh"
 #include "anderson.cuh"
+#include "broyden.cuh"
 #include "contact_host.cuh"
 #include "diagnostics.cuh"
 #include "setup_kernels.cuh"
@@ -150,6 +151,7 @@ struct Integrator {
     void RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync);
     void LaunchPreStep(StepParams const& q);
     void AndersonStep(StepParams const& p, int iterations, int substeps);
+    void BroydenStep(StepParams const& p, int iterations, int substeps);
     void StepPartial(double sdt, int kBegin, int kEnd, int totalIterations, int flags);
     void Objective(const double* xk, const double* xtilde, double dt, double* f, double* grad);
     template <class T>
@@ -165,15 +167,16 @@ void Integrator::Create(vbdx_data_desc const& d)
     Require(d.nV > 0 && d.nT > 0 && d.X && d.E, "need a volume mesh: X (3 x nV) and E (4 x nT)");
     Require(d.nV < (int64_t(1) << 31) - 1 && d.nT < (int64_t(1) << 29), "mesh too large for 32-bit device indices");
     Require(d.acceleration >= VBDX_ACCEL_NONE && d.acceleration <= VBDX_ACCEL_TRUST_REGION, "unknown acceleration strategy");
-    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV && d.acceleration != VBDX_ACCEL_ANDERSON)
-        throw Error(VBDX_UNSUPPORTED, "only the base, Chebyshev- and Anderson-accelerated VBD solves are implemented");
-    if (d.acceleration == VBDX_ACCEL_ANDERSON)
+    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV && d.acceleration != VBDX_ACCEL_ANDERSON &&
+        d.acceleration != VBDX_ACCEL_BROYDEN)
+        throw Error(VBDX_UNSUPPORTED, "only the base, Chebyshev-, Anderson- and Broyden-accelerated VBD solves are implemented");
+    if (d.acceleration == VBDX_ACCEL_ANDERSON || d.acceleration == VBDX_ACCEL_BROYDEN)
     {
         // sim/vbd/Data.cpp:277-283 (window >= 1); the device solver keeps the window's Gram matrix in registers
         Require(d.window_size >= 1, "Expected window size >= 1");
         if (d.window_size > kMaxAndersonWindow)
-            throw Error(VBDX_UNSUPPORTED, "Anderson windows larger than 16 are not supported");
-        Require(d.nF == 0 && d.nGhosts == 0, "Anderson acceleration is not combined with contact or domain decomposition yet");
+            throw Error(VBDX_UNSUPPORTED, "Anderson/Broyden windows larger than 16 are not supported");
+        Require(d.nF == 0 && d.nGhosts == 0, "Anderson/Broyden acceleration is not combined with contact or domain decomposition yet");
         window = d.window_size;
     }
     Require(d.material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN || d.material == VBDX_MATERIAL_STVK, "unknown material");
@@ -678,6 +681,8 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
     if (acceleration == VBDX_ACCEL_ANDERSON)
         AndersonStep(p, iterations, substeps);
+    else if (acceleration == VBDX_ACCEL_BROYDEN)
+        BroydenStep(p, iterations, substeps);
     else if (!contact.enabled)
         launchStep(p);
     else
@@ -777,6 +782,56 @@ void Integrator::AndersonStep(StepParams const& p, int iterations, int substeps)
             AndersonSolveSmall<<<1, 32, 0, stream>>>(a, dkl, mk, 1e-10);
             AndersonApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive);
             kernelLaunches += 3;
+        }
+        StepParams post = q;
+        post.iterations = 0, post.skipPostStep = 0;
+        LaunchStepKernel(post);  // velocity update only
+    }
+}
+
+// BroydenIntegrator::Solve inside Integrator::Step (sim/vbd/BroydenIntegrator.cpp:41-77), same launch structure as
+// AndersonStep; the window buffers are shared with it (dAndVec: xkm1, fkm1, fk, unused, X[m], GF[m]).
+void Integrator::BroydenStep(StepParams const& p, int iterations, int substeps)
+{
+    int const m = window;
+    if (dAndVec.n == 0)
+    {
+        dAndVec.Alloc(static_cast<size_t>(nV) * (4 + 2 * m), &deviceBytes);
+        dAndSmall.Alloc(static_cast<size_t>(m) * m + 3 * m, &deviceBytes);
+    }
+    BroydenView a{};
+    a.n = nV, a.m = m, a.pos = dPos.p;
+    a.xkm1 = dAndVec.p, a.fkm1 = a.xkm1 + nV, a.fk = a.fkm1 + nV, a.X = a.fk + 2 * static_cast<size_t>(nV);
+    a.GF      = a.X + static_cast<size_t>(m) * nV;
+    a.gram    = dAndSmall.p;
+    a.scratch = a.gram + m * m;
+    a.gamma   = a.scratch + 2 * m;
+    StepParams q   = p;
+    q.substeps     = 1;
+    q.skipPreStep  = 1;
+    q.skipPostStep = 1;
+    q.iterations   = 1;
+    int const grid = Blocks(nV, 256);
+    for (int s = 0; s < substeps; ++s)
+    {
+        LaunchPreStep(q);
+        VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, dAndSmall.n * sizeof(double), stream));
+        VBDX_CUDA(cudaMemcpyAsync(a.xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        // the reference sweeps once before its loop whatever `iterations` is (BroydenIntegrator.cpp:47-49)
+        q.iterBegin = 0;
+        LaunchStepKernel(q);
+        BroydenFirst<<<grid, 256, 0, stream>>>(a);
+        ++kernelLaunches;
+        for (int k = 1; k < iterations; ++k)
+        {
+            int const col = (k - 1) % m, mk = std::min(m, k);
+            BroydenBeforeSweep<<<grid, 256, 0, stream>>>(a, col);
+            q.iterBegin = k;
+            LaunchStepKernel(q);
+            BroydenWindow<kMaxAndersonWindow><<<std::min(grid, 4 * 148), 256, 0, stream>>>(a, col, mk);
+            BroydenSolveSmall<<<1, 32, 0, stream>>>(a, col, mk, std::max(1, m - k), 1e-10);
+            BroydenApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive);
+            kernelLaunches += 4;
         }
         StepParams post = q;
         post.iterations = 0, post.skipPostStep = 0;

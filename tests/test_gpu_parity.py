@@ -318,6 +318,46 @@ def test_anderson_acceleration():
         pbat.sim.vbd.Data().with_volume_mesh(X, T).with_anderson_acceleration(0).construct()
 
 
+def test_broyden_acceleration():
+    """BroydenIntegrator (sim/vbd/BroydenIntegrator.cpp:41-77): the reference's cube known answer (:83-135, 15
+    iterations, m = 5) and parity with the oracle on a cantilever where the window wraps around."""
+    d = pbat.sim.vbd.Data().with_volume_mesh(meshes.CUBE_P, meshes.CUBE_T).with_broyden_acceleration(5).construct()
+    vbd = pbat.sim.vbd.Integrator(d)
+    dt = 1e-2
+    x0 = vbd.x
+    xtilde = x0 + dt * vbd.v + dt * dt * d.aext
+    f0 = vbd.objective_function(x0, xtilde, dt)
+    vbd.step(dt, 15, 1)
+    dx = vbd.x - meshes.CUBE_P
+    assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+    assert np.linalg.norm(vbd.objective_function_gradient(vbd.x, xtilde, dt)) < 1e-4 * 50  # fp32 iterate, f in double
+    assert vbd.objective_function(vbd.x, xtilde, dt) < f0
+
+    X, T = meshes.tet_grid(12, 4, 4, 0.05)
+    dbc = np.flatnonzero(X[0] == 0)
+    for window, substeps in ((3, 1), (5, 2)):
+        d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_broyden_acceleration(window).construct()
+        vbd = pbat.gpu.vbd.Integrator(d)
+        ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors)
+        ref.set_acceleration(oracle.ACCEL_BROYDEN, window=window)
+        plain = oracle.Oracle(X, T, dbc=dbc, colors=d.colors)
+        # Tolerance as for Anderson (same amplification of the fp32 rounding of the iterates by the secant mixing):
+        # 2e-4 after the first step, 1.5e-3 after ten.
+        for step in range(10):
+            vbd.step(0.01, 10, substeps)
+            ref.step(0.01, 10, substeps)
+            plain.step(0.01, 10, substeps)
+            if step == 0:
+                print("broyden step 1:", rel_l2(vbd.x, ref.x))
+                assert rel_l2(vbd.x, ref.x) < 2e-4, rel_l2(vbd.x, ref.x)
+        err = rel_l2(vbd.x, ref.x)
+        print("broyden step 10:", err, rel_l2(plain.x, ref.x))
+        assert err < 1.5e-3, err
+        assert rel_l2(plain.x, ref.x) > 3 * err
+    with pytest.raises(ValueError):
+        pbat.sim.vbd.Data().with_volume_mesh(X, T).with_broyden_acceleration(0).construct()
+
+
 def test_objective_function_and_gradient():
     """Integrator::ObjectiveFunction / ObjectiveFunctionGradient (sim/vbd/Integrator.cpp:138-200) on the device
     (double precision) against the oracle, with per-element material parameters."""

@@ -59,6 +59,32 @@ def test_cube_anderson_known_answer(kind):
     assert o.objective(o.x, xtilde, dt) < f0
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_cube_broyden_known_answer(kind):
+    """sim/vbd/BroydenIntegrator.cpp:83-135 (m = 5, 15 iterations): dz < 0, |dxy| < 1e-4, |grad f| < 1e-4, f < f0."""
+    o = oracle.Oracle(meshes.CUBE_P, meshes.CUBE_T, kind=kind)
+    o.set_acceleration(oracle.ACCEL_BROYDEN, window=5)
+    dt = 1e-2
+    x0 = o.x
+    xtilde = x0 + dt * o.v + dt * dt * o.get("aext")
+    f0 = o.objective(x0, xtilde, dt)
+    o.step(dt, 15, 1)
+    dx = o.x - meshes.CUBE_P
+    assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+    assert np.linalg.norm(o.objective_gradient(o.x, xtilde, dt)) < 1e-4
+    assert o.objective(o.x, xtilde, dt) < f0
+
+
+def test_broyden_converges_faster_than_plain_sweeps():
+    X, T = meshes.tet_grid(6, 3, 3, 0.1)
+    dbc = np.flatnonzero(X[0] == 0)
+    plain, acc, conv = (oracle.Oracle(X, T, dbc=dbc) for _ in range(3))
+    acc.set_acceleration(oracle.ACCEL_BROYDEN, window=5)
+    for _ in range(5):
+        plain.step(0.01, 10, 1), acc.step(0.01, 10, 1), conv.step(0.01, 300, 1)
+    assert np.linalg.norm(acc.x - conv.x) < 0.25 * np.linalg.norm(plain.x - conv.x)
+
+
 def test_anderson_least_squares_is_numpy_lstsq():
     """The Anderson mixing weights are Eigen's CompleteOrthogonalDecomposition solve (minimum-norm least
     squares); the oracle's restatement must agree with LAPACK's on a beam where the window fills up."""
