@@ -1,0 +1,165 @@
+"""BASELINE.json configurations at their FULL sizes, through size-independent properties (the oracle needs about a
+second per step at these sizes, so it is consulted for single steps only):
+
+  configs[1]  58^3 cubes, 975,560 tets: analytic free fall, one full step against the oracle, run-to-run and
+              kernel-variant bit-identity, monotone objective
+  configs[2]  16 stacked bodies, 1.95 M tets, LBVH contact: the stack stays ordered, the first landing is caught by the penalty
+  configs[4]  batch of independent 5k-tet scenes: a scene inside a batch evolves exactly like the scene alone
+(configs[0] at full size: tests/test_gpu_parity.py; configs[3], domain decomposition: tests/test_gpu_dist.py.)
+"""
+import numpy as np
+import pytest
+
+import oracle
+import physicsbasedanimationtoolkit_b200 as pbat
+from physicsbasedanimationtoolkit_b200 import meshes
+
+pytestmark = pytest.mark.gpu
+GRID, ITERS, RHO, DT = 58, 30, 0.9, 0.01
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def config2():
+    X, T = meshes.tet_grid(GRID, GRID, GRID, 1.0 / GRID)
+    dbc = np.flatnonzero(X[2] == 0)
+    x0 = X + 0.05 / GRID * np.random.default_rng(0).uniform(-1, 1, X.shape)
+    x0[:, dbc] = X[:, dbc]
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
+         .with_chebyshev_acceleration(RHO).construct())
+    assert T.shape[1] == 975560 and X.shape[1] == 205379
+    return X, T, dbc, x0, d
+
+
+def test_config2_free_fall_known_answer():
+    """The reference's cube doctest (sim/vbd/Integrator.cpp:245-293) at full size: an unconstrained body at rest falls
+    rigidly, dz = -g dt^2 after the first step, nothing moves sideways.  Started from the inertial target
+    (KineticEnergyMinimum) this holds at any size, because the elastic force of a rigid translate vanishes; from the
+    default start it only holds once the sweeps have converged, which the 8-vertex cube does in 10 iterations and a
+    10^6-tet block does not -- in the reference either."""
+    X, T = meshes.tet_grid(GRID, GRID, GRID, 1.0 / GRID)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_chebyshev_acceleration(RHO)
+         .with_initialization_strategy(pbat.sim.vbd.InitializationStrategy.KineticEnergyMinimum).construct())
+    vbd = pbat.gpu.vbd.Integrator(d)
+    vbd.step(DT, 10, 1)
+    dx = vbd.x.astype(np.float64) - X
+    assert (dx[2] < 0).all()
+    assert np.abs(dx[:2]).max() < 1e-4
+    assert np.allclose(dx[2], -9.81e-4, atol=5e-6)
+    assert np.allclose(vbd.v[2], -9.81e-2, atol=5e-4)
+
+
+def test_config2_one_step_against_the_oracle(config2):
+    X, T, dbc, x0, d = config2
+    vbd = pbat.gpu.vbd.Integrator(d)
+    ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, accel=oracle.ACCEL_CHEBYSHEV, rho=RHO)
+    vbd.x = x0.astype(np.float32)
+    ref.x = x0.astype(np.float32).astype(np.float64)
+    vbd.step(DT, ITERS, 1)
+    ref.step(DT, ITERS, 1)
+    xr = ref.x
+    err = rel_l2(vbd.x, xr)
+    derr = np.linalg.norm(vbd.x - xr) / np.linalg.norm(xr - X)
+    print(f"config 2, one full step: rel L2 = {err:.3e}, displacement-relative = {derr:.3e}")
+    assert err < 1e-4
+    assert derr < 1e-2
+
+
+def test_config2_bit_identical_across_runs_and_kernel_variants(config2):
+    X, T, dbc, x0, d = config2
+    out = []
+    for variant in (0, 0, 1):  # default (pipelined) twice, then the direct kernel
+        vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=variant)
+        vbd.x = x0.astype(np.float32)
+        for _ in range(3):
+            vbd.step(DT, ITERS, 1)
+        out.append((vbd.x.copy(), vbd.v.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+
+
+def test_config2_sweeps_descend(config2):
+    """Block coordinate Newton steps on the backward-Euler objective: every batch of sweeps lowers f and the
+    gradient norm, at full size (objective evaluated on the device in double)."""
+    X, T, dbc, x0, _ = config2
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).construct()
+    vbd = pbat.sim.vbd.Integrator(d)
+    vbd.x = x0
+    free = np.ones(X.shape[1], bool)
+    free[dbc] = False
+    xtilde = x0 + DT * DT * d.aext
+    f = [vbd.objective_function(x0, xtilde, DT)]
+    g = [np.linalg.norm(vbd.objective_function_gradient(x0, xtilde, DT).reshape(-1, 3)[free])]
+    for k0 in range(0, 12, 4):
+        vbd.step_partial(DT, k0, k0 + 4, 12, flags=(1 if k0 == 0 else 0))
+        xk = vbd.x
+        f.append(vbd.objective_function(xk, xtilde, DT))
+        g.append(np.linalg.norm(vbd.objective_function_gradient(xk, xtilde, DT).reshape(-1, 3)[free]))
+    print("f:", f, "|grad|:", g)
+    assert all(b < a for a, b in zip(f, f[1:]))
+    assert g[-1] < 0.05 * g[0]
+
+
+def test_config3_stack_stays_ordered_and_lands():
+    n = 29
+    Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+    X, T, B = meshes.stack_bodies(Xb, Tb, 16, axis=2, gap_frac=0.1)
+    assert T.shape[1] == 1951120
+    F = meshes.boundary_facets(T)
+    V = np.unique(F)
+    assert F.shape[1] == 161472 and V.size == 80768
+    dbc = np.flatnonzero(X[2] <= X[2].min() + 0.01)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e6, 0.3, 1e-3).construct())
+    vbd = pbat.gpu.vbd.Integrator(d)
+    for _ in range(40):
+        vbd.step(DT, 20, 1)
+    x = vbd.x
+    assert np.isfinite(x).all()
+    lo = np.array([x[2, B == b].min() for b in range(16)])
+    hi = np.array([x[2, B == b].max() for b in range(16)])
+    assert (np.diff(lo) > 0).all()
+    # Penalty contact (muC = 1e6): a surface vertex carries k = muC * area ~ 1.2e3 N/m against the ~1.2 kg column
+    # above it, i.e. a static depth of ~0.01 = 0.3 cells per resting body and twice that on impact.  After 40 steps
+    # only body 1 has landed (on the fixed body 0): it may be in by less than a cell; every other gap is still open.
+    gaps = lo[1:] - hi[:-1]
+    assert gaps[0] > -1.0 / n, gaps[0]
+    assert (gaps[1:] > 0).all(), gaps
+    assert gaps[0] < 0.01  # ... and it HAS landed (free fall alone would have carried it 0.7 below body 0's top)
+    active, nn, n_active = vbd.contact_state()
+    # nActive = size of the step's compacted candidate list (InitializeActiveSet); FinalizeActiveSet then clears the
+    # flags of the vertices that ended on the positive side of their nearest triangle
+    assert 0 < np.count_nonzero(active) <= n_active < V.size // 10
+    tri = nn[nn >= 0]
+    assert (tri < F.shape[1]).all()
+    # a contact pairs a vertex with a triangle of ANOTHER body (VertexTriangleMixedCcdDcd.cuh:108-162)
+    vi, slot = np.nonzero(nn >= 0)
+    assert (B[V[vi]] != B[F[0, nn[vi, slot]]]).all()
+
+
+def test_config5_scene_in_a_batch_equals_the_scene_alone():
+    n_scenes = 256
+    Xs, Ts = meshes.tet_grid(10, 10, 10, 0.1)
+    assert Ts.shape[1] == 5000
+    X, T = meshes.batch_scenes(Xs, Ts, n_scenes, perturb=0.002)
+    nV = Xs.shape[1]
+    dbc1 = np.flatnonzero(Xs[2] == 0)
+    dbc = (dbc1[None, :] + nV * np.arange(n_scenes)[:, None]).reshape(-1)
+    single = pbat.sim.vbd.Data().with_volume_mesh(Xs, Ts).with_dirichlet_vertices(dbc1).construct()
+    colors = np.tile(single.colors, n_scenes)
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).construct()
+    batch = pbat.gpu.vbd.Integrator(d, colors=colors)
+    for _ in range(10):
+        batch.step(DT, 20, 1)
+    xb = batch.x
+    assert np.isfinite(xb).all()
+    for s in (0, 101, n_scenes - 1):
+        Xi = X[:, s * nV:(s + 1) * nV]
+        di = pbat.sim.vbd.Data().with_volume_mesh(Xi, Ts).with_dirichlet_vertices(dbc1).construct()
+        alone = pbat.gpu.vbd.Integrator(di, colors=single.colors)
+        for _ in range(10):
+            alone.step(DT, 20, 1)
+        assert np.array_equal(alone.x, xb[:, s * nV:(s + 1) * nV]), s
