@@ -227,8 +227,9 @@ __global__ void AndersonSolveSmall(AndersonView a, int dkl, int mk, double thres
         a.scratch[i] = 0.0;  // ready for the next accumulation
 }
 
-// x = G^k - DG alpha; the result is also the next iteration's x^{k-1}
-__global__ void AndersonApply(AndersonView a, int mk, int64_t nActive)
+// x = G^k - DG alpha; the result is also the next iteration's x^{k-1} (and, with contact, the snapshot the next
+// sweep reads same-colour triangle corners from: snapNext, step_kernel.cuh)
+__global__ void AndersonApply(AndersonView a, int mk, int64_t nActive, float4* snapNext)
 {
     int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= a.n)
@@ -245,6 +246,8 @@ __global__ void AndersonApply(AndersonView a, int mk, int64_t nActive)
         }
         x.x = static_cast<float>(x.x - dx), x.y = static_cast<float>(x.y - dy), x.z = static_cast<float>(x.z - dz);
         a.pos[i] = x;
+        if (snapNext != nullptr)
+            snapNext[i] = x;
     }
     a.xkm1[i] = x;
 }

@@ -146,8 +146,8 @@ __global__ void BroydenSolveSmall(BroydenView a, int col, int mk, int maxIters, 
         a.scratch[i] = 0.0;  // ready for the next accumulation
 }
 
-// x -= (X - GF) gamma
-__global__ void BroydenApply(BroydenView a, int mk, int64_t nActive)
+// x -= (X - GF) gamma  (snapNext: see AndersonApply)
+__global__ void BroydenApply(BroydenView a, int mk, int64_t nActive, float4* snapNext)
 {
     int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nActive)  // constrained vertices have identically zero window columns
@@ -163,6 +163,8 @@ __global__ void BroydenApply(BroydenView a, int mk, int64_t nActive)
     float4 x = a.pos[i];
     x.x = static_cast<float>(x.x - dx), x.y = static_cast<float>(x.y - dy), x.z = static_cast<float>(x.z - dz);
     a.pos[i] = x;
+    if (snapNext != nullptr)
+        snapNext[i] = x;
 }
 
 }  // namespace vbdx

@@ -150,8 +150,25 @@ struct Integrator {
     void LaunchStepKernel(StepParams const& q);
     void RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync);
     void LaunchPreStep(StepParams const& q);
-    void AndersonStep(StepParams const& p, int iterations, int substeps);
-    void BroydenStep(StepParams const& p, int iterations, int substeps);
+    void AndersonStep(StepParams const& p, double dt, int iterations, int substeps);
+    void BroydenStep(StepParams const& p, double dt, int iterations, int substeps);
+    // contact hooks shared by the windowed accelerators (same sequence as RunStep's contact branch)
+    void ContactBeginStep(StepParams const& p, double dt)
+    {
+        if (contact.enabled)
+            contact.InitializeActiveSet(dPos.p + p.pOff, dVel.p, dAext.p, nV, static_cast<float>(dt), stream, &kernelLaunches);
+    }
+    void ContactAfterPreStep(StepParams const& p, int s)
+    {
+        if (contact.enabled && s % contact.updateFrequency == 0)
+            contact.NearestPass(dPos.p + p.pOff, 0, stream, &kernelLaunches);
+    }
+    void ContactEndStep(StepParams const& p)
+    {
+        if (contact.enabled)
+            contact.NearestPass(dPos.p + p.pOff, 1, stream, &kernelLaunches);
+    }
+    float4* SnapNext(int k) { return contact.enabled ? contact.snap.p + static_cast<size_t>((k + 1) & 1) * nV : nullptr; }
     void StepPartial(double sdt, int kBegin, int kEnd, int totalIterations, int flags);
     void Objective(const double* xk, const double* xtilde, double dt, double* f, double* grad);
     template <class T>
@@ -176,7 +193,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         Require(d.window_size >= 1, "Expected window size >= 1");
         if (d.window_size > kMaxAndersonWindow)
             throw Error(VBDX_UNSUPPORTED, "Anderson/Broyden windows larger than 16 are not supported");
-        Require(d.nF == 0 && d.nGhosts == 0, "Anderson/Broyden acceleration is not combined with contact or domain decomposition yet");
+        Require(d.nGhosts == 0, "Anderson/Broyden acceleration is not combined with domain decomposition yet");
         window = d.window_size;
     }
     Require(d.material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN || d.material == VBDX_MATERIAL_STVK, "unknown material");
@@ -680,9 +697,9 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
     auto launchStep = [&](StepParams const& q) { LaunchStepKernel(q); };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
     if (acceleration == VBDX_ACCEL_ANDERSON)
-        AndersonStep(p, iterations, substeps);
+        AndersonStep(p, dt, iterations, substeps);
     else if (acceleration == VBDX_ACCEL_BROYDEN)
-        BroydenStep(p, iterations, substeps);
+        BroydenStep(p, dt, iterations, substeps);
     else if (!contact.enabled)
         launchStep(p);
     else
@@ -737,7 +754,7 @@ void Integrator::LaunchPreStep(StepParams const& q)
 
 // AndersonIntegrator::Solve inside Integrator::Step (sim/vbd/AndersonIntegrator.cpp:24-58): the sweeps are one-iteration
 // launches of the persistent step kernel, the window lives in anderson.cuh's kernels; nothing returns to the host.
-void Integrator::AndersonStep(StepParams const& p, int iterations, int substeps)
+void Integrator::AndersonStep(StepParams const& p, double dt, int iterations, int substeps)
 {
     int const m = window;
     if (dAndVec.n == 0)
@@ -758,9 +775,11 @@ void Integrator::AndersonStep(StepParams const& p, int iterations, int substeps)
     q.skipPostStep = 1;
     q.iterations   = 1;
     int const grid = Blocks(nV, 256);
+    ContactBeginStep(p, dt);
     for (int s = 0; s < substeps; ++s)
     {
         LaunchPreStep(q);
+        ContactAfterPreStep(p, s);
         if (iterations > 0)
         {
             VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, dAndSmall.n * sizeof(double), stream));
@@ -780,18 +799,19 @@ void Integrator::AndersonStep(StepParams const& p, int iterations, int substeps)
             int const dkl = (k - 1) % m, mk = std::min(m, k);
             AndersonWindow<kMaxAndersonWindow><<<std::min(grid, 4 * 148), 256, 0, stream>>>(a, dkl, mk);
             AndersonSolveSmall<<<1, 32, 0, stream>>>(a, dkl, mk, 1e-10);
-            AndersonApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive);
+            AndersonApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive, SnapNext(k));
             kernelLaunches += 3;
         }
         StepParams post = q;
         post.iterations = 0, post.skipPostStep = 0;
         LaunchStepKernel(post);  // velocity update only
     }
+    ContactEndStep(p);
 }
 
 // BroydenIntegrator::Solve inside Integrator::Step (sim/vbd/BroydenIntegrator.cpp:41-77), same launch structure as
 // AndersonStep; the window buffers are shared with it (dAndVec: xkm1, fkm1, fk, unused, X[m], GF[m]).
-void Integrator::BroydenStep(StepParams const& p, int iterations, int substeps)
+void Integrator::BroydenStep(StepParams const& p, double dt, int iterations, int substeps)
 {
     int const m = window;
     if (dAndVec.n == 0)
@@ -812,9 +832,11 @@ void Integrator::BroydenStep(StepParams const& p, int iterations, int substeps)
     q.skipPostStep = 1;
     q.iterations   = 1;
     int const grid = Blocks(nV, 256);
+    ContactBeginStep(p, dt);
     for (int s = 0; s < substeps; ++s)
     {
         LaunchPreStep(q);
+        ContactAfterPreStep(p, s);
         VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, dAndSmall.n * sizeof(double), stream));
         VBDX_CUDA(cudaMemcpyAsync(a.xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
         // the reference sweeps once before its loop whatever `iterations` is (BroydenIntegrator.cpp:47-49)
@@ -830,13 +852,14 @@ void Integrator::BroydenStep(StepParams const& p, int iterations, int substeps)
             LaunchStepKernel(q);
             BroydenWindow<kMaxAndersonWindow><<<std::min(grid, 4 * 148), 256, 0, stream>>>(a, col, mk);
             BroydenSolveSmall<<<1, 32, 0, stream>>>(a, col, mk, std::max(1, m - k), 1e-10);
-            BroydenApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive);
+            BroydenApply<<<grid, 256, 0, stream>>>(a, mk, plan.nActive, SnapNext(k));
             kernelLaunches += 4;
         }
         StepParams post = q;
         post.iterations = 0, post.skipPostStep = 0;
         LaunchStepKernel(post);  // velocity update only
     }
+    ContactEndStep(p);
 }
 
 // A slice of one substep: [pre-step] [iterations kBegin .. kEnd of a solve of totalIterations] [velocity update].

@@ -130,3 +130,29 @@ def test_contact_solve_matches_oracle(cheb):
     assert err < 1e-4
     # the top body must be resting on the bottom one, not passing through it
     assert xr[2, B == 1].min() > 0.45
+
+
+@pytest.mark.parametrize("accel", ["anderson", "broyden"])
+def test_windowed_accelerators_with_contact(accel):
+    """The reference's example (python/examples/vbd.py:297-330) combines a surface mesh with Anderson / Broyden
+    acceleration: its GPU accelerators call the same contact-aware sweep.  Same scene as above against the oracle;
+    tolerance of the windowed accelerators (tests/test_gpu_parity.py: 1.5e-3 after the window has mixed fp32 iterates)."""
+    X, T, B, F, V, dbc, v = stacked_scene()
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B).with_velocity(v)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e5, 0.3, 1e-3))
+    d = (d.with_anderson_acceleration(4) if accel == "anderson" else d.with_broyden_acceleration(4)).construct()
+    vbd = pbat.gpu.vbd.Integrator(d)
+    ref = oracle.Oracle(X, T, v=v, dbc=dbc, colors=d.colors, B=B, V=V, F=F, muC=1e5, muF=0.3, epsv=1e-3)
+    ref.set_acceleration(oracle.ACCEL_ANDERSON if accel == "anderson" else oracle.ACCEL_BROYDEN, window=4)
+    touched = False
+    for s in range(40):
+        vbd.step(0.01, 10, 1)
+        ref.step(0.01, 10, 1)
+        _, nn, _ = vbd.contact_state()
+        touched |= bool((nn >= 0).any())
+    assert touched, "the scene never produced a contact"
+    xr = ref.x
+    err = np.linalg.norm(vbd.x - xr) / np.linalg.norm(xr)
+    print(f"contact scene {accel}: rel L2 = {err:.3e}; top body lowest z = {xr[2, B == 1].min():.4f}")
+    assert err < 1.5e-3
+    assert xr[2, B == 1].min() > 0.45 and vbd.x[2, B == 1].min() > 0.45
