@@ -23,8 +23,8 @@ namespace vbdx {
 //   one warp owns a contiguous segment of kSortSegment items and walks it in chunks of 32, so that
 //   ranks within a digit follow item order (stability) without any cross-warp bookkeeping
 // ------------------------------------------------------------------------------------------
-constexpr int kSortSegment     = 2048;
-constexpr int kSortWarpsPerCta = 4;
+constexpr int kSortSegment     = 256;   // 8 chunks per warp: short dependent chains, n/256 warps in flight
+constexpr int kSortWarpsPerCta = 8;
 
 __global__ void RadixCount(const uint32_t* keys, uint32_t n, int shift, uint32_t nSeg, uint32_t* counts)
 {

@@ -421,6 +421,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (perSm < 1)
         throw Error(VBDX_CUDA_ERROR, "step kernel does not fit on an SM");
     gridBlocks = perSm * smCount;
+    if (char const* e = std::getenv("VBDX_GRID_BLOCKS"))  // tuning: fewer CTAs = cheaper grid barrier on small meshes
+        gridBlocks = std::max(1, std::min(std::atoi(e), gridBlocks));
     PartitionTiles(plan, gridBlocks);
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
