@@ -210,6 +210,14 @@ vbdx_status vbdx_set_initialization_strategy(vbdx_integrator* h, int32_t strateg
 /* Integrator::SetBlockSize                            gpu/vbd/Integrator.h:126
  * accepted for compatibility; the sweep is warp-tiled, so this is only a tuning hint */
 vbdx_status vbdx_set_block_size(vbdx_integrator* h, int32_t block_size);
+/* Extension (BASELINE north star: "fused 3x3 Newton solve with line-search guard"); no reference counterpart.
+ * 0 (default) = the reference's semantics: the full Newton step is always taken (sim/vbd/Kernels.h:329-339).
+ * 1 = guarded step: a step that is not a finite descent direction of the vertex' local objective is replaced by a
+ *     scaled steepest-descent step, and with the St. Venant-Kirchhoff energy (no damping / contact) the step length
+ *     is chosen by Armijo backtracking over t in {1, 1/2, 1/4} on the true local objective (none passes: the vertex
+ *     stays).  With the Stable Neo-Hookean energy the local objective is exactly quadratic and the Newton step is
+ *     its minimiser, so the guard never alters a step (tested: bit-identical results). */
+vbdx_status vbdx_set_line_search_guard(vbdx_integrator* h, int32_t enabled);
 /* Integrator::SetSceneBoundingBox                     gpu/vbd/Integrator.h:132-134 */
 vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3], const float max3[3]);
 

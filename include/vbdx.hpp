@@ -53,6 +53,8 @@ class Integrator
     void SetNumericalZeroForHessianDeterminant(float zero) { Check(vbdx_set_detH_zero(mImpl, zero)); }
     void SetRayleighDampingCoefficient(float kD) { Check(vbdx_set_rayleigh_damping(mImpl, kD)); }
     void SetInitializationStrategy(EInitializationStrategy s) { Check(vbdx_set_initialization_strategy(mImpl, static_cast<int>(s))); }
+    /// extension: guarded Newton step (include/vbdx.h vbdx_set_line_search_guard); off = the reference's behaviour
+    void SetLineSearchGuard(bool enabled) { Check(vbdx_set_line_search_guard(mImpl, enabled ? 1 : 0)); }
     void SetBlockSize(int blockSize) { Check(vbdx_set_block_size(mImpl, blockSize)); }
     void SetSceneBoundingBox(float const min3[3], float const max3[3]) { Check(vbdx_set_scene_bounding_box(mImpl, min3, max3)); }
     /// gpu/vbd/Integrator.h:139-144: 3 x nV, returned by value

@@ -83,6 +83,7 @@ def _load(kind: str) -> C.CDLL:
     lib.vbdo_stvk_eval.restype = C.c_double
     lib.vbdo_stvk_eval.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.vbdo_set_material.argtypes = [C.c_void_p, C.c_int]
+    lib.vbdo_set_line_search_guard.argtypes = [C.c_void_p, C.c_int]
     lib.vbdo_num_threads.restype = C.c_int
     lib.vbdo_set_num_threads.argtypes = [C.c_int]
     _libs[kind] = lib
@@ -189,6 +190,10 @@ class Oracle:
     def set(self, name, a):
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)
         assert self.lib.vbdo_set_f64(self.h, name.encode(), _ptr(a)) == 0
+
+    def set_line_search_guard(self, on):
+        """The product's guarded Newton step (include/vbdx.h vbdx_set_line_search_guard), restated; off = reference."""
+        self.lib.vbdo_set_line_search_guard(self.h, 1 if on else 0)
 
     def set_params(self, strategy, kD, detH_zero):
         self.lib.vbdo_set_params(self.h, strategy, kD, detH_zero)

@@ -189,6 +189,12 @@ class DeviceIntegrator:
         _lib.check(self._L.vbdx_set_initialization_strategy(self._h, int(strategy)))
         self._strategy = int(strategy)
 
+    def _set_line_search_guard(self, on):
+        _lib.check(self._L.vbdx_set_line_search_guard(self._h, 1 if on else 0))
+
+    line_search_guard = property(None, _set_line_search_guard,
+                                 doc="Extension (write-only): guarded Newton step, see include/vbdx.h vbdx_set_line_search_guard")
+
     def _set_block_size(self, n):
         _lib.check(self._L.vbdx_set_block_size(self._h, int(n)))
 

@@ -61,6 +61,7 @@ struct StepParams {
     int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path) or by an earlier partial launch
     int skipPostStep;                    // partial launch: more iterations of this substep follow
     int iterBegin;                       // partial launch: index (within the substep's solve) of this launch's first iteration
+    int lineSearch;                      // 0: accept the full Newton step (the reference, sim/vbd/Kernels.h:329-339); 1: guarded step
     // multi-GPU domain decomposition (world == 1: single GPU)
     uint32_t ghostBegin;                 // internal ids >= ghostBegin are ghosts: written by their owner GPU only
     const uint32_t* __restrict__ sendPtr;  // per internal vertex < ghostBegin: range into sendDst (null: nothing to send)
@@ -488,7 +489,9 @@ __device__ __forceinline__ void ProcessTile(
         h22 += t2 * Sz;
         hd += c1.z;
     }
-    afterAccumulate();
+    bool const secondPass = kStvk && !kDamping && p.lineSearch != 0;  // warp-uniform
+    if (!secondPass)
+        afterAccumulate();
     if (trace && lane == 0)
         trace[6] = GlobalTimer();  // incident tets accumulated
     // butterfly over the w lanes that share a vertex (fixed order => deterministic)
@@ -505,7 +508,9 @@ __device__ __forceinline__ void ProcessTile(
         g1 += __shfl_xor_sync(0xffffffffu, g1, o);
         g2 += __shfl_xor_sync(0xffffffffu, g2, o);
     }
-    if (valid && (lane & ((1u << lw) - 1u)) == 0u)
+    bool const leader = valid && (lane & ((1u << lw) - 1u)) == 0u;
+    float nx = xi.x, ny = xi.y, nz = xi.z;  // the vertex' new position (leader lane)
+    if (leader)
     {
         h00 = __fadd_rn(h00, hd);
         h11 = __fadd_rn(h11, hd);
@@ -594,6 +599,122 @@ __device__ __forceinline__ void ProcessTile(
             y = fmaf(-r, fmaf(i12, g2, fmaf(i11, g1, __fmul_rn(i01, g0))), y);
             z = fmaf(-r, fmaf(i22, g2, fmaf(i12, g1, __fmul_rn(i02, g0))), z);
         }
+        if constexpr (kStvk)
+        if (p.lineSearch != 0)
+        {
+            // Guard, part 1: the step must be a finite descent direction of the local objective whose gradient and
+            // Hessian were just accumulated.  Compiled for St. Venant-Kirchhoff only: with the Stable Neo-Hookean
+            // energy det F is affine in ONE vertex, so the local objective is exactly quadratic with the positive
+            // definite Hessian used above and the Newton step IS its minimiser -- there is nothing to guard.  StVK's
+            // full Hessian (the reference's energies return it unprojected) turns indefinite under compression.
+            // Fallback: steepest descent scaled by a bound on the spectral radius of H (Gershgorin).
+            float const dx = x - xi.x, dy = y - xi.y, dz = z - xi.z;
+            float const slope = g0 * dx + g1 * dy + g2 * dz;
+            if (!(slope < 0.f) || !isfinite(slope))
+            {
+                float const bound = fmaxf(fabsf(h00) + fabsf(h01) + fabsf(h02),
+                                          fmaxf(fabsf(h01) + fabsf(h11) + fabsf(h12), fabsf(h02) + fabsf(h12) + fabsf(h22)));
+                float const sc = bound > 0.f ? 1.f / bound : 0.f;
+                x = fmaf(-sc, g0, xi.x), y = fmaf(-sc, g1, xi.y), z = fmaf(-sc, g2, xi.z);
+            }
+        }
+        nx = x, ny = y, nz = z;
+    }
+    if constexpr (kStvk && !kDamping)
+    {
+        if (secondPass)
+        {
+            // Guard, part 2 (St. Venant-Kirchhoff, whose local objective is quartic in x_i): Armijo backtracking on the
+            // TRUE local objective  1/2 K |x - xtilde|^2 + sum_e w psi(F_e(x))  over t in {1, 1/2, 1/4}, all trial
+            // points evaluated in one more pass over the tile's records (still in shared memory).  A vertex for which
+            // no trial point passes keeps its position.
+            uint32_t const head = lane & ~((1u << lw) - 1u);
+            float const ddx = __shfl_sync(0xffffffffu, nx - xi.x, head);
+            float const ddy = __shfl_sync(0xffffffffu, ny - xi.y, head);
+            float const ddz = __shfl_sync(0xffffffffu, nz - xi.z, head);
+            float de1 = 0.f, de2 = 0.f, de4 = 0.f;  // psi(t) - psi(0) summed over this lane's tets, t = 1, 1/2, 1/4
+            src.Rewind(iters);
+            float4 m0, m1;
+            src.Fetch(m0, m1);
+#pragma unroll 1
+            for (uint32_t t = 0; t < iters; t += 2)
+            {
+                float4 const c0 = m0, c1 = m1;
+                float4 c2, c3;
+                src.Fetch(c2, c3);
+                if (t + 2 < iters)
+                    src.Fetch(m0, m1);
+                uint32_t const idx = __float_as_uint(c0.x);
+                float4 const p1 = stage[idx & 1023u];
+                float4 const p2 = stage[(idx >> 10) & 1023u];
+                float4 const p3 = stage[(idx >> 20) & 1023u];
+                float const da[3] = {p1.x - xi.x, p1.y - xi.y, p1.z - xi.z};
+                float const db[3] = {p2.x - xi.x, p2.y - xi.y, p2.z - xi.z};
+                float const dc[3] = {p3.x - xi.x, p3.y - xi.y, p3.z - xi.z};
+                float const ga[3] = {c0.y, c0.z, c0.w}, gb[3] = {c1.x, c1.y, c1.z}, gc[3] = {c2.x, c2.y, c2.z};
+                float const wmu = c1.w, wlam = c2.w;
+                float const gi[3] = {-(ga[0] + gb[0] + gc[0]), -(ga[1] + gb[1] + gc[1]), -(ga[2] + gb[2] + gc[2])};
+                float const dd[3] = {ddx, ddy, ddz};
+                float F[3][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        F[r][c] = da[r] * ga[c] + db[r] * gb[c] + dc[r] * gc[c];
+                auto psi = [&](float tt) {
+                    // F(t) = F + t d (x) grad N_i
+                    float G[3][3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            G[r][c] = fmaf(tt * dd[r], gi[c], F[r][c]);
+                    float const e00 = 0.5f * (G[0][0] * G[0][0] + G[1][0] * G[1][0] + G[2][0] * G[2][0] - 1.f);
+                    float const e11 = 0.5f * (G[0][1] * G[0][1] + G[1][1] * G[1][1] + G[2][1] * G[2][1] - 1.f);
+                    float const e22 = 0.5f * (G[0][2] * G[0][2] + G[1][2] * G[1][2] + G[2][2] * G[2][2] - 1.f);
+                    float const e01 = 0.5f * (G[0][0] * G[0][1] + G[1][0] * G[1][1] + G[2][0] * G[2][1]);
+                    float const e02 = 0.5f * (G[0][0] * G[0][2] + G[1][0] * G[1][2] + G[2][0] * G[2][2]);
+                    float const e12 = 0.5f * (G[0][1] * G[0][2] + G[1][1] * G[1][2] + G[2][1] * G[2][2]);
+                    float const tr = e00 + e11 + e22;
+                    return wmu * (e00 * e00 + e11 * e11 + e22 * e22 + 2.f * (e01 * e01 + e02 * e02 + e12 * e12)) + 0.5f * wlam * tr * tr;
+                };
+                float const psi0 = psi(0.f);
+                de1 += psi(1.f) - psi0;
+                de2 += psi(0.5f) - psi0;
+                de4 += psi(0.25f) - psi0;
+                (void)c3;
+            }
+            afterAccumulate();
+            for (uint32_t o = (1u << lw) >> 1; o > 0; o >>= 1)
+            {
+                de1 += __shfl_xor_sync(0xffffffffu, de1, o);
+                de2 += __shfl_xor_sync(0xffffffffu, de2, o);
+                de4 += __shfl_xor_sync(0xffffffffu, de4, o);
+            }
+            if (leader)
+            {
+                // g0..g2 hold the gradient of the same objective at x_i (elastic + inertia; this variant carries no
+                // damping or contact);  inertia difference: K t d.(x - xtilde) + 1/2 K t^2 |d|^2
+                float const K     = xm.w / p.sdt2;
+                float const slope = g0 * ddx + g1 * ddy + g2 * ddz;
+                float const lin   = K * (ddx * (xi.x - xm.x) + ddy * (xi.y - xm.y) + ddz * (xi.z - xm.z));
+                float const quad  = 0.5f * K * (ddx * ddx + ddy * ddy + ddz * ddz);
+                float const c1a   = 1e-4f;
+                float t = 0.f;
+                if (de1 + lin + quad <= c1a * slope)
+                    t = 1.f;
+                else if (de2 + 0.5f * lin + 0.25f * quad <= c1a * 0.5f * slope)
+                    t = 0.5f;
+                else if (de4 + 0.25f * lin + 0.0625f * quad <= c1a * 0.25f * slope)
+                    t = 0.25f;
+                if (t != 1.f)
+                    nx = fmaf(t, ddx, xi.x), ny = fmaf(t, ddy, xi.y), nz = fmaf(t, ddz, xi.z);
+            }
+        }
+    }
+    if (leader)
+    {
+        float const x = nx, y = ny, z = nz;
         float4 const raw = make_float4(x, y, z, 0.f);
         if constexpr (kChebyshev)
         {

@@ -43,6 +43,7 @@ struct SmemRecords {
         c1 = rec[32];
         rec += kBlockFloat4;
     }
+    __device__ __forceinline__ void Rewind(uint32_t blocks) { rec -= static_cast<size_t>(blocks) * kBlockFloat4; }
 };
 
 // Warp-specialised grid barrier.  The compute warps *arrive* (non-blocking), wait only until the

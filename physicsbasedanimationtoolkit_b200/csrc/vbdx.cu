@@ -60,6 +60,7 @@ struct Integrator {
     // Anderson acceleration (anderson.cuh)
     int window = 5;
     int material = VBDX_MATERIAL_STABLE_NEO_HOOKEAN;
+    int lineSearch = 0;  // vbdx_set_line_search_guard
     DevBuf<float4> dAndVec;   // xkm1, Gkm1, Fkm1, Fk, DF[m], DG[m]
     DevBuf<double> dAndSmall; // gram m*m, scratch 2m, alpha m
     // objective / gradient evaluation (diagnostics.cuh)
@@ -593,6 +594,7 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
 {
     bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
     StepParams p{};
+    p.lineSearch   = lineSearch;
     p.records      = dRecords.p;
     p.tiles        = reinterpret_cast<uint4 const*>(dTiles.p);
     p.ctaTileRange = dCtaRange.p;
@@ -1200,6 +1202,14 @@ vbdx_status vbdx_set_initialization_strategy(vbdx_integrator* h, int32_t strateg
         return VBDX_INVALID_ARGUMENT;
     }
     h->impl.strategy = strategy;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_set_line_search_guard(vbdx_integrator* h, int32_t enabled)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    h->impl.lineSearch = enabled != 0 ? 1 : 0;
     return VBDX_OK;
 }
 

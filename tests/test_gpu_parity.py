@@ -412,6 +412,62 @@ def test_stvk_material(tile_iters):
         pbat.sim.vbd.Integrator(d, kernel_variant=1)
 
 
+def test_line_search_guard():
+    """The north star's "fused 3x3 Newton solve with line-search guard" (vbdx_set_line_search_guard; off by default =
+    the reference's full Newton step).  (1) Stable Neo-Hookean: the local objective is exactly quadratic, the guard
+    cannot alter a step: bit-identical.  (2) StVK near rest: every full step passes Armijo: bit-identical.  (3) StVK
+    squashed to 60 % along x (indefinite Hessians): the unguarded sweep blows the objective up by orders of magnitude,
+    the guarded one descends; checked against the oracle's restatement of the same guard."""
+    X, T = meshes.tet_grid(8, 3, 3, 0.1)
+    dbc = np.flatnonzero(X[0] == 0)
+    E = pbat.sim.vbd.HyperElasticEnergy
+
+    def build(energy, guard, x0=None):
+        d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
+             .with_hyper_elastic_energy(energy).construct())
+        vbd = pbat.sim.vbd.Integrator(d)
+        vbd.line_search_guard = guard
+        if x0 is not None:
+            vbd.x = x0
+        return d, vbd
+
+    rng = np.random.default_rng(4)
+    xp = X + 0.002 * rng.uniform(-1, 1, X.shape)   # 2 % of a cell (at 10 % StVK is already unstable without the guard)
+    xp[:, dbc] = X[:, dbc]
+    for energy in (E.StableNeoHookean, E.SaintVenantKirchhoff):
+        out = []
+        for guard in (False, True):
+            _, vbd = build(energy, guard, xp)
+            for _ in range(5):
+                vbd.step(0.01, 10, 1)
+            out.append(vbd.x.copy())
+        assert np.array_equal(out[0], out[1]), energy
+
+    xs = X.copy()
+    xs[0] *= 0.6
+    xs[:, dbc] = X[:, dbc]
+    f = {}
+    for guard in (False, True):
+        d, vbd = build(E.SaintVenantKirchhoff, guard, xs)
+        ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, material=oracle.MATERIAL_STVK)
+        ref.set_line_search_guard(guard)
+        ref.x = xs
+        f[guard] = []
+        for step in range(6):
+            vbd.step(0.01, 10, 1)
+            ref.step(0.01, 10, 1)
+            xtilde = ref.get("xtilde")
+            f[guard].append((vbd.objective_function(vbd.x, xtilde, 0.01), ref.objective(ref.x, xtilde, 0.01)))
+        if guard:
+            err = rel_l2(vbd.x, ref.x)
+            print("guarded StVK, squashed: objective (gpu, oracle) per step:", f[guard], "rel L2 =", err)
+            assert err < 1e-3
+    fg = np.array(f[True])
+    assert np.isfinite(fg).all() and (np.diff(fg[:, 0]) < 0).all() and fg[-1, 0] < 0.05
+    assert np.allclose(fg[:, 0], fg[:, 1], rtol=0.05)
+    assert max(v[1] for v in f[False]) > 100 * fg[0, 0]   # without the guard the same start diverges (oracle, double)
+
+
 @pytest.mark.parametrize("cheb", [None, 0.8])
 def test_traced_steps(tmp_path, cheb):
     """TraceNextStep / ExportTrace (sim/vbd/Integrator.cpp:47-52,202-235) and the GPU TracedStep
