@@ -147,6 +147,14 @@ void vbdx_data_desc_init(vbdx_data_desc* desc);
 /* pbat::gpu::vbd::Integrator::Integrator(Data const&)   gpu/vbd/Integrator.h:45, gpu/vbd/Integrator.cu:15-33
  * pbat::sim::vbd::Integrator::Integrator(Data)          sim/vbd/Integrator.h:22 */
 vbdx_status vbdx_create(const vbdx_data_desc* desc, vbdx_integrator** out);
+/* Independent scenes (no coupling, no communication) stepped together: SURVEY.md 8e "independent scene batches",
+ * BASELINE configs[4].  descs[0..n) describe one scene each and must agree in the solver settings; the handle then
+ * behaves like an integrator over the concatenation of the scenes (scene s owns vertices
+ * [vertex_offsets[s], vertex_offsets[s+1]) of every get/set call).  A scene in a batch evolves bit-identically to the
+ * same scene stepped alone.  No reference counterpart (the reference steps one Data per Integrator). */
+vbdx_status vbdx_create_batch(const vbdx_data_desc* descs, int32_t n, vbdx_integrator** out);
+/* n_scenes and/or the n_scenes + 1 vertex offsets of a batch handle (either pointer may be NULL) */
+vbdx_status vbdx_batch_offsets(vbdx_integrator* h, int32_t* n_scenes, int64_t* vertex_offsets);
 /* ~Integrator   gpu/vbd/Integrator.h:62 */
 vbdx_status vbdx_destroy(vbdx_integrator* h);
 

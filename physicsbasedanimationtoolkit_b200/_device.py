@@ -20,14 +20,16 @@ def _interleaved(a, dtype, nV, name):
 class DeviceIntegrator:
     _dtype = np.float32
 
-    def __init__(self, data, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0, ghosts=None):
+    @staticmethod
+    def _describe(data, keep, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0,
+                  ghosts=None, rest=False):
+        """Fill a ``vbdx_data_desc`` from a constructed ``Data`` (arrays are parked in ``keep``)."""
         L = _lib.lib()
         if data.x.size == 0:
             raise ValueError("Data.construct() must be called before creating an integrator")
         nV, nT = data.X.shape[1], data.E.shape[1]
         d = _lib.DataDesc()
         L.vbdx_data_desc_init(C.byref(d))
-        keep = []
 
         def ptr(a, dtype, transpose=False):
             if a is None or np.size(a) == 0:
@@ -38,7 +40,9 @@ class DeviceIntegrator:
             return a.ctypes.data
 
         d.nV, d.nT = nV, nT
-        d.X = ptr(data.x, np.float64, True)       # the reference uploads data.x (gpu/impl/vbd/Integrator.cu:27)
+        # the reference uploads data.x (gpu/impl/vbd/Integrator.cu:27); the element rest data must come from X
+        # (sim/vbd/Data.cpp:220-221), which differs from x only if the caller edited data.x after construct()
+        d.X = ptr(data.X if rest else data.x, np.float64, True)
         d.E = ptr(data.E, np.int64, True)
         d.v = ptr(data.v, np.float64, True)
         d.aext = ptr(data.aext, np.float64, True)
@@ -69,15 +73,17 @@ class DeviceIntegrator:
         d.window_size = int(getattr(data, "manderson", 5))
         d.ghosts = ptr(ghosts, np.int64)
         d.nGhosts = 0 if ghosts is None else int(np.size(ghosts))
-        # rest positions differ from x only if the caller edited data.x after construct(); the
-        # element rest data must come from X (sim/vbd/Data.cpp:220-221)
-        self._rest_differs = not np.array_equal(data.x, data.X)
-        if self._rest_differs:
-            d.X = ptr(data.X, np.float64, True)
+        return d
+
+    def __init__(self, data, **tuning):
+        L = _lib.lib()
+        keep = []
+        self._rest_differs = data.x.size > 0 and not np.array_equal(data.x, data.X)
+        d = self._describe(data, keep, rest=self._rest_differs, **tuning)
         self._h = C.c_void_p()
         self._L = L
         _lib.check(L.vbdx_create(C.byref(d), C.byref(self._h)))
-        self.nV, self.nT = nV, nT
+        self.nV, self.nT = int(d.nV), int(d.nT)
         self._ncv = int(d.nCV)
         self._strategy, self._kD, self._detH = int(data.strategy), float(data.kD), float(data.detH_zero)
         if self._rest_differs:

@@ -79,6 +79,8 @@ SYMBOLS = {
     "vbdx_set_detH_zero": (C.c_int, [_H, C.c_double]),
     "vbdx_set_rayleigh_damping": (C.c_int, [_H, C.c_double]),
     "vbdx_set_initialization_strategy": (C.c_int, [_H, C.c_int32]),
+    "vbdx_create_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "vbdx_batch_offsets": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),
     "vbdx_set_line_search_guard": (C.c_int, [_H, C.c_int32]),
     "vbdx_set_scene_bounding_box": (C.c_int, [_H, C.c_void_p, C.c_void_p]),

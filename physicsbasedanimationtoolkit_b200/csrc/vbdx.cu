@@ -61,6 +61,7 @@ struct Integrator {
     int window = 5;
     int material = VBDX_MATERIAL_STABLE_NEO_HOOKEAN;
     int lineSearch = 0;  // vbdx_set_line_search_guard
+    std::vector<int64_t> batchOffsets;  // vbdx_create_batch: first vertex of every scene, then nV
     DevBuf<float4> dAndVec;   // xkm1, Gkm1, Fkm1, Fk, DF[m], DG[m]
     DevBuf<double> dAndSmall; // gram m*m, scratch 2m, alpha m
     // objective / gradient evaluation (diagnostics.cuh)
@@ -1033,6 +1034,115 @@ vbdx_status vbdx_create(const vbdx_data_desc* desc, vbdx_integrator** out)
     if (st == VBDX_OK)
         *out = h.release();
     return st;
+}
+
+// Independent scenes stepped as one problem (SURVEY.md 8e second row, BASELINE configs[4]): the scenes are
+// concatenated into one disconnected mesh, so that one persistent launch per step sweeps every scene's colour c together.
+// Colours are computed (or taken) per scene, which makes a scene inside a batch evolve bit-identically to the scene alone.
+vbdx_status vbdx_create_batch(const vbdx_data_desc* descs, int32_t n, vbdx_integrator** out)
+{
+    if (!descs || !out || n < 1)
+    {
+        gLastError = "vbdx_create_batch: null argument or no scenes";
+        return VBDX_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    std::unique_ptr<vbdx_integrator> h;
+    vbdx_status const st = Guard([&] {
+        using vbdx::Require;
+        vbdx_data_desc const& d0 = descs[0];
+        std::vector<int64_t> vOff(static_cast<size_t>(n) + 1, 0), tOff(static_cast<size_t>(n) + 1, 0);
+        bool anyV = false, anyA = false, anyM = false, allM = true, anyRho = false, anyLame = false;
+        int64_t nDbc = 0;
+        for (int32_t s = 0; s < n; ++s)
+        {
+            vbdx_data_desc const& d = descs[s];
+            Require(d.abi_version == VBDX_ABI_VERSION && d.struct_size == sizeof(vbdx_data_desc), "descriptor version / size mismatch (call vbdx_data_desc_init)");
+            Require(d.nV > 0 && d.nT > 0 && d.X && d.E, "every scene needs a mesh");
+            Require(d.nF == 0 && d.nCV == 0, "contact is not available in a batch (scenes share coordinates)");
+            Require(d.nGhosts == 0, "ghost vertices are not available in a batch");
+            Require(d.strategy == d0.strategy && d.acceleration == d0.acceleration && d.omega_mode == d0.omega_mode &&
+                        d.material == d0.material && d.kD == d0.kD && d.detHZero == d0.detHZero && d.rho == d0.rho &&
+                        d.flags == d0.flags && d.window_size == d0.window_size,
+                    "the scenes of a batch must share strategy, acceleration, material and solver scalars");
+            vOff[s + 1] = vOff[s] + d.nV;
+            tOff[s + 1] = tOff[s] + d.nT;
+            anyV |= d.v != nullptr, anyA |= d.aext != nullptr, anyM |= d.m != nullptr, allM &= d.m != nullptr;
+            anyRho |= d.rhoe != nullptr, anyLame |= d.lame != nullptr;
+            Require(d.nDbc >= 0 && (d.nDbc == 0 || d.dbc), "dbc pointer missing");
+            nDbc += d.nDbc;
+        }
+        Require(!anyM || allM, "either every scene of a batch passes lumped masses or none does");
+        int64_t const nV = vOff[n], nT = tOff[n];
+        std::vector<double> X(3 * nV), v(anyV ? 3 * nV : 0, 0.0), a(anyA ? 3 * nV : 0), m(anyM ? nV : 0), rhoe(anyRho ? nT : 0, 1e3), lame(anyLame ? 2 * nT : 0);
+        std::vector<int64_t> E(4 * nT), dbc(nDbc), colors(nV);
+        double const Y = 1e6, nu = 0.45;  // sim/vbd/Data.cpp:199-205
+        double const mu = Y / (2. * (1. + nu)), lam = (Y * nu) / ((1. + nu) * (1. - 2. * nu));
+        int64_t kd = 0;
+        for (int32_t s = 0; s < n; ++s)
+        {
+            vbdx_data_desc const& d = descs[s];
+            std::copy(d.X, d.X + 3 * d.nV, X.begin() + 3 * vOff[s]);
+            for (int64_t k = 0; k < 4 * d.nT; ++k)
+            {
+                Require(d.E[k] >= 0 && d.E[k] < d.nV, "element index out of range");
+                E[4 * tOff[s] + k] = d.E[k] + vOff[s];
+            }
+            if (d.v)
+                std::copy(d.v, d.v + 3 * d.nV, v.begin() + 3 * vOff[s]);
+            if (anyA)
+                for (int64_t i = 0; i < d.nV; ++i)
+                    for (int c = 0; c < 3; ++c)
+                        a[3 * (vOff[s] + i) + c] = d.aext ? d.aext[3 * i + c] : (c == 2 ? -9.81 : 0.0);  // sim/vbd/Data.cpp:191-195
+            if (d.m)
+                std::copy(d.m, d.m + d.nV, m.begin() + vOff[s]);
+            if (d.rhoe)
+                std::copy(d.rhoe, d.rhoe + d.nT, rhoe.begin() + tOff[s]);
+            if (anyLame)
+                for (int64_t e = 0; e < d.nT; ++e)
+                {
+                    lame[2 * (tOff[s] + e)]     = d.lame ? d.lame[2 * e] : mu;
+                    lame[2 * (tOff[s] + e) + 1] = d.lame ? d.lame[2 * e + 1] : lam;
+                }
+            for (int64_t k = 0; k < d.nDbc; ++k)
+            {
+                Require(d.dbc[k] >= 0 && d.dbc[k] < d.nV, "Dirichlet vertex index out of range");
+                dbc[kd++] = d.dbc[k] + vOff[s];
+            }
+            if (d.colors)
+                std::copy(d.colors, d.colors + d.nV, colors.begin() + vOff[s]);
+            else
+            {
+                std::vector<int64_t> c;
+                vbdx::GreedyColorMesh(d.nV, d.nT, d.E, d.ordering, d.selection, c);
+                std::copy(c.begin(), c.end(), colors.begin() + vOff[s]);
+            }
+        }
+        vbdx_data_desc big = d0;
+        big.nV = nV, big.nT = nT, big.X = X.data(), big.E = E.data();
+        big.v = anyV ? v.data() : nullptr, big.aext = anyA ? a.data() : nullptr, big.m = anyM ? m.data() : nullptr;
+        big.rhoe = anyRho ? rhoe.data() : nullptr, big.lame = anyLame ? lame.data() : nullptr;
+        big.dbc = nDbc ? dbc.data() : nullptr, big.nDbc = nDbc, big.colors = colors.data();
+        h = std::make_unique<vbdx_integrator>();
+        h->impl.Create(big);
+        h->impl.batchOffsets = vOff;
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+vbdx_status vbdx_batch_offsets(vbdx_integrator* h, int32_t* n_scenes, int64_t* vertex_offsets)
+{
+    if (vbdx_status s = NeedHandle(h))
+        return s;
+    return Guard([&] {
+        vbdx::Require(!h->impl.batchOffsets.empty(), "not a batch handle (vbdx_create_batch)");
+        if (n_scenes)
+            *n_scenes = static_cast<int32_t>(h->impl.batchOffsets.size()) - 1;
+        if (vertex_offsets)
+            std::copy(h->impl.batchOffsets.begin(), h->impl.batchOffsets.end(), vertex_offsets);
+    });
 }
 
 vbdx_status vbdx_destroy(vbdx_integrator* h)

@@ -51,3 +51,44 @@ class Integrator(DeviceIntegrator):
     strategy = _write_only(lambda s, v: s._set_strategy(v))
     gpu_block_size = _write_only(lambda s, v: s._set_block_size(v))
     scene_bounding_box = _write_only(lambda s, box: s._set_scene_bounding_box(box[0], box[1]))
+
+
+class BatchIntegrator(Integrator):
+    """Extension: independent scenes stepped together (``vbdx_create_batch``; SURVEY.md 8e, BASELINE configs[4]).
+
+    ``datas`` is a sequence of constructed ``pbat.sim.vbd.Data`` that agree in the solver settings.  The object is an
+    ``Integrator`` over the concatenation of the scenes: ``x`` / ``v`` are 3 x sum(nV); ``offsets[s]`` is the first
+    vertex of scene ``s`` and ``scene(a, s)`` slices an array.  A scene in a batch evolves bit-identically to the
+    scene stepped alone."""
+
+    def __init__(self, datas, **tuning):
+        import ctypes as C
+
+        from .. import _lib
+
+        datas = list(datas)
+        if not datas:
+            raise ValueError("a batch needs at least one scene")
+        L = _lib.lib()
+        keep = []
+        descs = (_lib.DataDesc * len(datas))()
+        for i, data in enumerate(datas):
+            if data.x.size and not np.array_equal(data.x, data.X):
+                raise ValueError("batch scenes must start from their rest positions (set x after construction)")
+            descs[i] = self._describe(data, keep, **tuning)
+        self._h = C.c_void_p()
+        self._L = L
+        _lib.check(L.vbdx_create_batch(descs, len(datas), C.byref(self._h)))
+        self.offsets = np.zeros(len(datas) + 1, np.int64)
+        _lib.check(L.vbdx_batch_offsets(self._h, None, self.offsets.ctypes.data))
+        self.nV, self.nT = int(self.offsets[-1]), int(sum(d.E.shape[1] for d in datas))
+        self.n_scenes = len(datas)
+        self._ncv = 0
+        self._rest_differs = False
+        d0 = datas[0]
+        self._strategy, self._kD, self._detH = int(d0.strategy), float(d0.kD), float(d0.detH_zero)
+        self._trace_static = None
+
+    def scene(self, a, s):
+        """Columns of a 3 x sum(nV) array that belong to scene ``s``."""
+        return a[:, self.offsets[s]:self.offsets[s + 1]]
