@@ -130,8 +130,11 @@ typedef enum vbdx_kernel_variant {
     VBDX_KERNEL_DIRECT  = 1, /* every warp loads its records straight from global memory */
     VBDX_KERNEL_TMA     = 2, /* warp-specialised: a producer warp streams records into a shared-memory ring with
                                 bulk asynchronous copies (TMA) across the colour barriers */
-    VBDX_KERNEL_PIPELINED = 3 /* every warp prefetches its next tile's static data with cp.async while it computes
+    VBDX_KERNEL_PIPELINED = 3, /* every warp prefetches its next tile's static data with cp.async while it computes
                                  the current one (the default when the per-warp buffers fit in shared memory) */
+    VBDX_KERNEL_CLUSTER = 4   /* small meshes: the whole problem is swept by ONE thread-block cluster (8 CTAs x 16 warps)
+                                 and colours are separated by the hardware cluster barrier instead of a grid barrier
+                                 through L2 (the default when a colour has at most a few tiles per warp of the cluster) */
 } vbdx_kernel_variant;
 
 #define VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY 1 /* AdaptiveVbd uses the stored v(t-1) like the reference's GPU

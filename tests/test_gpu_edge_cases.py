@@ -126,7 +126,7 @@ def test_extreme_valence_kernel_variants_agree():
     dbc = np.flatnonzero(X[2] > 0.25)
     d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.8).construct()
     out = []
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=variant)
         for _ in range(5):
             vbd.step(0.01, 10, 1)

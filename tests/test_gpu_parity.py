@@ -206,12 +206,13 @@ def test_against_reference_golden(name):
 @pytest.mark.parametrize("cheb", [None, 0.9])
 @pytest.mark.parametrize("ring_slots,consumer_warps", [(0, 0), (3, 0), (16, 16), (2, 3), (37, 7)])
 def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
-    """The direct, TMA-ring and pipelined kernels do the same arithmetic in the same order: identical bits.
-    Small rings force many wrap-arounds of the producer/consumer pipeline."""
+    """The direct, TMA-ring, pipelined and one-cluster (4: the pipelined kernel behind the hardware cluster barrier)
+    kernels do the same arithmetic in the same order: identical bits.  Small rings force many wrap-arounds of the
+    producer/consumer pipeline."""
     X, T = meshes.tet_grid(12, 6, 5, 0.1)
     dbc = np.flatnonzero(X[0] == 0)
     out = []
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kD=1e-4, kernel_variant=variant, ring_slots=ring_slots,
                            consumer_warps=consumer_warps, tile_iters=2)
         for _ in range(3):
@@ -222,6 +223,21 @@ def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
     for _ in range(3):
         ref.step(0.01, 7, 2)
     assert rel_l2(out[1][0], ref.x) < TOL
+
+
+def test_small_meshes_default_to_one_cluster_and_large_ones_do_not():
+    """VBDX_KERNEL_DEFAULT: a mesh whose colours fit one thread-block cluster is swept by 8 CTAs behind the hardware
+    cluster barrier; anything larger takes the whole GPU.  Contact, damping, substeps run on either."""
+    X, T = meshes.tet_grid(25, 9, 9, 0.04)
+    d, vbd, ref = make(X, T, dbc=np.flatnonzero(X[0] == 0), cheb=0.9, kD=1e-4)
+    assert vbd.info["gridBlocks"] == 8
+    for _ in range(10):
+        vbd.step(0.01, 20, 2)
+        ref.step(0.01, 20, 2)
+    assert rel_l2(vbd.x, ref.x) < TOL
+    Xl, Tl = meshes.tet_grid(40, 40, 40, 1 / 40)
+    dl = pbat.sim.vbd.Data().with_volume_mesh(Xl, Tl).construct()
+    assert pbat.gpu.vbd.Integrator(dl).info["gridBlocks"] >= 100
 
 
 def test_direct_variant_config1():
