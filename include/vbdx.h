@@ -232,6 +232,35 @@ vbdx_status vbdx_set_line_search_guard(vbdx_integrator* h, int32_t enabled);
 /* Integrator::SetSceneBoundingBox                     gpu/vbd/Integrator.h:132-134 */
 vbdx_status vbdx_set_scene_bounding_box(vbdx_integrator* h, const float min3[3], const float max3[3]);
 
+/* ---- stand-alone LBVH and vertex-triangle detector ------------------------------------------
+ * pbat::gpu::geometry::Bvh (gpu/geometry/Bvh.h; bindings/pypbat/gpu/geometry/Bvh.cpp:19-109).  Boxes are 3 x n
+ * column-major float arrays; node arrays use the reference's numbering (internal nodes 0..n-2, leaves n-1..2n-2 in
+ * Morton order). */
+typedef struct vbdx_bvh vbdx_bvh;
+vbdx_status vbdx_bvh_create(int64_t max_boxes, vbdx_bvh** out);                                   /* Bvh(max_boxes, .) */
+vbdx_status vbdx_bvh_destroy(vbdx_bvh* h);
+vbdx_status vbdx_bvh_build(vbdx_bvh* h, int64_t n, const float* lo, const float* hi, const float wmin[3], const float wmax[3]); /* Bvh::Build */
+/* child 2 x (n-1), parent 2n-1, rightmost 2 x (n-1), inds n, codes n, node boxes 3 x (2n-1), visits n-1; any may be NULL */
+vbdx_status vbdx_bvh_get(vbdx_bvh* h, int32_t* child, int32_t* parent, int32_t* rightmost, int32_t* inds, uint32_t* codes, float* node_lo,
+                         float* node_hi, int32_t* visits);
+/* Bvh::DetectOverlaps: self-overlaps (bi < bj) of the boxes given to build(); with set != NULL only pairs with
+ * set[bi] != set[bj].  pairs is 2 x max_overlaps (column per pair); *n_found may exceed max_overlaps (the rest is dropped) */
+vbdx_status vbdx_bvh_detect_overlaps(vbdx_bvh* h, const int32_t* set, int64_t max_overlaps, int32_t* pairs, int64_t* n_found);
+/* Bvh::PointTriangleNearestNeighbors: nearest triangle of nQ points; the tree was built over the nF triangles' boxes */
+vbdx_status vbdx_bvh_nearest_triangles(vbdx_bvh* h, int64_t nQ, const float* X, int64_t nP, const float* V, int64_t nF, const int32_t* F, int32_t* out);
+
+/* pbat::gpu::contact::VertexTriangleMixedCcdDcd (gpu/contact/VertexTriangleMixedCcdDcd.h;
+ * bindings/pypbat/gpu/contact/VertexTriangleMixedCcdDcd.cpp:18-82).  Positions are 3 x nV column-major float. */
+typedef struct vbdx_contact vbdx_contact;
+vbdx_status vbdx_contact_create(int64_t nV, const int64_t* B, const int64_t* V, int64_t nCV, const int64_t* F, int64_t nF, vbdx_contact** out);
+vbdx_status vbdx_contact_destroy(vbdx_contact* h);
+vbdx_status vbdx_contact_initialize_active_set(vbdx_contact* h, const float* xt, const float* xtp1, const float wmin[3], const float wmax[3]);
+vbdx_status vbdx_contact_update_active_set(vbdx_contact* h, const float* x);
+vbdx_status vbdx_contact_finalize_active_set(vbdx_contact* h, const float* x);
+vbdx_status vbdx_contact_set_eps(vbdx_contact* h, float eps);
+/* active mask (nCV), nearest triangles (nCV x 8, -1 terminated), compacted active vertices (first *n_active of nCV) */
+vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn, int32_t* av, int64_t* n_active);
+
 /* Use a caller-provided cudaStream_t for all subsequent work (NULL = the handle's own). */
 vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream);
 

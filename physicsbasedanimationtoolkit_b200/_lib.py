@@ -79,6 +79,19 @@ SYMBOLS = {
     "vbdx_set_detH_zero": (C.c_int, [_H, C.c_double]),
     "vbdx_set_rayleigh_damping": (C.c_int, [_H, C.c_double]),
     "vbdx_set_initialization_strategy": (C.c_int, [_H, C.c_int32]),
+    "vbdx_bvh_create": (C.c_int, [C.c_int64, C.POINTER(_H)]),
+    "vbdx_bvh_destroy": (C.c_int, [_H]),
+    "vbdx_bvh_build": (C.c_int, [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbdx_bvh_get": (C.c_int, [_H] + [C.c_void_p] * 8),
+    "vbdx_bvh_detect_overlaps": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vbdx_bvh_nearest_triangles": (C.c_int, [_H, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vbdx_contact_create": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(_H)]),
+    "vbdx_contact_destroy": (C.c_int, [_H]),
+    "vbdx_contact_initialize_active_set": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbdx_contact_update_active_set": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_contact_finalize_active_set": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_contact_set_eps": (C.c_int, [_H, C.c_float]),
+    "vbdx_contact_get": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_create_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "vbdx_batch_offsets": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),

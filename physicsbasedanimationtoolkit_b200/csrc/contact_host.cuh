@@ -68,6 +68,7 @@ struct ContactState {
     uint32_t nCV = 0, nF = 0;
     int updateFrequency = 1;
     bool hasWorldBox    = false;
+    float eps           = FLT_EPSILON;  // nearest-neighbour tie tolerance (VertexTriangleMixedCcdDcd.cuh: eps)
     // static (internal ids)
     DevBuf<int32_t> B, V;
     DevBuf<int4> F;
@@ -166,7 +167,7 @@ struct ContactState {
             FillI32<<<Blocks(static_cast<int64_t>(nCV) * kMaxContacts, 256), 256, 0, s>>>(nn.p, -1, static_cast<size_t>(nCV) * kMaxContacts);
             ++*launches;
         }
-        NearestTriangles<<<Blocks(nCV, 128), 128, 0, s>>>(mesh, bvh.View(), av.p, nActive.p, x, dupper.p, FLT_EPSILON, mode, nn.p, fc.p, active.p);
+        NearestTriangles<<<Blocks(nCV, 128), 128, 0, s>>>(mesh, bvh.View(), av.p, nActive.p, x, dupper.p, eps, mode, nn.p, fc.p, active.p);
         *launches += 2;
     }
 };

@@ -7,6 +7,7 @@
 #include "anderson.cuh"
 #include "broyden.cuh"
 #include "contact_host.cuh"
+#include "geometry_api.cuh"
 #include "diagnostics.cuh"
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
@@ -1571,6 +1572,298 @@ vbdx_status vbdx_debug_bvh_build(int64_t n, const float* lo, const float* hi, co
             if (nodeHi)
                 nodeHi[3 * k] = nh[k].x, nodeHi[3 * k + 1] = nh[k].y, nodeHi[3 * k + 2] = nh[k].z;
         }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stand-alone LBVH and vertex-triangle detector (geometry_api.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+struct vbdx_bvh {
+    vbdx::BvhHandle impl;
+};
+struct vbdx_contact {
+    vbdx::ContactHandle impl;
+};
+
+static void NeedDevice()
+{
+    if (vbdx_device_count() == 0)
+        throw vbdx::Error(VBDX_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+}
+
+vbdx_status vbdx_bvh_create(int64_t max_boxes, vbdx_bvh** out)
+{
+    if (!out)
+        return VBDX_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::unique_ptr<vbdx_bvh> h;
+    vbdx_status const st = Guard([&] {
+        vbdx::Require(max_boxes >= 1 && max_boxes < (int64_t(1) << 30), "vbdx_bvh_create: max_boxes out of range");
+        NeedDevice();
+        h = std::make_unique<vbdx_bvh>();
+        auto& b = h->impl;
+        VBDX_CUDA(cudaGetDevice(&b.device));
+        b.capacity = max_boxes;
+        b.bvh.Alloc(static_cast<uint32_t>(max_boxes), &b.bytes);
+        b.lo.Alloc(max_boxes, &b.bytes), b.hi.Alloc(max_boxes, &b.bytes), b.world.Alloc(1, &b.bytes);
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+vbdx_status vbdx_bvh_destroy(vbdx_bvh* h)
+{
+    delete h;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_bvh_build(vbdx_bvh* h, int64_t n, const float* lo, const float* hi, const float wmin[3], const float wmax[3])
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& b = h->impl;
+        vbdx::Require(n >= 1 && n <= b.capacity && lo && hi && wmin && wmax, "vbdx_bvh_build: bad arguments (n must be in [1, max_boxes])");
+        VBDX_CUDA(cudaSetDevice(b.device));
+        cudaStream_t s = nullptr;
+        vbdx::UploadXyz(b.lo, lo, n, s);
+        vbdx::UploadXyz(b.hi, hi, n, s);
+        vbdx::WorldBox w;
+        for (int d = 0; d < 3; ++d)
+            w.lo[d] = wmin[d], w.ext[d] = wmax[d] - wmin[d];
+        b.world.Upload(&w, 1, s);
+        b.n     = n;
+        b.bvh.n = static_cast<uint32_t>(n);
+        b.bvh.Build(b.lo.p, b.hi.p, b.world.p, s, &b.launches);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+vbdx_status vbdx_bvh_get(vbdx_bvh* h, int32_t* child, int32_t* parent, int32_t* rightmost, int32_t* inds, uint32_t* codes, float* node_lo,
+                         float* node_hi, int32_t* visits)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& b = h->impl;
+        vbdx::Require(b.n >= 1, "vbdx_bvh_get: build() has not been called");
+        VBDX_CUDA(cudaSetDevice(b.device));
+        cudaStream_t s  = nullptr;
+        int64_t const n = b.n;
+        size_t const ni = static_cast<size_t>(n - 1);
+        if (child && ni)
+            b.bvh.child0.Download(child, ni, s), b.bvh.child1.Download(child + ni, ni, s);
+        if (rightmost && ni)
+            b.bvh.right0.Download(rightmost, ni, s), b.bvh.right1.Download(rightmost + ni, ni, s);
+        if (parent)
+            b.bvh.parent.Download(parent, 2 * n - 1, s);
+        if (inds)
+            b.bvh.inds.Download(reinterpret_cast<uint32_t*>(inds), n, s);
+        if (codes)
+            b.bvh.codes.Download(codes, n, s);
+        if (visits && ni)
+            b.bvh.visits.Download(reinterpret_cast<uint32_t*>(visits), ni, s);
+        std::vector<float4> nl(2 * n - 1), nh(2 * n - 1);
+        b.bvh.nodeLo.Download(nl.data(), 2 * n - 1, s);
+        b.bvh.nodeHi.Download(nh.data(), 2 * n - 1, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        for (int64_t k = 0; k < 2 * n - 1; ++k)
+        {
+            if (node_lo)
+                node_lo[3 * k] = nl[k].x, node_lo[3 * k + 1] = nl[k].y, node_lo[3 * k + 2] = nl[k].z;
+            if (node_hi)
+                node_hi[3 * k] = nh[k].x, node_hi[3 * k + 1] = nh[k].y, node_hi[3 * k + 2] = nh[k].z;
+        }
+    });
+}
+
+vbdx_status vbdx_bvh_detect_overlaps(vbdx_bvh* h, const int32_t* set, int64_t max_overlaps, int32_t* pairs, int64_t* n_found)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& b = h->impl;
+        vbdx::Require(b.n >= 1 && max_overlaps >= 0 && (pairs || max_overlaps == 0) && n_found, "vbdx_bvh_detect_overlaps: bad arguments");
+        VBDX_CUDA(cudaSetDevice(b.device));
+        cudaStream_t s = nullptr;
+        vbdx::DevBuf<int32_t> dSet, dPairs;
+        vbdx::DevBuf<unsigned long long> dCount;
+        if (set)
+        {
+            dSet.Alloc(b.n);
+            dSet.Upload(set, b.n, s);
+        }
+        dPairs.Alloc(2 * static_cast<size_t>(std::max<int64_t>(max_overlaps, 1)));
+        dCount.Alloc(1);
+        VBDX_CUDA(cudaMemsetAsync(dCount.p, 0, sizeof(unsigned long long), s));
+        vbdx::BvhSelfOverlaps<<<vbdx::Blocks(b.n, 128), 128, 0, s>>>(b.bvh.View(), dSet.p, dPairs.p, dCount.p, static_cast<unsigned long long>(max_overlaps));
+        ++b.launches;
+        unsigned long long found = 0;
+        dCount.Download(&found, 1, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        *n_found = static_cast<int64_t>(found);
+        int64_t const keep = std::min<int64_t>(static_cast<int64_t>(found), max_overlaps);
+        if (keep > 0)
+        {
+            dPairs.Download(pairs, 2 * static_cast<size_t>(keep), s);
+            VBDX_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+vbdx_status vbdx_bvh_nearest_triangles(vbdx_bvh* h, int64_t nQ, const float* X, int64_t nP, const float* V, int64_t nF, const int32_t* F, int32_t* out)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& b = h->impl;
+        vbdx::Require(b.n >= 1 && nF == b.n, "vbdx_bvh_nearest_triangles: the tree must have been built over these triangles' boxes");
+        vbdx::Require(nQ >= 0 && nP >= 1 && X && V && F && out, "vbdx_bvh_nearest_triangles: bad arguments");
+        if (nQ == 0)
+            return;
+        VBDX_CUDA(cudaSetDevice(b.device));
+        cudaStream_t s = nullptr;
+        vbdx::DevBuf<float4> dX, dV;
+        vbdx::DevBuf<int4> dF;
+        vbdx::DevBuf<int32_t> dOut;
+        dX.Alloc(nQ), dV.Alloc(nP), dF.Alloc(nF), dOut.Alloc(nQ);
+        vbdx::UploadXyz(dX, X, nQ, s);
+        vbdx::UploadXyz(dV, V, nP, s);
+        std::vector<int4> Fh(static_cast<size_t>(nF));
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            for (int k = 0; k < 3; ++k)
+                vbdx::Require(F[3 * f + k] >= 0 && F[3 * f + k] < nP, "triangle index out of range");
+            Fh[f] = make_int4(F[3 * f], F[3 * f + 1], F[3 * f + 2], 0);
+        }
+        dF.Upload(Fh.data(), nF, s);
+        vbdx::BvhNearestTriangle<<<vbdx::Blocks(nQ, 128), 128, 0, s>>>(b.bvh.View(), dX.p, nQ, dV.p, dF.p, dOut.p);
+        ++b.launches;
+        dOut.Download(out, nQ, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+vbdx_status vbdx_contact_create(int64_t nV, const int64_t* B, const int64_t* V, int64_t nCV, const int64_t* F, int64_t nF, vbdx_contact** out)
+{
+    if (!out)
+        return VBDX_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::unique_ptr<vbdx_contact> h;
+    vbdx_status const st = Guard([&] {
+        vbdx::Require(nV >= 1 && nCV >= 1 && nF >= 1 && V && F, "vbdx_contact_create: a collision mesh is needed");
+        NeedDevice();
+        h = std::make_unique<vbdx_contact>();
+        auto& c = h->impl;
+        VBDX_CUDA(cudaGetDevice(&c.device));
+        c.nV = nV;
+        auto& cs = c.cs;
+        cs.nCV = static_cast<uint32_t>(nCV), cs.nF = static_cast<uint32_t>(nF);
+        std::vector<int32_t> Bh(nV), Vh(nCV);
+        std::vector<int4> Fh(nF);
+        for (int64_t i = 0; i < nV; ++i)
+            Bh[i] = B ? static_cast<int32_t>(B[i]) : 1;
+        for (int64_t k = 0; k < nCV; ++k)
+        {
+            vbdx::Require(V[k] >= 0 && V[k] < nV, "collision vertex index out of range");
+            Vh[k] = static_cast<int32_t>(V[k]);
+        }
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            for (int k = 0; k < 3; ++k)
+                vbdx::Require(F[3 * f + k] >= 0 && F[3 * f + k] < nV, "collision triangle index out of range");
+            Fh[f] = make_int4(static_cast<int>(F[3 * f]), static_cast<int>(F[3 * f + 1]), static_cast<int>(F[3 * f + 2]), 0);
+        }
+        cudaStream_t s = nullptr;
+        cs.B.Alloc(nV, &c.bytes), cs.V.Alloc(nCV, &c.bytes), cs.F.Alloc(nF, &c.bytes);
+        cs.B.Upload(Bh.data(), nV, s), cs.V.Upload(Vh.data(), nCV, s), cs.F.Upload(Fh.data(), nF, s);
+        cs.mesh = vbdx::ContactMesh{cs.B.p, cs.V.p, cs.F.p, cs.nCV, cs.nF};
+        cs.Alloc(nV, &c.bytes, s);
+        cs.enabled = true;
+        c.xa.Alloc(nV, &c.bytes), c.xb.Alloc(nV, &c.bytes), c.zero.Alloc(nV, &c.bytes);
+        VBDX_CUDA(cudaMemsetAsync(c.zero.p, 0, nV * sizeof(float4), s));
+        VBDX_CUDA(cudaStreamSynchronize(s));
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+vbdx_status vbdx_contact_destroy(vbdx_contact* h)
+{
+    delete h;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_contact_initialize_active_set(vbdx_contact* h, const float* xt, const float* xtp1, const float wmin[3], const float wmax[3])
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& c = h->impl;
+        vbdx::Require(xt && xtp1 && wmin && wmax, "vbdx_contact_initialize_active_set: null argument");
+        VBDX_CUDA(cudaSetDevice(c.device));
+        cudaStream_t s = nullptr;
+        // the detector's predictor is x + dt v + dt^2 a (gpu/impl/vbd/Integrator.cu:163-188): v = xtp1 - xt, dt = 1, a = 0
+        vbdx::UploadXyz(c.xa, xt, c.nV, s);
+        vbdx::UploadXyz(c.xb, xtp1, c.nV, s, xt);
+        c.cs.SetWorldBox(wmin, wmax, s);
+        c.cs.InitializeActiveSet(c.xa.p, c.xb.p, c.zero.p, c.nV, 1.f, s, &c.launches);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+static vbdx_status ContactNearest(vbdx_contact* h, const float* x, int mode)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& c = h->impl;
+        vbdx::Require(x != nullptr, "positions missing");
+        VBDX_CUDA(cudaSetDevice(c.device));
+        cudaStream_t s = nullptr;
+        vbdx::UploadXyz(c.xa, x, c.nV, s);
+        c.cs.eps = c.eps;
+        c.cs.NearestPass(c.xa.p, mode, s, &c.launches);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+vbdx_status vbdx_contact_update_active_set(vbdx_contact* h, const float* x) { return ContactNearest(h, x, 0); }
+vbdx_status vbdx_contact_finalize_active_set(vbdx_contact* h, const float* x) { return ContactNearest(h, x, 1); }
+
+vbdx_status vbdx_contact_set_eps(vbdx_contact* h, float eps)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    h->impl.eps = eps;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn, int32_t* av, int64_t* n_active)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& c  = h->impl;
+        auto& cs = c.cs;
+        VBDX_CUDA(cudaSetDevice(c.device));
+        cudaStream_t s = nullptr;
+        std::vector<uint8_t> a(cs.nCV);
+        cs.active.Download(a.data(), cs.nCV, s);
+        if (nn)
+            cs.nn.Download(nn, static_cast<size_t>(cs.nCV) * vbdx::kMaxContacts, s);
+        if (av)
+            cs.av.Download(av, cs.nCV, s);
+        uint32_t na = 0;
+        cs.nActive.Download(&na, 1, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        if (active_mask)
+            for (uint32_t k = 0; k < cs.nCV; ++k)
+                active_mask[k] = a[k];
+        if (n_active)
+            *n_active = na;
     });
 }
 

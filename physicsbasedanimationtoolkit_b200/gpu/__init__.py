@@ -1,4 +1,3 @@
-"""``pbat.gpu`` -- only the ``vbd`` sub-module is in scope."""
-from . import vbd  # noqa: F401
-
-from . import geometry  # noqa: F401,E402
+"""``pbat.gpu``: the VBD integrator (``vbd``) and the pieces of its contact path that the reference also exposes on their
+own (``geometry.Aabb`` / ``geometry.Bvh``, ``contact.VertexTriangleMixedCcdDcd``, ``common.Buffer``)."""
+from . import common, contact, geometry, vbd  # noqa: F401
