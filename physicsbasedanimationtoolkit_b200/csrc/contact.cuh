@@ -161,11 +161,21 @@ __global__ void SceneBoundsReduce(const float4* pos, uint32_t n, int* bounds)
             lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
             hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
-        if ((threadIdx.x & 31) == 0)
-        {
-            atomicMin(&bounds[d], FloatToOrdered(lo[d]));
-            atomicMax(&bounds[3 + d], FloatToOrdered(hi[d]));
-        }
+    }
+    // one atomic per block and component: same-address atomics serialise
+    __shared__ float sLo[32][3], sHi[32][3];
+    uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
+    if (lane == 0)
+        for (int d = 0; d < 3; ++d)
+            sLo[warp][d] = lo[d], sHi[warp][d] = hi[d];
+    __syncthreads();
+    if (threadIdx.x < 3)
+    {
+        float l = sLo[0][threadIdx.x], h = sHi[0][threadIdx.x];
+        for (uint32_t w = 1; w < nWarps; ++w)
+            l = fminf(l, sLo[w][threadIdx.x]), h = fmaxf(h, sHi[w][threadIdx.x]);
+        atomicMin(&bounds[threadIdx.x], FloatToOrdered(l));
+        atomicMax(&bounds[3 + threadIdx.x], FloatToOrdered(h));
     }
 }
 

@@ -136,7 +136,7 @@ struct ContactState {
         {
             // the reference needs SetSceneBoundingBox from the caller; without it use the scene's bounds
             SceneBoundsReset<<<1, 32, 0, s>>>(bounds.p);
-            SceneBoundsReduce<<<std::min(Blocks(nV, 256), 1184), 256, 0, s>>>(x, static_cast<uint32_t>(nV), bounds.p);
+            SceneBoundsReduce<<<std::min(Blocks(nV, 256), 296), 256, 0, s>>>(x, static_cast<uint32_t>(nV), bounds.p);
             SceneBoundsFinish<<<1, 32, 0, s>>>(bounds.p, world.p);
             *launches += 3;
         }

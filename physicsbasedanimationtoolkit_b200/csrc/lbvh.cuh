@@ -267,12 +267,14 @@ __global__ void BvhInternalBoxes(BvhView t)
     int p = t.parent[t.n - 1 + k];
     while (p >= 0)
     {
-        __threadfence();
-        if (atomicAdd(&t.visits[p], 1u) == 0u)
+        // acq_rel arrival: the box this thread wrote one level below is released with it, and the sibling's box (written
+        // by the thread that arrived first) is acquired with it -- one ordered atomic instead of two full fences
+        unsigned int old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(t.visits + p), "r"(1u) : "memory");
+        if (old == 0u)
             break;
-        __threadfence();
         int const lc = t.child[0][p], rc = t.child[1][p];
-        float4 const al = t.nodeLo[lc], ah = t.nodeHi[lc], bl = t.nodeLo[rc], bh = t.nodeHi[rc];
+        float4 const al = __ldcg(t.nodeLo + lc), ah = __ldcg(t.nodeHi + lc), bl = __ldcg(t.nodeLo + rc), bh = __ldcg(t.nodeHi + rc);
         t.nodeLo[p] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
         t.nodeHi[p] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
         p           = t.parent[p];
