@@ -1,0 +1,49 @@
+"""Tiny cases for compute-sanitizer (memcheck / racecheck / synccheck):
+  compute-sanitizer --tool memcheck python tools/sanitize_case.py
+Every kernel family runs once: set-up, the step kernel in its direct / pipelined / one-cluster forms, Chebyshev,
+St. Venant-Kirchhoff with the guarded step, Anderson, the contact prologue (radix sort, LBVH, active set), the
+stand-alone BVH queries, objective evaluation."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import physicsbasedanimationtoolkit_b200 as pbat
+from physicsbasedanimationtoolkit_b200 import meshes
+
+X, T = meshes.tet_grid(5, 3, 3, 0.1)
+dbc = np.flatnonzero(X[0] == 0)
+for variant in (1, 3, 4):
+    d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.8).construct()
+    vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=variant)
+    vbd.step(0.01, 3, 2)
+    assert np.isfinite(vbd.x).all()
+d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
+     .with_hyper_elastic_energy(pbat.sim.vbd.HyperElasticEnergy.SaintVenantKirchhoff).construct())
+vbd = pbat.sim.vbd.Integrator(d)
+vbd.line_search_guard = True
+vbd.step(0.01, 3, 1)
+vbd.objective_function_gradient(vbd.x, vbd.x, 0.01)
+d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_anderson_acceleration(3).construct()
+pbat.gpu.vbd.Integrator(d).step(0.01, 5, 1)
+# contact
+Xb, Tb = meshes.tet_grid(2, 2, 1, 0.5)
+Xt, Tt = meshes.tet_grid(1, 1, 1, 0.5, origin=(0.2, 0.3, 0.53))
+Xc = np.concatenate([Xb, Xt], axis=1)
+Tc = np.concatenate([Tb, Tt + Xb.shape[1]], axis=1)
+B = np.concatenate([np.zeros(Xb.shape[1], np.int64), np.ones(Xt.shape[1], np.int64)])
+F = meshes.boundary_facets(Tc)
+V = np.unique(F)
+v = np.zeros_like(Xc)
+v[2, Xb.shape[1]:] = -1.0
+d = (pbat.sim.vbd.Data().with_volume_mesh(Xc, Tc).with_surface_mesh(V, F).with_bodies(B).with_velocity(v)
+     .with_dirichlet_vertices(np.flatnonzero(Xc[2] == 0)).construct())
+vbd = pbat.gpu.vbd.Integrator(d)
+for _ in range(4):
+    vbd.step(0.01, 3, 1)
+assert np.isfinite(vbd.x).all()
+aabbs = pbat.gpu.geometry.Aabb()
+aabbs.construct(Xc, F)
+bvh = pbat.gpu.geometry.Bvh(F.shape[1], 64 * F.shape[1])
+bvh.build(aabbs, Xc.min(axis=1), Xc.max(axis=1))
+bvh.detect_overlaps(aabbs)
+bvh.point_triangle_nearest_neighbours(aabbs, Xc[:, :5], Xc, F)
+print("sanitize_case: done")
