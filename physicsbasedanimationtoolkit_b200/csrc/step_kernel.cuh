@@ -61,6 +61,7 @@ struct StepParams {
     int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path) or by an earlier partial launch
     int skipPostStep;                    // partial launch: more iterations of this substep follow
     int iterBegin;                       // partial launch: index (within the substep's solve) of this launch's first iteration
+    uint32_t activeEnd;                  // internal ids >= activeEnd are never swept (Dirichlet vertices, then ghosts)
     int lineSearch;                      // 0: accept the full Newton step (the reference, sim/vbd/Kernels.h:329-339); 1: guarded step
     // multi-GPU domain decomposition (world == 1: single GPU)
     uint32_t ghostBegin;                 // internal ids >= ghostBegin are ghosts: written by their owner GPU only
@@ -287,13 +288,16 @@ __device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, i
     float3 const x0 = InitialPosition(
         make_float3(x4.x, x4.y, x4.z), vtm1, make_float3(v4.x, v4.y, v4.z), make_float3(a4.x, a4.y, a4.z), p.sdt,
         p.sdt2, p.strategy);
-    float4 const o = make_float4(x0.x, x0.y, x0.z, 0.f);
+    // .w carries the number of the write (pre-step of substep s; sweep k adds k + 1): the halo exchange of the domain
+    // decomposition and the barrier-free sweep (step_kernel_pipe.cuh, PipeParams::dataflow) read it back
+    uint32_t const tag = p.tagBase + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.iterations + 1);
+    float4 const o = make_float4(x0.x, x0.y, x0.z, __uint_as_float(tag));
     p.pos[i]       = o;
     if constexpr (kChebyshev)
         p.pos[p.pOff + i] = o;
     if (p.snap != nullptr)
         p.snap[i] = o;
-    SendToPeers(p, i, o, o, p.tagBase + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.iterations + 1));
+    SendToPeers(p, i, o, o, tag);
 }
 
 // velocity update of the last substep (sim/vbd/Integrator.cpp:39); with the GPU-history flag also
@@ -715,7 +719,7 @@ __device__ __forceinline__ void ProcessTile(
     if (leader)
     {
         float const x = nx, y = ny, z = nz;
-        float4 const raw = make_float4(x, y, z, 0.f);
+        float4 const raw = make_float4(x, y, z, __uint_as_float(sendTag));
         if constexpr (kChebyshev)
         {
             // Q <- raw sweep result (read by higher colours in this iteration);

@@ -23,6 +23,8 @@ struct PipeParams {
     StepParams base;
     uint32_t maxIters;  // record buffer capacity per warp, in blocks
     int clusterBarrier; // the grid is ONE thread-block cluster: colours are separated by the hardware cluster barrier
+    int dataflow;       // no barrier between colours: every position carries the number of its write in .w, a tile checks
+                        // the values it gathered and polls the few that are not there yet (see AwaitTags)
 };
 
 constexpr int kPipeMaxThreads = 544;  // compiled for up to 16 compute warps + 1 barrier warp per CTA (<= 120 registers)
@@ -80,6 +82,13 @@ __device__ __forceinline__ void StoreReleaseSys(unsigned int* p, unsigned int v)
 __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float4 LoadPosGpu(const float4* q)
+{
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ float4 LoadPosSys(const float4* q)
@@ -225,6 +234,17 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             }
             return;
         }
+        if (pp.dataflow)
+        {
+            // barriers only around the pre-step pass: after it, and after the last sweep of the substep
+            for (int s = 0; s < p.substeps; ++s)
+            {
+                BarrierWarpStep(p, target, epoch, lane, 0u, nullptr);
+                if (p.iterations > 0)
+                    BarrierWarpStep(p, target, epoch, lane, 0u, nullptr);
+            }
+            return;
+        }
         for (int s = 0; s < p.substeps; ++s)
         {
             BarrierWarpStep(p, target, epoch, lane, p.iterations > 0 ? lagIn : 0u, nullptr);  // after the pre-step pass
@@ -367,6 +387,58 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
         __syncwarp();
     };
 
+    // Barrier-free sweep (pp.dataflow): the staged positions of tile s must carry the numbers of the writes this sweep
+    // reads -- tagLow + 1 (this iteration) for neighbours of a lower colour, tagLow (the previous iteration, or the
+    // pre-step) for neighbours of a higher colour and for the tile's own start values.  A value that is not there yet
+    // is polled.  Dependencies are exactly the 1-rings, every warp walks its tiles in (iteration, colour) order and all
+    // warps are co-resident, so the earliest unfinished tile can always proceed; and a vertex cannot be overwritten
+    // before its readers have read it, because its next update needs THEIR results first.
+    bool dfDead = false;  // a dependency timed out (reported to the host): stop waiting, just finish
+    auto AwaitTags = [&](uint32_t s, uint32_t chunks, uint32_t tagLow, uint32_t vbase) {
+        uint32_t const* ids = idsBuf + (s & 1u) * SE + lane;
+        if (!dfDead && LoadAcquire(p.distError) != 0u)
+            dfDead = true;
+        if (dfDead)
+            return;
+        for (uint32_t j = 0; j < chunks; ++j)
+        {
+            uint32_t const id   = ids[32 * j];
+            uint32_t const base = id & ~kPrevFlag;
+            bool const prev     = (id & kPrevFlag) != 0u;
+            if (base >= p.activeEnd || (base == vbase && !prev))  // constrained vertices never change; padding entries
+                continue;
+            uint32_t const expect = tagLow + (prev ? 0u : 1u);
+            float4 q              = stage[32 * j + lane];
+            if (__float_as_uint(q.w) != expect)
+            {
+                float4 const* src           = p.pos + base + (prev ? p.pOff : 0u);
+                unsigned long long const t0 = GlobalTimer();
+                for (uint32_t polls = 1;; ++polls)
+                {
+                    q = LoadPosGpu(src);
+                    if (__float_as_uint(q.w) == expect)
+                        break;
+                    if ((polls & 1023u) == 0u && (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u))
+                    {
+                        // a bug, not a slow peer: never hang the GPU; leave what was being waited for to the host
+                        if (atomicCAS(p.distError, 0u, 2u) == 0u)
+                        {
+                            p.distError[1] = base | (prev ? kPrevFlag : 0u);
+                            p.distError[2] = expect;
+                            p.distError[3] = __float_as_uint(q.w);
+                            p.distError[4] = vbase;
+                            p.distError[5] = tagLow - p.tagBase;
+                        }
+                        dfDead = true;
+                        break;
+                    }
+                }
+                stage[32 * j + lane] = q;
+            }
+        }
+        __syncwarp();
+    };
+
     Cursor c1{0, -1, 0, totalSweeps > 0 && warpHasTiles}, c2;
     Advance(c1);  // tile 0
     Cursor const c0 = c1;
@@ -443,11 +515,14 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     __syncwarp();
                     if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
                         AwaitGhosts(seq, chunks, tagLow);
+                    if (pp.dataflow)
+                        AwaitTags(seq, chunks, tagLow, td.y);
                     // Next tile in this same colour sweep (multi-round colours): all its positions are final, so
                     // everything it needs is requested as soon as this tile's buffers are free.  Otherwise the
                     // requests are issued in the shadow of the grid barrier (after GridArrive below).
                     bool const nextValid = c1.valid;
-                    bool const sameSweep = nextValid && c1.k == s * p.iterations + k && c1.c == static_cast<int>(c);
+                    // (barrier-free mode: every next tile is requested at once; what was not final yet is re-read above)
+                    bool const sameSweep = nextValid && (pp.dataflow || (c1.k == s * p.iterations + k && c1.c == static_cast<int>(c)));
                     uint32_t const seqNext = seq + 1;
                     uint32_t nextGathered  = 0;
                     auto prefetchNext = [&]() {
@@ -476,6 +551,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     Advance(c2);
                     ++seq;
                 }
+                if (pp.dataflow && !(k + 1 == p.iterations && c + 1 == nC))
+                    continue;  // no barrier between colours
                 if (pp.clusterBarrier)
                 {
                     __syncwarp();

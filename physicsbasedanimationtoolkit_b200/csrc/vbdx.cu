@@ -44,6 +44,9 @@ struct Integrator {
     Plan plan;
     int gridBlocks = 0, blockThreads = 256;
     int variant = VBDX_KERNEL_DIRECT;
+    bool dataflow    = true;   // barrier-free sweeps where they apply (PipeParams::dataflow); VBDX_DATAFLOW=0 turns them off
+    bool usedDataflow  = false;
+    unsigned int dfTag = 1;    // write numbers used by earlier launches (single GPU)
     bool clusterMode = false;  // the pipelined kernel launched as ONE thread-block cluster (VBDX_KERNEL_CLUSTER)
     uint32_t ringSlots = 0, maxTileIters = 1;
     size_t smemBytes   = 0;
@@ -380,6 +383,8 @@ void Integrator::Create(vbdx_data_desc const& d)
             variant = VBDX_KERNEL_CLUSTER;
     }
     // the cluster variant IS the pipelined kernel, launched as one cluster and told to use the cluster barrier
+    if (char const* e = std::getenv("VBDX_DATAFLOW"))
+        dataflow = std::atoi(e) != 0;
     clusterMode = variant == VBDX_KERNEL_CLUSTER;
     if (clusterMode)
     {
@@ -648,7 +653,19 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
     p.substeps     = substeps;
     p.barrier      = dBarrier.p;
     p.ghostBegin   = static_cast<uint32_t>(plan.ghostBegin);
+    p.activeEnd    = static_cast<uint32_t>(plan.nActive);
     p.rank = distRank, p.world = distWorld;
+    if (distWorld == 1)
+    {
+        // write numbers carried in .w of every position (barrier-free sweeps); a dependency that never arrives is a bug:
+        // give up after VBDX_DATAFLOW_TIMEOUT_S instead of hanging the GPU
+        p.tagBase   = dfTag;
+        dfTag += static_cast<unsigned int>(substeps) * (static_cast<unsigned int>(iterations) + 1u);
+        p.distError = dDistFlags.p + 9;
+        const char* t   = std::getenv("VBDX_DATAFLOW_TIMEOUT_S");
+        double const ts = t ? std::atof(t) : 10.0;
+        p.distTimeoutNs = static_cast<unsigned long long>((ts > 0 ? ts : 10.0) * 1e9);
+    }
     if (distWorld > 1)
     {
         p.sendPtr = dSendPtr.p, p.sendDst = dSendDst.p;
@@ -697,6 +714,11 @@ void Integrator::LaunchStepKernel(StepParams const& q)
             PipeParams pp{};
             pp.base      = q;
             pp.maxIters  = maxTileIters;
+            // barrier-free sweeps: whole steps of the base / Chebyshev solve without damping or contact (whose reads go
+            // beyond the 1-rings) on one GPU (the halo exchange has its own protocol)
+            pp.dataflow = dataflow && distWorld == 1 && q.fc == nullptr && kD == 0.0 && !q.skipPreStep && !q.skipPostStep &&
+                          q.iterBegin == 0 && q.iterations > 0 && q.trace == nullptr;
+            usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
             VBDX_CUDA(cudaLaunchCooperativeKernel(
                 reinterpret_cast<void const*>(KernelPipe()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
@@ -781,10 +803,20 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
     if (sync)
     {
         VBDX_CUDA(cudaStreamSynchronize(stream));
-        if (distWorld > 1)
+        if (distWorld > 1 || usedDataflow)
         {
             unsigned int e = 0;
             VBDX_CUDA(cudaMemcpy(&e, dDistFlags.p + 9, sizeof(e), cudaMemcpyDeviceToHost));
+            if (e == 2u)
+            {
+                unsigned int dbg[6] = {0, 0, 0, 0, 0, 0};
+                VBDX_CUDA(cudaMemcpy(dbg, dDistFlags.p + 9, sizeof(dbg), cudaMemcpyDeviceToHost));
+                VBDX_CUDA(cudaMemset(dDistFlags.p + 9, 0, sizeof(dbg)));
+                throw Error(VBDX_CUDA_ERROR, "internal error: a barrier-free sweep waited for a vertex update that never came (vertex " +
+                                                 std::to_string(dbg[1] & 0x7fffffffu) + ((dbg[1] >> 31) ? " [previous-iterate buffer]" : "") + ", expected write " +
+                                                 std::to_string(dbg[2]) + ", found " + std::to_string(dbg[3]) + ", tile of vertex " + std::to_string(dbg[4]) +
+                                                 ", sweep " + std::to_string(dbg[5]) + ", write base " + std::to_string(dfTag) + "; VBDX_DATAFLOW=0 selects the barrier sweep)");
+            }
             if (e)
                 throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not deliver its halo or reach the colour barrier in time (VBDX_DIST_TIMEOUT_S, default 30 s)");
         }
