@@ -216,6 +216,16 @@ def main():
         data = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc)
                 .with_chebyshev_acceleration(RHO).construct())
         vbd = pbat.gpu.vbd.Integrator(data, device=local_rank, tile_iters=args.tile_iters)
+        try:
+            # The default sweep is barrier-free.  Its dependency waits carry a time-out that turns a
+            # bug into an exception; should that ever fire, measure the barrier sweep instead of reporting nothing.
+            vbd.x = np.ascontiguousarray(x0, dtype=np.float32)
+            vbd.step(DT, ITERS, 1)
+        except RuntimeError as e:
+            print(f"bench.py: barrier-free sweep failed ({e}); falling back to the barrier sweep", file=sys.stderr)
+            os.environ["VBDX_DATAFLOW"] = "0"
+            vbd = pbat.gpu.vbd.Integrator(data, device=local_rank, tile_iters=args.tile_iters)
+        config["sweep"] = "barrier" if os.environ.get("VBDX_DATAFLOW") == "0" else "barrier-free (dataflow-synchronised colours)"
         info = vbd.info
         n_active = info["nActiveVertices"]
         n_active_job = n_active * world
@@ -322,7 +332,7 @@ def main():
                     "d2h_bytes_per_step": int(nV * 12), "ms_per_step": e2e_ms / steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vbdx::StepKernelPipe<true,false> (one persistent cooperative launch per step)",
+                         "traffic": traffic, "kernel": "vbdx::StepKernelPipe<true,false,false,%s> (one persistent cooperative launch per step)" % ("false" if os.environ.get("VBDX_DATAFLOW") == "0" or world > 1 else "true"),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "bytes_per_vertex_iteration": B, "kbar": kbar, "nbar": nbar,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",

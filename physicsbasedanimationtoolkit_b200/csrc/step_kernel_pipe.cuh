@@ -181,7 +181,7 @@ __device__ __forceinline__ void ClusterWait()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool kChebyshev, bool kDamping, bool kStvk = false>
+template <bool kChebyshev, bool kDamping, bool kStvk = false, bool kDataflow = false>
 __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __grid_constant__ PipeParams pp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             }
             return;
         }
-        if (pp.dataflow)
+        if constexpr (kDataflow)
         {
             // barriers only around the pre-step pass: after it, and after the last sweep of the substep
             for (int s = 0; s < p.substeps; ++s)
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             uint32_t const id   = ids[32 * j];
             uint32_t const base = id & ~kPrevFlag;
             bool const prev     = (id & kPrevFlag) != 0u;
-            uint32_t const at   = base >= ghostFrom ? GhostIndex(p, base, prev, tagLow + (prev ? 0u : 1u)) : base + (prev ? p.pOff : 0u);
+            uint32_t const at   = !kDataflow && base >= ghostFrom ? GhostIndex(p, base, prev, tagLow + (prev ? 0u : 1u)) : base + (prev ? p.pOff : 0u);
             CpAsync16(dst + 512 * j, p.pos + at);
         }
     };
@@ -513,16 +513,17 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     CpAsyncCommit();
                     CpAsyncWaitGroup<1>();  // positions have landed; the descriptor may still be in flight
                     __syncwarp();
-                    if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
-                        AwaitGhosts(seq, chunks, tagLow);
-                    if (pp.dataflow)
+                    if constexpr (!kDataflow)  // (the barrier-free sweep is single-GPU: the halo exchange has its own protocol)
+                        if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
+                            AwaitGhosts(seq, chunks, tagLow);
+                    if constexpr (kDataflow)
                         AwaitTags(seq, chunks, tagLow, td.y);
                     // Next tile in this same colour sweep (multi-round colours): all its positions are final, so
                     // everything it needs is requested as soon as this tile's buffers are free.  Otherwise the
                     // requests are issued in the shadow of the grid barrier (after GridArrive below).
                     bool const nextValid = c1.valid;
                     // (barrier-free mode: every next tile is requested at once; what was not final yet is re-read above)
-                    bool const sameSweep = nextValid && (pp.dataflow || (c1.k == s * p.iterations + k && c1.c == static_cast<int>(c)));
+                    bool const sameSweep = nextValid && (kDataflow || (c1.k == s * p.iterations + k && c1.c == static_cast<int>(c)));
                     uint32_t const seqNext = seq + 1;
                     uint32_t nextGathered  = 0;
                     auto prefetchNext = [&]() {
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     Advance(c2);
                     ++seq;
                 }
-                if (pp.dataflow && !(k + 1 == p.iterations && c + 1 == nC))
+                if (kDataflow && !(k + 1 == p.iterations && c + 1 == nC))
                     continue;  // no barrier between colours
                 if (pp.clusterBarrier)
                 {

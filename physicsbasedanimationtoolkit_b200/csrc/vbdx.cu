@@ -128,16 +128,21 @@ struct Integrator {
         return damp ? StepKernel<false, true> : StepKernel<false, false>;
     }
 
-    PipeKernelFn KernelPipe() const
+    // dataflowSweep = the barrier-free instantiation (no damping / contact: their reads go beyond the 1-rings)
+    PipeKernelFn KernelPipe(bool dataflowSweep = false) const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
         bool const damp = kD != 0.0 || contact.enabled;  // the "extras" variants carry damping and contact
         if (material == VBDX_MATERIAL_STVK)
         {
+            if (dataflowSweep && !damp)
+                return cheb ? StepKernelPipe<true, false, true, true> : StepKernelPipe<false, false, true, true>;
             if (cheb)
                 return damp ? StepKernelPipe<true, true, true> : StepKernelPipe<true, false, true>;
             return damp ? StepKernelPipe<false, true, true> : StepKernelPipe<false, false, true>;
         }
+        if (dataflowSweep && !damp)
+            return cheb ? StepKernelPipe<true, false, false, true> : StepKernelPipe<false, false, false, true>;
         if (cheb)
             return damp ? StepKernelPipe<true, true> : StepKernelPipe<true, false>;
         return damp ? StepKernelPipe<false, true> : StepKernelPipe<false, false>;
@@ -404,7 +409,9 @@ void Integrator::Create(vbdx_data_desc const& d)
              {stvk ? (cheb0 ? StepKernelPipe<true, false, true> : StepKernelPipe<false, false, true>)
                    : (cheb0 ? StepKernelPipe<true, false> : StepKernelPipe<false, false>),
               stvk ? (cheb0 ? StepKernelPipe<true, true, true> : StepKernelPipe<false, true, true>)
-                   : (cheb0 ? StepKernelPipe<true, true> : StepKernelPipe<false, true>)})
+                   : (cheb0 ? StepKernelPipe<true, true> : StepKernelPipe<false, true>),
+              stvk ? (cheb0 ? StepKernelPipe<true, false, true, true> : StepKernelPipe<false, false, true, true>)
+                   : (cheb0 ? StepKernelPipe<true, false, false, true> : StepKernelPipe<false, false, false, true>)})
         {
             VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
             int n = 0;
@@ -663,8 +670,8 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
         dfTag += static_cast<unsigned int>(substeps) * (static_cast<unsigned int>(iterations) + 1u);
         p.distError = dDistFlags.p + 9;
         const char* t   = std::getenv("VBDX_DATAFLOW_TIMEOUT_S");
-        double const ts = t ? std::atof(t) : 10.0;
-        p.distTimeoutNs = static_cast<unsigned long long>((ts > 0 ? ts : 10.0) * 1e9);
+        double const ts = t ? std::atof(t) : 2.0;  // a dependency is microseconds away
+        p.distTimeoutNs = static_cast<unsigned long long>((ts > 0 ? ts : 2.0) * 1e9);
     }
     if (distWorld > 1)
     {
@@ -721,7 +728,7 @@ void Integrator::LaunchStepKernel(StepParams const& q)
             usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
             VBDX_CUDA(cudaLaunchCooperativeKernel(
-                reinterpret_cast<void const*>(KernelPipe()), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+                reinterpret_cast<void const*>(KernelPipe(pp.dataflow != 0)), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
         }
         else if (variant == VBDX_KERNEL_PIPELINED)
         {
@@ -812,6 +819,7 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
                 unsigned int dbg[6] = {0, 0, 0, 0, 0, 0};
                 VBDX_CUDA(cudaMemcpy(dbg, dDistFlags.p + 9, sizeof(dbg), cudaMemcpyDeviceToHost));
                 VBDX_CUDA(cudaMemset(dDistFlags.p + 9, 0, sizeof(dbg)));
+                dataflow = false;  // this handle sweeps with barriers from now on
                 throw Error(VBDX_CUDA_ERROR, "internal error: a barrier-free sweep waited for a vertex update that never came (vertex " +
                                                  std::to_string(dbg[1] & 0x7fffffffu) + ((dbg[1] >> 31) ? " [previous-iterate buffer]" : "") + ", expected write " +
                                                  std::to_string(dbg[2]) + ", found " + std::to_string(dbg[3]) + ", tile of vertex " + std::to_string(dbg[4]) +

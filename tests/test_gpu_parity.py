@@ -225,6 +225,30 @@ def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
     assert rel_l2(out[1][0], ref.x) < TOL
 
 
+@pytest.mark.parametrize("cheb", [None, 0.9])
+def test_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, monkeypatch):
+    """The default whole-GPU sweep has no barrier between colours: positions carry the number of their write, tiles
+    validate what they gathered and poll what is not there yet.  Same reads, same arithmetic: identical bits to the
+    barrier sweep (VBDX_DATAFLOW=0), here with several tiles per warp and colour, substeps, and against the oracle."""
+    X, T = meshes.tet_grid(34, 30, 26, 1 / 30)
+    dbc = np.flatnonzero(X[2] == 0)
+    x0 = X + 0.002 * np.random.default_rng(3).uniform(-1, 1, X.shape)
+    x0[:, dbc] = X[:, dbc]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VBDX_DATAFLOW", mode)
+        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kernel_variant=3)
+        vbd.x = x0.astype(np.float32)
+        for _ in range(4):
+            vbd.step(0.01, 12, 2)
+        out[mode] = (vbd.x.copy(), vbd.v.copy())
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    ref.x = x0.astype(np.float32).astype(np.float64)
+    for _ in range(4):
+        ref.step(0.01, 12, 2)
+    assert rel_l2(out["1"][0], ref.x) < TOL
+
+
 def test_small_meshes_default_to_one_cluster_and_large_ones_do_not():
     """VBDX_KERNEL_DEFAULT: a mesh whose colours fit one thread-block cluster is swept by 8 CTAs behind the hardware
     cluster barrier; anything larger takes the whole GPU.  Contact, damping, substeps run on either."""

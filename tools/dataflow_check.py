@@ -30,7 +30,7 @@ else:
     grid = sys.argv[1] if len(sys.argv) > 1 else "58"
     res = {}
     for mode in ("0", "1"):
-        env = dict(os.environ, VBDX_DATAFLOW=mode, VBDX_DATAFLOW_TIMEOUT_S="0.5")
+        env = dict(os.environ, VBDX_DATAFLOW=mode, VBDX_DATAFLOW_TIMEOUT_S="3")
         r = subprocess.run([sys.executable, __file__, grid, "child"], env=env, capture_output=True, text=True, timeout=50)
         print(f"dataflow={mode}:", r.stdout.strip()[-400:], r.stderr.strip()[-600:])
         try:
