@@ -225,8 +225,8 @@ def test_kernel_variants_bitwise_identical(cheb, ring_slots, consumer_warps):
     assert rel_l2(out[1][0], ref.x) < TOL
 
 
-@pytest.mark.parametrize("cheb", [None, 0.9])
-def test_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, monkeypatch):
+@pytest.mark.parametrize("cheb,material", [(None, 0), (0.9, 0), (0.8, 1), (None, 1)])
+def test_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, material, monkeypatch):
     """The default whole-GPU sweep has no barrier between colours: positions carry the number of their write, tiles
     validate what they gathered and poll what is not there yet.  Same reads, same arithmetic: identical bits to the
     barrier sweep (VBDX_DATAFLOW=0), here with several tiles per warp and colour, substeps, and against the oracle."""
@@ -237,12 +237,14 @@ def test_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, monkeypa
     out = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("VBDX_DATAFLOW", mode)
-        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kernel_variant=3)
+        d, vbd, ref = make(X, T, dbc=dbc, cheb=cheb, kernel_variant=3, material=material)
+        vbd.line_search_guard = material == 1 and cheb is None      # the guarded StVK step walks the records twice
         vbd.x = x0.astype(np.float32)
         for _ in range(4):
             vbd.step(0.01, 12, 2)
         out[mode] = (vbd.x.copy(), vbd.v.copy())
     assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    ref.set_line_search_guard(material == 1 and cheb is None)
     ref.x = x0.astype(np.float32).astype(np.float64)
     for _ in range(4):
         ref.step(0.01, 12, 2)
