@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
             uint32_t const id   = ids[32 * j];
             uint32_t const base = id & ~kPrevFlag;
             bool const prev     = (id & kPrevFlag) != 0u;
-            uint32_t const at   = !kDataflow && base >= ghostFrom ? GhostIndex(p, base, prev, tagLow + (prev ? 0u : 1u)) : base + (prev ? p.pOff : 0u);
+            uint32_t const at   = base >= ghostFrom ? GhostIndex(p, base, prev, tagLow + (prev ? 0u : 1u)) : base + (prev ? p.pOff : 0u);
             CpAsync16(dst + 512 * j, p.pos + at);
         }
     };
@@ -513,9 +513,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                     CpAsyncCommit();
                     CpAsyncWaitGroup<1>();  // positions have landed; the descriptor may still be in flight
                     __syncwarp();
-                    if constexpr (!kDataflow)  // (the barrier-free sweep is single-GPU: the halo exchange has its own protocol)
-                        if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
-                            AwaitGhosts(seq, chunks, tagLow);
+                    if (ghostFrom != 0xffffffffu && TileReadsGhosts(td.z))
+                        AwaitGhosts(seq, chunks, tagLow);
                     if constexpr (kDataflow)
                         AwaitTags(seq, chunks, tagLow, td.y);
                     // Next tile in this same colour sweep (multi-round colours): all its positions are final, so
@@ -534,7 +533,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                         __syncwarp();
                         IssueRecords(seqNext);
                         nextGathered = TileChunks(tdBuf[seqNext & 3u].z);
-                        IssueGather(seqNext, 0, nextGathered, tagLow);
+                        // (the next tile may belong to a later sweep in barrier-free mode: its own write numbers select the ghost copies)
+                        IssueGather(seqNext, 0, nextGathered, kDataflow ? p.tagBase + static_cast<uint32_t>(c1.k + c1.k / p.iterations) : tagLow);
                         if (c2.valid)
                             IssueIds(seq + 2);
                         CpAsyncCommit();

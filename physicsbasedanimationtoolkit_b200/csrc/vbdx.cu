@@ -164,6 +164,10 @@ struct Integrator {
     void LaunchStepKernel(StepParams const& q);
     void RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync);
     void LaunchPreStep(StepParams const& q);
+    bool WillSweepBarrierFree(int iterations) const
+    {
+        return dataflow && variant == VBDX_KERNEL_PIPELINED && !clusterMode && !contact.enabled && kD == 0.0 && iterations > 0 && traceIteration < 0;
+    }
     void AndersonStep(StepParams const& p, double dt, int iterations, int substeps);
     void BroydenStep(StepParams const& p, double dt, int iterations, int substeps);
     // contact hooks shared by the windowed accelerators (same sequence as RunStep's contact branch)
@@ -695,7 +699,10 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
         for (int r = 0; r < 8; ++r)
             p.peerGhostExt[r] = peerGhostExt[r], p.peerGhostBegin[r] = peerGhostBegin[r], p.peerNGhost[r] = peerNGhost[r];
         distTag += static_cast<unsigned int>(substeps) * (static_cast<unsigned int>(iterations) + 1u);
-        distEpoch += static_cast<unsigned int>(substeps) * (1u + static_cast<unsigned int>(iterations) * static_cast<unsigned int>(plan.nColors));
+        // barriers per substep: after the pre-step and after every colour -- or, with the barrier-free sweep, after the
+        // pre-step and after the last sweep only (every rank takes the same decision: same settings, same environment)
+        distEpoch += static_cast<unsigned int>(substeps) *
+                     (WillSweepBarrierFree(iterations) ? 2u : 1u + static_cast<unsigned int>(iterations) * static_cast<unsigned int>(plan.nColors));
     }
     p.trace        = traceIteration >= 0 ? dTrace.p : nullptr;
     p.traceIteration = traceIteration;
@@ -722,9 +729,8 @@ void Integrator::LaunchStepKernel(StepParams const& q)
             pp.base      = q;
             pp.maxIters  = maxTileIters;
             // barrier-free sweeps: whole steps of the base / Chebyshev solve without damping or contact (whose reads go
-            // beyond the 1-rings) on one GPU (the halo exchange has its own protocol)
-            pp.dataflow = dataflow && distWorld == 1 && q.fc == nullptr && kD == 0.0 && !q.skipPreStep && !q.skipPostStep &&
-                          q.iterBegin == 0 && q.iterations > 0 && q.trace == nullptr;
+            // beyond the 1-rings); partial launches (traces, windowed accelerators) keep the colour barriers
+            pp.dataflow = WillSweepBarrierFree(q.iterations) && !q.skipPreStep && !q.skipPostStep && q.iterBegin == 0;
             usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
             VBDX_CUDA(cudaLaunchCooperativeKernel(
