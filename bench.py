@@ -201,7 +201,26 @@ def main():
 
         Xg, Tg, dbc_g, x0g = workload(seed=0, slabs=world)
         config["tets"], config["vertices"] = int(Tg.shape[1]), int(Xg.shape[1])
+        os.environ.setdefault("VBDX_DIST_TIMEOUT_S", "10")  # the ranks start together here: a peer that is 10 s late is gone
         dd = DomainDecomposedIntegrator(Xg, Tg, dbc=dbc_g, rho_chebyshev=RHO, axis=0, tile_iters=args.tile_iters)
+        # The sweeps are barrier-free across the GPUs; every dependency wait carries a time-out.  Probe
+        # two steps; should any rank see a time-out, ALL ranks rebuild with colour barriers instead of reporting nothing.
+        ok = 1
+        try:
+            dd.vbd.x = np.ascontiguousarray(x0g[:, dd.local.l2g], dtype=np.float32)
+            dist.barrier()
+            for _ in range(2):
+                dd.vbd.step(DT, ITERS, 1)
+        except RuntimeError as e:
+            print(f"bench.py[{rank}]: barrier-free sweep failed ({e})", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            os.environ["VBDX_DATAFLOW"] = "0"
+            del dd
+            dist.barrier()
+            dd = DomainDecomposedIntegrator(Xg, Tg, dbc=dbc_g, rho_chebyshev=RHO, axis=0, tile_iters=args.tile_iters)
         vbd, lp = dd.vbd, dd.local
         X, T, dbc = lp.X, lp.T, np.concatenate([lp.dbc, lp.ghost_local])
         x0 = x0g[:, lp.l2g]
