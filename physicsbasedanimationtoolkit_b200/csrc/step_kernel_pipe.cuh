@@ -243,20 +243,22 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
                 if (p.iterations > 0)
                     BarrierWarpStep(p, target, epoch, lane, 0u, nullptr);
             }
-            return;
         }
-        for (int s = 0; s < p.substeps; ++s)
+        else
         {
-            BarrierWarpStep(p, target, epoch, lane, p.iterations > 0 ? lagIn : 0u, nullptr);  // after the pre-step pass
-            for (int k = 0; k < p.iterations; ++k)
-                for (uint32_t c = 0; c < nC; ++c)
-                {
-                    unsigned long long* tr = nullptr;
-                    if (p.trace != nullptr && k == p.traceIteration)
-                        tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
-                    bool const lastOfSubstep = k + 1 == p.iterations && c + 1 == nC;
-                    BarrierWarpStep(p, target, epoch, lane, lastOfSubstep ? 0u : lagIn, tr);
-                }
+            for (int s = 0; s < p.substeps; ++s)
+            {
+                BarrierWarpStep(p, target, epoch, lane, p.iterations > 0 ? lagIn : 0u, nullptr);  // after the pre-step pass
+                for (int k = 0; k < p.iterations; ++k)
+                    for (uint32_t c = 0; c < nC; ++c)
+                    {
+                        unsigned long long* tr = nullptr;
+                        if (p.trace != nullptr && k == p.traceIteration)
+                            tr = p.trace + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * kTraceStamps;
+                        bool const lastOfSubstep = k + 1 == p.iterations && c + 1 == nC;
+                        BarrierWarpStep(p, target, epoch, lane, lastOfSubstep ? 0u : lagIn, tr);
+                    }
+            }
         }
         return;
     }
