@@ -109,3 +109,42 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(base, f)).read()
                 assert "oracle" not in src.replace("the parity oracle", "").replace("parity oracle", ""), f
+
+
+def test_geometry_host_classes():
+    """pbat.gpu.common.Buffer and pbat.gpu.geometry.Aabb are host-side holders: their logic needs no device."""
+    Buffer, Aabb = pbat.gpu.common.Buffer, pbat.gpu.geometry.Aabb
+    b = Buffer(np.arange(6, dtype=np.float32).reshape(3, 2))
+    assert (b.dims, b.size, b.type) == (3, 2, np.float32)
+    b.set(np.arange(4, dtype=np.int64))
+    assert (b.dims, b.size) == (1, 4) and b.type == np.int64
+    b.resize(3, 5)
+    assert b.to_numpy().shape == (3, 5)
+    a = Aabb(3, 0)
+    a.construct(meshes.CUBE_P, meshes.CUBE_T)               # boxes of simplices (gpu/impl/geometry/Aabb.cu:18-74)
+    assert a.n_boxes == 5 and a.dims == 3 and (a.min == 0).all() and (a.max == 1).all()
+    P = np.array([[0., 2., 1.], [0., 0., 3.], [1., 1., 1.]])
+    a.construct(Buffer(P.astype(np.float32)), Buffer(np.array([[0, 1], [1, 2]], dtype=np.int32)))   # two segments
+    assert np.array_equal(a.min, [[0, 1], [0, 0], [1, 1]]) and np.array_equal(a.max, [[2, 2], [0, 3], [1, 1]])
+    a.construct(np.zeros((3, 4)), np.ones((3, 4)))          # explicit min / max
+    assert a.n_boxes == 4 and (a.max == 1).all()
+    with pytest.raises(ValueError):
+        a.construct(P, np.array([[0], [7]]))                # simplex index out of range
+    with pytest.raises(ValueError):
+        a.construct(np.zeros((3, 4)), np.ones((3, 5)))
+    with pytest.raises(ValueError):
+        Aabb(2, 4)
+
+
+def test_batch_and_handles_fail_loudly_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    d = pbat.sim.vbd.Data().with_volume_mesh(*meshes.tet_grid(2, 2, 2, 0.5)).construct()
+    for make in (lambda: pbat.gpu.vbd.BatchIntegrator([d, d]), lambda: pbat.gpu.geometry.Bvh(8, 8),
+                 lambda: pbat.gpu.contact.VertexTriangleMixedCcdDcd(np.zeros(4, int), np.arange(4), np.array([[0], [1], [2]]))):
+        with pytest.raises(RuntimeError):
+            make()
+    with pytest.raises(ValueError):
+        pbat.gpu.vbd.BatchIntegrator([])
