@@ -261,6 +261,17 @@ vbdx_status vbdx_contact_set_eps(vbdx_contact* h, float eps);
 /* active mask (nCV), nearest triangles (nCV x 8, -1 terminated), compacted active vertices (first *n_active of nCV) */
 vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn, int32_t* av, int64_t* n_active);
 
+/* Host-only debug access to the sweep plan (tiles, ring lists with their previous-iterate flags and padding, colour
+ * ranges, internal numbering) of a mesh: what the CPU test-suite model-checks the barrier-free sweep protocol against.
+ * is_constrained: 0 = swept, 1 = Dirichlet, 2 = ghost.  vbdx_debug_plan_get(what): 0 sizes {nTiles, nRingIds, nColors,
+ * nActive, ghostBegin} (int64 x 5), 1 tiles (uint32 x 4 each: blockStart, vbase, meta, ringStart), 2 ring ids (uint32),
+ * 3 colour tile begins (uint32 x (nColors + 1)), 4 new2old (int32 x nV). */
+typedef struct vbdx_plan vbdx_plan;
+vbdx_status vbdx_debug_plan_create(int64_t nV, int64_t nT, const int64_t* E, const int64_t* colors, const uint8_t* is_constrained,
+                                   const double* X, int32_t tile_iters, vbdx_plan** out);
+vbdx_status vbdx_debug_plan_get(vbdx_plan* h, int32_t what, void* out);
+vbdx_status vbdx_debug_plan_destroy(vbdx_plan* h);
+
 /* Use a caller-provided cudaStream_t for all subsequent work (NULL = the handle's own). */
 vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream);
 

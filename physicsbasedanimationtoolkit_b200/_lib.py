@@ -92,6 +92,9 @@ SYMBOLS = {
     "vbdx_contact_finalize_active_set": (C.c_int, [_H, C.c_void_p]),
     "vbdx_contact_set_eps": (C.c_int, [_H, C.c_float]),
     "vbdx_contact_get": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbdx_debug_plan_create": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(_H)]),
+    "vbdx_debug_plan_get": (C.c_int, [_H, C.c_int32, C.c_void_p]),
+    "vbdx_debug_plan_destroy": (C.c_int, [_H]),
     "vbdx_create_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "vbdx_batch_offsets": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "vbdx_set_block_size": (C.c_int, [_H, C.c_int32]),

@@ -1913,6 +1913,79 @@ vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn,
     });
 }
 
+// Host-only: the planner's output for a mesh (no device needed).  Lets the CPU test-suite model-check the protocol of the
+// barrier-free sweep against the very ring lists, flags and padding the kernels consume.
+struct vbdx_plan {
+    vbdx::Plan plan;
+};
+
+vbdx_status vbdx_debug_plan_create(int64_t nV, int64_t nT, const int64_t* E, const int64_t* colors, const uint8_t* is_constrained,
+                                   const double* X, int32_t tile_iters, vbdx_plan** out)
+{
+    if (!out)
+        return VBDX_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::unique_ptr<vbdx_plan> h;
+    vbdx_status const st = Guard([&] {
+        vbdx::Require(nV >= 1 && nT >= 1 && E && colors && is_constrained && X, "vbdx_debug_plan_create: bad arguments");
+        std::vector<int32_t> E32(static_cast<size_t>(4 * nT));
+        std::vector<uint32_t> ptr(static_cast<size_t>(nV) + 1, 0), adj(static_cast<size_t>(4 * nT));
+        for (int64_t k = 0; k < 4 * nT; ++k)
+        {
+            vbdx::Require(E[k] >= 0 && E[k] < nV, "element index out of range");
+            E32[k] = static_cast<int32_t>(E[k]);
+            ++ptr[E[k] + 1];
+        }
+        for (int64_t i = 0; i < nV; ++i)
+            ptr[i + 1] += ptr[i];
+        std::vector<uint32_t> cursor(ptr.begin(), ptr.end() - 1);
+        for (int64_t k = 0; k < 4 * nT; ++k)  // ascending k per vertex = ascending element id (sim/vbd/Data.cpp:223-226)
+            adj[cursor[E32[k]]++] = static_cast<uint32_t>(k);
+        h = std::make_unique<vbdx_plan>();
+        try
+        {
+            vbdx::BuildPlan(nV, E32.data(), ptr.data(), adj.data(), colors, is_constrained, X, tile_iters > 0 ? tile_iters : 8, false, 1, h->plan);
+        }
+        catch (std::length_error const& e)
+        {
+            throw vbdx::Error(VBDX_UNSUPPORTED, e.what());
+        }
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+/* what: 0 sizes {nTiles, nRingIds, nColors, nActive, ghostBegin} (int64 x 5), 1 tiles (uint32 x 4 per tile), 2 ring ids, 3 colour tile
+ * begins (nColors + 1), 4 new2old (int32 x nV) */
+vbdx_status vbdx_debug_plan_get(vbdx_plan* h, int32_t what, void* out)
+{
+    if (!h || !out)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        vbdx::Plan const& p = h->plan;
+        switch (what)
+        {
+            case 0: {
+                int64_t* o = static_cast<int64_t*>(out);
+                o[0] = static_cast<int64_t>(p.tiles.size()), o[1] = static_cast<int64_t>(p.ringIds.size()), o[2] = p.nColors, o[3] = p.nActive, o[4] = p.ghostBegin;
+                break;
+            }
+            case 1: std::memcpy(out, p.tiles.data(), p.tiles.size() * sizeof(vbdx::TileDesc)); break;
+            case 2: std::memcpy(out, p.ringIds.data(), p.ringIds.size() * sizeof(uint32_t)); break;
+            case 3: std::memcpy(out, p.colorTileBegin.data(), p.colorTileBegin.size() * sizeof(uint32_t)); break;
+            case 4: std::memcpy(out, p.new2old.data(), p.new2old.size() * sizeof(int32_t)); break;
+            default: throw vbdx::Error(VBDX_INVALID_ARGUMENT, "vbdx_debug_plan_get: unknown item");
+        }
+    });
+}
+
+vbdx_status vbdx_debug_plan_destroy(vbdx_plan* h)
+{
+    delete h;
+    return VBDX_OK;
+}
+
 vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream)
 {
     if (vbdx_status s = NeedHandle(h))

@@ -1,0 +1,164 @@
+"""CPU model check of the barrier-free sweep against the planner's real output.
+
+The kernels drop the colour barrier: every position carries the number of its write, and a tile may run once every entry of
+its ring list carries the number it expects -- `tagLow + 1` for entries without the previous-iterate flag (neighbours of a
+lower colour), `tagLow` for flagged entries (neighbours of a higher colour, the tile's own vertices); constrained vertices
+and padding entries are not checked (csrc/step_kernel_pipe.cuh: AwaitTags).  Here warps are scheduled by an adversarial
+random scheduler over the tiles, ring lists, flags and padding that `BuildPlan` (csrc/plan.cpp) produced, and every read is
+checked:
+
+  * progress: until all tiles are done, some warp can always run (no deadlock);
+  * no overwrite hazard: when a tile's dependencies are met, no entry carries a NEWER write than expected (the poll waits
+    for equality, so a newer value would also mean a hang on the device);
+  * the values read are exactly the ones the barrier schedule reads (Gauss-Seidel order): lower colours from this sweep,
+    higher colours from the previous one.
+
+Reads happen when the dependencies are met, writes an arbitrary time later (other warps run in between), as on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import physicsbasedanimationtoolkit_b200 as pbat
+from physicsbasedanimationtoolkit_b200 import _lib, meshes
+
+PREV = 0x80000000
+
+
+def plan_of(X, T, colors, constrained, tile_iters=0):
+    L = _lib.lib()
+    nV, nT = X.shape[1], T.shape[1]
+    Xc = np.ascontiguousarray(X.T, np.float64)
+    Ec = np.ascontiguousarray(T.T, np.int64)
+    col = np.ascontiguousarray(colors, np.int64)
+    con = np.ascontiguousarray(constrained, np.uint8)
+    h = C.c_void_p()
+    _lib.check(L.vbdx_debug_plan_create(nV, nT, Ec.ctypes.data, col.ctypes.data, con.ctypes.data, Xc.ctypes.data, tile_iters, C.byref(h)))
+    try:
+        sizes = np.zeros(5, np.int64)
+        _lib.check(L.vbdx_debug_plan_get(h, 0, sizes.ctypes.data))
+        n_tiles, n_ids, n_colors, n_active, ghost_begin = (int(v) for v in sizes)
+        tiles = np.zeros((n_tiles, 4), np.uint32)
+        ids = np.zeros(n_ids, np.uint32)
+        ctb = np.zeros(n_colors + 1, np.uint32)
+        new2old = np.zeros(nV, np.int32)
+        for what, a in ((1, tiles), (2, ids), (3, ctb), (4, new2old)):
+            _lib.check(L.vbdx_debug_plan_get(h, what, a.ctypes.data))
+    finally:
+        L.vbdx_debug_plan_destroy(h)
+    return dict(tiles=tiles, ids=ids, ctb=ctb, new2old=new2old, n_active=n_active, n_colors=n_colors)
+
+
+def simulate(plan, colors, iterations, n_warps, rng, neighbours):
+    tiles, ids, ctb = plan["tiles"], plan["ids"], plan["ctb"]
+    n_active, n_colors, new2old = plan["n_active"], plan["n_colors"], plan["new2old"]
+    icolor = np.asarray(colors)[new2old]                      # colour by internal id
+    nV = new2old.size
+    T0 = 5
+    tagQ = np.full(nV, T0, np.int64)                          # pre-step: every vertex carries T0 in both buffers
+    tagP = np.full(nV, T0, np.int64)
+    # per-warp programme: (sweep k, tile) in (k, colour) order, tiles of a colour dealt round-robin
+    prog = [[] for _ in range(n_warps)]
+    for k in range(iterations):
+        for c in range(n_colors):
+            for j, t in enumerate(range(int(ctb[c]), int(ctb[c + 1]))):
+                prog[j % n_warps].append((k, t))
+    pc = [0] * n_warps
+    pending = [None] * n_warps                                # a tile that has read but not written yet
+    remaining = sum(len(p) for p in prog)
+    reads_checked = 0
+    while remaining:
+        order = rng.permutation(n_warps)
+        progressed = False
+        for w in order:
+            if pending[w] is not None:
+                if rng.random() < 0.5:                        # the write lands some time after the read
+                    k, t = pending[w]
+                    vbase, meta = int(tiles[t, 1]), int(tiles[t, 2])
+                    nverts = (meta >> 3) & 63
+                    tagQ[vbase:vbase + nverts] = T0 + k + 1
+                    tagP[vbase:vbase + nverts] = T0 + k + 1
+                    pending[w] = None
+                    pc[w] += 1
+                    remaining -= 1
+                progressed = True
+                continue
+            if pc[w] >= len(prog[w]):
+                continue
+            k, t = prog[w][pc[w]]
+            vbase, meta, ring_start = int(tiles[t, 1]), int(tiles[t, 2]), int(tiles[t, 3])
+            chunks = (meta >> 9) & 63
+            nverts = (meta >> 3) & 63
+            entries = ids[ring_start:ring_start + 32 * chunks]
+            base = (entries & ~np.uint32(PREV)).astype(np.int64)
+            prev = (entries & np.uint32(PREV)) != 0
+            checked = (base < n_active) & ~((base == vbase) & ~prev)
+            expect = T0 + k + np.where(prev, 0, 1)
+            have = np.where(prev, tagP[base], tagQ[base])
+            newer = checked & (have > expect)
+            assert not newer.any(), f"overwrite hazard: tile {t} sweep {k} would read a newer write of vertex {base[newer][0]}"
+            if (checked & (have != expect)).any():
+                continue                                       # keeps polling
+            # dependencies met: this is what the barrier schedule reads
+            my_color = icolor[vbase]
+            nb = base[checked]
+            lower = icolor[nb] < my_color
+            assert np.array_equal(prev[checked], ~lower | (nb >= vbase) & (nb < vbase + nverts)), "previous-iterate flags"
+            # every swept neighbour of every vertex of the tile is listed (else it could be overwritten unnoticed)
+            for v in range(vbase, vbase + nverts):
+                need = neighbours[v]
+                assert np.isin(need[need < n_active], nb).all(), f"tile {t}: a swept neighbour of vertex {v} is missing from its ring list"
+            reads_checked += int(checked.sum())
+            pending[w] = (k, t)
+            progressed = True
+        assert progressed, "deadlock: no warp can proceed"
+    assert (tagQ[:n_active] == T0 + iterations).all()
+    return reads_checked
+
+
+def ring_neighbours(T, old2new, nV):
+    nb = [set() for _ in range(nV)]
+    for tet in T.T:
+        for a in tet:
+            for b in tet:
+                if a != b:
+                    nb[old2new[a]].add(old2new[b])
+    return [np.fromiter(s, dtype=np.int64, count=len(s)) for s in nb]
+
+
+def case(X, T, dbc, tile_iters, n_warps, seed, iterations=3):
+    nV = X.shape[1]
+    colors = pbat.graph.mesh_greedy_color(T, nV)
+    constrained = np.zeros(nV, np.uint8)
+    constrained[dbc] = 1
+    plan = plan_of(X, T, colors, constrained, tile_iters)
+    old2new = np.empty(nV, np.int64)
+    old2new[plan["new2old"]] = np.arange(nV)
+    nbs = ring_neighbours(T, old2new, nV)
+    return simulate(plan, colors, iterations, n_warps, np.random.default_rng(seed), nbs)
+
+
+@pytest.mark.parametrize("tile_iters,n_warps", [(0, 3), (0, 64), (1, 7), (3, 1000)])
+def test_protocol_on_a_grid(tile_iters, n_warps):
+    X, T = meshes.tet_grid(6, 5, 4, 0.1)
+    assert case(X, T, np.flatnonzero(X[0] == 0), tile_iters, n_warps, seed=tile_iters + n_warps) > 1000
+
+
+def test_protocol_with_extreme_valence_and_ragged_components():
+    from test_gpu_edge_cases import icosphere_star
+
+    Xs, Ts = icosphere_star()                                   # a vertex with 80 incident tets: rings of several chunks
+    Xa, Ta = meshes.tet_grid(3, 3, 2, 0.2, origin=(2.0, 0.0, 0.0))
+    Xb = np.array([[5., 5.3, 5., 5.], [0., 0., 0.3, 0.], [0., 0., 0., 0.3]])
+    Tb = np.array([[0], [1], [2], [3]], dtype=np.int64)
+    X = np.concatenate([Xs, Xa, Xb], axis=1)
+    T = np.concatenate([Ts, Ta + Xs.shape[1], Tb + Xs.shape[1] + Xa.shape[1]], axis=1)
+    dbc = np.flatnonzero(X[2] > 0.25)
+    for tile_iters, n_warps, seed in ((0, 5, 1), (2, 2, 2), (8, 40, 3)):
+        assert case(X, T, dbc, tile_iters, n_warps, seed) > 500
+
+
+def test_protocol_without_constraints_and_single_warp():
+    X, T = meshes.tet_grid(3, 3, 3, 0.1)
+    assert case(X, T, np.zeros(0, int), 0, 1, seed=9, iterations=4) > 500      # one warp: pure programme order
