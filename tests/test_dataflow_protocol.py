@@ -162,3 +162,108 @@ def test_protocol_with_extreme_valence_and_ragged_components():
 def test_protocol_without_constraints_and_single_warp():
     X, T = meshes.tet_grid(3, 3, 3, 0.1)
     assert case(X, T, np.zeros(0, int), 0, 1, seed=9, iterations=4) > 500      # one warp: pure programme order
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# several GPUs: the same protocol across the halo.  A ghost exists twice on the reading GPU (one copy per
+# parity of the write number); the owner's store of write t goes into copy t & 1 and may take arbitrarily long to arrive.
+# ---------------------------------------------------------------------------------------------------------------------
+def simulate_ranks(X, T, dbc, world, iterations, n_warps, rng, tile_iters=0):
+    from physicsbasedanimationtoolkit_b200.dist import LocalProblem, partition_slabs
+
+    nV = X.shape[1]
+    colors = pbat.graph.mesh_greedy_color(T, nV)
+    owner = partition_slabs(X, world, 0)
+    T0 = 6
+    ranks = []
+    for r in range(world):
+        lp = LocalProblem(r, owner, X, T, colors, dbc)
+        con = np.zeros(lp.l2g.size, np.uint8)
+        con[lp.dbc] = 1
+        con[lp.ghost_local] = 2
+        plan = plan_of(lp.X, lp.T, lp.colors, con, tile_iters)
+        n_loc = lp.l2g.size
+        glob_of_internal = lp.l2g[plan["new2old"]]
+        ghost_begin = n_loc - lp.ghost_local.size
+        prog = [[] for _ in range(n_warps)]
+        for k in range(iterations):
+            for c in range(plan["n_colors"]):
+                for j, t in enumerate(range(int(plan["ctb"][c]), int(plan["ctb"][c + 1]))):
+                    prog[j % n_warps].append((k, t))
+        ranks.append(dict(lp=lp, plan=plan, glob=glob_of_internal, ghost_begin=ghost_begin, prog=prog, pc=[0] * n_warps,
+                          pending=[None] * n_warps, tagQ=np.full(n_loc, T0, np.int64), tagP=np.full(n_loc, T0, np.int64),
+                          gQ=np.full((2, n_loc), -1, np.int64), gP=np.full((2, n_loc), -1, np.int64)))
+    # the pre-step pushed every ghost with T0 and a barrier followed
+    for R in ranks:
+        R["gQ"][T0 & 1, R["ghost_begin"]:] = T0
+        R["gP"][T0 & 1, R["ghost_begin"]:] = T0
+    # where an owned vertex is a ghost: global id -> [(rank, internal ghost id)]
+    holders = {}
+    for r, R in enumerate(ranks):
+        for i in range(R["ghost_begin"], R["glob"].size):
+            holders.setdefault(int(R["glob"][i]), []).append((r, i))
+    wire = []                                                     # stores under way: (rank, ghost, tag)
+    remaining = sum(len(p) for R in ranks for p in R["prog"])
+    checked_ghost_reads = 0
+    while remaining:
+        progressed = False
+        # some stores arrive, in any order
+        rng.shuffle(wire)
+        while wire and rng.random() < 0.6:
+            r, i, tag = wire.pop()
+            slotQ, slotP = ranks[r]["gQ"][tag & 1], ranks[r]["gP"][tag & 1]
+            assert slotQ[i] < tag, "a store overtook a later store to the same ghost copy"
+            slotQ[i] = slotP[i] = tag
+            progressed = True
+        for r in rng.permutation(world):
+            R = ranks[r]
+            plan = R["plan"]
+            tiles, ids, n_active = plan["tiles"], plan["ids"], plan["n_active"]
+            for w in rng.permutation(n_warps):
+                if R["pending"][w] is not None:
+                    if rng.random() < 0.5:
+                        k, t = R["pending"][w]
+                        vbase, nverts = int(tiles[t, 1]), (int(tiles[t, 2]) >> 3) & 63
+                        tag = T0 + k + 1
+                        R["tagQ"][vbase:vbase + nverts] = tag
+                        R["tagP"][vbase:vbase + nverts] = tag
+                        for v in range(vbase, vbase + nverts):
+                            for dest in holders.get(int(R["glob"][v]), ()):
+                                wire.append((dest[0], dest[1], tag))
+                        R["pending"][w] = None
+                        R["pc"][w] += 1
+                        remaining -= 1
+                    progressed = True
+                    continue
+                if R["pc"][w] >= len(R["prog"][w]):
+                    continue
+                k, t = R["prog"][w][R["pc"][w]]
+                vbase, meta, ring_start = int(tiles[t, 1]), int(tiles[t, 2]), int(tiles[t, 3])
+                entries = ids[ring_start:ring_start + 32 * ((meta >> 9) & 63)]
+                base = (entries & ~np.uint32(PREV)).astype(np.int64)
+                prev = (entries & np.uint32(PREV)) != 0
+                expect = T0 + k + np.where(prev, 0, 1)
+                local = (base < n_active) & ~((base == vbase) & ~prev)
+                ghost = base >= R["ghost_begin"]
+                have = np.where(prev, R["tagP"][base], R["tagQ"][base])
+                par = expect & 1
+                have_g = np.where(prev, R["gP"][par, base], R["gQ"][par, base])
+                have = np.where(ghost, have_g, have)
+                check = local | ghost
+                assert not (check & (have > expect)).any(), f"rank {r} tile {t} sweep {k}: a value was overwritten before it was read"
+                if (check & (have != expect)).any():
+                    continue
+                checked_ghost_reads += int(ghost.sum())
+                R["pending"][w] = (k, t)
+                progressed = True
+        assert progressed or wire, "deadlock: no warp on any GPU can proceed and nothing is under way"
+    for R in ranks:
+        assert (R["tagQ"][:R["plan"]["n_active"]] == T0 + iterations).all()
+    return checked_ghost_reads
+
+
+@pytest.mark.parametrize("world,n_warps", [(2, 4), (3, 2), (4, 16), (8, 3)])
+def test_protocol_across_gpus(world, n_warps):
+    X, T = meshes.tet_grid(3 * world, 4, 3, 0.1)
+    dbc = np.flatnonzero(X[2] == 0)                              # a constrained face crossing every interface
+    assert simulate_ranks(X, T, dbc, world, 4, n_warps, np.random.default_rng(world * 100 + n_warps)) > 200
