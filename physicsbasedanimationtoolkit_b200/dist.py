@@ -29,6 +29,30 @@ def partition_slabs(X, nparts: int, axis: int = 0):
     return owner
 
 
+def partition_rcb(X, nparts: int):
+    """Owner rank of every vertex by recursive coordinate bisection (general meshes): the
+    current vertex set is split along the longest axis of its bounding box into two sets whose sizes are proportional
+    to the numbers of ranks they will hold, recursively; ties on the coordinate are broken by vertex id.  A rank may
+    then have more than two neighbours (the device side allows up to 8 ranks in all)."""
+    n = X.shape[1]
+    owner = np.empty(n, dtype=np.int64)
+
+    def split(idx, first, parts):
+        if parts == 1:
+            owner[idx] = first
+            return
+        ext = X[:, idx].max(axis=1) - X[:, idx].min(axis=1)
+        ax = int(np.argmax(ext))
+        order = idx[np.lexsort((idx, X[ax, idx]))]
+        left = parts // 2
+        cut = (order.size * left) // parts
+        split(order[:cut], first, left)
+        split(order[cut:], first + left, parts - left)
+
+    split(np.arange(n), 0, int(nparts))
+    return owner
+
+
 class LocalProblem:
     """What one rank simulates: global ids of its local vertices (owned first, ascending; then the
     constrained vertices of other ranks its tets touch; then ghosts, ascending), the local tets in local
@@ -123,7 +147,7 @@ class DomainDecomposedIntegrator:
     lock-step with its peers.  ``x``/``v`` return the *owned* part; ``gather_x()`` assembles the global
     array on every rank."""
 
-    def __init__(self, X, T, *, dbc=None, v=None, rho_chebyshev=None, colors=None, axis=0, **tuning):
+    def __init__(self, X, T, *, dbc=None, v=None, rho_chebyshev=None, colors=None, axis=0, partition="slabs", **tuning):
         import torch
         import torch.distributed as dist
 
@@ -135,7 +159,16 @@ class DomainDecomposedIntegrator:
         nV = X.shape[1]
         if colors is None:
             colors = graph.mesh_greedy_color(T, nV)         # global colouring: colour c means the same everywhere
-        owner = partition_slabs(X, self.world, axis)
+        # partition: "slabs" along `axis` (the default, at most two neighbours per GPU), "rcb" (recursive coordinate
+        # bisection, general shapes), or an explicit owner rank per vertex
+        if isinstance(partition, str):
+            if partition not in ("slabs", "rcb"):
+                raise ValueError("partition must be 'slabs', 'rcb' or an array of owner ranks")
+            owner = partition_slabs(X, self.world, axis) if partition == "slabs" else partition_rcb(X, self.world)
+        else:
+            owner = np.asarray(partition, dtype=np.int64)
+            if owner.shape != (nV,) or owner.min() < 0 or owner.max() >= self.world:
+                raise ValueError("an explicit partition needs one owner rank in [0, world) per vertex")
         self.local = lp = LocalProblem(self.rank, owner, X, T, colors, dbc, v)
         self.nV_global = nV
         data = Data().with_volume_mesh(lp.X, lp.T)

@@ -168,12 +168,12 @@ def test_protocol_without_constraints_and_single_warp():
 # several GPUs: the same protocol across the halo.  A ghost exists twice on the reading GPU (one copy per
 # parity of the write number); the owner's store of write t goes into copy t & 1 and may take arbitrarily long to arrive.
 # ---------------------------------------------------------------------------------------------------------------------
-def simulate_ranks(X, T, dbc, world, iterations, n_warps, rng, tile_iters=0):
-    from physicsbasedanimationtoolkit_b200.dist import LocalProblem, partition_slabs
+def simulate_ranks(X, T, dbc, world, iterations, n_warps, rng, tile_iters=0, partition="slabs"):
+    from physicsbasedanimationtoolkit_b200.dist import LocalProblem, partition_rcb, partition_slabs
 
     nV = X.shape[1]
     colors = pbat.graph.mesh_greedy_color(T, nV)
-    owner = partition_slabs(X, world, 0)
+    owner = partition_slabs(X, world, 0) if partition == "slabs" else partition_rcb(X, world)
     T0 = 6
     ranks = []
     for r in range(world):
@@ -267,3 +267,11 @@ def test_protocol_across_gpus(world, n_warps):
     X, T = meshes.tet_grid(3 * world, 4, 3, 0.1)
     dbc = np.flatnonzero(X[2] == 0)                              # a constrained face crossing every interface
     assert simulate_ranks(X, T, dbc, world, 4, n_warps, np.random.default_rng(world * 100 + n_warps)) > 200
+
+
+@pytest.mark.parametrize("world", [4, 7, 8])
+def test_protocol_across_gpus_with_many_neighbours(world):
+    """Recursive coordinate bisection of a cube: GPUs with up to world - 1 neighbours."""
+    X, T = meshes.tet_grid(6, 6, 6, 0.1)
+    dbc = np.flatnonzero(X[2] == 0)
+    assert simulate_ranks(X, T, dbc, world, 3, 5, np.random.default_rng(world), partition="rcb") > 500

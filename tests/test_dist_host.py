@@ -34,6 +34,24 @@ def test_partition_and_local_problem_serial():
     assert (seen_tets >= 1).all()
 
 
+@pytest.mark.parametrize("nparts", [2, 3, 5, 8])
+def test_recursive_coordinate_bisection(nparts):
+    X, T = meshes.tet_grid(7, 6, 5, 0.1)
+    colors = pbat.graph.mesh_greedy_color(T, X.shape[1])
+    owner = dd.partition_rcb(X, nparts)
+    counts = np.bincount(owner, minlength=nparts)
+    assert counts.min() > 0 and counts.max() - counts.min() <= nparts          # balanced up to rounding at every level
+    assert np.array_equal(owner, dd.partition_rcb(X, nparts))                  # deterministic
+    # compact parts: every part's bounding box holds few foreign vertices compared with a random assignment
+    seen = np.zeros(T.shape[1], int)
+    for r in range(nparts):
+        lp = dd.LocalProblem(r, owner, X, T, colors, dbc=np.flatnonzero(X[2] == 0))
+        seen[lp.tet_ids] += 1
+        assert lp.ghost_local.size < lp.n_owned * 4
+        assert set(np.unique(lp.ghost_owner)) <= set(range(nparts)) - {r}
+    assert (seen >= 1).all()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
