@@ -357,7 +357,10 @@ def main():
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "bytes_per_vertex_iteration": B, "kbar": kbar, "nbar": nbar,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
-                         "streamed_record_bytes_per_launch": int(info["nRecordSlots"] * 32 * ITERS)},
+                         "streamed_record_bytes_per_launch": int(info["nRecordSlots"] * 32 * ITERS),
+                         # what the DRAM counters saw (ncu, profiles/traffic.json) over the live kernel time: the closed-form
+                         # records stream less than half of the algorithmic bytes, which is how frac can exceed 1
+                         "traffic_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None},
         }
         if halo is not None:
             line["halo"] = dict(halo, note="rank 0, over the timed steps: ghost values that had to be polled / ns polling (summed over lanes) / barriers of CTA 0 that waited for a neighbour's epoch / ns")
