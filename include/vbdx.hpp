@@ -72,7 +72,6 @@ class Integrator
     }
     vbdx_integrator* Handle() const { return mImpl; }
 
-  private:
     static void Check(vbdx_status s)
     {
         if (s == VBDX_OK)
@@ -82,11 +81,118 @@ class Integrator
             throw std::invalid_argument(what);
         throw std::runtime_error(what);
     }
+
+  protected:
+    explicit Integrator(vbdx_integrator* adopted) : mImpl(adopted) {}
+    void SetVertexCount(int64_t nV) { mNV = nV; }
+
+  private:
     vbdx_integrator* mImpl{nullptr};
     int64_t mNV{0};
 };
 
+/// Independent scenes behind one handle (vbdx_create_batch): an Integrator over the concatenation of the scenes.
+class BatchIntegrator : public Integrator
+{
+  public:
+    explicit BatchIntegrator(std::vector<vbdx_data_desc> const& scenes) : Integrator(Create(scenes))
+    {
+        int32_t n = 0;
+        vbdx_batch_offsets(Handle(), &n, nullptr);
+        mOffsets.resize(static_cast<std::size_t>(n) + 1);
+        vbdx_batch_offsets(Handle(), nullptr, mOffsets.data());
+        SetVertexCount(mOffsets.back());
+    }
+    /// first vertex of every scene, then the total
+    std::vector<int64_t> const& Offsets() const { return mOffsets; }
+
+  private:
+    static vbdx_integrator* Create(std::vector<vbdx_data_desc> const& scenes)
+    {
+        vbdx_integrator* h = nullptr;
+        Check(vbdx_create_batch(scenes.data(), static_cast<int32_t>(scenes.size()), &h));
+        return h;
+    }
+    std::vector<int64_t> mOffsets;
+};
+
 }  // namespace vbd
+
+namespace geometry {
+
+/// pbat::gpu::geometry::Bvh (gpu/geometry/Bvh.h:33-148) over raw 3 x n column-major float boxes
+class Bvh
+{
+  public:
+    Bvh(int64_t maxBoxes, int64_t maxOverlaps) : mMaxOverlaps(maxOverlaps) { vbd::Integrator::Check(vbdx_bvh_create(maxBoxes, &mImpl)); }
+    Bvh(Bvh const&)            = delete;
+    Bvh& operator=(Bvh const&) = delete;
+    ~Bvh() { vbdx_bvh_destroy(mImpl); }
+    void Build(int64_t n, float const* lo, float const* hi, float const wmin[3], float const wmax[3])
+    {
+        vbd::Integrator::Check(vbdx_bvh_build(mImpl, n, lo, hi, wmin, wmax));
+        mN = n;
+    }
+    /// 2 x #overlaps (column per pair, bi < bj); set == nullptr: all pairs, else only pairs from different sets
+    std::vector<int32_t> DetectOverlaps(int32_t const* set = nullptr)
+    {
+        std::vector<int32_t> pairs(2 * static_cast<std::size_t>(mMaxOverlaps > 0 ? mMaxOverlaps : 1));
+        int64_t found = 0;
+        vbd::Integrator::Check(vbdx_bvh_detect_overlaps(mImpl, set, mMaxOverlaps, pairs.data(), &found));
+        pairs.resize(2 * static_cast<std::size_t>(found < mMaxOverlaps ? found : mMaxOverlaps));
+        return pairs;
+    }
+    std::vector<int32_t> PointTriangleNearestNeighbors(int64_t nQ, float const* X, int64_t nP, float const* V, int32_t const* F)
+    {
+        std::vector<int32_t> nn(static_cast<std::size_t>(nQ));
+        vbd::Integrator::Check(vbdx_bvh_nearest_triangles(mImpl, nQ, X, nP, V, mN, F, nn.data()));
+        return nn;
+    }
+    vbdx_bvh* Handle() const { return mImpl; }
+
+  private:
+    vbdx_bvh* mImpl{nullptr};
+    int64_t mMaxOverlaps{0}, mN{0};
+};
+
+}  // namespace geometry
+
+namespace contact {
+
+/// pbat::gpu::contact::VertexTriangleMixedCcdDcd (gpu/contact/VertexTriangleMixedCcdDcd.h) over raw arrays
+class VertexTriangleMixedCcdDcd
+{
+  public:
+    VertexTriangleMixedCcdDcd(int64_t nV, int64_t const* B, int64_t const* V, int64_t nCV, int64_t const* F, int64_t nF) : mNCV(nCV)
+    {
+        vbd::Integrator::Check(vbdx_contact_create(nV, B, V, nCV, F, nF, &mImpl));
+    }
+    VertexTriangleMixedCcdDcd(VertexTriangleMixedCcdDcd const&)            = delete;
+    VertexTriangleMixedCcdDcd& operator=(VertexTriangleMixedCcdDcd const&) = delete;
+    ~VertexTriangleMixedCcdDcd() { vbdx_contact_destroy(mImpl); }
+    void InitializeActiveSet(float const* xt, float const* xtp1, float const wmin[3], float const wmax[3])
+    {
+        vbd::Integrator::Check(vbdx_contact_initialize_active_set(mImpl, xt, xtp1, wmin, wmax));
+    }
+    void UpdateActiveSet(float const* x) { vbd::Integrator::Check(vbdx_contact_update_active_set(mImpl, x)); }
+    void FinalizeActiveSet(float const* x) { vbd::Integrator::Check(vbdx_contact_finalize_active_set(mImpl, x)); }
+    void SetNearestNeighbourFloatingPointTolerance(float eps) { vbd::Integrator::Check(vbdx_contact_set_eps(mImpl, eps)); }
+    /// indices (into V) of the active vertices
+    std::vector<int32_t> ActiveVertices() const
+    {
+        std::vector<int32_t> av(static_cast<std::size_t>(mNCV));
+        int64_t n = 0;
+        vbd::Integrator::Check(vbdx_contact_get(mImpl, nullptr, nullptr, av.data(), &n));
+        av.resize(static_cast<std::size_t>(n));
+        return av;
+    }
+
+  private:
+    vbdx_contact* mImpl{nullptr};
+    int64_t mNCV{0};
+};
+
+}  // namespace contact
 }  // namespace gpu
 }  // namespace pbat_b200
 

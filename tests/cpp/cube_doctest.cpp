@@ -92,3 +92,20 @@ int main()
     std::printf("%s (%d failed checks)\n", bad ? "FAIL" : "PASS", bad);
     return bad ? 1 : 0;
 }
+
+// the other wrappers of include/vbdx.hpp must at least compile and link (they are exercised from Python on the GPU)
+[[maybe_unused]] static void CompileOnly()
+{
+    vbdx_data_desc d;
+    vbdx_data_desc_init(&d);
+    pbat_b200::gpu::vbd::BatchIntegrator batch(std::vector<vbdx_data_desc>{d, d});
+    (void)batch.Offsets();
+    float const box[3] = {0, 0, 0};
+    pbat_b200::gpu::geometry::Bvh bvh(4, 8);
+    bvh.Build(1, box, box, box, box);
+    (void)bvh.DetectOverlaps();
+    int64_t const ids[3] = {0, 1, 2};
+    pbat_b200::gpu::contact::VertexTriangleMixedCcdDcd ccd(3, nullptr, ids, 3, ids, 1);
+    ccd.InitializeActiveSet(box, box, box, box);
+    (void)ccd.ActiveVertices();
+}
