@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvbdx.so")
+LIB_PATH = os.environ.get("VBDX_LIBRARY") or os.path.join(_HERE, "libvbdx.so")  # VBDX_LIBRARY: A/B runs against another build
 
 VBDX_OK, VBDX_INVALID_ARGUMENT, VBDX_NO_DEVICE, VBDX_CUDA_ERROR, VBDX_OUT_OF_MEMORY, VBDX_UNSUPPORTED = range(6)
 FLAG_ADAPTIVE_VBD_GPU_HISTORY = 1

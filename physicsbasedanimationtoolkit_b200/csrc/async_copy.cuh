@@ -91,4 +91,10 @@ __device__ __forceinline__ void BulkLoad(uint32_t dstSmem, const void* srcGmem, 
         : "memory");
 }
 
+// asks the L2 to fetch a contiguous range (no destination, no completion): one instruction of one lane
+__device__ __forceinline__ void BulkPrefetchL2(const void* srcGmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(srcGmem), "r"(bytes) : "memory");
+}
+
 }  // namespace vbdx

@@ -747,6 +747,8 @@ __device__ __forceinline__ void ProcessTile(
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;
         }
     }
+    if (trace && lane == 0)
+        trace[11] = GlobalTimer();  // new positions stored
 }
 
 // Sweep of one colour: every warp walks its share of the colour's tiles.

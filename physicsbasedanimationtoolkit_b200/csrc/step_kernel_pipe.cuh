@@ -25,15 +25,21 @@ struct PipeParams {
     int clusterBarrier; // the grid is ONE thread-block cluster: colours are separated by the hardware cluster barrier
     int dataflow;       // no barrier between colours: every position carries the number of its write in .w, a tile checks
                         // the values it gathered and polls the few that are not there yet (see AwaitTags)
+    // the lean barrier-free kernel (step_kernel_flow.cuh) walks a schedule the host laid out (BuildFlowSchedule)
+    const uint32_t* __restrict__ flowWarpBegin;  // [grid warps + 1]: range of warp w (w = warp-in-CTA * gridDim.x + CTA) in flowTiles
+    const uint4* __restrict__ flowTiles;         // tile descriptors in warp-major order; .w = first entry of the tile in flowIds
+    const uint32_t* __restrict__ flowIds;        // pre-decoded ring entries, [group of 4 chunks][lane][4]
 };
+// per-warp shared memory besides the staging, id and record buffers: 4 tile descriptors, 2 mbarriers, 4 sweep numbers
+constexpr uint32_t kPipeWarpFixed = 4 * 16 + 16 + 16;
 
 constexpr int kPipeMaxThreads = 544;  // compiled for up to 16 compute warps + 1 barrier warp per CTA (<= 120 registers)
 
 // shared-memory footprint (host and device must agree)
 __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
 {
-    size_t b = ((static_cast<size_t>(nColors) + 1 + 3) / 4) * 16;  // colour -> first tile table
-    b += static_cast<size_t>(warps) * (4 * 16 + 16 + 2 * stageEntries * 4 + stageEntries * 16 + static_cast<size_t>(maxIters) * kBlockBytes);
+    size_t b = 2 * ((static_cast<size_t>(nColors) + 1 + 3) / 4) * 16;  // colour -> first tile table, colour -> first warp of the deal
+    b += static_cast<size_t>(warps) * (kPipeWarpFixed + 2 * stageEntries * 4 + stageEntries * 16 + static_cast<size_t>(maxIters) * kBlockBytes);
     return b;
 }
 
@@ -107,12 +113,11 @@ __device__ __forceinline__ float4 LoadPosSys(const float4* q)
 // (lag = 2 inside a substep -- a copy is rewritten nColors + 1 phases after its last reader at the earliest --
 // and 0 at the end of a substep, whose pre-step rewrites every ghost).  A peer that never shows up raises
 // distError instead of hanging the GPU.
-__device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
-                                                unsigned int lag, unsigned long long* trace)
+// first half: this CTA's arrival (release: everything its threads wrote is ordered before the arrival)
+__device__ __forceinline__ void BarrierSignal(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
+                                              unsigned long long* trace)
 {
-    NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
     ++epoch;
-    unsigned int const e = p.epochBase + epoch;
     if (lane == 0)
     {
         if (trace)
@@ -123,7 +128,13 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
             trace[1] = GlobalTimer();
     }
     __syncwarp();
-    NamedArrive(kBarFenced, blockDim.x);
+}
+
+// second half: wait for every CTA of this GPU and -- domain decomposition -- for the neighbours' epochs
+__device__ __forceinline__ void BarrierAwait(StepParams const& p, unsigned int const& target, unsigned int const& epoch, uint32_t lane,
+                                             unsigned int lag, unsigned long long* trace)
+{
+    unsigned int const e = p.epochBase + epoch;
     if (lane == 0)
     {
         // The neighbours' epochs: one relaxed look before the local wait (e - lag is old news in steady state; the
@@ -165,6 +176,15 @@ __device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned in
             trace[3] = GlobalTimer();
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void BarrierWarpStep(StepParams const& p, unsigned int& target, unsigned int& epoch, uint32_t lane,
+                                                unsigned int lag, unsigned long long* trace)
+{
+    NamedSync(kBarArrived, blockDim.x);  // every compute thread of this CTA is done with the phase
+    BarrierSignal(p, target, epoch, lane, trace);
+    NamedArrive(kBarFenced, blockDim.x);
+    BarrierAwait(p, target, epoch, lane, lag, trace);
     NamedArrive(kBarReleased, blockDim.x);
 }
 
@@ -193,14 +213,14 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) StepKernelPipe(const __gri
     uint32_t const gwarp = warp * gridDim.x + blockIdx.x, gWarps = nWarps * gridDim.x;
 
     uint32_t* const colorTab = reinterpret_cast<uint32_t*>(smem);
-    unsigned char* mine      = smem + ((static_cast<size_t>(nC) + 1 + 3) / 4) * 16 +
-                          static_cast<size_t>(warp) * (64 + 16 + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
+    unsigned char* mine      = smem + 2 * ((static_cast<size_t>(nC) + 1 + 3) / 4) * 16 +
+                          static_cast<size_t>(warp) * (kPipeWarpFixed + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
     float4* const recBuf   = reinterpret_cast<float4*>(mine);
     float4* const stage    = recBuf + static_cast<size_t>(pp.maxIters) * kBlockFloat4;
     uint4* const tdBuf     = reinterpret_cast<uint4*>(stage + SE);
     uint32_t const barRec  = SmemAddr(tdBuf + 4);      // completion of the bulk copy of a tile's records
     uint32_t const barIds  = barRec + 8;                // ... of a tile's ring ids
-    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(tdBuf + 5);
+    uint32_t* const idsBuf = reinterpret_cast<uint32_t*>(tdBuf + 6);
 
     for (uint32_t c = threadIdx.x; c <= nC; c += blockDim.x)
         colorTab[c] = p.colorTileBegin[c];

@@ -12,6 +12,7 @@
 #include "setup_kernels.cuh"
 #include "step_kernel.cuh"
 #include "step_kernel_pipe.cuh"
+#include "step_kernel_flow.cuh"
 #include "step_kernel_tma.cuh"
 #include "vbdx_internal.h"
 
@@ -45,6 +46,7 @@ struct Integrator {
     int gridBlocks = 0, blockThreads = 256;
     int variant = VBDX_KERNEL_DIRECT;
     bool dataflow    = true;   // barrier-free sweeps where they apply (PipeParams::dataflow); VBDX_DATAFLOW=0 turns them off
+    bool flowKernel  = true;   // ... run by the lean kernel of step_kernel_flow.cuh; VBDX_FLOW=0 selects StepKernelPipe<.., dataflow>
     bool usedDataflow  = false;
     unsigned int dfTag = 1;    // write numbers used by earlier launches (single GPU)
     bool clusterMode = false;  // the pipelined kernel launched as ONE thread-block cluster (VBDX_KERNEL_CLUSTER)
@@ -83,6 +85,11 @@ struct Integrator {
     DevBuf<uint32_t> dCtaRange, dCtaBlockBegin, dRingIds, dColorTileBegin;
     uint32_t stageEntries = 32;
     DevBuf<int32_t> dNew2Old, dOld2New;
+    // schedule of the lean barrier-free kernel (step_kernel_flow.cuh; BuildFlowSchedule)
+    DevBuf<uint32_t> dFlowWarpBegin, dFlowIds;
+    DevBuf<uint4> dFlowTiles;
+    int pipeWarpsPerCta = 16;
+    void BuildFlowSchedule();
 
     // state
     DevBuf<float4> dPos, dHist, dXtildeM, dXt, dVel, dVtm1, dAext;
@@ -148,6 +155,27 @@ struct Integrator {
         return damp ? StepKernelPipe<false, true> : StepKernelPipe<false, false>;
     }
 
+    // the lean barrier-free kernel (step_kernel_flow.cuh): Stable Neo-Hookean, with or without Chebyshev / Rayleigh damping
+    PipeKernelFn KernelFlow() const
+    {
+        bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
+        bool const damp = kD != 0.0;
+        if (distWorld > 1 || nGhost > 0)
+        {
+            if (cheb)
+                return damp ? StepKernelFlow<true, true, true> : StepKernelFlow<true, false, true>;
+            return damp ? StepKernelFlow<false, true, true> : StepKernelFlow<false, false, true>;
+        }
+        if (cheb)
+            return damp ? StepKernelFlow<true, true, false> : StepKernelFlow<true, false, false>;
+        return damp ? StepKernelFlow<false, true, false> : StepKernelFlow<false, false, false>;
+    }
+    bool UseFlow(int iterations) const
+    {
+        return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterMode && !contact.enabled &&
+               material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && iterations > 0;
+    }
+
     TmaKernelFn KernelTma() const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
@@ -166,7 +194,8 @@ struct Integrator {
     void LaunchPreStep(StepParams const& q);
     bool WillSweepBarrierFree(int iterations) const
     {
-        return dataflow && variant == VBDX_KERNEL_PIPELINED && !clusterMode && !contact.enabled && kD == 0.0 && iterations > 0 && traceIteration < 0;
+        return UseFlow(iterations) ||
+               (dataflow && variant == VBDX_KERNEL_PIPELINED && !clusterMode && !contact.enabled && kD == 0.0 && iterations > 0);
     }
     void AndersonStep(StepParams const& p, double dt, int iterations, int substeps);
     void BroydenStep(StepParams const& p, double dt, int iterations, int substeps);
@@ -377,6 +406,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (d.consumer_warps <= 0 && PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters) > static_cast<size_t>(maxOptin))
         pipeWarps = 8;
     int const pipeThreads = pipeWarps * 32 + 32;
+    pipeWarpsPerCta       = pipeWarps;
     size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters);
     if (variant == VBDX_KERNEL_DEFAULT)
     {
@@ -394,6 +424,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     // the cluster variant IS the pipelined kernel, launched as one cluster and told to use the cluster barrier
     if (char const* e = std::getenv("VBDX_DATAFLOW"))
         dataflow = std::atoi(e) != 0;
+    if (char const* e = std::getenv("VBDX_FLOW"))
+        flowKernel = std::atoi(e) != 0;
     clusterMode = variant == VBDX_KERNEL_CLUSTER;
     if (clusterMode)
     {
@@ -420,6 +452,17 @@ void Integrator::Create(vbdx_data_desc const& d)
             VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
             int n = 0;
             VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
+            perSm = std::min(perSm, n);
+        }
+        // the lean barrier-free kernel: the same compute warps without the barrier warp
+        for (PipeKernelFn fn : {cheb0 ? StepKernelFlow<true, false, false> : StepKernelFlow<false, false, false>,
+                                cheb0 ? StepKernelFlow<true, true, false> : StepKernelFlow<false, true, false>,
+                                cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
+                                cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>})
+        {
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            int n = 0;
+            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads - 32, smemBytes));
             perSm = std::min(perSm, n);
         }
     }
@@ -468,6 +511,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && !clusterMode)  // tuning: fewer CTAs = cheaper grid barrier on small meshes
         gridBlocks = std::max(1, std::min(std::atoi(e), gridBlocks));
     PartitionTiles(plan, gridBlocks);
+    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN)
+        BuildFlowSchedule();
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
     dTiles.Upload(plan.tiles.data(), plan.tiles.size(), stream);
@@ -593,6 +638,70 @@ void Integrator::Create(vbdx_data_desc const& d)
         VBDX_CUDA(cudaStreamSynchronize(stream));
         cs.enabled = true;
     }
+}
+
+// What the lean barrier-free kernel walks (step_kernel_flow.cuh): per warp of the persistent grid the tiles it runs in one
+// sweep, in order (a colour's tiles are dealt round-robin over the warps, heaviest first, like the other kernels do on the
+// fly), and every tile's ring entries pre-decoded: final index into the position buffers plus previous-iterate / never-changes
+// / ghost bits, the four chunks of a lane packed into one 16-byte word.
+void Integrator::BuildFlowSchedule()
+{
+    uint32_t const gWarps = static_cast<uint32_t>(gridBlocks) * static_cast<uint32_t>(pipeWarpsPerCta);
+    size_t const nTiles   = plan.tiles.size();
+    bool const cheb       = acceleration == VBDX_ACCEL_CHEBYSHEV;
+    uint32_t const pOff   = cheb ? static_cast<uint32_t>(nV) : 0u;
+    Require(2 * static_cast<int64_t>(nV) < (int64_t(1) << 29), "mesh too large for the packed ring entries of the barrier-free kernel");
+    std::vector<uint32_t> idsStart(nTiles + 1, 0);
+    for (size_t t = 0; t < nTiles; ++t)
+        idsStart[t + 1] = idsStart[t] + ((TileChunks(plan.tiles[t].meta) + 3u) / 4u) * 128u;
+    std::vector<uint32_t> ids(idsStart[nTiles], kFlowStatic);
+    uint32_t const activeEnd = static_cast<uint32_t>(plan.nActive), ghostBegin = static_cast<uint32_t>(plan.ghostBegin);
+    for (size_t t = 0; t < nTiles; ++t)
+    {
+        TileDesc const& td    = plan.tiles[t];
+        uint32_t const chunks = TileChunks(td.meta);
+        for (uint32_t j = 0; j < ((chunks + 3u) / 4u) * 4u; ++j)
+            for (uint32_t lane = 0; lane < 32; ++lane)
+            {
+                uint32_t e = kFlowStatic | td.vbase;  // chunks beyond the tile's: never loaded
+                if (j < chunks)
+                {
+                    uint32_t const raw  = plan.ringIds[td.ringStart + 32u * j + lane];
+                    uint32_t const base = raw & ~kPrevFlag;
+                    bool const prev     = (raw & kPrevFlag) != 0u;
+                    if (raw == td.vbase)  // padding: the tile's first vertex without the flag
+                        e = kFlowStatic | base;
+                    else if (base >= ghostBegin)
+                        e = kFlowGhost | (prev ? kFlowPrev : 0u) | (base - ghostBegin);
+                    else
+                        e = (prev ? kFlowPrev : 0u) | (base >= activeEnd ? kFlowStatic : 0u) | (base + (prev ? pOff : 0u));
+                }
+                ids[idsStart[t] + (j >> 2) * 128u + lane * 4u + (j & 3u)] = e;
+            }
+    }
+    std::vector<uint32_t> wBegin(static_cast<size_t>(gWarps) + 1, 0);
+    for (int32_t c = 0; c < plan.nColors; ++c)
+        for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
+            ++wBegin[(t - plan.colorTileBegin[c]) % gWarps + 1];
+    for (uint32_t w = 0; w < gWarps; ++w)
+        wBegin[w + 1] += wBegin[w];
+    std::vector<uint4> seqTiles(nTiles);
+    std::vector<uint32_t> cursor(wBegin.begin(), wBegin.end() - 1);
+    for (int32_t c = 0; c < plan.nColors; ++c)
+        for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
+        {
+            TileDesc const& td = plan.tiles[t];
+            seqTiles[cursor[(t - plan.colorTileBegin[c]) % gWarps]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[t]);
+        }
+    dFlowWarpBegin.Alloc(wBegin.size(), &deviceBytes);
+    dFlowWarpBegin.Upload(wBegin.data(), wBegin.size(), stream);
+    dFlowTiles.Alloc(nTiles + 1, &deviceBytes);
+    if (nTiles)
+        dFlowTiles.Upload(seqTiles.data(), nTiles, stream);
+    dFlowIds.Alloc(ids.size() + 128, &deviceBytes);
+    if (!ids.empty())
+        dFlowIds.Upload(ids.data(), ids.size(), stream);
+    VBDX_CUDA(cudaStreamSynchronize(stream));  // the host vectors go out of scope
 }
 
 void Integrator::Step(double dt, int iterations, int substeps, bool sync)
@@ -731,10 +840,14 @@ void Integrator::LaunchStepKernel(StepParams const& q)
             // barrier-free sweeps: whole steps of the base / Chebyshev solve without damping or contact (whose reads go
             // beyond the 1-rings); partial launches (traces, windowed accelerators) keep the colour barriers
             pp.dataflow = WillSweepBarrierFree(q.iterations) && !q.skipPreStep && !q.skipPostStep && q.iterBegin == 0;
+            pp.flowWarpBegin = dFlowWarpBegin.p, pp.flowTiles = dFlowTiles.p, pp.flowIds = dFlowIds.p;
             usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
+            bool const flow = pp.dataflow != 0 && UseFlow(q.iterations);
+            // (the lean kernel has no barrier warp: same compute warps, same shared-memory layout, 32 threads fewer)
             VBDX_CUDA(cudaLaunchCooperativeKernel(
-                reinterpret_cast<void const*>(KernelPipe(pp.dataflow != 0)), dim3(gridBlocks), dim3(blockThreads), args, smemBytes, stream));
+                reinterpret_cast<void const*>(flow ? KernelFlow() : KernelPipe(pp.dataflow != 0)), dim3(gridBlocks),
+                dim3(flow ? blockThreads - 32 : blockThreads), args, smemBytes, stream));
         }
         else if (variant == VBDX_KERNEL_PIPELINED)
         {
