@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VBDX_ABI_VERSION 1
+#define VBDX_ABI_VERSION 2
 
 typedef enum vbdx_status {
     VBDX_OK               = 0,
@@ -45,8 +45,9 @@ typedef enum vbdx_initialization_strategy {
     VBDX_INIT_ADAPTIVE_PBAT          = 4
 } vbdx_initialization_strategy;
 
-/* sim/vbd/Enums.h:21-28 (only None and Chebyshev are implemented; the others return
- * VBDX_UNSUPPORTED at creation -- SURVEY.md section 8f) */
+/* sim/vbd/Enums.h:21-28.  All six are implemented: the base and Chebyshev solves run inside one persistent launch per
+ * step; Anderson, Nesterov, Broyden and TrustRegion wrap one-iteration launches of the same kernel with their device-side
+ * window / path kernels. */
 typedef enum vbdx_acceleration_strategy {
     VBDX_ACCEL_NONE         = 0,
     VBDX_ACCEL_CHEBYSHEV    = 1,
@@ -121,7 +122,14 @@ typedef struct vbdx_data_desc {
                               the pre-step; their positions are written by the owner.  NULL for a single-GPU problem */
     int64_t nGhosts;
     int32_t consumer_warps;/* tuning: (consumer) warps per CTA of the pipelined / TMA kernels (0 = default) */
-    int32_t window_size;   /* Anderson acceleration window (Data::mWindowSize, default 5) */
+    int32_t window_size;   /* Anderson / Broyden acceleration window (Data::mWindowSize, default 5) */
+    int32_t n_colors;      /* colours of the WHOLE problem when this handle simulates a part of it (domain decomposition: every
+                              rank must sweep the same number of colours); 0 = largest colour of this handle's vertices + 1 */
+    int32_t nesterov_start;/* Data::mNesterovAccelerationStart (sim/vbd/Data.h:239; default 3) */
+    double nesterov_L;     /* Data::mNesterovLipschitzConstant (sim/vbd/Data.h:238; default 1) */
+    double tr_eta, tr_tau; /* trust-region acceptance ratio and radius growth factor (sim/vbd/Data.h:241-242; defaults 0.2, 2) */
+    int32_t tr_curved;     /* Data::bCurved: curved (default) or linear accelerated path (sim/vbd/Data.h:243) */
+    int32_t reserved0;
 } vbdx_data_desc;
 
 /* Which persistent step kernel runs the sweeps.  Both compute the same arithmetic in the same order. */
@@ -283,13 +291,16 @@ vbdx_status vbdx_set_stream(vbdx_integrator* h, void* cuda_stream);
 typedef struct vbdx_info {
     int64_t nV, nT, nActiveVertices; /* nActiveVertices = vertices that are swept (non-Dirichlet) */
     int64_t nIncidences;             /* sum over swept vertices of incident tets */
-    int64_t nRecordSlots;            /* incidence record slots incl. padding (x 64 B = streamed bytes/sweep) */
+    int64_t nRecordSlots;            /* incidence record slots incl. padding (x 32 B = streamed bytes/sweep) */
     int32_t nColors, nTiles;
     int32_t gridBlocks, blockThreads; /* persistent launch shape */
     int32_t device, smCount;
     int64_t deviceBytes;             /* device memory held by the handle */
     int64_t kernelLaunches;          /* CUDA kernels launched by this handle since creation */
     double  lastStepMs;              /* device time of the last vbdx_step (CUDA events on its stream) */
+    int64_t nRingEntries;            /* sum over tiles of the distinct vertices they stage (own vertices + 1-rings, unpadded) */
+    int64_t nGhosts;                 /* vertices owned by another GPU (domain decomposition) */
+    int64_t nonFiniteVertices;       /* sentinel: owned vertices whose position was NaN/Inf at the end of the last step (0 = healthy) */
 } vbdx_info;
 vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out);
 
@@ -352,6 +363,12 @@ vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned lon
 vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int64_t* colors_out);
 
 const char* vbdx_last_error(void);
+/* Test hooks (GPU): the sweep's vertex-triangle contact term (csrc/contact.cuh, restating sim/vbd/Kernels.h:223-302) and its
+ * area-scaled penalties (gpu/impl/vbd/Kernels.cuh:80-114) on caller-supplied inputs.  in28 = per pair xtv(3) xv(3) xtf(3 x 3,
+ * one triangle vertex after the other) xf(3 x 3) dt k muF epsv;  out13 = 0, g(3), H(3 x 3).  fc = 8 triangle ids per vertex. */
+vbdx_status vbdx_debug_contact_pairs(int32_t n, const float* in28, float* out13);
+vbdx_status vbdx_debug_contact_penalties(int32_t nVerts, int32_t nTris, const int32_t* fc, const float* XVA, const float* FA, float muC,
+                                         int32_t* nContacts, float* penalty);
 int32_t vbdx_abi_version(void);
 /* number of CUDA devices visible (0 when there is no driver/GPU) */
 int32_t vbdx_device_count(void);

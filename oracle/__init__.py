@@ -21,7 +21,7 @@ REF_LIB = os.path.join(_HERE, "_ref", "liboracle_ref.so")
 
 # enums shared with the product (sim/vbd/Enums.h:9-28, graph/Enums.h)
 POSITION, INERTIA, KINETIC_ENERGY_MINIMUM, ADAPTIVE_VBD, ADAPTIVE_PBAT = range(5)
-ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV, ACCEL_BROYDEN = 0, 1, 2, 3, 4   # = vbdx_acceleration_strategy
+ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_NESTEROV, ACCEL_BROYDEN, ACCEL_TRUST_REGION = 0, 1, 2, 3, 4, 5   # = vbdx_acceleration_strategy
 ORDER_NATURAL, ORDER_SMALLEST_DEGREE, ORDER_LARGEST_DEGREE = range(3)
 SELECT_LEAST_USED, SELECT_FIRST_AVAILABLE = range(2)
 MATERIAL_STABLE_NEO_HOOKEAN, MATERIAL_STVK = range(2)  # = vbdx_material
@@ -75,6 +75,8 @@ def _load(kind: str) -> C.CDLL:
     lib.vbdo_set_params.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     lib.vbdo_set_acceleration.restype = C.c_int
     lib.vbdo_set_acceleration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64]
+    lib.vbdo_set_trust_region.restype = C.c_int
+    lib.vbdo_set_trust_region.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
     lib.vbdo_objective.restype = C.c_double
     lib.vbdo_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     lib.vbdo_objective_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -206,6 +208,11 @@ class Oracle:
         Data::Construct, sim/vbd/Data.cpp:268-296)."""
         if self.lib.vbdo_set_acceleration(self.h, int(accel), float(rho), float(L), int(start), int(window)):
             raise ValueError("invalid acceleration parameters")
+
+    def set_trust_region(self, eta=0.2, tau=2.0, curved=True):
+        """Data::WithTrustRegionAcceleration (sim/vbd/Data.cpp); the solve follows gpu/impl/vbd/TrustRegionIntegrator.cu."""
+        if self.lib.vbdo_set_trust_region(self.h, float(eta), float(tau), int(bool(curved))):
+            raise ValueError("Expected eta >= 0 and tau > 1")
 
     def objective(self, xk, xtilde, dt):
         a = np.ascontiguousarray(np.asarray(xk, np.float64).T)

@@ -22,7 +22,7 @@ class DeviceIntegrator:
 
     @staticmethod
     def _describe(data, keep, *, device=-1, tile_iters=0, flags=0, colors=None, kernel_variant=0, ring_slots=0, consumer_warps=0,
-                  ghosts=None, rest=False):
+                  ghosts=None, rest=False, n_colors=0):
         """Fill a ``vbdx_data_desc`` from a constructed ``Data`` (arrays are parked in ``keep``)."""
         L = _lib.lib()
         if data.x.size == 0:
@@ -71,6 +71,9 @@ class DeviceIntegrator:
         d.kernel_variant, d.ring_slots = int(kernel_variant), int(ring_slots)
         d.consumer_warps = int(consumer_warps)
         d.window_size = int(getattr(data, "manderson", 5))
+        d.n_colors = int(n_colors)
+        d.nesterov_L, d.nesterov_start = float(getattr(data, "nesterov_L", 1.0)), int(getattr(data, "nesterov_start", 3))
+        d.tr_eta, d.tr_tau, d.tr_curved = float(getattr(data, "eta", 0.2)), float(getattr(data, "tau", 2.0)), int(bool(getattr(data, "curved", True)))
         d.ghosts = ptr(ghosts, np.int64)
         d.nGhosts = 0 if ghosts is None else int(np.size(ghosts))
         return d

@@ -36,6 +36,8 @@ class DataDesc(C.Structure):
         ("kernel_variant", C.c_int32), ("ring_slots", C.c_int32),
         ("ghosts", C.c_void_p), ("nGhosts", C.c_int64),
         ("consumer_warps", C.c_int32), ("window_size", C.c_int32),
+        ("n_colors", C.c_int32), ("nesterov_start", C.c_int32), ("nesterov_L", C.c_double),
+        ("tr_eta", C.c_double), ("tr_tau", C.c_double), ("tr_curved", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -48,6 +50,7 @@ class Info(C.Structure):
         ("gridBlocks", C.c_int32), ("blockThreads", C.c_int32),
         ("device", C.c_int32), ("smCount", C.c_int32),
         ("deviceBytes", C.c_int64), ("kernelLaunches", C.c_int64), ("lastStepMs", C.c_double),
+        ("nRingEntries", C.c_int64), ("nGhosts", C.c_int64), ("nonFiniteVertices", C.c_int64),
     ]
 
 
@@ -113,6 +116,8 @@ SYMBOLS = {
     "vbdx_get_element_data": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_get_colors": (C.c_int, [_H, C.c_void_p]),
     "vbdx_greedy_color": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vbdx_debug_contact_pairs": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
+    "vbdx_debug_contact_penalties": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "vbdx_last_error": (C.c_char_p, []),
     "vbdx_abi_version": (C.c_int32, []),
     "vbdx_device_count": (C.c_int32, []),

@@ -118,6 +118,26 @@ __device__ __forceinline__ void AccumulateVertexTriangleContact(
     H[3] += c * (T0.y * T0.y + T1.y * T1.y), H[4] += c * (T0.y * T0.z + T1.y * T1.z), H[5] += c * (T0.z * T0.z + T1.z * T1.z);
 }
 
+// Area-scaled penalty of a vertex' contacts (ContactPenalty, gpu/impl/vbd/Kernels.cuh:80-114): the triangles listed in
+// the vertex' row of fc (the non-negative entries, which come first), kC = XVA[v] muC / sum of their areas; contact c is
+// penalised with kC * FA[f[c]].  Returns kC (0 without contacts).
+__device__ __forceinline__ float ContactPenaltyScale(const int* __restrict__ fcv, const float* __restrict__ FA, float xva, float muC,
+                                                    int f[kMaxContacts], int& nContacts)
+{
+    nContacts   = 0;
+    float sumfa = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxContacts; ++c)
+    {
+        f[c] = __ldcg(fcv + c);
+        if (f[c] >= 0)
+            ++nContacts;
+    }
+    for (int c = 0; c < nContacts; ++c)
+        sumfa += __ldg(FA + f[c]);
+    return nContacts > 0 ? xva * muC / sumfa : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------
 // active-set kernels.  Vertex and triangle ids are *internal* ids; q indexes the sorted query order.
 // ------------------------------------------------------------------------------------------

@@ -159,6 +159,7 @@ void BuildPlan(
     int tileIters,
     bool naturalOrder,
     int blocksPerIncidence,
+    int minColors,
     Plan& plan)
 {
     plan      = Plan{};
@@ -216,7 +217,7 @@ void BuildPlan(
     };
     std::vector<Item> items;
     items.reserve(nV);
-    int64_t nColors = 0;
+    int64_t nColors = std::max(0, minColors);
     for (int64_t i = 0; i < nV; ++i)
     {
         nColors = std::max<int64_t>(nColors, colors[i] + 1);

@@ -50,6 +50,7 @@ struct StepParams {
     int strategy;
     int iterations, substeps;
     unsigned int* barrier;  // zeroed before launch
+    unsigned int* nonFinite;  // sentinel: owned vertices whose final position is NaN/Inf (counted by the velocity update; zeroed per step)
     // vertex-triangle contact (fc == nullptr: disabled)
     const int32_t* __restrict__ fc;      // 8 triangle ids per internal vertex, -1 terminated
     const int4* __restrict__ triF;       // collision triangles (internal vertex ids)
@@ -178,6 +179,27 @@ __device__ __forceinline__ float4 LoadPos(const float4* p)
     return __ldcg(p);  // L2-coherent load: positions change between colours
 }
 
+// A position and the number of its write travel as ONE 16-byte datum (x, y, z, tag).  The barrier-free sweep and the halo
+// exchange compare only the tag of what they read, so the 16 bytes must be written and read as a unit.  PTX models a
+// vector access (st.v4 / ld.v4) as four scalar accesses; a .b128 access is a single access, hence these helpers: every
+// tagged position is stored with st.relaxed.{gpu,sys}.b128 and every poll re-reads with ld.relaxed.{gpu,sys}.b128
+// (SASS: STG.E.128.STRONG / LDG.E.128.STRONG).  The first read of a tile goes through cp.async 16 (one 16-byte request
+// to the L2, which holds the line's only coherent copy: .cg bypasses the L1); its tag is checked the same way.
+__device__ __forceinline__ void StorePosGpu(float4* p, float4 v)
+{
+    asm volatile("{\n .reg .b128 t;\n mov.b128 t, {%1, %2};\n st.relaxed.gpu.global.b128 [%0], t;\n}\n" ::"l"(p),
+                 "l"(static_cast<unsigned long long>(__float_as_uint(v.x)) | (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32)),
+                 "l"(static_cast<unsigned long long>(__float_as_uint(v.z)) | (static_cast<unsigned long long>(__float_as_uint(v.w)) << 32))
+                 : "memory");
+}
+__device__ __forceinline__ void StorePosSys(float4* p, float4 v)
+{
+    asm volatile("{\n .reg .b128 t;\n mov.b128 t, {%1, %2};\n st.relaxed.sys.global.b128 [%0], t;\n}\n" ::"l"(p),
+                 "l"(static_cast<unsigned long long>(__float_as_uint(v.x)) | (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32)),
+                 "l"(static_cast<unsigned long long>(__float_as_uint(v.z)) | (static_cast<unsigned long long>(__float_as_uint(v.w)) << 32))
+                 : "memory");
+}
+
 // InitialPositionsForSolve (sim/vbd/Kernels.h:45-94).  Roundings are spelled out (no implicit
 // multiply-add contraction) so that every kernel that inlines this code produces the same bits.
 __device__ __forceinline__ float3 InitialPosition(
@@ -236,9 +258,9 @@ __device__ __forceinline__ void SendToPeers(StepParams const& p, uint32_t vi, fl
         uint32_t const dst = __ldg(p.sendDst + k);
         uint32_t const r = dst >> 28, slot = dst & 0x0fffffffu;
         uint32_t const q = odd ? p.peerGhostExt[r] + (slot - p.peerGhostBegin[r]) : slot;
-        p.peerPos[r][q] = raw;
+        StorePosSys(p.peerPos[r] + q, raw);
         if (p.peerPOff[r] != 0u)
-            p.peerPos[r][q + (odd ? p.peerNGhost[r] : p.peerPOff[r])] = blended;
+            StorePosSys(p.peerPos[r] + q + (odd ? p.peerNGhost[r] : p.peerPOff[r]), blended);
     }
 }
 
@@ -292,9 +314,9 @@ __device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, i
     // decomposition and the barrier-free sweep (step_kernel_pipe.cuh, PipeParams::dataflow) read it back
     uint32_t const tag = p.tagBase + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.iterations + 1);
     float4 const o = make_float4(x0.x, x0.y, x0.z, __uint_as_float(tag));
-    p.pos[i]       = o;
+    StorePosGpu(p.pos + i, o);
     if constexpr (kChebyshev)
-        p.pos[p.pOff + i] = o;
+        StorePosGpu(p.pos + p.pOff + i, o);
     if (p.snap != nullptr)
         p.snap[i] = o;
     SendToPeers(p, i, o, o, tag);
@@ -313,6 +335,8 @@ __device__ __forceinline__ void PostStepVertex(StepParams const& p, uint32_t i)
     v4.y     = __fdiv_rn(__fsub_rn(x4.y, xt4.y), p.sdt);
     v4.z     = __fdiv_rn(__fsub_rn(x4.z, xt4.z), p.sdt);
     p.vel[i] = v4;
+    if (!isfinite(x4.x + x4.y + x4.z) && p.nonFinite != nullptr)
+        atomicAdd(p.nonFinite, 1u);
 }
 
 template <bool kChebyshev>
@@ -542,22 +566,11 @@ __device__ __forceinline__ void ProcessTile(
             // being swept -> the values it had when the iteration started (snapshot).
             if (p.fc != nullptr)
             {
-                int const* fcv = p.fc + static_cast<size_t>(vi) * kMaxContacts;
                 int f[kMaxContacts];
-                int nContacts = 0;
-                float sumfa   = 0.f;
-#pragma unroll
-                for (int c = 0; c < kMaxContacts; ++c)
-                {
-                    f[c] = __ldcg(fcv + c);
-                    if (f[c] >= 0)
-                        ++nContacts;
-                }
-                for (int c = 0; c < nContacts; ++c)
-                    sumfa += __ldg(p.FA + f[c]);
+                int nContacts  = 0;
+                float const kC = ContactPenaltyScale(p.fc + static_cast<size_t>(vi) * kMaxContacts, p.FA, __ldg(p.XVA + vi), p.muC, f, nContacts);
                 if (nContacts > 0)
                 {
-                    float const kC      = __ldg(p.XVA + vi) * p.muC / sumfa;
                     uint32_t const cb   = __ldg(p.colorVertexBegin + color), ce = __ldg(p.colorVertexBegin + color + 1);
                     float4 const* snapK = p.snap + static_cast<size_t>(k & 1) * p.nVerts;
                     float3 const xtv    = F3(__ldcg(p.xt + vi));
@@ -732,16 +745,16 @@ __device__ __forceinline__ void ProcessTile(
                 out.y = fmaf(omega, y - h2.y, h2.y);
                 out.z = fmaf(omega, z - h2.z, h2.z);
             }
-            p.hist[vi]         = make_float4(xi.x, xi.y, xi.z, 0.f);
-            p.pos[vi]          = raw;
-            p.pos[p.pOff + vi] = out;
+            p.hist[vi] = make_float4(xi.x, xi.y, xi.z, 0.f);
+            StorePosGpu(p.pos + vi, raw);
+            StorePosGpu(p.pos + p.pOff + vi, out);
             SendToPeers(p, vi, raw, out, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = out;  // what iteration k+1 starts from
         }
         else
         {
-            p.pos[vi] = raw;
+            StorePosGpu(p.pos + vi, raw);
             SendToPeers(p, vi, raw, raw, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;

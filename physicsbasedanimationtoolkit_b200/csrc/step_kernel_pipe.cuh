@@ -90,18 +90,24 @@ __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// polls of a tagged position: one 16-byte access (see StorePosGpu, step_kernel.cuh)
+__device__ __forceinline__ float4 UnpackB128(unsigned long long lo, unsigned long long hi)
+{
+    return make_float4(__uint_as_float(static_cast<unsigned>(lo)), __uint_as_float(static_cast<unsigned>(lo >> 32)),
+                       __uint_as_float(static_cast<unsigned>(hi)), __uint_as_float(static_cast<unsigned>(hi >> 32)));
+}
 __device__ __forceinline__ float4 LoadPosGpu(const float4* q)
 {
-    float4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
-    return v;
+    unsigned long long lo, hi;
+    asm volatile("{\n .reg .b128 t;\n ld.relaxed.gpu.global.b128 t, [%2];\n mov.b128 {%0, %1}, t;\n}\n" : "=l"(lo), "=l"(hi) : "l"(q) : "memory");
+    return UnpackB128(lo, hi);
 }
 
 __device__ __forceinline__ float4 LoadPosSys(const float4* q)
 {
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
-    return v;
+    unsigned long long lo, hi;
+    asm volatile("{\n .reg .b128 t;\n ld.relaxed.sys.global.b128 t, [%2];\n mov.b128 {%0, %1}, t;\n}\n" : "=l"(lo), "=l"(hi) : "l"(q) : "memory");
+    return UnpackB128(lo, hi);
 }
 
 // One barrier of the barrier warp.  Single GPU: arrive on the counter, poll it.

@@ -5,6 +5,7 @@
 
 #include "device_buffer.cuh"
 #include "anderson.cuh"
+#include "accelerators.cuh"
 #include "broyden.cuh"
 #include "contact_host.cuh"
 #include "geometry_api.cuh"
@@ -68,6 +69,10 @@ struct Integrator {
     double mu0 = 0, lambda0 = 0;
     // Anderson acceleration (anderson.cuh)
     int window = 5;
+    double nesterovL = 1.0;
+    int nesterovStart = 3;
+    double trEta = 0.2, trTau = 2.0;
+    bool trCurved = true;
     int material = VBDX_MATERIAL_STABLE_NEO_HOOKEAN;
     int lineSearch = 0;  // vbdx_set_line_search_guard
     std::vector<int64_t> batchOffsets;  // vbdx_create_batch: first vertex of every scene, then nV
@@ -192,6 +197,7 @@ struct Integrator {
     void LaunchStepKernel(StepParams const& q);
     void RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync);
     void LaunchPreStep(StepParams const& q);
+    void CheckAsyncErrors();
     bool WillSweepBarrierFree(int iterations) const
     {
         return UseFlow(iterations) ||
@@ -199,6 +205,9 @@ struct Integrator {
     }
     void AndersonStep(StepParams const& p, double dt, int iterations, int substeps);
     void BroydenStep(StepParams const& p, double dt, int iterations, int substeps);
+    void NesterovStep(StepParams const& p, double dt, int iterations, int substeps);
+    void TrustRegionStep(StepParams const& p, double dt, int iterations, int substeps);
+    double ObjectiveOfState(double sdt);
     // contact hooks shared by the windowed accelerators (same sequence as RunStep's contact branch)
     void ContactBeginStep(StepParams const& p, double dt)
     {
@@ -231,9 +240,24 @@ void Integrator::Create(vbdx_data_desc const& d)
     Require(d.nV > 0 && d.nT > 0 && d.X && d.E, "need a volume mesh: X (3 x nV) and E (4 x nT)");
     Require(d.nV < (int64_t(1) << 31) - 1 && d.nT < (int64_t(1) << 29), "mesh too large for 32-bit device indices");
     Require(d.acceleration >= VBDX_ACCEL_NONE && d.acceleration <= VBDX_ACCEL_TRUST_REGION, "unknown acceleration strategy");
-    if (d.acceleration != VBDX_ACCEL_NONE && d.acceleration != VBDX_ACCEL_CHEBYSHEV && d.acceleration != VBDX_ACCEL_ANDERSON &&
-        d.acceleration != VBDX_ACCEL_BROYDEN)
-        throw Error(VBDX_UNSUPPORTED, "only the base, Chebyshev-, Anderson- and Broyden-accelerated VBD solves are implemented");
+    if (d.acceleration == VBDX_ACCEL_NESTEROV)
+    {
+        // sim/vbd/Data.cpp:284-293
+        Require(d.nesterov_L > 0, "Expected L > 0");
+        Require(d.nesterov_start >= 0, "Expected start >= 0");
+        Require(d.nGhosts == 0, "Nesterov acceleration is not combined with domain decomposition");
+        nesterovL = d.nesterov_L, nesterovStart = d.nesterov_start;
+    }
+    if (d.acceleration == VBDX_ACCEL_TRUST_REGION)
+    {
+        // sim/vbd/Data.cpp:294-303
+        Require(d.tr_eta >= 0, "Expected eta >= 0");
+        Require(d.tr_tau > 1, "Expected tau > 1");
+        Require(d.nGhosts == 0, "trust-region acceleration is not combined with domain decomposition");
+        if (d.nF > 0 && d.nCV > 0)
+            throw Error(VBDX_UNSUPPORTED, "the trust-region accelerator's objective carries no contact term here: use it without a collision mesh");
+        trEta = d.tr_eta, trTau = d.tr_tau, trCurved = d.tr_curved != 0;
+    }
     if (d.acceleration == VBDX_ACCEL_ANDERSON || d.acceleration == VBDX_ACCEL_BROYDEN)
     {
         // sim/vbd/Data.cpp:277-283 (window >= 1); the device solver keeps the window's Gram matrix in registers
@@ -381,7 +405,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     try
     {
         BuildPlan(nV, E32.data(), ptrHost.data(), adjHost.data(), colors.data(), isDbc.data(), d.X, tileIters,
-                  (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, material == VBDX_MATERIAL_STVK ? 2 : 1, plan);
+                  (flags & VBDX_FLAG_NATURAL_VERTEX_ORDER) != 0, material == VBDX_MATERIAL_STVK ? 2 : 1, d.n_colors, plan);
     }
     catch (std::length_error const& e)
     {
@@ -555,7 +579,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     dAext.Alloc(nV, &deviceBytes);
     if (flags & VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY)
         dVtm1.Alloc(nV, &deviceBytes);
-    dBarrier.Alloc(1, &deviceBytes);
+    dBarrier.Alloc(2, &deviceBytes);  // [0] grid barrier counter, [1] non-finite sentinel
+    VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 2 * sizeof(unsigned int), stream));
     dDistFlags.Alloc(16, &deviceBytes);
     VBDX_CUDA(cudaMemsetAsync(dDistFlags.p, 0, 16 * sizeof(unsigned int), stream));
     dStaging.Alloc(3 * nV, &deviceBytes);
@@ -772,6 +797,7 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
     p.iterations   = iterations;
     p.substeps     = substeps;
     p.barrier      = dBarrier.p;
+    p.nonFinite    = dBarrier.p + 1;
     p.ghostBegin   = static_cast<uint32_t>(plan.ghostBegin);
     p.activeEnd    = static_cast<uint32_t>(plan.nActive);
     p.rank = distRank, p.world = distWorld;
@@ -895,10 +921,18 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
     bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
     auto launchStep = [&](StepParams const& q) { LaunchStepKernel(q); };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
+    VBDX_CUDA(cudaMemsetAsync(dBarrier.p + 1, 0, sizeof(unsigned int), stream));  // the step's non-finite sentinel
     if (acceleration == VBDX_ACCEL_ANDERSON)
         AndersonStep(p, dt, iterations, substeps);
     else if (acceleration == VBDX_ACCEL_BROYDEN)
         BroydenStep(p, dt, iterations, substeps);
+    else if (acceleration == VBDX_ACCEL_NESTEROV)
+        NesterovStep(p, dt, iterations, substeps);
+    else if (acceleration == VBDX_ACCEL_TRUST_REGION && !trCurved)
+        TrustRegionStep(p, dt, iterations, substeps);
+    // (the trust region's curved path: the reference's SolveCurvedTrustRegionConstraint is a stub that returns 0
+    // (TrustRegionIntegrator.cu:700-703), which empties the admissible step interval: no accelerated step is ever tried,
+    // every iteration falls back to the plain sweep -- the iterates ARE the base solve's, so that is what runs)
     else if (!contact.enabled)
         launchStep(p);
     else
@@ -929,28 +963,42 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
     if (sync)
     {
         VBDX_CUDA(cudaStreamSynchronize(stream));
-        if (distWorld > 1 || usedDataflow)
-        {
-            unsigned int e = 0;
-            VBDX_CUDA(cudaMemcpy(&e, dDistFlags.p + 9, sizeof(e), cudaMemcpyDeviceToHost));
-            if (e == 2u)
-            {
-                unsigned int dbg[6] = {0, 0, 0, 0, 0, 0};
-                VBDX_CUDA(cudaMemcpy(dbg, dDistFlags.p + 9, sizeof(dbg), cudaMemcpyDeviceToHost));
-                VBDX_CUDA(cudaMemset(dDistFlags.p + 9, 0, sizeof(dbg)));
-                dataflow = false;  // this handle sweeps with barriers from now on
-                throw Error(VBDX_CUDA_ERROR, "internal error: a barrier-free sweep waited for a vertex update that never came (vertex " +
-                                                 std::to_string(dbg[1] & 0x7fffffffu) + ((dbg[1] >> 31) ? " [previous-iterate buffer]" : "") + ", expected write " +
-                                                 std::to_string(dbg[2]) + ", found " + std::to_string(dbg[3]) + ", tile of vertex " + std::to_string(dbg[4]) +
-                                                 ", sweep " + std::to_string(dbg[5]) + ", write base " + std::to_string(dfTag) + "; VBDX_DATAFLOW=0 selects the barrier sweep)");
-            }
-            if (e)
-                throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not deliver its halo or reach the colour barrier in time (VBDX_DIST_TIMEOUT_S, default 30 s)");
-        }
+        CheckAsyncErrors();
         float ms = 0;
         VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
         lastStepMs = ms;
     }
+}
+
+// Called with the stream idle (vbdx_step, vbdx_synchronize): did a dependency or halo wait of the last step(s) time out?
+// Such a step finished with stale inputs: its result is discarded (positions go back to the start of the step's last
+// substep; velocities are undefined until the caller sets them), the error word is cleared so that later launches wait
+// again, and the failure is reported.  A barrier-free sweep that failed makes the handle sweep with barriers from then on.
+void Integrator::CheckAsyncErrors()
+{
+    if (!(distWorld > 1 || usedDataflow))
+        return;
+    unsigned int dbg[6] = {0, 0, 0, 0, 0, 0};
+    VBDX_CUDA(cudaMemcpy(dbg, dDistFlags.p + 9, sizeof(dbg), cudaMemcpyDeviceToHost));
+    unsigned int const e = dbg[0];
+    if (e == 0u)
+        return;
+    VBDX_CUDA(cudaMemset(dDistFlags.p + 9, 0, sizeof(dbg)));
+    size_t const owned = static_cast<size_t>(plan.ghostBegin);
+    VBDX_CUDA(cudaMemcpy(dPos.p, dXt.p, owned * sizeof(float4), cudaMemcpyDeviceToDevice));
+    if (acceleration == VBDX_ACCEL_CHEBYSHEV)
+        VBDX_CUDA(cudaMemcpy(dPos.p + nV, dXt.p, owned * sizeof(float4), cudaMemcpyDeviceToDevice));
+    if (e == 2u)
+    {
+        dataflow = false;  // this handle sweeps with barriers from now on
+        throw Error(VBDX_CUDA_ERROR, "internal error: a barrier-free sweep waited for a vertex update that never came (entry " +
+                                         std::to_string(dbg[1] & 0x1fffffffu) + ((dbg[1] >> 31) ? " [previous-iterate buffer]" : "") + ", expected write " +
+                                         std::to_string(dbg[2]) + ", found " + std::to_string(dbg[3]) + ", tile of vertex " + std::to_string(dbg[4]) +
+                                         ", sweep " + std::to_string(dbg[5]) + ", write base " + std::to_string(dfTag) +
+                                         "); the step was discarded (positions restored, set the velocities before continuing); VBDX_DATAFLOW=0 selects the barrier sweep");
+    }
+    throw Error(VBDX_CUDA_ERROR, "domain decomposition: a peer GPU did not deliver its halo or reach the barrier in time (VBDX_DIST_TIMEOUT_S, default 30 s); "
+                                 "the step was discarded on this rank (positions restored, set the velocities before continuing)");
 }
 
 void Integrator::LaunchPreStep(StepParams const& q)
@@ -990,8 +1038,8 @@ void Integrator::AndersonStep(StepParams const& p, double dt, int iterations, in
     {
         LaunchPreStep(q);
         ContactAfterPreStep(p, s);
-        if (iterations > 0)
         {
+            // the reference sweeps once before its loop whatever `iterations` is (AndersonIntegrator.cpp:30-33)
             VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, dAndSmall.n * sizeof(double), stream));
             VBDX_CUDA(cudaMemcpyAsync(a.xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
             q.iterBegin = 0;
@@ -1070,6 +1118,177 @@ void Integrator::BroydenStep(StepParams const& p, double dt, int iterations, int
         LaunchStepKernel(post);  // velocity update only
     }
     ContactEndStep(p);
+}
+
+
+// NesterovIntegrator::Solve inside Integrator::Step (sim/vbd/NesterovIntegrator.cpp:18-44), literally: x^{k-1} is captured
+// once before the loop, the sweep starts from x, and from iteration start + 1 on x <- y^k - (x_swept - x^{k-1}) / L.
+void Integrator::NesterovStep(StepParams const& p, double dt, int iterations, int substeps)
+{
+    if (dAndVec.n == 0)
+        dAndVec.Alloc(static_cast<size_t>(nV) * 2, &deviceBytes);
+    float4* const xkm1 = dAndVec.p;
+    float4* const yk   = xkm1 + nV;
+    StepParams q   = p;
+    q.substeps     = 1;
+    q.skipPreStep  = 1;
+    q.skipPostStep = 1;
+    q.iterations   = 1;
+    int const grid = Blocks(nV, 256);
+    ContactBeginStep(p, dt);
+    for (int s = 0; s < substeps; ++s)
+    {
+        LaunchPreStep(q);
+        ContactAfterPreStep(p, s);
+        VBDX_CUDA(cudaMemcpyAsync(xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        double const alpha = 1.0 / nesterovL;
+        double lambda = 0.0, beta = 0.0;
+        for (int k = 0; k < iterations; ++k)
+        {
+            bool const on = nesterovStart < k;
+            if (on)
+            {
+                NesterovExtrapolate<<<grid, 256, 0, stream>>>(nV, dPos.p, xkm1, yk, static_cast<float>(beta));
+                ++kernelLaunches;
+            }
+            q.iterBegin = k;
+            LaunchStepKernel(q);
+            if (on)
+            {
+                NesterovCorrect<<<grid, 256, 0, stream>>>(nV, dPos.p, xkm1, yk, static_cast<float>(alpha), plan.nActive, SnapNext(k));
+                ++kernelLaunches;
+                double const lambdak = lambda;
+                lambda               = (1.0 + std::sqrt(1.0 + 4.0 * lambda * lambda)) / 2.0;
+                beta                 = (lambdak - 1.0) / lambda;
+            }
+        }
+        StepParams post = q;
+        post.iterations = 0, post.skipPostStep = 0;
+        LaunchStepKernel(post);  // velocity update only
+    }
+    ContactEndStep(p);
+}
+
+// K/2 + dt^2 U of the CURRENT device state (TrustRegionIntegrator::ObjectiveFunction, TrustRegionIntegrator.cu:265-364,
+// without the contact term): positions and inertial targets go to the double-precision diagnostics kernels.
+double Integrator::ObjectiveOfState(double sdt)
+{
+    if (dObjX.n == 0)
+    {
+        dObjX.Alloc(3 * nV, &deviceBytes), dObjXt.Alloc(3 * nV, &deviceBytes), dObjGrad.Alloc(3 * nV, &deviceBytes);
+        dObjVal.Alloc(1, &deviceBytes);
+    }
+    GatherToCaller<double><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, dPos.p, dObjX.p, 1, 3);
+    GatherToCaller<double><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, dXtildeM.p, dObjXt.p, 1, 3);
+    VBDX_CUDA(cudaMemsetAsync(dObjVal.p, 0, sizeof(double), stream));
+    ObjectiveKinetic<<<std::min(Blocks(nV, 256), 1184), 256, 0, stream>>>(dObjX.p, dObjXt.p, dMass.p, nV, dObjVal.p, nullptr);
+    ObjectiveElastic<<<std::min(Blocks(nT, 256), 1184), 256, 0, stream>>>(dObjX.p, dE.p, dJinv.p, dVol.p, dLame.p, mu0, lambda0, nT, sdt * sdt,
+                                                                            material == VBDX_MATERIAL_STVK ? 1 : 0, dObjVal.p, nullptr);
+    kernelLaunches += 4;
+    double f = 0;
+    dObjVal.Download(&f, 1, stream);
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+    return f;
+}
+
+// TrustRegionIntegrator::SolveWithLinearAcceleratedPath inside Integrator::Step (gpu/impl/vbd/TrustRegionIntegrator.cu:47-166).
+// Like the reference, the scalar logic runs on the host and needs the objective value after every sweep (one small
+// read-back per evaluation); iterates, step sizes and path updates stay on the device.
+void Integrator::TrustRegionStep(StepParams const& p, double dt, int iterations, int substeps)
+{
+    if (dAndVec.n == 0)
+    {
+        dAndVec.Alloc(static_cast<size_t>(nV) * 2, &deviceBytes);
+        dAndSmall.Alloc(1, &deviceBytes);
+    }
+    float4* const xkm1 = dAndVec.p;
+    float4* const xkm2 = xkm1 + nV;
+    double const sdt   = dt / substeps;
+    StepParams q   = p;
+    q.substeps     = 1;
+    q.skipPreStep  = 1;
+    q.skipPostStep = 1;
+    q.iterations   = 1;
+    int const grid = Blocks(nV, 256);
+    double const eta = static_cast<float>(trEta), tau = static_cast<float>(trTau);
+    double const zero = 1e-6f, fltMin = 1.17549435e-38, fltMax = 3.40282347e+38;
+    for (int s = 0; s < substeps; ++s)
+    {
+        LaunchPreStep(q);
+        double fk = ObjectiveOfState(sdt), fkm1 = 0, fkm2 = 0, tk = -1.0, tkm1 = 0, tkm2 = 0, R2 = 0.0;
+        // (the reference's xkm1 / xkm2 start as whatever the constructor left there; they are overwritten before use)
+        auto updateIterates = [&]() {
+            VBDX_CUDA(cudaMemcpyAsync(xkm2, xkm1, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            VBDX_CUDA(cudaMemcpyAsync(xkm1, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            fkm2 = fkm1, fkm1 = fk;
+            tkm2 = tkm1, tkm1 = tk;
+        };
+        for (int k = 0; k < iterations; ++k)
+        {
+            q.iterBegin = k;
+            if (k < 2)
+            {
+                updateIterates();
+                LaunchStepKernel(q);
+                fk = ObjectiveOfState(sdt);
+                tk = static_cast<double>(k);
+                continue;
+            }
+            // ConstructModel: parabola through (t, f) of the last three iterates, time translated so that t_k = 0
+            tkm2 -= tk, tkm1 -= tk, tk = 0.0;
+            double const d2 = fkm2 - fk, d1 = fkm1 - fk, det = tkm2 * tkm2 * tkm1 - tkm1 * tkm1 * tkm2;
+            double const a2 = (d2 * tkm1 - d1 * tkm2) / det, a1 = (tkm2 * tkm2 * d1 - tkm1 * tkm1 * d2) / det, a0 = fk;
+            updateIterates();
+            LaunchStepKernel(q);
+            VBDX_CUDA(cudaMemsetAsync(dAndSmall.p, 0, sizeof(double), stream));
+            SquaredStepSize<<<std::min(grid, 1184), 256, 0, stream>>>(nV, dPos.p, xkm1, dAndSmall.p);
+            ++kernelLaunches;
+            double dx2 = 0;
+            dAndSmall.Download(&dx2, 1, stream);
+            VBDX_CUDA(cudaStreamSynchronize(stream));
+            if (R2 < dx2 + zero)
+                R2 = tau * tau * dx2;
+            double const lower = 1.0, upper = std::sqrt(R2 / dx2);
+            double tstar;
+            if (std::fabs(a2) > fltMin)
+                tstar = a2 > fltMin ? -a1 / (2.0 * a2) : fltMax;
+            else if (std::fabs(a1) > fltMin)
+                tstar = a1 > 0 ? -fltMax : fltMax;
+            else
+                tstar = 0.0;
+            double const t     = tstar < lower ? lower : (upper < tstar ? upper : tstar);
+            bool const tryStep = !(std::fabs(t - lower) < zero);
+            bool accepted      = false;
+            if (tryStep)
+            {
+                ScaleStep<<<grid, 256, 0, stream>>>(nV, dPos.p, xkm1, static_cast<float>(t), plan.nActive, nullptr);
+                ++kernelLaunches;
+                fk               = ObjectiveOfState(sdt);
+                double const rho = (fkm1 - fk) / (fkm1 - (a2 * t * t + a1 * t + a0));
+                accepted         = rho > eta;
+            }
+            if (accepted)
+            {
+                if ((upper - t) < zero)
+                    R2 *= tau * tau;
+                tk = t;
+            }
+            else
+            {
+                R2 /= tau * tau;
+                if (tryStep)
+                {
+                    ScaleStep<<<grid, 256, 0, stream>>>(nV, dPos.p, xkm1, static_cast<float>(1.0 / t), plan.nActive, nullptr);
+                    ++kernelLaunches;
+                }
+                fk = ObjectiveOfState(sdt);
+                tk = tkm1 + 1;
+            }
+        }
+        StepParams post = q;
+        post.iterations = 0, post.skipPostStep = 0;
+        LaunchStepKernel(post);  // velocity update only
+    }
 }
 
 // A slice of one substep: [pre-step] [iterations kBegin .. kEnd of a solve of totalIterations] [velocity update].
@@ -1207,6 +1426,8 @@ void vbdx_data_desc_init(vbdx_data_desc* d)
     d->abi_version  = VBDX_ABI_VERSION;
     d->struct_size  = sizeof(vbdx_data_desc);
     d->window_size  = 5;  // sim/vbd/Data.h:237
+    d->nesterov_L = 1.0, d->nesterov_start = 3;  // sim/vbd/Data.h:238-239
+    d->tr_eta = 0.2, d->tr_tau = 2.0, d->tr_curved = 1;  // sim/vbd/Data.h:241-243
     d->ordering     = VBDX_ORDER_LARGEST_DEGREE;  // sim/vbd/Data.h:211-216
     d->selection    = VBDX_SELECT_LEAST_USED;
     d->strategy     = VBDX_INIT_ADAPTIVE_PBAT;    // sim/vbd/Data.h:222-223
@@ -1382,6 +1603,7 @@ vbdx_status vbdx_synchronize(vbdx_integrator* h)
     return Guard([&] {
         VBDX_CUDA(cudaSetDevice(h->impl.device));
         VBDX_CUDA(cudaStreamSynchronize(h->impl.stream));
+        h->impl.CheckAsyncErrors();  // a time-out inside an asynchronous step surfaces here
         if (h->impl.stepTimed)
         {
             float ms = 0;
@@ -2026,6 +2248,77 @@ vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn,
     });
 }
 
+// Test hooks: the sweep's contact term and penalty scaling on caller-supplied inputs, so that the GPU tests can put
+// csrc/contact.cuh next to the reference's own functions (oracle/contact_ref.cu).  Same layouts as contact_ref_*.
+}  // extern "C"
+namespace vbdx {
+__global__ void DebugContactPairs(int n, const float* in, float* out)
+{
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* q = in + 28 * i;
+    float3 const xtv = make_float3(q[0], q[1], q[2]), xv = make_float3(q[3], q[4], q[5]);
+    float3 xtf[3], xf[3];
+    for (int c = 0; c < 3; ++c)
+    {
+        xtf[c] = make_float3(q[6 + 3 * c], q[7 + 3 * c], q[8 + 3 * c]);
+        xf[c]  = make_float3(q[15 + 3 * c], q[16 + 3 * c], q[17 + 3 * c]);
+    }
+    float g[3] = {0.f, 0.f, 0.f}, H[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    AccumulateVertexTriangleContact(xtv, xv, xtf, xf, q[24], q[25], q[26], q[27], g, H);
+    float* o = out + 13 * i;
+    o[0]     = 0.f;  // the sweep needs no energy
+    o[1] = g[0], o[2] = g[1], o[3] = g[2];
+    o[4] = H[0], o[5] = H[1], o[6] = H[2];
+    o[7] = H[1], o[8] = H[3], o[9] = H[4];
+    o[10] = H[2], o[11] = H[4], o[12] = H[5];
+}
+__global__ void DebugContactPenalties(int nVerts, const int* fc, const float* XVA, const float* FA, float muC, int* nContacts, float* penalty)
+{
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nVerts)
+        return;
+    int f[kMaxContacts];
+    int n          = 0;
+    float const kC = ContactPenaltyScale(fc + static_cast<size_t>(i) * kMaxContacts, FA, XVA[i], muC, f, n);
+    nContacts[i]   = n;
+    for (int c = 0; c < kMaxContacts; ++c)
+        penalty[kMaxContacts * i + c] = c < n ? kC * FA[f[c]] : 0.f;
+}
+}  // namespace vbdx
+extern "C" {
+
+vbdx_status vbdx_debug_contact_pairs(int32_t n, const float* in28, float* out13)
+{
+    return Guard([&] {
+        vbdx::Require(n >= 1 && in28 && out13, "vbdx_debug_contact_pairs: bad arguments");
+        NeedDevice();
+        vbdx::DevBuf<float> di, dout;
+        di.Alloc(static_cast<size_t>(28) * n), dout.Alloc(static_cast<size_t>(13) * n);
+        di.Upload(in28, static_cast<size_t>(28) * n, nullptr);
+        vbdx::DebugContactPairs<<<vbdx::Blocks(n, 128), 128>>>(n, di.p, dout.p);
+        dout.Download(out13, static_cast<size_t>(13) * n, nullptr);
+        VBDX_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+vbdx_status vbdx_debug_contact_penalties(int32_t nVerts, int32_t nTris, const int32_t* fc, const float* XVA, const float* FA, float muC,
+                                         int32_t* nContacts, float* penalty)
+{
+    return Guard([&] {
+        vbdx::Require(nVerts >= 1 && nTris >= 1 && fc && XVA && FA && nContacts && penalty, "vbdx_debug_contact_penalties: bad arguments");
+        NeedDevice();
+        vbdx::DevBuf<int32_t> dfc, dn;
+        vbdx::DevBuf<float> dx, df, dp;
+        dfc.Alloc(static_cast<size_t>(8) * nVerts), dn.Alloc(nVerts), dx.Alloc(nVerts), df.Alloc(nTris), dp.Alloc(static_cast<size_t>(8) * nVerts);
+        dfc.Upload(fc, static_cast<size_t>(8) * nVerts, nullptr), dx.Upload(XVA, nVerts, nullptr), df.Upload(FA, nTris, nullptr);
+        vbdx::DebugContactPenalties<<<vbdx::Blocks(nVerts, 128), 128>>>(nVerts, dfc.p, dx.p, df.p, muC, dn.p, dp.p);
+        dn.Download(nContacts, nVerts, nullptr), dp.Download(penalty, static_cast<size_t>(8) * nVerts, nullptr);
+        VBDX_CUDA(cudaDeviceSynchronize());
+    });
+}
+
 // Host-only: the planner's output for a mesh (no device needed).  Lets the CPU test-suite model-check the protocol of the
 // barrier-free sweep against the very ring lists, flags and padding the kernels consume.
 struct vbdx_plan {
@@ -2057,7 +2350,7 @@ vbdx_status vbdx_debug_plan_create(int64_t nV, int64_t nT, const int64_t* E, con
         h = std::make_unique<vbdx_plan>();
         try
         {
-            vbdx::BuildPlan(nV, E32.data(), ptr.data(), adj.data(), colors, is_constrained, X, tile_iters > 0 ? tile_iters : 8, false, 1, h->plan);
+            vbdx::BuildPlan(nV, E32.data(), ptr.data(), adj.data(), colors, is_constrained, X, tile_iters > 0 ? tile_iters : 8, false, 1, 0, h->plan);
         }
         catch (std::length_error const& e)
         {
@@ -2152,6 +2445,18 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out)
     out->deviceBytes     = I.deviceBytes;
     out->kernelLaunches  = I.kernelLaunches;
     out->lastStepMs      = I.lastStepMs;
+    out->nRingEntries    = I.plan.nRingEntries;
+    out->nGhosts         = I.nGhost;
+    out->nonFiniteVertices = 0;
+    if (I.dBarrier.p != nullptr)
+    {
+        unsigned int bad = 0;
+        cudaSetDevice(I.device);
+        if (cudaStreamSynchronize(I.stream) == cudaSuccess && cudaMemcpy(&bad, I.dBarrier.p + 1, sizeof(bad), cudaMemcpyDeviceToHost) == cudaSuccess)
+            out->nonFiniteVertices = bad;
+        else
+            cudaGetLastError();
+    }
     return VBDX_OK;
 }
 

@@ -104,6 +104,7 @@ void BuildPlan(
     int tileIters,
     bool naturalOrder,
     int blocksPerIncidence,  // record blocks per incident tet: 1 (Stable Neo-Hookean), 2 (St. Venant-Kirchhoff)
+    int minColors,           // sweep at least this many colours (domain decomposition: the colour count of the whole mesh)
     Plan& plan);
 
 // Second planning step, once the persistent grid size is known: which tiles / record blocks of each

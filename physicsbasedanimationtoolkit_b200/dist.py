@@ -169,6 +169,7 @@ class DomainDecomposedIntegrator:
             owner = np.asarray(partition, dtype=np.int64)
             if owner.shape != (nV,) or owner.min() < 0 or owner.max() >= self.world:
                 raise ValueError("an explicit partition needs one owner rank in [0, world) per vertex")
+        self.colors = np.asarray(colors)
         self.local = lp = LocalProblem(self.rank, owner, X, T, colors, dbc, v)
         self.nV_global = nV
         data = Data().with_volume_mesh(lp.X, lp.T)
@@ -180,7 +181,8 @@ class DomainDecomposedIntegrator:
             data = data.with_chebyshev_acceleration(rho_chebyshev)
         data = data.construct()
         data.colors = lp.colors                              # not the local greedy colouring
-        self.vbd = Integrator(data, ghosts=lp.ghost_local, kernel_variant=3, **tuning)
+        # every rank sweeps the colours of the WHOLE mesh (a slab may lack the last ones: the epochs would drift apart)
+        self.vbd = Integrator(data, ghosts=lp.ghost_local, kernel_variant=3, n_colors=int(np.max(colors)) + 1, **tuning)
         if self.world > 1:
             ids = self.vbd.internal_ids()
             sl, sp, sr = exchange_lists(lp, ids[lp.ghost_local], self.world, torch_all_to_all)

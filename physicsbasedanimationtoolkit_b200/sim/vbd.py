@@ -78,12 +78,11 @@ class Data:
         self.xtilde = e((3, 0))
         self.vt = e((3, 0))
         self.wg = e(0)
-        self.GP = e((4, 0))
+        self._GP = e((4, 0))
         self.rhoe = e(0)
         self.lame = e((2, 0))
-        self.GVGp = e(0, dtype=np.int64)
-        self.GVGe = e(0, dtype=np.int64)
-        self.GVGilocal = e(0, dtype=np.int64)
+        self._GVG = (e(0, dtype=np.int64), e(0, dtype=np.int64), e(0, dtype=np.int64))
+        self._lazy = set()   # fields construct() has not materialised yet (see GP, GVGp, GVGe, GVGilocal)
         self.muD = 1.0
         self.dbc = e(0, dtype=np.int64)
         self.vertex_coloring_ordering = _graph.GreedyColorOrderingStrategy.LargestDegree
@@ -112,6 +111,43 @@ class Data:
         self.omega_mode = 0
         # extension: elastic energy (HyperElasticEnergy); the reference's only choice is the default
         self.energy = HyperElasticEnergy.StableNeoHookean
+
+    # ---- fields materialised on demand ---------------------------------------------------
+    @property
+    def GP(self):
+        """Shape function gradients at the quadrature points, 4 x 3|#elements| (fem/ShapeFunctions.h:267-297): rows 1..3 of
+        element e's 4 x 3 block are the inverse of J = [X1-X0, X2-X0, X3-X0], row 0 is minus their sum."""
+        if "GP" in self._lazy:
+            X, E = self.X, self.E
+            nT = E.shape[1]
+            c0, c1, c2 = (X[:, E[a]] - X[:, E[0]] for a in (1, 2, 3))          # columns of J, 3 x nT each
+            r0, r1, r2 = np.cross(c1, c2, axis=0), np.cross(c2, c0, axis=0), np.cross(c0, c1, axis=0)
+            det = np.einsum("ij,ij->j", c0, r0)
+            Jinv = np.stack([r0, r1, r2], axis=0) / det                           # [row, component, e]: rows of J^-1
+            G = np.concatenate([-Jinv.sum(axis=0, keepdims=True), Jinv], axis=0)  # 4 x 3 x nT
+            self._GP = np.ascontiguousarray(G.transpose(0, 2, 1).reshape(4, 3 * nT))
+            self._lazy.discard("GP")
+        return self._GP
+
+    @GP.setter
+    def GP(self, a):
+        self._GP = a
+        self._lazy.discard("GP")
+
+    def _adjacency(self):
+        if "GVG" in self._lazy:
+            # vertex -> tet adjacency, ascending element id per vertex (sim/vbd/Data.cpp:223-226)
+            E, nV = self.E, self.X.shape[1]
+            flat = E.T.reshape(-1)                       # entry k = 4 e + ilocal
+            order = np.argsort(flat, kind="stable")
+            ptr = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=nV))]).astype(np.int64)
+            self._GVG = (ptr, (order // 4).astype(np.int64), (order % 4).astype(np.int64))
+            self._lazy.discard("GVG")
+        return self._GVG
+
+    GVGp = property(lambda s: s._adjacency()[0])
+    GVGe = property(lambda s: s._adjacency()[1])
+    GVGilocal = property(lambda s: s._adjacency()[2])
 
     # ---- fluent builder (sim/vbd/Data.cpp:20-177) ----------------------------------------
     def with_volume_mesh(self, X, T):
@@ -237,23 +273,16 @@ class Data:
             self.lame[0], self.lame[1] = mu, lam
         if self.rhoe.size == 0:
             self.rhoe = np.full(nT, 1e3)
-        # shape function gradients (fem/ShapeFunctions.h:267-297), quadrature weights
-        # (fem/MeshQuadrature.h:75-88) and lumped mass (fem/Mass.h:791-830) for linear tets
-        J = np.stack([X[:, E[a]] - X[:, E[0]] for a in (1, 2, 3)], axis=2).transpose(1, 0, 2)  # nT x 3 x 3
-        det = np.linalg.det(J)
+        # quadrature weights (fem/MeshQuadrature.h:75-88) and lumped mass (fem/Mass.h:791-830) for linear tets.  The shape
+        # function gradients GP and the vertex -> tet adjacency GVG* are large and the device recomputes both (the north
+        # star: CSR built on device), so they are materialised on first access (properties below).
+        e1, e2, e3 = (X[:, E[a]] - X[:, E[0]] for a in (1, 2, 3))
+        det = np.einsum("ij,ij->j", e1, np.cross(e2, e3, axis=0))
         if np.any(det <= 1e-10):
             raise ValueError("inverted or degenerate tetrahedron in the rest mesh")  # fem/Jacobian.h:68-80
-        Jinv = np.linalg.inv(J)                      # rows = gradients of local vertices 1..3
-        G = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)  # nT x 4 x 3
-        self.GP = np.ascontiguousarray(G.transpose(1, 0, 2).reshape(4, 3 * nT))
         self.wg = det / 6.0
         self.m = np.bincount(E.reshape(-1), weights=np.tile(self.rhoe * self.wg / 4.0, 4), minlength=nV)
-        # vertex -> tet adjacency, ascending element id per vertex (sim/vbd/Data.cpp:223-226)
-        flat = E.T.reshape(-1)                       # entry k = 4 e + ilocal
-        order = np.argsort(flat, kind="stable")
-        self.GVGp = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=nV))]).astype(np.int64)
-        self.GVGe = (order // 4).astype(np.int64)
-        self.GVGilocal = (order % 4).astype(np.int64)
+        self._lazy = {"GP", "GVG"}
         # colouring and partitions (sim/vbd/Data.cpp:228-231)
         self.colors = _graph.mesh_greedy_color(E, nV, self.vertex_coloring_ordering,
                                                self.vertex_coloring_selection)
@@ -297,8 +326,8 @@ class Data:
 class Integrator(DeviceIntegrator):
     """``pbat.sim.vbd.Integrator`` (bindings/pypbat/sim/vbd/Integrator.cpp:30-90): positions and
     velocities cross the boundary as float64 3 x nV arrays.  Dispatch on ``data.accelerator``
-    happens at construction like the reference's factory: Base, Chebyshev and Anderson are
-    implemented, the others raise ``NotImplementedError``."""
+    happens at construction like the reference's factory (all of ``AccelerationStrategy``: Base, Chebyshev, Anderson,
+    Nesterov, Broyden, TrustRegion)."""
 
     _dtype = np.float64
 

@@ -1,5 +1,7 @@
 """GPU tests of the contact path: LBVH (against the reference's golden topology), active set
 (the reference's own detector test) and the contact-aware solve (against the contact oracle)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -156,3 +158,107 @@ def test_windowed_accelerators_with_contact(accel):
     print(f"contact scene {accel}: rel L2 = {err:.3e}; top body lowest z = {xr[2, B == 1].min():.4f}")
     assert err < 1.5e-3
     assert xr[2, B == 1].min() > 0.45 and vbd.x[2, B == 1].min() > 0.45
+
+
+def _contact_ref():
+    """The reference's own contact code compiled for the GPU (oracle/contact_ref.cu -> oracle/_ref/libcontact_ref.so)."""
+    import ctypes as C
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcontact_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libcontact_ref.so has not been built (needs the reference tree: make -C oracle contact_ref)")
+    lib = C.CDLL(path)
+    lib.contact_ref_pairs.restype = C.c_int
+    lib.contact_ref_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    lib.contact_ref_penalties.restype = C.c_int
+    lib.contact_ref_penalties.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def test_contact_term_against_the_reference_function():
+    """csrc/contact.cuh vs pbat::sim::vbd::kernels::AccumulateVertexTriangleContact (sim/vbd/Kernels.h:223-302) itself, both
+    run on the GPU in fp32 on the same (vertex, triangle) pairs: random penetrating / separated / sliding / sticking pairs,
+    projections outside the triangle, on an edge and on a corner, zero distance, degenerate triangles."""
+    from physicsbasedanimationtoolkit_b200 import _lib
+
+    ref = _contact_ref()
+    rng = np.random.default_rng(7)
+    rows = []
+
+    def pair(xtv, xv, xtf, xf, dt=0.01, k=1e4, muF=0.3, epsv=1e-3):
+        rows.append(np.concatenate([xtv, xv, np.asarray(xtf).reshape(-1), np.asarray(xf).reshape(-1), [dt, k, muF, epsv]]))
+
+    for _ in range(4000):
+        tri = rng.uniform(-1, 1, (3, 3))                                  # rows = triangle vertices
+        n = np.cross(tri[1] - tri[0], tri[2] - tri[0])
+        if np.linalg.norm(n) < 0.2:
+            continue
+        n /= np.linalg.norm(n)
+        b = rng.dirichlet([1, 1, 1]) if rng.random() < 0.8 else rng.uniform(-0.5, 1.5, 3)   # 20 %: projection may fall outside
+        b = b / b.sum()
+        # depth and relative motion well above fp32 resolution of O(1) coordinates: the term differences its inputs
+        # ((x_v - x_b) . n, (x_v - x_v^t) - (x_b - x_b^t)), smaller values would only measure cancellation noise -- the
+        # stick regime |u| < epsv dt is covered by the exactly representable cases below and by epsv up to 10 here
+        depth = rng.choice([-1, 1]) * 10.0 ** rng.uniform(-2.5, -0.5)     # penetrating (< 0) or separated (> 0)
+        xv = b @ tri + depth * n
+        slide = 10.0 ** rng.uniform(-2.5, -1) * rng.normal(size=3)
+        tri_t = tri - 10.0 ** rng.uniform(-3, -1.5) * rng.normal(size=(3, 3))
+        pair(xv - slide, xv, tri_t, tri, k=10.0 ** rng.uniform(2, 6), muF=rng.uniform(0, 1), epsv=10.0 ** rng.uniform(-3, 1))
+    A, B, Cc = np.array([0., 0, 0]), np.array([1., 0, 0]), np.array([0., 1, 0])
+    T0 = [A, B, Cc]
+    up = np.array([0., 0, 1])
+    tiny = 2.0 ** -20                                                      # below epsv dt = 1e-5: sticking
+    for xv in ([0.25, 0.25, -0.125], [0.25, 0.25, 0.0], [0.5, 0.0, -0.25], [0.0, 0.0, -0.25], [0.5, 0.5, -0.5], [1.0, 0.0, -0.5],
+               [0.25, 0.25, 0.5], [1.5, 0.25, -0.25], [-0.25, 0.25, -0.25], [0.75, 0.75, -0.25]):
+        xv = np.array(xv)
+        pair(xv + 2.0 ** -10 * up, xv, T0, T0)                             # moved straight down: no tangential motion
+        pair(xv - np.array([2.0 ** -8, 2.0 ** -9, 0.0]), xv, T0, T0)      # slid along the triangle (slipping)
+        pair(xv - np.array([tiny, 0.0, 0.0]), xv, T0, T0)                 # ... by less than the threshold (sticking)
+        pair(xv, xv, [A, B, Cc + np.array([2.0 ** -9, 0, 0])], T0)         # the triangle moved instead
+    pair(np.array([0.1, 0.1, -0.1]), np.array([0.1, 0.1, -0.1]), [A, A, A], [A, A + 1e-12, A])   # degenerate triangle
+    pair(np.array([0.1, 0.1, -0.1]), np.array([0.1, 0.1, -0.1]), [A, B, 2 * B], [A, B, 2 * B])   # collinear
+    X = np.ascontiguousarray(np.stack(rows), dtype=np.float32)
+    n = X.shape[0]
+    want = np.zeros((n, 13), np.float32)
+    got = np.zeros((n, 13), np.float32)
+    assert ref.contact_ref_pairs(n, X.ctypes.data, want.ctypes.data) == 0
+    _lib.check(_lib.lib().vbdx_debug_contact_pairs(n, X.ctypes.data, got.ctypes.data))
+    assert np.isfinite(want).all() and np.isfinite(got).all()
+    # the two agree on WHICH pairs respond (a pair whose projection is within rounding of the triangle's rim may differ:
+    # none of the random ones may, the constructed rim cases are exact in binary)
+    resp_w, resp_g = np.abs(want[:, 4:]).sum(axis=1) > 0, np.abs(got[:, 4:]).sum(axis=1) > 0
+    assert np.array_equal(resp_w, resp_g), np.flatnonzero(resp_w != resp_g)
+    assert resp_w.sum() > 2500 and (~resp_w).sum() > 300
+    scale_g = np.abs(want[:, 1:4]).max(axis=1, keepdims=True) + 1e-30
+    scale_h = np.abs(want[:, 4:]).max(axis=1, keepdims=True) + 1e-30
+    err_g = (np.abs(got[:, 1:4] - want[:, 1:4]) / scale_g)[resp_w].max()
+    err_h = (np.abs(got[:, 4:] - want[:, 4:]) / scale_h)[resp_w].max()
+    # fp32 on both sides, different operation order (expression templates vs scalar code)
+    assert err_h < 2e-4 and err_g < 2e-4, (err_g, err_h)
+    # gradient direction and magnitude on all responding pairs in aggregate
+    assert np.linalg.norm(got[resp_w, 1:4] - want[resp_w, 1:4]) / np.linalg.norm(want[resp_w, 1:4]) < 1e-5
+
+
+def test_contact_penalty_against_the_reference_struct():
+    """The area-scaled penalties of the sweep vs pbat::gpu::impl::vbd::kernels::ContactPenalty<8> (gpu/impl/vbd/Kernels.cuh:80-114)."""
+    from physicsbasedanimationtoolkit_b200 import _lib
+
+    ref = _contact_ref()
+    rng = np.random.default_rng(3)
+    nv, nf = 500, 64
+    fc = np.full((nv, 8), -1, np.int32)
+    for i in range(nv):
+        k = rng.integers(0, 9)
+        fc[i, :k] = rng.integers(0, nf, k)
+    XVA = rng.uniform(0.01, 1.0, nv).astype(np.float32)
+    FA = rng.uniform(0.01, 1.0, nf).astype(np.float32)
+    out = {}
+    for name in ("ref", "ours"):
+        nc, pen = np.zeros(nv, np.int32), np.zeros((nv, 8), np.float32)
+        if name == "ref":
+            assert ref.contact_ref_penalties(nv, nf, fc.ctypes.data, XVA.ctypes.data, FA.ctypes.data, 1e6, nc.ctypes.data, pen.ctypes.data) == 0
+        else:
+            _lib.check(_lib.lib().vbdx_debug_contact_penalties(nv, nf, fc.ctypes.data, XVA.ctypes.data, FA.ctypes.data, 1e6, nc.ctypes.data, pen.ctypes.data))
+        out[name] = (nc, pen)
+    assert np.array_equal(out["ref"][0], out["ours"][0]) and np.array_equal(out["ref"][0], (fc >= 0).sum(axis=1))
+    assert np.allclose(out["ref"][1], out["ours"][1], rtol=2e-6, atol=0)

@@ -23,7 +23,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/vbdx.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert _lib.lib().vbdx_abi_version() == 1
+    assert _lib.lib().vbdx_abi_version() == 2
 
 
 def test_desc_struct_matches_header_size():
