@@ -2249,7 +2249,7 @@ vbdx_status vbdx_contact_get(vbdx_contact* h, int32_t* active_mask, int32_t* nn,
 }
 
 // Test hooks: the sweep's contact term and penalty scaling on caller-supplied inputs, so that the GPU tests can put
-// csrc/contact.cuh next to the reference's own functions (oracle/contact_ref.cu).  Same layouts as contact_ref_*.
+// csrc/contact.cuh next to the reference's own functions (compiled by the test infrastructure).  Layouts: include/vbdx.h.
 }  // extern "C"
 namespace vbdx {
 __global__ void DebugContactPairs(int n, const float* in, float* out)
