@@ -704,6 +704,25 @@ void Integrator::BuildFlowSchedule()
                 ids[idsStart[t] + (j >> 2) * 128u + lane * 4u + (j & 3u)] = e;
             }
     }
+    // Deal order of a colour's tiles: the planner's (heaviest first).  Domain decomposition: the tiles next to another GPU's
+    // vertices go first -- their vertices are what the peers wait for, and the ghosts THEY read were sent at the start of
+    // the peers' previous colour, so both directions of the halo get a whole colour's worth of time to cross NVLink.
+    std::vector<uint32_t> order(nTiles);
+    bool boundaryFirst = nGhost > 0;
+    if (char const* e = std::getenv("VBDX_BOUNDARY_FIRST"))
+        boundaryFirst = boundaryFirst && std::atoi(e) != 0;
+    for (int32_t c = 0; c < plan.nColors; ++c)
+    {
+        uint32_t const tb = plan.colorTileBegin[c], te = plan.colorTileBegin[c + 1];
+        uint32_t k = tb;
+        for (int pass = 0; pass < 2; ++pass)
+            for (uint32_t t = tb; t < te; ++t)
+                if ((boundaryFirst && TileReadsGhosts(plan.tiles[t].meta)) == (pass == 0))
+                    order[k++] = t;
+        if (!boundaryFirst)
+            for (uint32_t t = tb; t < te; ++t)
+                order[t] = t;
+    }
     std::vector<uint32_t> wBegin(static_cast<size_t>(gWarps) + 1, 0);
     for (int32_t c = 0; c < plan.nColors; ++c)
         for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
@@ -715,8 +734,8 @@ void Integrator::BuildFlowSchedule()
     for (int32_t c = 0; c < plan.nColors; ++c)
         for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
         {
-            TileDesc const& td = plan.tiles[t];
-            seqTiles[cursor[(t - plan.colorTileBegin[c]) % gWarps]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[t]);
+            TileDesc const& td = plan.tiles[order[t]];
+            seqTiles[cursor[(t - plan.colorTileBegin[c]) % gWarps]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[order[t]]);
         }
     dFlowWarpBegin.Alloc(wBegin.size(), &deviceBytes);
     dFlowWarpBegin.Upload(wBegin.data(), wBegin.size(), stream);

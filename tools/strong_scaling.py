@@ -6,7 +6,7 @@ x-slabs over the GPUs of the box (N = 1: the plain single-GPU integrator).
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/strong_scaling.py
 
 Prints one JSON line on rank 0: vertex-iterations/s of the whole job (device time, max over ranks), ms/step and the
-HBM roofline fraction of the algorithmic bytes per GPU.
+HBM roofline fraction of the record format's bytes per GPU.
 """
 import json
 import os
@@ -19,7 +19,7 @@ import torch
 
 import physicsbasedanimationtoolkit_b200 as pbat
 from physicsbasedanimationtoolkit_b200 import meshes
-from bench import algorithmic_bytes_per_vertex_iteration
+from bench import format_bytes_per_vertex_iteration
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -78,8 +78,7 @@ ms = float(ms[0])
 if rank == 0:
     active = np.ones(nV, bool)
     active[dbc] = False
-    # 117^3 computed once offline (kbar = 19.578, nbar = 12.873; takes 20 s on the host); other grids on the fly
-    B = 1569.8083810281453 if grid == 117 else algorithmic_bytes_per_vertex_iteration(T, nV, active)[0]
+    B = format_bytes_per_vertex_iteration(vbd.info)["total"]  # bytes the record format moves per vertex solve (this rank's counts)
     n_active = int(active.sum())
     value = n_active * ITERS * steps / (ms * 1e-3)
     peak = 6552.0
