@@ -48,9 +48,8 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
     uint32_t const nC     = static_cast<uint32_t>(p.nColors);
     uint32_t const gwarp  = warp * gridDim.x + blockIdx.x;
 
-    // shared-memory layout of StepKernelPipe (PipeSmemBytes); the id buffers stay unused
-    unsigned char* mine = smem + 2 * ((static_cast<size_t>(nC) + 1 + 3) / 4) * 16 +
-                          static_cast<size_t>(warp) * (kPipeWarpFixed + 2 * SE * 4 + SE * 16 + static_cast<size_t>(pp.maxIters) * kBlockBytes);
+    // per warp (FlowWarpBytes): record buffer | staged positions | 4 descriptors | mbarrier | 4 sweep numbers
+    unsigned char* mine   = smem + static_cast<size_t>(warp) * FlowWarpBytes(SE, pp.maxIters);
     float4* const recBuf  = reinterpret_cast<float4*>(mine);
     float4* const stage   = recBuf + static_cast<size_t>(pp.maxIters) * kBlockFloat4;
     uint4* const tdRing   = reinterpret_cast<uint4*>(stage + SE);  // descriptors of tiles seq .. seq+3 of this warp's sequence

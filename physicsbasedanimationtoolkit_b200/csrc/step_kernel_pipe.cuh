@@ -43,6 +43,16 @@ __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps
     return b;
 }
 
+// ... of the lean barrier-free kernel (step_kernel_flow.cuh): no id buffers (the ring entries live in registers)
+__host__ __device__ inline size_t FlowWarpBytes(uint32_t stageEntries, uint32_t maxIters)
+{
+    return kPipeWarpFixed + static_cast<size_t>(stageEntries) * 16 + static_cast<size_t>(maxIters) * kBlockBytes;
+}
+__host__ __device__ inline size_t FlowSmemBytes(uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
+{
+    return static_cast<size_t>(warps) * FlowWarpBytes(stageEntries, maxIters);
+}
+
 // records of the current tile, already in this warp's shared-memory buffer
 struct SmemRecords {
     float4 const* rec;

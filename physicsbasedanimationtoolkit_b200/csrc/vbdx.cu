@@ -93,7 +93,8 @@ struct Integrator {
     // schedule of the lean barrier-free kernel (step_kernel_flow.cuh; BuildFlowSchedule)
     DevBuf<uint32_t> dFlowWarpBegin, dFlowIds;
     DevBuf<uint4> dFlowTiles;
-    int pipeWarpsPerCta = 16;
+    int flowWarps = 16, flowGridBlocks = 0;  // launch shape of the lean kernel (no barrier warp, no id buffers)
+    size_t flowSmemBytes = 0;
     void BuildFlowSchedule();
 
     // state
@@ -426,11 +427,17 @@ void Integrator::Create(vbdx_data_desc const& d)
         maxTileIters = std::max(maxTileIters, TileIters(t.meta));
     // pipelined kernel: compute warps + one barrier warp per CTA.  Default: one CTA of 16 compute warps per SM
     // (fewer arrivals at the grid barrier) when its tile buffers fit in shared memory, else 8 compute warps.
+    // (as many compute warps as the per-warp tile buffers leave room for: a mesh whose largest tile stages 288 instead of
+    // 256 vertices must get 15 warps, not half the machine)
     int pipeWarps = d.consumer_warps > 0 ? std::min(d.consumer_warps, kPipeMaxThreads / 32 - 1) : 16;
-    if (d.consumer_warps <= 0 && PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters) > static_cast<size_t>(maxOptin))
-        pipeWarps = 8;
+    if (d.consumer_warps <= 0)
+        while (pipeWarps > 1 && PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters) > static_cast<size_t>(maxOptin))
+            --pipeWarps;
     int const pipeThreads = pipeWarps * 32 + 32;
-    pipeWarpsPerCta       = pipeWarps;
+    flowWarps             = d.consumer_warps > 0 ? std::min(d.consumer_warps, kFlowMaxThreads / 32) : kFlowMaxThreads / 32;
+    while (flowWarps > 1 && FlowSmemBytes(flowWarps, stageEntries, maxTileIters) > static_cast<size_t>(maxOptin))
+        --flowWarps;
+    flowSmemBytes = FlowSmemBytes(flowWarps, stageEntries, maxTileIters);
     size_t const pipeSmem = PipeSmemBytes(plan.nColors, pipeWarps, stageEntries, maxTileIters);
     if (variant == VBDX_KERNEL_DEFAULT)
     {
@@ -478,16 +485,21 @@ void Integrator::Create(vbdx_data_desc const& d)
             VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
             perSm = std::min(perSm, n);
         }
-        // the lean barrier-free kernel: the same compute warps without the barrier warp
-        for (PipeKernelFn fn : {cheb0 ? StepKernelFlow<true, false, false> : StepKernelFlow<false, false, false>,
-                                cheb0 ? StepKernelFlow<true, true, false> : StepKernelFlow<false, true, false>,
-                                cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
-                                cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>})
+        // the lean barrier-free kernel has its own launch shape: no barrier warp, no id buffers
+        if (!stvk && flowSmemBytes <= static_cast<size_t>(maxOptin))
         {
-            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
-            int n = 0;
-            VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads - 32, smemBytes));
-            perSm = std::min(perSm, n);
+            int flowPerSm = 1 << 30;
+            for (PipeKernelFn fn : {cheb0 ? StepKernelFlow<true, false, false> : StepKernelFlow<false, false, false>,
+                                    cheb0 ? StepKernelFlow<true, true, false> : StepKernelFlow<false, true, false>,
+                                    cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
+                                    cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>})
+            {
+                VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flowSmemBytes)));
+                int n = 0;
+                VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, flowWarps * 32, flowSmemBytes));
+                flowPerSm = std::min(flowPerSm, n);
+            }
+            flowGridBlocks = std::max(0, flowPerSm) * smCount;
         }
     }
     else
@@ -535,7 +547,9 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && !clusterMode)  // tuning: fewer CTAs = cheaper grid barrier on small meshes
         gridBlocks = std::max(1, std::min(std::atoi(e), gridBlocks));
     PartitionTiles(plan, gridBlocks);
-    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN)
+    if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && flowGridBlocks > 0)
+        flowGridBlocks = std::max(1, std::min(std::atoi(e), flowGridBlocks));
+    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && flowGridBlocks > 0)
         BuildFlowSchedule();
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
@@ -671,7 +685,7 @@ void Integrator::Create(vbdx_data_desc const& d)
 // / ghost bits, the four chunks of a lane packed into one 16-byte word.
 void Integrator::BuildFlowSchedule()
 {
-    uint32_t const gWarps = static_cast<uint32_t>(gridBlocks) * static_cast<uint32_t>(pipeWarpsPerCta);
+    uint32_t const gWarps = static_cast<uint32_t>(flowGridBlocks) * static_cast<uint32_t>(flowWarps);
     size_t const nTiles   = plan.tiles.size();
     bool const cheb       = acceleration == VBDX_ACCEL_CHEBYSHEV;
     uint32_t const pOff   = cheb ? static_cast<uint32_t>(nV) : 0u;
@@ -889,10 +903,12 @@ void Integrator::LaunchStepKernel(StepParams const& q)
             usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
             bool const flow = pp.dataflow != 0 && UseFlow(q.iterations);
-            // (the lean kernel has no barrier warp: same compute warps, same shared-memory layout, 32 threads fewer)
-            VBDX_CUDA(cudaLaunchCooperativeKernel(
-                reinterpret_cast<void const*>(flow ? KernelFlow() : KernelPipe(pp.dataflow != 0)), dim3(gridBlocks),
-                dim3(flow ? blockThreads - 32 : blockThreads), args, smemBytes, stream));
+            if (flow)
+                VBDX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(KernelFlow()), dim3(flowGridBlocks), dim3(flowWarps * 32), args,
+                                                      flowSmemBytes, stream));
+            else
+                VBDX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(KernelPipe(pp.dataflow != 0)), dim3(gridBlocks),
+                                                      dim3(blockThreads), args, smemBytes, stream));
         }
         else if (variant == VBDX_KERNEL_PIPELINED)
         {
@@ -2457,8 +2473,10 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out)
     out->nRecordSlots    = I.nRecordSlots;
     out->nColors         = I.plan.nColors;
     out->nTiles          = static_cast<int32_t>(I.plan.tiles.size());
-    out->gridBlocks      = I.gridBlocks;
-    out->blockThreads    = I.blockThreads;
+    // launch shape of the kernel that runs whole steps: the lean barrier-free one where it applies
+    bool const flowShape = I.dFlowTiles.p != nullptr && I.dataflow && I.flowKernel && !I.contact.enabled;
+    out->gridBlocks      = flowShape ? I.flowGridBlocks : I.gridBlocks;
+    out->blockThreads    = flowShape ? I.flowWarps * 32 : I.blockThreads;
     out->device          = I.device;
     out->smCount         = I.smCount;
     out->deviceBytes     = I.deviceBytes;
