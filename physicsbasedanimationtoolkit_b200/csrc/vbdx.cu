@@ -420,6 +420,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     Require(variant >= VBDX_KERNEL_DEFAULT && variant <= VBDX_KERNEL_CLUSTER, "unknown kernel variant");
     if (variant == VBDX_KERNEL_CLUSTER)
         Require(d.nGhosts == 0, "the cluster kernel variant is single-GPU only");
+    // (every kernel is allowed the device's maximum of dynamic shared memory: the attribute belongs to the FUNCTION, not to
+    // a handle -- a second handle with smaller tiles must not lower it under the first one's launches)
     int maxOptin = 0;
     VBDX_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     maxTileIters = 1;
@@ -480,7 +482,7 @@ void Integrator::Create(vbdx_data_desc const& d)
               stvk ? (cheb0 ? StepKernelPipe<true, false, true, true> : StepKernelPipe<false, false, true, true>)
                    : (cheb0 ? StepKernelPipe<true, false, false, true> : StepKernelPipe<false, false, false, true>)})
         {
-            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));
             int n = 0;
             VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
             perSm = std::min(perSm, n);
@@ -494,7 +496,7 @@ void Integrator::Create(vbdx_data_desc const& d)
                                     cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
                                     cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>})
             {
-                VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(flowSmemBytes)));
+                VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));
                 int n = 0;
                 VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, flowWarps * 32, flowSmemBytes));
                 flowPerSm = std::min(flowPerSm, n);
@@ -519,7 +521,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         for (TmaKernelFn fn : {cheb0 ? StepKernelTma<true, false> : StepKernelTma<false, false>,
                                cheb0 ? StepKernelTma<true, true> : StepKernelTma<false, true>})
         {
-            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));
             int n = 0;
             VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
             perSm = std::min(perSm, n);
@@ -535,7 +537,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         for (StepKernelFn fn : {cheb0 ? StepKernel<true, false> : StepKernel<false, false>,
                                 cheb0 ? StepKernel<true, true> : StepKernel<false, true>})
         {
-            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)));
+            VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));
             int n = 0;
             VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, blockThreads, smemBytes));
             perSm = std::min(perSm, n);

@@ -92,3 +92,58 @@ class BatchIntegrator(Integrator):
     def scene(self, a, s):
         """Columns of a 3 x sum(nV) array that belong to scene ``s``."""
         return a[:, self.offsets[s]:self.offsets[s + 1]]
+
+
+class MultiGpuBatchIntegrator:
+    """Extension: independent scenes sharded over several GPUs of one node (SURVEY.md 8e second row, BASELINE configs[4]:
+    4096 scenes over 8 GPUs).  The scenes are split into contiguous blocks, one ``BatchIntegrator`` (one persistent launch per
+    step) per device; a step enqueues all devices' launches and then waits for all of them -- there is no communication.
+    ``x`` / ``v`` are 3 x sum(nV) over all scenes in the caller's scene order; scene ``s`` lives on ``device_of[s]``."""
+
+    def __init__(self, datas, devices=None, **tuning):
+        from .. import _lib
+
+        datas = list(datas)
+        if devices is None:
+            devices = list(range(max(1, _lib.lib().vbdx_device_count())))
+        devices = list(devices)[:max(1, len(datas))]
+        if not devices:
+            raise ValueError("no device")
+        bounds = [(len(datas) * i) // len(devices) for i in range(len(devices) + 1)]
+        self.devices = devices
+        self.parts = [BatchIntegrator(datas[bounds[i]:bounds[i + 1]], device=dev, **tuning) for i, dev in enumerate(devices)]
+        self.device_of = np.concatenate([np.full(bounds[i + 1] - bounds[i], dev) for i, dev in enumerate(devices)])
+        self.n_scenes = len(datas)
+        offs = [0]
+        for p in self.parts:
+            offs.extend((offs[-1] - p.offsets[0] + p.offsets[1:]).tolist())
+        self.offsets = np.asarray(offs, np.int64)
+        self._vbounds = np.concatenate([[0], np.cumsum([p.nV for p in self.parts])])
+        self.nV = int(self._vbounds[-1])
+
+    def step(self, dt=0.01, iterations=20, substeps=1):
+        for p in self.parts:
+            p.step_async(dt, iterations, substeps)
+        for p in self.parts:
+            p.synchronize()
+
+    def _gather(self, what):
+        return np.concatenate([getattr(p, what) for p in self.parts], axis=1)
+
+    def _scatter(self, what, a):
+        a = np.asarray(a)
+        if a.shape != (3, self.nV):
+            raise ValueError(f"{what} must be 3 x {self.nV}, got {a.shape}")
+        for i, p in enumerate(self.parts):
+            setattr(p, what, np.ascontiguousarray(a[:, self._vbounds[i]:self._vbounds[i + 1]]))
+
+    x = property(lambda s: s._gather("x"), lambda s, a: s._scatter("x", a))
+    v = property(lambda s: s._gather("v"), lambda s, a: s._scatter("v", a))
+
+    def scene(self, a, s):
+        """Columns of a 3 x sum(nV) array that belong to scene ``s``."""
+        return a[:, self.offsets[s]:self.offsets[s + 1]]
+
+    @property
+    def info(self):
+        return [p.info for p in self.parts]

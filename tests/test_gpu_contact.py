@@ -134,6 +134,54 @@ def test_contact_solve_matches_oracle(cheb):
     assert xr[2, B == 1].min() > 0.45
 
 
+def test_config3_replica_against_oracle():
+    """BASELINE configs[2] scaled down (SURVEY.md 8d "C3": bodies stacked in z with a gap of 0.1 x extent, body ids 0.., the
+    bottom body's lowest 1 % fixed, muC = 1e6, muF = 0.3, epsv = 1e-3, active-set frequency 1, dt = 0.01, 20 iterations,
+    50 steps): three bodies of 6^3 cubes instead of sixteen of 29^3, against the contact oracle.
+
+    Every body is shifted sideways by a generic fraction of a cell: with identical grids exactly above each other every
+    surface vertex projects onto a VERTEX or an EDGE of the triangle below, and whether such a pair responds (barycentric
+    coordinates in [0, 1], sim/vbd/Kernels.h:253-258) is decided by the last bit -- fp32 and double then disagree at first
+    touch (tools/contact_diag.py: 85 = 85 contacts, different lists, 2.5e-5 -> 2.6e-2).  In generic position the two agree on
+    every contact list for the first 30 steps (free fall, first impacts, 146 vertices in contact) with positions equal to
+    6e-6; the stiff penalty (k = 1e6 x area) then amplifies the first borderline decision, so beyond that only the outcome
+    is compared."""
+    n = 6
+    Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+    X, T, B = meshes.stack_bodies(Xb, Tb, 3, axis=2, gap_frac=0.1)
+    for b in range(3):
+        X[0, B == b] += 0.37 * b / n
+        X[1, B == b] += 0.21 * b / n
+    F = meshes.boundary_facets(T)
+    V = np.unique(F)
+    dbc = np.flatnonzero(X[2] <= X[2].min() + 0.01)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e6, 0.3, 1e-3).construct())
+    vbd = pbat.gpu.vbd.Integrator(d)
+    ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, B=B, V=V, F=F, muC=1e6, muF=0.3, epsv=1e-3)
+    contacts = 0
+    for s in range(50):
+        vbd.step(0.01, 20, 1)
+        ref.step(0.01, 20, 1)
+        act, nn, _ = vbd.contact_state()
+        if s < 30:
+            rnn = ref.get("nn").reshape(-1, 8)
+            assert np.array_equal(np.sort(nn, axis=1), np.sort(rnn, axis=1)), f"contact lists differ at step {s}"
+            assert np.array_equal(act, ref.get("active").astype(bool))
+            err = np.linalg.norm(vbd.x - ref.x) / np.linalg.norm(ref.x)
+            assert err < 1e-4, (s, err)
+            contacts = max(contacts, int((nn >= 0).any(axis=1).sum()))
+    assert contacts > 100, "the bodies never touched"
+    xr, xg = ref.x, vbd.x
+    err = np.linalg.norm(xg - xr) / np.linalg.norm(xr)
+    print(f"config 3 replica: vertices in contact within 30 steps = {contacts}; rel L2 after 50 steps = {err:.3e}")
+    assert np.isfinite(xg).all() and err < 3e-2
+    for x in (xr, xg):   # same outcome: the stack stays ordered, nothing has passed through (a body is 6 cells high)
+        lo = np.array([x[2, B == b].min() for b in range(3)])
+        hi = np.array([x[2, B == b].max() for b in range(3)])
+        assert (np.diff(lo) > 0).all() and (lo[1:] - hi[:-1] > -3.0 / n).all()
+
+
 @pytest.mark.parametrize("accel", ["anderson", "broyden"])
 def test_windowed_accelerators_with_contact(accel):
     """The reference's example (python/examples/vbd.py:297-330) combines a surface mesh with Anderson / Broyden

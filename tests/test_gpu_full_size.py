@@ -52,20 +52,25 @@ def test_config2_free_fall_known_answer():
     assert np.allclose(vbd.v[2], -9.81e-2, atol=5e-4)
 
 
-def test_config2_one_step_against_the_oracle(config2):
+def test_config2_three_steps_against_the_oracle(config2):
+    """BASELINE configs[1] at full size, three steps (90 sweeps of 198,651 vertices) against the double-precision oracle from
+    the same fp32-representable start: position error and the stricter error relative to the DISPLACEMENT."""
     X, T, dbc, x0, d = config2
     vbd = pbat.gpu.vbd.Integrator(d)
     ref = oracle.Oracle(X, T, dbc=dbc, colors=d.colors, accel=oracle.ACCEL_CHEBYSHEV, rho=RHO)
     vbd.x = x0.astype(np.float32)
     ref.x = x0.astype(np.float32).astype(np.float64)
-    vbd.step(DT, ITERS, 1)
-    ref.step(DT, ITERS, 1)
+    for _ in range(3):
+        vbd.step(DT, ITERS, 1)
+        ref.step(DT, ITERS, 1)
     xr = ref.x
     err = rel_l2(vbd.x, xr)
     derr = np.linalg.norm(vbd.x - xr) / np.linalg.norm(xr - X)
-    print(f"config 2, one full step: rel L2 = {err:.3e}, displacement-relative = {derr:.3e}")
+    verr = np.linalg.norm(vbd.v - ref.v) / np.linalg.norm(ref.v)
+    print(f"config 2, three full steps: rel L2 = {err:.3e}, displacement-relative = {derr:.3e}, velocity-relative = {verr:.3e}")
     assert err < 1e-4
-    assert derr < 1e-2
+    assert derr < 1e-3
+    assert vbd.info["nonFiniteVertices"] == 0
 
 
 def test_config2_bit_identical_across_runs_and_kernel_variants(config2):
@@ -199,3 +204,30 @@ def test_batch_entry_point_with_ragged_scenes():
     other = pbat.sim.vbd.Data().with_volume_mesh(*meshes.tet_grid(2, 2, 2, 0.1)).construct()
     with pytest.raises(ValueError):
         pbat.gpu.vbd.BatchIntegrator([datas[0], other])
+
+
+def test_scene_batches_sharded_over_devices():
+    """BASELINE configs[4] at reduced size: scenes block-partitioned over several handles / devices (no communication) evolve
+    bit-identically to the same scenes in ONE batch.  Uses every visible GPU, or two handles on the only one."""
+    from physicsbasedanimationtoolkit_b200 import _lib
+
+    Xs, Ts = meshes.tet_grid(6, 6, 6, 0.1)
+    fixed = np.flatnonzero(Xs[2] == 0)
+    datas = []
+    for s in range(24):
+        xs = Xs + 0.002 * np.random.default_rng(s).uniform(-1, 1, Xs.shape)
+        datas.append(pbat.sim.vbd.Data().with_volume_mesh(xs, Ts).with_dirichlet_vertices(fixed).construct())
+    n_dev = _lib.lib().vbdx_device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    one = pbat.gpu.vbd.BatchIntegrator(datas)
+    many = pbat.gpu.vbd.MultiGpuBatchIntegrator(datas, devices=devices)
+    assert many.n_scenes == 24 and many.nV == one.nV and np.array_equal(many.offsets, one.offsets)
+    for _ in range(5):
+        one.step(0.01, 10, 1)
+        many.step(0.01, 10, 1)
+    assert np.array_equal(one.x, many.x) and np.array_equal(one.v, many.v)
+    x = many.x
+    x[2] += 0.01
+    many.x = x
+    assert np.array_equal(many.x, x.astype(np.float32))
+    assert np.array_equal(many.scene(x, 5), x[:, one.offsets[5]:one.offsets[6]])
