@@ -17,6 +17,8 @@
 #include "step_kernel_tma.cuh"
 #include "vbdx_internal.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +29,16 @@
 #include <vector>
 
 namespace vbdx {
+
+// NVTX ranges named like the reference's Tracy zones (PBAT_PROFILE_CUDA_NAMED_SCOPE in gpu/impl/vbd/Integrator.cu:84,93,165,...):
+// a profiler timeline (nsys, ncu --nvtx) shows the same phase names on both implementations.  Host-side ranges around the
+// enqueue of each phase; the header-only NVTX v3 costs a pointer check when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(char const* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(NvtxRange const&)            = delete;
+    NvtxRange& operator=(NvtxRange const&) = delete;
+};
 
 using StepKernelFn = void (*)(StepParams);
 using TmaKernelFn  = void (*)(TmaParams);
@@ -955,8 +967,12 @@ void Integrator::LaunchStepKernel(StepParams const& q)
 
 void Integrator::RunStep(StepParams const& p, double dt, int iterations, int substeps, bool sync)
 {
+    NvtxRange const zone("pbat.gpu.impl.vbd.Integrator.Step");
     bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-    auto launchStep = [&](StepParams const& q) { LaunchStepKernel(q); };
+    auto launchStep = [&](StepParams const& q) {
+        NvtxRange const z("pbat.gpu.impl.vbd.Integrator.Solve");
+        LaunchStepKernel(q);
+    };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
     VBDX_CUDA(cudaMemsetAsync(dBarrier.p + 1, 0, sizeof(unsigned int), stream));  // the step's non-finite sentinel
     if (acceleration == VBDX_ACCEL_ANDERSON)
@@ -978,19 +994,28 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
         // inertial targets + initial guess, (every `frequency` substeps) nearest triangles from the initial
         // guess, the solve, the velocity update; finally prune vertices that left the surface
         float4 const* xFinal = dPos.p + p.pOff;
-        contact.InitializeActiveSet(xFinal, dVel.p, dAext.p, nV, static_cast<float>(dt), stream, &kernelLaunches);
+        {
+            NvtxRange const z("pbat.gpu.impl.vbd.Integrator.InitializeActiveSet");
+            contact.InitializeActiveSet(xFinal, dVel.p, dAext.p, nV, static_cast<float>(dt), stream, &kernelLaunches);
+        }
         StepParams q  = p;
         q.substeps    = 1;
         q.skipPreStep = 1;
         for (int s = 0; s < substeps; ++s)
         {
-            if (cheb)
-                PreStepKernel<true><<<Blocks(nV, 256), 256, 0, stream>>>(q);
-            else
-                PreStepKernel<false><<<Blocks(nV, 256), 256, 0, stream>>>(q);
-            ++kernelLaunches;
+            {
+                NvtxRange const z("pbat.gpu.impl.vbd.Integrator.ComputeInertialTargets");  // + InitializeBcdSolution: one fused kernel
+                if (cheb)
+                    PreStepKernel<true><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+                else
+                    PreStepKernel<false><<<Blocks(nV, 256), 256, 0, stream>>>(q);
+                ++kernelLaunches;
+            }
             if (s % contact.updateFrequency == 0)
+            {
+                NvtxRange const z("pbat.gpu.impl.vbd.Integrator.UpdateActiveSet");
                 contact.NearestPass(xFinal, 0, stream, &kernelLaunches);
+            }
             launchStep(q);
         }
         contact.NearestPass(xFinal, 1, stream, &kernelLaunches);
@@ -1051,6 +1076,7 @@ void Integrator::LaunchPreStep(StepParams const& q)
 // launches of the persistent step kernel, the window lives in anderson.cuh's kernels; nothing returns to the host.
 void Integrator::AndersonStep(StepParams const& p, double dt, int iterations, int substeps)
 {
+    NvtxRange const zone("pbat.gpu.impl.vbd.AndersonIntegrator.Solve");
     int const m = window;
     if (dAndVec.n == 0)
     {
@@ -1233,6 +1259,7 @@ double Integrator::ObjectiveOfState(double sdt)
 // read-back per evaluation); iterates, step sizes and path updates stay on the device.
 void Integrator::TrustRegionStep(StepParams const& p, double dt, int iterations, int substeps)
 {
+    NvtxRange const zone("pbat.gpu.impl.vbd.TrustRegionIntegrator.SolveWithLinearAcceleratedPath");
     if (dAndVec.n == 0)
     {
         dAndVec.Alloc(static_cast<size_t>(nV) * 2, &deviceBytes);
