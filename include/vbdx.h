@@ -363,6 +363,61 @@ vbdx_status vbdx_debug_trace(vbdx_integrator* h, int32_t iteration, unsigned lon
 vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int64_t* colors_out);
 
 const char* vbdx_last_error(void);
+/* ---- XPBD over the same contact pipeline -------------------------------------------------
+ * Replaces pbat::gpu::xpbd::Integrator (gpu/xpbd/Integrator.h:27-170; impl gpu/impl/xpbd/Integrator.cu:88-448), constructed from
+ * what pbat::sim::xpbd::Data holds after Construct() (sim/xpbd/Data.h:19-104, sim/xpbd/Data.cpp:102-160).  Arrays follow the
+ * reference's conventions: X 3 x nV and T 4 x nT column-major, Pptr / Padj (and SGptr, SGadj, Cptr, Cadj for clustered
+ * partitions) compressed sparse lists of constraint (= element) ids.  One persistent cooperative launch runs a whole
+ * substep (a whole Step without a collision mesh); partitions are separated by grid barriers inside the kernel. */
+typedef enum vbdx_xpbd_constraint { VBDX_XPBD_STABLE_NEO_HOOKEAN = 0, VBDX_XPBD_COLLISION = 1 } vbdx_xpbd_constraint; /* sim/xpbd/Enums.h:9-11 */
+typedef struct vbdx_xpbd_desc {
+    uint32_t abi_version, struct_size;
+    int64_t nV, nT;
+    const double* X;        /* 3 x nV particle positions (Data::x) */
+    const int64_t* T;       /* 4 x nT tetrahedra */
+    const double* v;        /* 3 x nV or NULL (zero) */
+    const double* aext;     /* 3 x nV or NULL (gravity -9.81 along z, sim/xpbd/Data.cpp:108-112) */
+    const double* minv;     /* nV inverse masses or NULL (1e-3, sim/xpbd/Data.cpp:113-116) */
+    const double* lame;     /* 2 x nT or NULL (Y = 1e6, nu = 0.45, sim/xpbd/Data.cpp:127-133) */
+    const int64_t* dbc;     /* Dirichlet vertices: minv = 0, v = a = 0 (sim/xpbd/Data.cpp:122-125) */
+    int64_t nDbc;
+    const int64_t* Pptr;    /* nPartitions + 1 */
+    const int64_t* Padj;
+    int32_t nPartitions, nClusterPartitions;
+    const int64_t *SGptr, *SGadj, *Cptr, *Cadj; /* clustered partitions (Data::WithClusterPartitions) or NULL */
+    const double* alphaSNH; /* 2 x nT compliances or NULL (1 / (lame * volume), sim/xpbd/Data.cpp:145-148) */
+    const double* betaSNH;  /* 2 x nT damping or NULL (0) */
+    const int64_t* BV;      /* nV body ids or NULL (one body) */
+    const int64_t* V;       /* nCV collision vertices */
+    int64_t nCV;
+    const int64_t* F;       /* 3 x nF collision triangles */
+    int64_t nF;
+    const double* muV;      /* nCV collision penalties or NULL (1) */
+    const double* alphaC;   /* nCV contact compliances / damping or NULL (0); per collision vertex (the reference indexes them by slot */
+    const double* betaC;    /*   in its active list, gpu/impl/xpbd/Integrator.cu:372-414: identical for the uniform values it is used with) */
+    double muS, muD;        /* static / dynamic friction (sim/xpbd/Data.h:85-86) */
+    int32_t active_set_update_frequency;
+    int32_t device;
+} vbdx_xpbd_desc;
+typedef struct vbdx_xpbd vbdx_xpbd;
+void vbdx_xpbd_desc_init(vbdx_xpbd_desc* d);
+vbdx_status vbdx_xpbd_create(const vbdx_xpbd_desc* desc, vbdx_xpbd** out);
+vbdx_status vbdx_xpbd_destroy(vbdx_xpbd* h);
+vbdx_status vbdx_xpbd_step(vbdx_xpbd* h, double dt, int32_t iterations, int32_t substeps);      /* gpu/xpbd/Integrator.h:66 */
+vbdx_status vbdx_xpbd_set_positions(vbdx_xpbd* h, const double* x, int64_t nV);                   /* :77 */
+vbdx_status vbdx_xpbd_set_velocities(vbdx_xpbd* h, const double* v, int64_t nV);                  /* :82 */
+vbdx_status vbdx_xpbd_set_external_acceleration(vbdx_xpbd* h, const double* a, int64_t nV);       /* :87 */
+vbdx_status vbdx_xpbd_get_positions(vbdx_xpbd* h, double* x, int64_t nV);                         /* :71 */
+vbdx_status vbdx_xpbd_get_velocities(vbdx_xpbd* h, double* v, int64_t nV);
+vbdx_status vbdx_xpbd_set_compliance(vbdx_xpbd* h, int32_t constraint, const double* alpha, int64_t n); /* :119 */
+vbdx_status vbdx_xpbd_set_friction_coefficients(vbdx_xpbd* h, double muS, double muD);            /* :126 */
+vbdx_status vbdx_xpbd_set_scene_bounding_box(vbdx_xpbd* h, const float min3[3], const float max3[3]); /* :133 */
+/* out8 = nV, nT, partitions, grid blocks, kernel launches, device bytes, last step in ns, nCV */
+vbdx_status vbdx_xpbd_get_info(vbdx_xpbd* h, int64_t* out8);
+vbdx_status vbdx_xpbd_get_contact_state(vbdx_xpbd* h, int32_t* active, int32_t* nn, int64_t* nActive);
+/* graph/Color.h:45-135 on a graph in compressed sparse format (bindings/pypbat/graph/Color.cpp:28-60 greedy_color); host only */
+vbdx_status vbdx_graph_greedy_color(int64_t n, const int64_t* ptr, const int64_t* adj, int32_t ordering, int32_t selection, int64_t* colors_out);
+
 /* Test hooks (GPU): the sweep's vertex-triangle contact term (csrc/contact.cuh, restating sim/vbd/Kernels.h:223-302) and its
  * area-scaled penalties (gpu/impl/vbd/Kernels.cuh:80-114) on caller-supplied inputs.  in28 = per pair xtv(3) xv(3) xtf(3 x 3,
  * one triangle vertex after the other) xf(3 x 3) dt k muF epsv;  out13 = 0, g(3), H(3 x 3).  fc = 8 triangle ids per vertex. */

@@ -75,6 +75,10 @@ def _load(kind: str) -> C.CDLL:
     lib.vbdo_set_params.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     lib.vbdo_set_acceleration.restype = C.c_int
     lib.vbdo_set_acceleration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64]
+    lib.vbdo_xpbd_setup.restype = C.c_int
+    lib.vbdo_xpbd_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vbdo_xpbd_step.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_int64]
     lib.vbdo_set_trust_region.restype = C.c_int
     lib.vbdo_set_trust_region.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
     lib.vbdo_objective.restype = C.c_double
@@ -208,6 +212,22 @@ class Oracle:
         Data::Construct, sim/vbd/Data.cpp:268-296)."""
         if self.lib.vbdo_set_acceleration(self.h, int(accel), float(rho), float(L), int(start), int(window)):
             raise ValueError("invalid acceleration parameters")
+
+    def xpbd_setup(self, Pptr, Padj, minv=None, muV=None, muS=0.3, muD=0.2, beta_snh=None, alpha_c=None, beta_c=None):
+        """Turns this problem into an XPBD one (sim/xpbd/Data.cpp:102-160): constraint partitions ``Pptr`` / ``Padj`` over the
+        tets, inverse masses (default 1e-3), collision penalties per collision vertex (default 1), friction coefficients,
+        optional damping of the elastic constraints (2 per tet) and compliance / damping of the contacts."""
+        def arr(a, dt=np.float64):
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        Pptr, Padj = arr(Pptr, np.int64), arr(Padj, np.int64)
+        minv, muV, beta_snh, alpha_c, beta_c = arr(minv), arr(muV), arr(beta_snh), arr(alpha_c), arr(beta_c)
+        if self.lib.vbdo_xpbd_setup(self.h, _ptr(minv), _ptr(muV), float(muS), float(muD), _ptr(Pptr), Pptr.size - 1, _ptr(Padj),
+                                    _ptr(beta_snh), _ptr(alpha_c), _ptr(beta_c)):
+            raise ValueError(self.lib.vbdo_last_error().decode())
+
+    def xpbd_step(self, dt, iterations, substeps=1):
+        """sim/xpbd/Integrator.cpp:31-139 with the GPU path's contact pipeline (gpu/impl/xpbd/Integrator.cu:88-186)."""
+        self.lib.vbdo_xpbd_step(self.h, float(dt), int(iterations), int(substeps))
 
     def set_trust_region(self, eta=0.2, tau=2.0, curved=True):
         """Data::WithTrustRegionAcceleration (sim/vbd/Data.cpp); the solve follows gpu/impl/vbd/TrustRegionIntegrator.cu."""

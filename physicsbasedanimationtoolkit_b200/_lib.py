@@ -41,6 +41,23 @@ class DataDesc(C.Structure):
     ]
 
 
+class XpbdDesc(C.Structure):
+    """``vbdx_xpbd_desc`` (include/vbdx.h)."""
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("struct_size", C.c_uint32),
+        ("nV", C.c_int64), ("nT", C.c_int64),
+        ("X", C.c_void_p), ("T", C.c_void_p), ("v", C.c_void_p), ("aext", C.c_void_p), ("minv", C.c_void_p), ("lame", C.c_void_p),
+        ("dbc", C.c_void_p), ("nDbc", C.c_int64),
+        ("Pptr", C.c_void_p), ("Padj", C.c_void_p), ("nPartitions", C.c_int32), ("nClusterPartitions", C.c_int32),
+        ("SGptr", C.c_void_p), ("SGadj", C.c_void_p), ("Cptr", C.c_void_p), ("Cadj", C.c_void_p),
+        ("alphaSNH", C.c_void_p), ("betaSNH", C.c_void_p),
+        ("BV", C.c_void_p), ("V", C.c_void_p), ("nCV", C.c_int64), ("F", C.c_void_p), ("nF", C.c_int64),
+        ("muV", C.c_void_p), ("alphaC", C.c_void_p), ("betaC", C.c_void_p),
+        ("muS", C.c_double), ("muD", C.c_double),
+        ("active_set_update_frequency", C.c_int32), ("device", C.c_int32),
+    ]
+
+
 class Info(C.Structure):
     """``vbdx_info`` (include/vbdx.h)."""
     _fields_ = [
@@ -118,6 +135,21 @@ SYMBOLS = {
     "vbdx_greedy_color": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "vbdx_debug_contact_pairs": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
     "vbdx_debug_contact_penalties": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "vbdx_xpbd_desc_init": (None, [C.POINTER(XpbdDesc)]),
+    "vbdx_xpbd_create": (C.c_int, [C.POINTER(XpbdDesc), C.POINTER(_H)]),
+    "vbdx_xpbd_destroy": (C.c_int, [_H]),
+    "vbdx_xpbd_step": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32]),
+    "vbdx_xpbd_set_positions": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_set_velocities": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_set_external_acceleration": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_get_positions": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_get_velocities": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_set_compliance": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int64]),
+    "vbdx_xpbd_set_friction_coefficients": (C.c_int, [_H, C.c_double, C.c_double]),
+    "vbdx_xpbd_set_scene_bounding_box": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "vbdx_xpbd_get_info": (C.c_int, [_H, C.c_void_p]),
+    "vbdx_xpbd_get_contact_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vbdx_graph_greedy_color": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "vbdx_last_error": (C.c_char_p, []),
     "vbdx_abi_version": (C.c_int32, []),
     "vbdx_device_count": (C.c_int32, []),

@@ -90,38 +90,46 @@ void GreedyColorMesh(
                 }
             }
     }
-    // visiting order: stable by degree == counting sort over degrees
-    std::vector<int64_t> order(nV);
+    GreedyColorGraph(nV, ringPtr.data(), ring.data(), ordering, selection, colors);
+}
+
+// graph/Color.h:45-135 on a graph in compressed sparse format (ptr, adj): vertices are visited in natural order or in
+// (stable) order of their degree ptr[u+1] - ptr[u]; a vertex takes, among the colours none of its neighbours has, the
+// one with the fewest vertices (LeastUsed; ties to the lowest index) or the lowest one (FirstAvailable); a new colour is
+// opened only when all are blocked.
+void GreedyColorGraph(int64_t n, const int64_t* ptr, const int32_t* adj, int ordering, int selection, std::vector<int64_t>& colors)
+{
+    std::vector<int64_t> order(n);
     if (ordering == 0 /* Natural */)
         std::iota(order.begin(), order.end(), int64_t(0));
     else
     {
         int64_t maxDeg = 0;
-        for (int64_t u = 0; u < nV; ++u)
-            maxDeg = std::max(maxDeg, ringPtr[u + 1] - ringPtr[u]);
+        for (int64_t u = 0; u < n; ++u)
+            maxDeg = std::max(maxDeg, ptr[u + 1] - ptr[u]);
         std::vector<int64_t> bucket(maxDeg + 2, 0);
         bool const largestFirst = (ordering == 2);
         auto slot = [&](int64_t u) {
-            int64_t const d = ringPtr[u + 1] - ringPtr[u];
+            int64_t const d = ptr[u + 1] - ptr[u];
             return largestFirst ? (maxDeg - d) : d;
         };
-        for (int64_t u = 0; u < nV; ++u)
+        for (int64_t u = 0; u < n; ++u)
             ++bucket[slot(u) + 1];
         for (int64_t d = 0; d <= maxDeg; ++d)
             bucket[d + 1] += bucket[d];
-        for (int64_t u = 0; u < nV; ++u)
+        for (int64_t u = 0; u < n; ++u)
             order[bucket[slot(u)]++] = u;
     }
-    colors.assign(nV, -1);
+    colors.assign(n, -1);
     std::vector<int64_t> used;     // vertices per colour
     std::vector<uint8_t> blocked;  // per colour, for the vertex being coloured
     for (int64_t u : order)
     {
         std::fill(blocked.begin(), blocked.end(), uint8_t(0));
         size_t nBlocked = 0;
-        for (int64_t k = ringPtr[u]; k < ringPtr[u + 1]; ++k)
+        for (int64_t k = ptr[u]; k < ptr[u + 1]; ++k)
         {
-            int64_t const c = colors[ring[k]];
+            int64_t const c = colors[adj[k]];
             if (c >= 0 && !blocked[c])
             {
                 blocked[c] = 1;

@@ -2602,3 +2602,520 @@ vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t 
 }
 
 }  // extern "C"
+
+// ============================================================================================
+// XPBD (xpbd.cuh): host driver and C ABI
+// ============================================================================================
+#include "xpbd.cuh"
+
+namespace vbdx {
+
+__global__ void XpbdSetXyz(int64_t n, const double* src, float4* dst, int keepW)
+{
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = make_float4(static_cast<float>(src[3 * i]), static_cast<float>(src[3 * i + 1]), static_cast<float>(src[3 * i + 2]),
+                             keepW ? dst[i].w : 0.f);
+}
+__global__ void XpbdGetXyz(int64_t n, const float4* src, double* dst)
+{
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[3 * i] = src[i].x, dst[3 * i + 1] = src[i].y, dst[3 * i + 2] = src[i].z;
+}
+__global__ void XpbdSetW(int64_t n, const float* w, float4* dst)
+{
+    int64_t const i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i].w = w[i];
+}
+
+struct XpbdIntegrator {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+    int64_t nV = 0, nT = 0, nCV = 0, nF = 0;
+    int64_t deviceBytes = 0, kernelLaunches = 0;
+    double lastStepMs = 0;
+    int gridBlocks = 0, nPartitions = 0;
+    double muS = 0.3, muD = 0.2;
+    std::vector<int32_t> slotOfTet;  // caller tet id -> constraint slot (partition-major order)
+    DevBuf<float4> dX, dXt, dVel, dAext, dRec, dXb;
+    DevBuf<int4> dTetIds;
+    DevBuf<float2> dBeta, dLambda;
+    DevBuf<uint32_t> dItemBegin, dPartBegin;
+    DevBuf<float> dMuV, dAlphaC, dBetaC, dLambdaC;
+    DevBuf<unsigned int> dBarrier;
+    DevBuf<double> dStaging;
+    std::vector<float> alphaHost;  // 2 per slot (compliances can be replaced: SetCompliance)
+    ContactState contact;
+
+    ~XpbdIntegrator()
+    {
+        if (evBegin)
+            cudaEventDestroy(evBegin);
+        if (evEnd)
+            cudaEventDestroy(evEnd);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+
+    void Create(vbdx_xpbd_desc const& d);
+    XpbdParams MakeParams(double sdt, int iterations, int substeps);
+    void Step(double dt, int iterations, int substeps);
+    void UploadRecords(std::vector<float4> const& rec) { dRec.Upload(rec.data(), rec.size(), stream); }
+    std::vector<float4> recHost;
+};
+
+void XpbdIntegrator::Create(vbdx_xpbd_desc const& d)
+{
+    Require(d.abi_version == VBDX_ABI_VERSION && d.struct_size == sizeof(vbdx_xpbd_desc), "vbdx_xpbd_desc: ABI version / struct size mismatch");
+    Require(d.nV > 0 && d.nT > 0 && d.X && d.T, "need a volume mesh: X (3 x nV) and T (4 x nT)");
+    Require(d.nV < (int64_t(1) << 31) - 1 && d.nT < (int64_t(1) << 30), "mesh too large for 32-bit device indices");
+    nV = d.nV, nT = d.nT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        throw Error(VBDX_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (d.device >= 0)
+    {
+        Require(d.device < count, "device ordinal out of range");
+        VBDX_CUDA(cudaSetDevice(d.device));
+    }
+    VBDX_CUDA(cudaGetDevice(&device));
+    VBDX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    VBDX_CUDA(cudaEventCreate(&evBegin));
+    VBDX_CUDA(cudaEventCreate(&evEnd));
+    for (int64_t k = 0; k < 4 * nT; ++k)
+        Require(d.T[k] >= 0 && d.T[k] < nV, "element index out of range");
+    // ---- partitions: plain (every constraint its own work item) or clustered (sim/xpbd/Data.h:95-103)
+    Require(d.Pptr && d.Padj && d.nPartitions >= 1, "XPBD needs constraint partitions (Data::WithPartitions)");
+    bool const clustered = d.SGptr != nullptr && d.nClusterPartitions > 0;
+    if (clustered)
+        Require(d.SGadj && d.Cptr && d.Cadj, "cluster partitions need SGptr, SGadj, Cptr and Cadj");
+    std::vector<uint32_t> partBegin, itemBegin;
+    std::vector<int64_t> order;  // constraint (tet) of every slot
+    if (!clustered)
+    {
+        nPartitions = d.nPartitions;
+        for (int32_t q = 0; q <= d.nPartitions; ++q)
+            partBegin.push_back(static_cast<uint32_t>(d.Pptr[q]));
+        for (int64_t k = 0; k < d.Pptr[d.nPartitions]; ++k)
+        {
+            itemBegin.push_back(static_cast<uint32_t>(order.size()));
+            order.push_back(d.Padj[k]);
+        }
+    }
+    else
+    {
+        nPartitions = d.nClusterPartitions;
+        for (int32_t q = 0; q < d.nClusterPartitions; ++q)
+        {
+            partBegin.push_back(static_cast<uint32_t>(itemBegin.size()));
+            for (int64_t k = d.SGptr[q]; k < d.SGptr[q + 1]; ++k)
+            {
+                int64_t const cl = d.SGadj[k];
+                itemBegin.push_back(static_cast<uint32_t>(order.size()));
+                for (int64_t j = d.Cptr[cl]; j < d.Cptr[cl + 1]; ++j)
+                    order.push_back(d.Cadj[j]);
+            }
+        }
+        partBegin.push_back(static_cast<uint32_t>(itemBegin.size()));
+    }
+    itemBegin.push_back(static_cast<uint32_t>(order.size()));
+    Require(static_cast<int64_t>(order.size()) == nT, "the partitions must list every element exactly once");
+    slotOfTet.assign(nT, -1);
+    for (size_t sidx = 0; sidx < order.size(); ++sidx)
+    {
+        Require(order[sidx] >= 0 && order[sidx] < nT && slotOfTet[order[sidx]] < 0, "the partitions must list every element exactly once");
+        slotOfTet[order[sidx]] = static_cast<int32_t>(sidx);
+    }
+    {
+        // no two constraints of a partition that run concurrently may share a vertex
+        std::vector<int32_t> owner(nV, -1), ownerPart(nV, -1);
+        for (int32_t q = 0; q < nPartitions; ++q)
+            for (uint32_t it = partBegin[q]; it < partBegin[q + 1]; ++it)
+                for (uint32_t c = itemBegin[it]; c < itemBegin[it + 1]; ++c)
+                    for (int a = 0; a < 4; ++a)
+                    {
+                        int64_t const vtx = d.T[4 * order[c] + a];
+                        Require(!(ownerPart[vtx] == q && owner[vtx] != static_cast<int32_t>(it)),
+                                "invalid partitioning: two constraints of one partition share a vertex");
+                        ownerPart[vtx] = q, owner[vtx] = static_cast<int32_t>(it);
+                    }
+    }
+    // ---- per-constraint data (sim/xpbd/Data.cpp:131-153): DmInv, compliance 1 / (lame * volume), gamma = 1 + mu / lambda
+    double const Y = 1e6, nu = 0.45;
+    double const muDefault = Y / (2. * (1. + nu)), lamDefault = (Y * nu) / ((1. + nu) * (1. - 2. * nu));
+    std::vector<int4> ids(nT);
+    recHost.assign(3 * static_cast<size_t>(nT), make_float4(0, 0, 0, 0));
+    std::vector<float2> beta(nT, make_float2(0.f, 0.f));
+    for (int64_t sidx = 0; sidx < nT; ++sidx)
+    {
+        int64_t const t = order[sidx];
+        int64_t const* e = d.T + 4 * t;
+        ids[sidx]        = make_int4(static_cast<int>(e[0]), static_cast<int>(e[1]), static_cast<int>(e[2]), static_cast<int>(e[3]));
+        double Ds[3][3];
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r)
+                Ds[r][c] = d.X[3 * e[c + 1] + r] - d.X[3 * e[0] + r];
+        double const det = Ds[0][0] * (Ds[1][1] * Ds[2][2] - Ds[1][2] * Ds[2][1]) - Ds[0][1] * (Ds[1][0] * Ds[2][2] - Ds[1][2] * Ds[2][0]) +
+                           Ds[0][2] * (Ds[1][0] * Ds[2][1] - Ds[1][1] * Ds[2][0]);
+        Require(det > 1e-300, "inverted or degenerate tetrahedron in the rest mesh");
+        double inv[3][3];
+        inv[0][0] = (Ds[1][1] * Ds[2][2] - Ds[1][2] * Ds[2][1]) / det, inv[0][1] = (Ds[0][2] * Ds[2][1] - Ds[0][1] * Ds[2][2]) / det;
+        inv[0][2] = (Ds[0][1] * Ds[1][2] - Ds[0][2] * Ds[1][1]) / det, inv[1][0] = (Ds[1][2] * Ds[2][0] - Ds[1][0] * Ds[2][2]) / det;
+        inv[1][1] = (Ds[0][0] * Ds[2][2] - Ds[0][2] * Ds[2][0]) / det, inv[1][2] = (Ds[0][2] * Ds[1][0] - Ds[0][0] * Ds[1][2]) / det;
+        inv[2][0] = (Ds[1][0] * Ds[2][1] - Ds[1][1] * Ds[2][0]) / det, inv[2][1] = (Ds[0][1] * Ds[2][0] - Ds[0][0] * Ds[2][1]) / det;
+        inv[2][2] = (Ds[0][0] * Ds[1][1] - Ds[0][1] * Ds[1][0]) / det;
+        double const mu = d.lame ? d.lame[2 * t] : muDefault, lam = d.lame ? d.lame[2 * t + 1] : lamDefault, vol = det / 6.0;
+        double const aD = d.alphaSNH ? d.alphaSNH[2 * t] : 1.0 / (mu * vol), aH = d.alphaSNH ? d.alphaSNH[2 * t + 1] : 1.0 / (lam * vol);
+        // record = DmInv column c in xyz, w = gamma / alpha_D / alpha_H
+        for (int c = 0; c < 3; ++c)
+            recHost[3 * sidx + c] = make_float4(static_cast<float>(inv[0][c]), static_cast<float>(inv[1][c]), static_cast<float>(inv[2][c]),
+                                                static_cast<float>(c == 0 ? 1.0 + mu / lam : c == 1 ? aD : aH));
+        if (d.betaSNH)
+            beta[sidx] = make_float2(static_cast<float>(d.betaSNH[2 * t]), static_cast<float>(d.betaSNH[2 * t + 1]));
+    }
+    // ---- particles (sim/xpbd/Data.cpp:104-126): minv default 1e-3, Dirichlet vertices get minv = 0 and v = a = 0
+    std::vector<float4> x(nV), v(nV, make_float4(0, 0, 0, 0)), a(nV, make_float4(0.f, 0.f, -9.81f, 0.f));
+    for (int64_t i = 0; i < nV; ++i)
+    {
+        x[i] = make_float4(static_cast<float>(d.X[3 * i]), static_cast<float>(d.X[3 * i + 1]), static_cast<float>(d.X[3 * i + 2]),
+                           static_cast<float>(d.minv ? d.minv[i] : 1e-3));
+        if (d.v)
+            v[i] = make_float4(static_cast<float>(d.v[3 * i]), static_cast<float>(d.v[3 * i + 1]), static_cast<float>(d.v[3 * i + 2]), 0.f);
+        if (d.aext)
+            a[i] = make_float4(static_cast<float>(d.aext[3 * i]), static_cast<float>(d.aext[3 * i + 1]), static_cast<float>(d.aext[3 * i + 2]), 0.f);
+    }
+    for (int64_t k = 0; k < d.nDbc; ++k)
+    {
+        Require(d.dbc && d.dbc[k] >= 0 && d.dbc[k] < nV, "Dirichlet vertex index out of range");
+        x[d.dbc[k]].w = 0.f;
+        v[d.dbc[k]] = a[d.dbc[k]] = make_float4(0, 0, 0, 0);
+    }
+    dX.Alloc(nV, &deviceBytes), dXt.Alloc(nV, &deviceBytes), dVel.Alloc(nV, &deviceBytes), dAext.Alloc(nV, &deviceBytes);
+    dX.Upload(x.data(), nV, stream), dXt.Upload(x.data(), nV, stream), dVel.Upload(v.data(), nV, stream), dAext.Upload(a.data(), nV, stream);
+    dTetIds.Alloc(nT, &deviceBytes), dRec.Alloc(3 * static_cast<size_t>(nT), &deviceBytes), dBeta.Alloc(nT, &deviceBytes), dLambda.Alloc(nT, &deviceBytes);
+    dTetIds.Upload(ids.data(), nT, stream), dRec.Upload(recHost.data(), recHost.size(), stream), dBeta.Upload(beta.data(), nT, stream);
+    VBDX_CUDA(cudaMemsetAsync(dLambda.p, 0, nT * sizeof(float2), stream));
+    dItemBegin.Alloc(itemBegin.size(), &deviceBytes), dPartBegin.Alloc(partBegin.size(), &deviceBytes);
+    dItemBegin.Upload(itemBegin.data(), itemBegin.size(), stream), dPartBegin.Upload(partBegin.data(), partBegin.size(), stream);
+    dBarrier.Alloc(1, &deviceBytes);
+    dStaging.Alloc(3 * nV, &deviceBytes);
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+    muS = d.muS, muD = d.muD;
+    // ---- contact
+    if (d.nF > 0 && d.nCV > 0)
+    {
+        Require(d.F != nullptr && d.V != nullptr, "collision mesh pointers missing");
+        Require(d.active_set_update_frequency >= 1, "active set update frequency must be >= 1");
+        nCV = d.nCV, nF = d.nF;
+        ContactState& cs = contact;
+        cs.nCV = static_cast<uint32_t>(nCV), cs.nF = static_cast<uint32_t>(nF);
+        cs.updateFrequency = d.active_set_update_frequency;
+        std::vector<int32_t> Bh(nV), Vh(nCV);
+        std::vector<int4> Fh(nF);
+        for (int64_t i = 0; i < nV; ++i)
+            Bh[i] = d.BV ? static_cast<int32_t>(d.BV[i]) : 0;  // sim/xpbd/Data.cpp:121-124: one body by default
+        for (int64_t k = 0; k < nCV; ++k)
+        {
+            Require(d.V[k] >= 0 && d.V[k] < nV, "collision vertex index out of range");
+            Vh[k] = static_cast<int32_t>(d.V[k]);
+        }
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            for (int k = 0; k < 3; ++k)
+                Require(d.F[3 * f + k] >= 0 && d.F[3 * f + k] < nV, "collision triangle index out of range");
+            Fh[f] = make_int4(static_cast<int>(d.F[3 * f]), static_cast<int>(d.F[3 * f + 1]), static_cast<int>(d.F[3 * f + 2]), 0);
+        }
+        cs.B.Alloc(nV, &deviceBytes), cs.V.Alloc(nCV, &deviceBytes), cs.F.Alloc(nF, &deviceBytes);
+        cs.B.Upload(Bh.data(), nV, stream), cs.V.Upload(Vh.data(), nCV, stream), cs.F.Upload(Fh.data(), nF, stream);
+        cs.mesh = ContactMesh{cs.B.p, cs.V.p, cs.F.p, cs.nCV, cs.nF};
+        cs.Alloc(nV, &deviceBytes, stream);
+        cs.enabled = true;
+        std::vector<float> muV(nCV, 1.f), aC(nCV, 0.f), bC(nCV, 0.f);
+        for (int64_t k = 0; k < nCV; ++k)
+        {
+            if (d.muV)
+                muV[k] = static_cast<float>(d.muV[k]);
+            if (d.alphaC)
+                aC[k] = static_cast<float>(d.alphaC[k]);
+            if (d.betaC)
+                bC[k] = static_cast<float>(d.betaC[k]);
+        }
+        dMuV.Alloc(nCV, &deviceBytes), dAlphaC.Alloc(nCV, &deviceBytes), dBetaC.Alloc(nCV, &deviceBytes), dLambdaC.Alloc(nCV, &deviceBytes);
+        dXb.Alloc(nCV, &deviceBytes);
+        dMuV.Upload(muV.data(), nCV, stream), dAlphaC.Upload(aC.data(), nCV, stream), dBetaC.Upload(bC.data(), nCV, stream);
+        VBDX_CUDA(cudaMemsetAsync(dLambdaC.p, 0, nCV * sizeof(float), stream));
+        VBDX_CUDA(cudaStreamSynchronize(stream));
+    }
+    int perSm = 0;
+    VBDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, XpbdSolveKernel, 256, 0));
+    cudaDeviceProp prop;
+    VBDX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (perSm < 1 || !prop.cooperativeLaunch)
+        throw Error(VBDX_CUDA_ERROR, "the XPBD solve kernel does not fit on an SM");
+    // no more CTAs than the largest partition can feed
+    uint32_t maxItems = 1;
+    for (int32_t q = 0; q < nPartitions; ++q)
+        maxItems = std::max(maxItems, partBegin[q + 1] - partBegin[q]);
+    int64_t const want = std::max<int64_t>(Blocks(std::max<int64_t>(maxItems, nCV), 256), 1);
+    gridBlocks         = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(perSm) * prop.multiProcessorCount, std::max<int64_t>(want, prop.multiProcessorCount)));
+}
+
+XpbdParams XpbdIntegrator::MakeParams(double sdt, int iterations, int substeps)
+{
+    XpbdParams p{};
+    p.x = dX.p, p.xt = dXt.p, p.vel = dVel.p, p.aext = dAext.p;
+    p.tetIds = dTetIds.p, p.rec = dRec.p, p.beta = dBeta.p, p.lambda = dLambda.p;
+    p.itemBegin = dItemBegin.p, p.partBegin = dPartBegin.p;
+    p.nPartitions = nPartitions, p.nV = static_cast<int>(nV), p.nT = static_cast<int>(nT);
+    p.sdt = static_cast<float>(sdt), p.sdt2 = static_cast<float>(sdt * sdt);
+    p.iterations = iterations, p.substeps = substeps;
+    p.barrier = dBarrier.p;
+    if (contact.enabled)
+    {
+        p.nCV = static_cast<int>(nCV);
+        p.nActive = contact.nActive.p, p.av = contact.av.p, p.V = contact.V.p, p.triF = contact.F.p, p.nn = contact.nn.p;
+        p.xb = dXb.p, p.muV = dMuV.p, p.alphaC = dAlphaC.p, p.betaC = dBetaC.p, p.lambdaC = dLambdaC.p;
+        p.muS = static_cast<float>(muS), p.muD = static_cast<float>(muD);
+    }
+    return p;
+}
+
+void XpbdIntegrator::Step(double dt, int iterations, int substeps)
+{
+    Require(dt > 0 && iterations >= 0 && substeps >= 1, "Step: need dt > 0, iterations >= 0, substeps >= 1");
+    NvtxRange const zone("pbat.gpu.impl.xpbd.Integrator.Step");
+    VBDX_CUDA(cudaSetDevice(device));
+    double const sdt = dt / substeps;
+    VBDX_CUDA(cudaEventRecord(evBegin, stream));
+    auto solve = [&](XpbdParams& p) {
+        VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
+        void* args[] = {&p};
+        VBDX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(XpbdSolveKernel), dim3(gridBlocks), dim3(256), args, 0, stream));
+        ++kernelLaunches;
+    };
+    if (!contact.enabled)
+    {
+        XpbdParams p = MakeParams(sdt, iterations, substeps);
+        solve(p);
+    }
+    else
+    {
+        // active set from the full-step predictor x + dt v + dt^2 a (gpu/impl/xpbd/Integrator.cu:96-117)
+        contact.InitializeActiveSet(dX.p, dVel.p, dAext.p, nV, static_cast<float>(dt), stream, &kernelLaunches);
+        XpbdParams p  = MakeParams(sdt, iterations, 1);
+        p.skipPreStep = 1;
+        int const n   = static_cast<int>(std::max(std::max(nV, nT), nCV));
+        for (int s = 0; s < substeps; ++s)
+        {
+            XpbdPreStepKernel<<<Blocks(n, 256), 256, 0, stream>>>(p);
+            ++kernelLaunches;
+            if (s % contact.updateFrequency == 0)
+                contact.NearestPass(dX.p, 0, stream, &kernelLaunches);
+            solve(p);
+        }
+        contact.NearestPass(dX.p, 1, stream, &kernelLaunches);
+    }
+    VBDX_CUDA(cudaEventRecord(evEnd, stream));
+    VBDX_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    VBDX_CUDA(cudaEventElapsedTime(&ms, evBegin, evEnd));
+    lastStepMs = ms;
+}
+
+}  // namespace vbdx
+
+struct vbdx_xpbd {
+    vbdx::XpbdIntegrator impl;
+};
+
+extern "C" {
+
+void vbdx_xpbd_desc_init(vbdx_xpbd_desc* d)
+{
+    std::memset(d, 0, sizeof(*d));
+    d->abi_version = VBDX_ABI_VERSION;
+    d->struct_size = sizeof(vbdx_xpbd_desc);
+    d->muS = 0.3, d->muD = 0.2;  // sim/xpbd/Data.h:85-86
+    d->active_set_update_frequency = 1;
+    d->device = -1;
+}
+
+vbdx_status vbdx_xpbd_create(const vbdx_xpbd_desc* desc, vbdx_xpbd** out)
+{
+    if (!desc || !out)
+    {
+        gLastError = "vbdx_xpbd_create: null argument";
+        return VBDX_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    std::unique_ptr<vbdx_xpbd> h;
+    vbdx_status const st = Guard([&] {
+        h = std::make_unique<vbdx_xpbd>();
+        h->impl.Create(*desc);
+    });
+    if (st == VBDX_OK)
+        *out = h.release();
+    return st;
+}
+
+vbdx_status vbdx_xpbd_destroy(vbdx_xpbd* h)
+{
+    if (h)
+    {
+        cudaSetDevice(h->impl.device);
+        cudaStreamSynchronize(h->impl.stream);
+        delete h;
+    }
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_xpbd_step(vbdx_xpbd* h, double dt, int32_t iterations, int32_t substeps)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] { h->impl.Step(dt, iterations, substeps); });
+}
+
+static vbdx_status XpbdSet(vbdx_xpbd* h, const double* a, int64_t nV, float4* dst, int keepW)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& I = h->impl;
+        vbdx::Require(a != nullptr && nV == I.nV, "expected a 3 x nV array");
+        VBDX_CUDA(cudaSetDevice(I.device));
+        VBDX_CUDA(cudaMemcpyAsync(I.dStaging.p, a, 3 * nV * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+        vbdx::XpbdSetXyz<<<vbdx::Blocks(nV, 256), 256, 0, I.stream>>>(nV, I.dStaging.p, dst, keepW);
+        ++I.kernelLaunches;
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+    });
+}
+static vbdx_status XpbdGet(vbdx_xpbd* h, double* a, int64_t nV, const float4* src)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& I = h->impl;
+        vbdx::Require(a != nullptr && nV == I.nV, "expected a 3 x nV array");
+        VBDX_CUDA(cudaSetDevice(I.device));
+        vbdx::XpbdGetXyz<<<vbdx::Blocks(nV, 256), 256, 0, I.stream>>>(nV, src, I.dStaging.p);
+        ++I.kernelLaunches;
+        VBDX_CUDA(cudaMemcpyAsync(a, I.dStaging.p, 3 * nV * sizeof(double), cudaMemcpyDeviceToHost, I.stream));
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+    });
+}
+vbdx_status vbdx_xpbd_set_positions(vbdx_xpbd* h, const double* x, int64_t nV) { return XpbdSet(h, x, nV, h ? h->impl.dX.p : nullptr, 1); }
+vbdx_status vbdx_xpbd_set_velocities(vbdx_xpbd* h, const double* v, int64_t nV) { return XpbdSet(h, v, nV, h ? h->impl.dVel.p : nullptr, 0); }
+vbdx_status vbdx_xpbd_set_external_acceleration(vbdx_xpbd* h, const double* a, int64_t nV) { return XpbdSet(h, a, nV, h ? h->impl.dAext.p : nullptr, 0); }
+vbdx_status vbdx_xpbd_get_positions(vbdx_xpbd* h, double* x, int64_t nV) { return XpbdGet(h, x, nV, h ? h->impl.dX.p : nullptr); }
+vbdx_status vbdx_xpbd_get_velocities(vbdx_xpbd* h, double* v, int64_t nV) { return XpbdGet(h, v, nV, h ? h->impl.dVel.p : nullptr); }
+
+vbdx_status vbdx_xpbd_set_compliance(vbdx_xpbd* h, int32_t constraint, const double* alpha, int64_t n)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& I = h->impl;
+        VBDX_CUDA(cudaSetDevice(I.device));
+        if (constraint == VBDX_XPBD_STABLE_NEO_HOOKEAN)
+        {
+            vbdx::Require(alpha != nullptr && n == 2 * I.nT, "expected 2 compliances per element");
+            for (int64_t t = 0; t < I.nT; ++t)
+            {
+                int64_t const s = I.slotOfTet[t];
+                I.recHost[3 * s + 1].w = static_cast<float>(alpha[2 * t]);
+                I.recHost[3 * s + 2].w = static_cast<float>(alpha[2 * t + 1]);
+            }
+            I.dRec.Upload(I.recHost.data(), I.recHost.size(), I.stream);
+        }
+        else if (constraint == VBDX_XPBD_COLLISION)
+        {
+            vbdx::Require(alpha != nullptr && n == I.nCV && I.nCV > 0, "expected one compliance per collision vertex");
+            std::vector<float> a(alpha, alpha + n);
+            I.dAlphaC.Upload(a.data(), n, I.stream);
+        }
+        else
+            throw vbdx::Error(VBDX_INVALID_ARGUMENT, "unknown constraint type");
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+    });
+}
+
+vbdx_status vbdx_xpbd_set_friction_coefficients(vbdx_xpbd* h, double muS, double muD)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    h->impl.muS = muS, h->impl.muD = muD;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_xpbd_set_scene_bounding_box(vbdx_xpbd* h, const float min3[3], const float max3[3])
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        vbdx::Require(min3 && max3 && max3[0] > min3[0] && max3[1] > min3[1] && max3[2] > min3[2], "scene bounding box must have positive extent");
+        if (h->impl.contact.enabled)
+        {
+            VBDX_CUDA(cudaSetDevice(h->impl.device));
+            h->impl.contact.SetWorldBox(min3, max3, h->impl.stream);
+        }
+    });
+}
+
+vbdx_status vbdx_xpbd_get_info(vbdx_xpbd* h, int64_t* out8)
+{
+    if (!h || !out8)
+        return VBDX_INVALID_ARGUMENT;
+    auto const& I = h->impl;
+    out8[0] = I.nV, out8[1] = I.nT, out8[2] = I.nPartitions, out8[3] = I.gridBlocks, out8[4] = I.kernelLaunches, out8[5] = I.deviceBytes;
+    out8[6] = static_cast<int64_t>(I.lastStepMs * 1e6), out8[7] = I.nCV;
+    return VBDX_OK;
+}
+
+vbdx_status vbdx_xpbd_get_contact_state(vbdx_xpbd* h, int32_t* active, int32_t* nn, int64_t* nActive)
+{
+    if (!h)
+        return VBDX_INVALID_ARGUMENT;
+    return Guard([&] {
+        auto& I  = h->impl;
+        auto& cs = I.contact;
+        vbdx::Require(cs.enabled, "the integrator was created without a collision mesh");
+        VBDX_CUDA(cudaSetDevice(I.device));
+        std::vector<uint8_t> a(cs.nCV);
+        cs.active.Download(a.data(), cs.nCV, I.stream);
+        if (nn)
+            cs.nn.Download(nn, static_cast<size_t>(cs.nCV) * vbdx::kMaxContacts, I.stream);
+        uint32_t na = 0;
+        cs.nActive.Download(&na, 1, I.stream);
+        VBDX_CUDA(cudaStreamSynchronize(I.stream));
+        if (active)
+            for (uint32_t k = 0; k < cs.nCV; ++k)
+                active[k] = a[k];
+        if (nActive)
+            *nActive = na;
+    });
+}
+
+vbdx_status vbdx_graph_greedy_color(int64_t n, const int64_t* ptr, const int64_t* adj, int32_t ordering, int32_t selection, int64_t* colors_out)
+{
+    return Guard([&] {
+        vbdx::Require(n >= 0 && ptr && colors_out && (adj || ptr[n] == 0), "vbdx_graph_greedy_color: bad arguments");
+        std::vector<int32_t> adj32(static_cast<size_t>(ptr[n]));
+        for (int64_t k = 0; k < ptr[n]; ++k)
+        {
+            vbdx::Require(adj[k] >= 0 && adj[k] < n, "adjacency entry out of range");
+            adj32[k] = static_cast<int32_t>(adj[k]);
+        }
+        std::vector<int64_t> colors;
+        vbdx::GreedyColorGraph(n, ptr, adj32.data(), ordering, selection, colors);
+        std::memcpy(colors_out, colors.data(), colors.size() * sizeof(int64_t));
+    });
+}
+
+}  // extern "C"

@@ -120,4 +120,7 @@ void GreedyColorMesh(
     int selection,
     std::vector<int64_t>& colors);
 
+// ... and on any graph in compressed sparse format (bindings/pypbat/graph/Color.cpp:28-60 greedy_color)
+void GreedyColorGraph(int64_t n, const int64_t* ptr, const int32_t* adj, int ordering, int selection, std::vector<int64_t>& colors);
+
 }  // namespace vbdx

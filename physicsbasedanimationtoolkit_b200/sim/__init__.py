@@ -1,2 +1,2 @@
-"""``pbat.sim`` -- only the ``vbd`` sub-module is in scope."""
-from . import vbd  # noqa: F401
+"""``pbat.sim`` -- the ``vbd`` sub-module (the hot path) and ``xpbd`` (section 8f rank 4)."""
+from . import vbd, xpbd  # noqa: F401

@@ -148,3 +148,32 @@ def test_batch_and_handles_fail_loudly_without_a_device():
             make()
     with pytest.raises(ValueError):
         pbat.gpu.vbd.BatchIntegrator([])
+
+
+def test_graph_helpers_and_xpbd_data():
+    """pbat.graph.greedy_color on a compressed sparse graph equals the mesh colouring it generalises; map_to_adjacency;
+    pbat.sim.xpbd.Data defaults and validation (sim/xpbd/Data.cpp:102-243)."""
+    X, T = meshes.tet_grid(4, 3, 2, 0.1)
+    G = pbat.graph.mesh_primal_graph(T, X.shape[1])
+    for ordering in pbat.graph.GreedyColorOrderingStrategy:
+        for selection in pbat.graph.GreedyColorSelectionStrategy:
+            a = pbat.graph.greedy_color(G.indptr, G.indices, ordering, selection)
+            b = pbat.graph.mesh_greedy_color(T, X.shape[1], ordering, selection)
+            assert np.array_equal(a, b)
+    ptr, adj = pbat.graph.map_to_adjacency(np.array([2, 0, 2, 1, 0]))
+    assert ptr.tolist() == [0, 2, 3, 5] and adj.tolist() == [1, 4, 3, 0, 2]
+    D = pbat.graph.mesh_dual_graph(T, X.shape[1])
+    assert D.shape == (T.shape[1], T.shape[1]) and (D.diagonal() == 4).all()
+    Pptr, Padj, GC = pbat.sim.xpbd.partition_mesh_constraints(X, T)
+    d = pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_partitions(Pptr, Padj).construct()
+    assert np.allclose(d.minv, 1e-3) and (d.aext[2] == -9.81).all() and d.BV.sum() == 0 and d.gammaSNH.shape == (T.shape[1],)
+    mu, lam = pbat.sim.vbd.lame_coefficients(1e6, 0.45)
+    vol = np.abs(meshes.tet_volumes(X, T))
+    assert np.allclose(d.alpha[0][0::2], 1 / (mu * vol)) and np.allclose(d.alpha[0][1::2], 1 / (lam * vol))
+    e = 3
+    Ds = np.stack([X[:, T[a, e]] - X[:, T[0, e]] for a in (1, 2, 3)], axis=1)
+    assert np.allclose(d.DmInv[:, 3 * e:3 * e + 3] @ Ds, np.eye(3))
+    with pytest.raises(ValueError):
+        pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_mass_inverse(np.ones(3)).construct()
+    with pytest.raises(ValueError):
+        pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_surface_mesh(np.arange(4), np.zeros((3, 1), int)).with_collision_penalties(np.ones(2)).construct()

@@ -242,3 +242,35 @@ def test_contact_oracle_supports_a_resting_body(kind):
     assert z.min() > 0.45 and (o.get("nn") >= 0).any()
 
 
+
+
+def test_xpbd_oracle_reference_doctest_and_header_build():
+    """XPBD restatement (oracle/vbd_oracle.cpp, XpbdStep): the reference's known answer (sim/xpbd/Integrator.cpp:213-262: the
+    unit cube falls, nothing moves sideways) and agreement of the port with the build that CALLS the reference's
+    ProjectBlockNeoHookean / ProjectVertexTriangle (sim/xpbd/Kernels.h:78-141,169-246)."""
+    from physicsbasedanimationtoolkit_b200 import meshes
+    import physicsbasedanimationtoolkit_b200 as pbat
+
+    P, T, F = meshes.CUBE_P, meshes.CUBE_T, meshes.CUBE_F
+    kinds = ["port"] + (["reference"] if oracle.have_ref() else [])
+    for kind in kinds:
+        o = oracle.Oracle(P, T, V=np.arange(8), F=F, B=np.zeros(8, np.int64), kind=kind)
+        o.xpbd_setup([0, 1, 2, 3, 4, 5], [0, 1, 2, 3, 4])
+        o.xpbd_step(1e-2, 1, 20)
+        dx = o.x - P
+        assert (dx[2] < 0).all() and (np.abs(dx[:2]) < 1e-4).all()
+    if len(kinds) == 2:
+        X, T = meshes.tet_grid(8, 3, 3, 0.1)
+        dbc = np.flatnonzero(X[0] == 0)
+        Pptr, Padj, GC = pbat.sim.xpbd.partition_mesh_constraints(X, T)
+        for c in range(GC.max() + 1):                      # a valid partitioning: no shared vertex inside a partition
+            vs = T[:, GC == c].reshape(-1)
+            assert vs.size == np.unique(vs).size
+        out = []
+        for kind in kinds:
+            o = oracle.Oracle(X, T, dbc=dbc, kind=kind)
+            o.xpbd_setup(Pptr, Padj, minv=np.full(X.shape[1], 0.1), beta_snh=np.full(2 * T.shape[1], 1e-3))
+            for _ in range(5):
+                o.xpbd_step(0.01, 5, 4)
+            out.append(o.x)
+        assert np.abs(out[0] - out[1]).max() < 1e-12 and np.abs(out[0] - X).max() > 1e-3
