@@ -252,6 +252,33 @@ def test_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, material
     assert rel_l2(out["1"][0], ref.x) < TOL
 
 
+@pytest.mark.parametrize("shape,kd", [((12, 10, 8), 0.0), ((12, 10, 8), 0.02), ((50, 44, 40), 0.02), ((70, 64, 60), 0.0)])
+def test_three_sweep_kernels_agree_bitwise_over_sizes_and_damping(shape, kd, monkeypatch):
+    """One scene, twenty steps, three schedules of the same arithmetic: the lean barrier-free kernel (default), the
+    pipelined kernel sweeping barrier-free (VBDX_FLOW=0; it has no damping form, so it falls to barriers there) and the
+    barrier sweep (VBDX_DATAFLOW=0).  From one tile per warp and colour up to a dozen; Rayleigh damping on and off."""
+    X, T = meshes.tet_grid(*shape, 1 / shape[0])
+    dbc = np.flatnonzero(X[2] == 0)
+    x0 = X + 0.1 / shape[0] * np.random.default_rng(11).uniform(-1, 1, X.shape)
+    x0[:, dbc] = X[:, dbc]
+    out = []
+    for env in ({}, {"VBDX_FLOW": "0"}, {"VBDX_DATAFLOW": "0"}):
+        for k in ("VBDX_FLOW", "VBDX_DATAFLOW"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        d, vbd, _ = make(X, T, dbc=dbc, cheb=0.85, kernel_variant=3)
+        vbd.kD = kd
+        vbd.x = x0.astype(np.float32)
+        for _ in range(20):
+            vbd.step(0.01, 9, 1)
+        out.append((vbd.x.copy(), vbd.v.copy(), vbd.info))
+    assert out[0][2]["blockThreads"] != out[2][2]["blockThreads"]      # the lean kernel has no barrier warp
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0]) and np.array_equal(out[0][1], o[1])
+    assert np.isfinite(out[0][0]).all()
+
+
 def test_small_meshes_default_to_one_cluster_and_large_ones_do_not():
     """VBDX_KERNEL_DEFAULT: a mesh whose colours fit one thread-block cluster is swept by 8 CTAs behind the hardware
     cluster barrier; anything larger takes the whole GPU.  Contact, damping, substeps run on either."""

@@ -24,6 +24,29 @@ vbd.step(0.01, 3, 1)
 vbd.objective_function_gradient(vbd.x, vbd.x, 0.01)
 d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_anderson_acceleration(3).construct()
 pbat.gpu.vbd.Integrator(d).step(0.01, 5, 1)
+# the lean barrier-free kernel (variant 3 default) with Rayleigh damping, then the pipelined kernel's own barrier-free sweep
+d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(0.8).construct()
+vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=3)
+vbd.kD = 0.01
+vbd.step(0.01, 4, 2)
+os.environ["VBDX_FLOW"] = "0"
+vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=3)
+vbd.step(0.01, 4, 2)
+del os.environ["VBDX_FLOW"]
+assert np.isfinite(vbd.x).all()
+d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_nesterov_acceleration(1.0, 1).construct()
+pbat.gpu.vbd.Integrator(d).step(0.01, 4, 1)
+d = pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_trust_region_acceleration(0.2, 2.0, False).construct()
+pbat.gpu.vbd.Integrator(d).step(0.01, 6, 1)
+# XPBD: partitions behind grid barriers, with contact
+Fx = meshes.boundary_facets(T)
+Pptr, Padj, _ = pbat.sim.xpbd.partition_mesh_constraints(X, T)
+dx = (pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_surface_mesh(np.unique(Fx), Fx)
+      .with_bodies(np.zeros(X.shape[1], np.int64)).with_mass_inverse(np.full(X.shape[1], 0.1))
+      .with_dirichlet_constrained_vertices(dbc).with_partitions(Pptr, Padj).construct())
+xp = pbat.gpu.xpbd.Integrator(dx)
+xp.step(0.01, 3, 2)
+assert np.isfinite(xp.x).all()
 # contact
 Xb, Tb = meshes.tet_grid(2, 2, 1, 0.5)
 Xt, Tt = meshes.tet_grid(1, 1, 1, 0.5, origin=(0.2, 0.3, 0.53))
