@@ -49,7 +49,7 @@ struct StepParams {
     float detHZero;
     int strategy;
     int iterations, substeps;
-    unsigned int* barrier;  // zeroed before launch
+    unsigned int* barrier;  // zeroed before launch; [1]: warps x sweeps finished (barrier-free sweeps with contact)
     unsigned int* nonFinite;  // sentinel: owned vertices whose final position is NaN/Inf (counted by the velocity update; zeroed per step)
     // vertex-triangle contact (fc == nullptr: disabled)
     const int32_t* __restrict__ fc;      // 8 triangle ids per internal vertex, -1 terminated
@@ -57,6 +57,7 @@ struct StepParams {
     const float* __restrict__ XVA;       // vertex areas (internal order)
     const float* __restrict__ FA;        // triangle areas
     float4* snap;                        // 2 x nVerts: positions as they were when the iteration started
+    float4* hist4;                       // barrier-free sweeps with contact (null otherwise): the last 4 writes of every vertex, see HistSlot
     const uint32_t* __restrict__ colorVertexBegin;  // nColors + 1: internal id range of every colour
     float muC, muF, epsv;
     int skipPreStep;                     // the pre-step pass was done by PreStepKernel (contact path) or by an earlier partial launch
@@ -113,6 +114,13 @@ __device__ __forceinline__ unsigned int LoadAcquire(const unsigned int* p)
 {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned int LoadRelaxedGpu(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -270,6 +278,59 @@ __device__ __forceinline__ uint32_t GhostIndex(StepParams const& p, uint32_t bas
     return (tag & 1u) ? p.ghostExt + (prev && p.pOff != 0u ? p.nGhost : 0u) + (base - p.ghostBegin) : base + (prev ? p.pOff : 0u);
 }
 
+// polls of a tagged position: one 16-byte access (see StorePosGpu, step_kernel.cuh)
+__device__ __forceinline__ float4 UnpackB128(unsigned long long lo, unsigned long long hi)
+{
+    return make_float4(__uint_as_float(static_cast<unsigned>(lo)), __uint_as_float(static_cast<unsigned>(lo >> 32)),
+                       __uint_as_float(static_cast<unsigned>(hi)), __uint_as_float(static_cast<unsigned>(hi >> 32)));
+}
+__device__ __forceinline__ float4 LoadPosGpu(const float4* q)
+{
+    unsigned long long lo, hi;
+    asm volatile("{\n .reg .b128 t;\n ld.relaxed.gpu.global.b128 t, [%2];\n mov.b128 {%0, %1}, t;\n}\n" : "=l"(lo), "=l"(hi) : "l"(q) : "memory");
+    return UnpackB128(lo, hi);
+}
+
+// Contact reads go beyond the 1-rings, to vertices of OTHER bodies whose tiles share no dependency with the reader's: in a
+// barrier-free sweep such a vertex may be a sweep behind or ahead.  So with contact every write also goes to a history of
+// the vertex' last four writes, slot = write number mod 4, separately the raw sweep result and (Chebyshev) the blended
+// iterate: a reader takes the write it needs (this sweep's raw result of a lower colour; the previous sweep's iterate of
+// its own or a higher colour -- what the reference's per-colour write buffer exposes, gpu/impl/vbd/Kernels.cuh:203-223),
+// waiting for it if it is not there yet.  That no slot is overwritten while somebody may still read it is the kernel's
+// part: no warp starts sweep k before every warp has finished sweep k - 2 (StepKernelFlow).
+__device__ __forceinline__ float4* HistSlot(StepParams const& p, uint32_t tag, bool blended)
+{
+    uint32_t const per = p.pOff != 0u ? 2u : 1u;  // Chebyshev keeps both
+    return p.hist4 + static_cast<size_t>((tag & 3u) * per + ((blended && per == 2u) ? 1u : 0u)) * static_cast<size_t>(p.nVerts);
+}
+__device__ __noinline__ float4 AwaitHist(StepParams const& p, float4 const* src, uint32_t want)
+{
+    float4 q              = LoadPosGpu(src);
+    unsigned long long t0 = 0;
+    for (uint32_t polls = 1; __float_as_uint(q.w) != want; ++polls)
+    {
+        if ((polls & 255u) == 0u)
+        {
+            if (t0 == 0)
+                t0 = GlobalTimer();
+            if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)
+            {
+                if (atomicCAS(p.distError, 0u, 2u) == 0u)
+                {
+                    p.distError[1] = static_cast<uint32_t>(src - p.hist4) % static_cast<uint32_t>(p.nVerts);
+                    p.distError[2] = want;
+                    p.distError[3] = __float_as_uint(q.w);
+                    p.distError[4] = 0xffffffffu;  // a contact read
+                    p.distError[5] = want - p.tagBase;
+                }
+                break;
+            }
+        }
+        q = LoadPosGpu(src);
+    }
+    return q;
+}
+
 // Per-vertex pre-step, fused with the velocity update of the previous substep
 // (sim/vbd/Integrator.cpp:31-35,39; sim/vbd/Kernels.h:29-94):
 //   v = (x - xt)/h [s > 0];  xt = x;  xtilde = xt + h v + h^2 a;  x = initial guess
@@ -319,6 +380,8 @@ __device__ __forceinline__ void PreStepVertex(StepParams const& p, uint32_t i, i
         StorePosGpu(p.pos + p.pOff + i, o);
     if (p.snap != nullptr)
         p.snap[i] = o;
+    if (p.hist4 != nullptr)
+        StorePosGpu(HistSlot(p, tag, true) + i, o);
     SendToPeers(p, i, o, o, tag);
 }
 
@@ -571,7 +634,13 @@ __device__ __forceinline__ void ProcessTile(
                 float const kC = ContactPenaltyScale(p.fc + static_cast<size_t>(vi) * kMaxContacts, p.FA, __ldg(p.XVA + vi), p.muC, f, nContacts);
                 if (nContacts > 0)
                 {
-                    uint32_t const cb   = __ldg(p.colorVertexBegin + color), ce = __ldg(p.colorVertexBegin + color + 1);
+                    uint32_t cb = 0u, ce = 0u;
+                    if (p.hist4 == nullptr)
+                        cb = __ldg(p.colorVertexBegin + color), ce = __ldg(p.colorVertexBegin + color + 1);
+                    else
+                        for (int c = 0; c < p.nColors; ++c)  // (the barrier-free kernel does not know a tile's colour)
+                            if (__ldg(p.colorVertexBegin + c + 1) <= vi)
+                                cb = __ldg(p.colorVertexBegin + c + 1);
                     float4 const* snapK = p.snap + static_cast<size_t>(k & 1) * p.nVerts;
                     float3 const xtv    = F3(__ldcg(p.xt + vi));
                     float gC[3] = {0.f, 0.f, 0.f}, HC[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -583,7 +652,13 @@ __device__ __forceinline__ void ProcessTile(
                         for (int a = 0; a < 3; ++a)
                         {
                             uint32_t const j = static_cast<uint32_t>(id[a]);
-                            float4 const q   = j < cb ? __ldcg(p.pos + j) : j >= ce ? __ldcg(p.pos + p.pOff + j) : __ldcg(snapK + j);
+                            float4 q;
+                            if (p.hist4 == nullptr)
+                                q = j < cb ? __ldcg(p.pos + j) : j >= ce ? __ldcg(p.pos + p.pOff + j) : __ldcg(snapK + j);
+                            else if (j >= p.activeEnd)
+                                q = __ldcg(p.pos + p.pOff + j);  // never swept
+                            else
+                                q = AwaitHist(p, HistSlot(p, j < cb ? sendTag : sendTag - 1u, j >= cb) + j, j < cb ? sendTag : sendTag - 1u);
                             xf[a]            = F3(q);
                             xtf[a]           = F3(__ldcg(p.xt + j));
                         }
@@ -751,6 +826,11 @@ __device__ __forceinline__ void ProcessTile(
             SendToPeers(p, vi, raw, out, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = out;  // what iteration k+1 starts from
+            if (p.hist4 != nullptr)
+            {
+                StorePosGpu(HistSlot(p, sendTag, false) + vi, raw);
+                StorePosGpu(HistSlot(p, sendTag, true) + vi, out);
+            }
         }
         else
         {
@@ -758,6 +838,8 @@ __device__ __forceinline__ void ProcessTile(
             SendToPeers(p, vi, raw, raw, sendTag);
             if (p.snap != nullptr)
                 p.snap[static_cast<size_t>((k + 1) & 1) * p.nVerts + vi] = raw;
+            if (p.hist4 != nullptr)
+                StorePosGpu(HistSlot(p, sendTag, false) + vi, raw);
         }
     }
     if (trace && lane == 0)

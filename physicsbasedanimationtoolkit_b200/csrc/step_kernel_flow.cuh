@@ -251,10 +251,18 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
     uint32_t const gstride = gridDim.x * (nWarps * 32);
     float omega            = 1.f;
     int omegaOf            = -1;
+    // Contact (p.hist4 != nullptr; launched per substep, after PreStepKernel and the active-set update): readers of the
+    // write history (step_kernel.cuh, HistSlot) must find the slot they need un-overwritten, so no warp starts sweep k
+    // before every warp that has tiles finished sweep k - 2.  One relaxed add per warp and sweep; the counter is looked
+    // at when a warp finishes a sweep, a sweep ahead of its use, and in steady state never waited for.
+    bool const lagBound     = p.hist4 != nullptr;
+    unsigned int sweepsSeen = 0;
+    int sweepOf             = 0;  // the sweep the tile about to run belongs to, as far as the bound was checked
     for (int s = 0; s < p.substeps; ++s)
     {
-        for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
-            PreStepVertex<kChebyshev>(p, i, s);
+        if (!p.skipPreStep)
+            for (uint32_t i = gtid; i < p.ghostBegin; i += gstride)
+                PreStepVertex<kChebyshev>(p, i, s);
         // this substep's tile sequence; the first tile's static data is requested in the shadow of the barrier
         Gen g{0u, 0};
         __syncwarp();  // the previous substep's readers of the ring are done
@@ -271,7 +279,8 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
             idA = LoadIds(td, 0);
             idB = LoadIds(td, 1);  // (a tile of <= 4 chunks has no second word: what follows it is read and ignored)
         }
-        GridSync();
+        if (!p.skipPreStep)
+            GridSync();
         // the pre-step wrote tagBase + s (I + 1); sweep kk of this substep writes that + kk + 1
         uint32_t const tagSub = p.tagBase + static_cast<uint32_t>(s) * static_cast<uint32_t>(I + 1);
         if (kkRing[seq & 3u] >= 0)
@@ -284,6 +293,31 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
             if (k0 < 0)
                 break;
             uint32_t const tagLow = tagSub + static_cast<uint32_t>(k0);
+            if (lagBound && k0 != sweepOf)
+            {
+                sweepOf = k0;
+                if (k0 >= 2 && !dead)
+                {
+                    unsigned int const need = pp.flowActiveWarps * static_cast<unsigned int>(k0 - 1);
+                    unsigned long long t0   = 0;
+                    for (uint32_t polls = 1; sweepsSeen < need; ++polls)
+                    {
+                        sweepsSeen = LoadRelaxedGpu(p.barrier + 1);
+                        if ((polls & 255u) == 0u)
+                        {
+                            if (t0 == 0)
+                                t0 = GlobalTimer();
+                            if (GlobalTimer() - t0 > p.distTimeoutNs || LoadAcquire(p.distError) != 0u)
+                            {
+                                atomicCAS(p.distError, 0u, 2u);
+                                dead = true;
+                                break;
+                            }
+                        }
+                    }
+                    dead = __any_sync(0xffffffffu, dead);
+                }
+            }
             if (kChebyshev && omegaOf != k0)
             {
                 omega   = __ldg(p.omega + k0);
@@ -331,6 +365,13 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
             ProcessTile<kChebyshev, kDamping, false, SmemRecords, decltype(afterAccumulate), false>(
                 p, td0, stage, src, 0, k0, omega, lane, tr, afterAccumulate, tagLow + 1u);
             __syncwarp();  // ... and with the staged positions
+            if (lagBound && k1 != k0)
+            {
+                // this warp's last tile of sweep k0 (its history reads are done: their values were used)
+                if (lane == 0)
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier + 1) : "memory");
+                sweepsSeen = LoadRelaxedGpu(p.barrier + 1);
+            }
             if (k1 >= 0)
                 Gather(td1, idA, idB, tagSub + static_cast<uint32_t>(k1));
             Fetch(g, (seq + 3u) & 3u);

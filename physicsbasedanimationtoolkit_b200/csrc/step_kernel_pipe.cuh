@@ -26,6 +26,7 @@ struct PipeParams {
     int dataflow;       // no barrier between colours: every position carries the number of its write in .w, a tile checks
                         // the values it gathered and polls the few that are not there yet (see AwaitTags)
     // the lean barrier-free kernel (step_kernel_flow.cuh) walks a schedule the host laid out (BuildFlowSchedule)
+    uint32_t flowActiveWarps;                    // warps that have tiles (the sweep-lag bound of the contact path counts them)
     const uint32_t* __restrict__ flowWarpBegin;  // [grid warps + 1]: range of warp w (w = warp-in-CTA * gridDim.x + CTA) in flowTiles
     const uint4* __restrict__ flowTiles;         // tile descriptors in warp-major order; .w = first entry of the tile in flowIds
     const uint32_t* __restrict__ flowIds;        // pre-decoded ring entries, [group of 4 chunks][lane][4]
@@ -98,19 +99,6 @@ __device__ __forceinline__ void StoreReleaseSys(unsigned int* p, unsigned int v)
 __device__ __forceinline__ void StoreReleaseGpu(unsigned int* p, unsigned int v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// polls of a tagged position: one 16-byte access (see StorePosGpu, step_kernel.cuh)
-__device__ __forceinline__ float4 UnpackB128(unsigned long long lo, unsigned long long hi)
-{
-    return make_float4(__uint_as_float(static_cast<unsigned>(lo)), __uint_as_float(static_cast<unsigned>(lo >> 32)),
-                       __uint_as_float(static_cast<unsigned>(hi)), __uint_as_float(static_cast<unsigned>(hi >> 32)));
-}
-__device__ __forceinline__ float4 LoadPosGpu(const float4* q)
-{
-    unsigned long long lo, hi;
-    asm volatile("{\n .reg .b128 t;\n ld.relaxed.gpu.global.b128 t, [%2];\n mov.b128 {%0, %1}, t;\n}\n" : "=l"(lo), "=l"(hi) : "l"(q) : "memory");
-    return UnpackB128(lo, hi);
 }
 
 __device__ __forceinline__ float4 LoadPosSys(const float4* q)

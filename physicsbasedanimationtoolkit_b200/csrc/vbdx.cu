@@ -107,6 +107,8 @@ struct Integrator {
     DevBuf<uint4> dFlowTiles;
     int flowWarps = 16, flowGridBlocks = 0;  // launch shape of the lean kernel (no barrier warp, no id buffers)
     size_t flowSmemBytes = 0;
+    uint32_t flowActiveWarps = 0;  // warps of the lean kernel's grid that have tiles
+    DevBuf<float4> dHist4;         // contact under barrier-free sweeps: every vertex' last four writes (step_kernel.cuh, HistSlot)
     void BuildFlowSchedule();
 
     // state
@@ -177,7 +179,7 @@ struct Integrator {
     PipeKernelFn KernelFlow() const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
-        bool const damp = kD != 0.0;
+        bool const damp = kD != 0.0 || contact.enabled;  // the damping variants carry the contact term
         if (distWorld > 1 || nGhost > 0)
         {
             if (cheb)
@@ -190,8 +192,8 @@ struct Integrator {
     }
     bool UseFlow(int iterations) const
     {
-        return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterMode && !contact.enabled &&
-               material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && iterations > 0;
+        return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterMode &&
+               (!contact.enabled || dHist4.p != nullptr) && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && iterations > 0;
     }
 
     TmaKernelFn KernelTma() const
@@ -607,8 +609,8 @@ void Integrator::Create(vbdx_data_desc const& d)
     dAext.Alloc(nV, &deviceBytes);
     if (flags & VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY)
         dVtm1.Alloc(nV, &deviceBytes);
-    dBarrier.Alloc(2, &deviceBytes);  // [0] grid barrier counter, [1] non-finite sentinel
-    VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 2 * sizeof(unsigned int), stream));
+    dBarrier.Alloc(3, &deviceBytes);  // [0] grid barrier counter, [1] finished warp-sweeps (contact, barrier-free), [2] non-finite sentinel
+    VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 3 * sizeof(unsigned int), stream));
     dDistFlags.Alloc(16, &deviceBytes);
     VBDX_CUDA(cudaMemsetAsync(dDistFlags.p, 0, 16 * sizeof(unsigned int), stream));
     dStaging.Alloc(3 * nV, &deviceBytes);
@@ -688,6 +690,12 @@ void Integrator::Create(vbdx_data_desc const& d)
         cs.Alloc(nV, &deviceBytes, stream);
         // snapshot buffer 0 = initial positions
         VBDX_CUDA(cudaMemcpyAsync(cs.snap.p, dPos.p, nV * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        if (dFlowTiles.p != nullptr && distWorld == 1)
+        {
+            size_t const n = 4 * (acceleration == VBDX_ACCEL_CHEBYSHEV ? 2 : 1) * static_cast<size_t>(nV);
+            dHist4.Alloc(n, &deviceBytes);
+            VBDX_CUDA(cudaMemsetAsync(dHist4.p, 0, n * sizeof(float4), stream));  // write number 0: never asked for
+        }
         VBDX_CUDA(cudaStreamSynchronize(stream));
         cs.enabled = true;
     }
@@ -765,6 +773,9 @@ void Integrator::BuildFlowSchedule()
             TileDesc const& td = plan.tiles[order[t]];
             seqTiles[cursor[(t - plan.colorTileBegin[c]) % gWarps]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[order[t]]);
         }
+    flowActiveWarps = 0;
+    for (uint32_t w = 0; w < gWarps; ++w)
+        flowActiveWarps += wBegin[w + 1] > wBegin[w] ? 1u : 0u;
     dFlowWarpBegin.Alloc(wBegin.size(), &deviceBytes);
     dFlowWarpBegin.Upload(wBegin.data(), wBegin.size(), stream);
     dFlowTiles.Alloc(nTiles + 1, &deviceBytes);
@@ -844,7 +855,7 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
     p.iterations   = iterations;
     p.substeps     = substeps;
     p.barrier      = dBarrier.p;
-    p.nonFinite    = dBarrier.p + 1;
+    p.nonFinite    = dBarrier.p + 2;
     p.ghostBegin   = static_cast<uint32_t>(plan.ghostBegin);
     p.activeEnd    = static_cast<uint32_t>(plan.nActive);
     p.rank = distRank, p.world = distWorld;
@@ -904,16 +915,19 @@ StepParams Integrator::MakeParams(double sdt, int iterations, int substeps)
 void Integrator::LaunchStepKernel(StepParams const& q)
 {
     {
-        VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, sizeof(unsigned int), stream));
+        VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 2 * sizeof(unsigned int), stream));
         if (variant == VBDX_KERNEL_PIPELINED && !clusterMode)
         {
             PipeParams pp{};
             pp.base      = q;
             pp.maxIters  = maxTileIters;
-            // barrier-free sweeps: whole steps of the base / Chebyshev solve without damping or contact (whose reads go
-            // beyond the 1-rings); partial launches (traces, windowed accelerators) keep the colour barriers
-            pp.dataflow = WillSweepBarrierFree(q.iterations) && !q.skipPreStep && !q.skipPostStep && q.iterBegin == 0;
+            // barrier-free sweeps: whole steps of the base / Chebyshev solve; partial launches (traces, windowed accelerators)
+            // keep the colour barriers.  With contact the step is one launch per substep behind PreStepKernel and the
+            // active-set update: barrier-free where RunStep set up the write history (q.hist4).
+            pp.dataflow = WillSweepBarrierFree(q.iterations) && !q.skipPostStep && q.iterBegin == 0 &&
+                          (contact.enabled ? q.hist4 != nullptr : !q.skipPreStep);
             pp.flowWarpBegin = dFlowWarpBegin.p, pp.flowTiles = dFlowTiles.p, pp.flowIds = dFlowIds.p;
+            pp.flowActiveWarps = flowActiveWarps;
             usedDataflow |= pp.dataflow != 0;
             void* args[] = {&pp};
             bool const flow = pp.dataflow != 0 && UseFlow(q.iterations);
@@ -974,7 +988,7 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
         LaunchStepKernel(q);
     };
     VBDX_CUDA(cudaEventRecord(evBegin, stream));
-    VBDX_CUDA(cudaMemsetAsync(dBarrier.p + 1, 0, sizeof(unsigned int), stream));  // the step's non-finite sentinel
+    VBDX_CUDA(cudaMemsetAsync(dBarrier.p + 2, 0, sizeof(unsigned int), stream));  // the step's non-finite sentinel
     if (acceleration == VBDX_ACCEL_ANDERSON)
         AndersonStep(p, dt, iterations, substeps);
     else if (acceleration == VBDX_ACCEL_BROYDEN)
@@ -1001,8 +1015,11 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
         StepParams q  = p;
         q.substeps    = 1;
         q.skipPreStep = 1;
+        if (UseFlow(iterations))
+            q.hist4 = dHist4.p, q.snap = nullptr;  // barrier-free sweeps: contact reads go to the write history
         for (int s = 0; s < substeps; ++s)
         {
+            q.tagBase = p.tagBase + static_cast<unsigned int>(s) * (static_cast<unsigned int>(iterations) + 1u);  // write numbers of this substep
             {
                 NvtxRange const z("pbat.gpu.impl.vbd.Integrator.ComputeInertialTargets");  // + InitializeBcdSolution: one fused kernel
                 if (cheb)
@@ -2503,7 +2520,7 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out)
     out->nColors         = I.plan.nColors;
     out->nTiles          = static_cast<int32_t>(I.plan.tiles.size());
     // launch shape of the kernel that runs whole steps: the lean barrier-free one where it applies
-    bool const flowShape = I.dFlowTiles.p != nullptr && I.dataflow && I.flowKernel && !I.contact.enabled;
+    bool const flowShape = I.dFlowTiles.p != nullptr && I.dataflow && I.flowKernel && (!I.contact.enabled || I.dHist4.p != nullptr);
     out->gridBlocks      = flowShape ? I.flowGridBlocks : I.gridBlocks;
     out->blockThreads    = flowShape ? I.flowWarps * 32 : I.blockThreads;
     out->device          = I.device;
@@ -2518,7 +2535,7 @@ vbdx_status vbdx_get_info(vbdx_integrator* h, vbdx_info* out)
     {
         unsigned int bad = 0;
         cudaSetDevice(I.device);
-        if (cudaStreamSynchronize(I.stream) == cudaSuccess && cudaMemcpy(&bad, I.dBarrier.p + 1, sizeof(bad), cudaMemcpyDeviceToHost) == cudaSuccess)
+        if (cudaStreamSynchronize(I.stream) == cudaSuccess && cudaMemcpy(&bad, I.dBarrier.p + 2, sizeof(bad), cudaMemcpyDeviceToHost) == cudaSuccess)
             out->nonFiniteVertices = bad;
         else
             cudaGetLastError();

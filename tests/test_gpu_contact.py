@@ -182,6 +182,45 @@ def test_config3_replica_against_oracle():
         assert (np.diff(lo) > 0).all() and (lo[1:] - hi[:-1] > -3.0 / n).all()
 
 
+@pytest.mark.parametrize("cheb,substeps,kd", [(None, 1, 0.0), (0.8, 1, 0.0), (None, 2, 1e-4), (0.7, 3, 0.0)])
+def test_contact_barrier_free_sweep_is_bit_identical_to_the_barrier_sweep(cheb, substeps, kd, monkeypatch):
+    """With contact the whole-GPU kernel sweeps barrier-free too: triangle corners (vertices of OTHER bodies, whose tiles
+    may be a sweep ahead or behind) are read from the history of every vertex' last four writes, by write number.  Same
+    values read, same arithmetic: identical bits to the sweep with colour barriers (VBDX_DATAFLOW=0), contact lists
+    included, over impacts, sliding and several substeps."""
+    n = 8
+    Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+    X, T, B = meshes.stack_bodies(Xb, Tb, 4, axis=2, gap_frac=0.05)
+    for b in range(4):
+        X[0, B == b] += 0.37 * b / n
+        X[1, B == b] += 0.21 * b / n
+    F = meshes.boundary_facets(T)
+    V = np.unique(F)
+    dbc = np.flatnonzero(X[2] <= X[2].min() + 0.01)
+    v = np.zeros_like(X)
+    v[2] = -0.5 * B
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B).with_velocity(v)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e5, 0.3, 1e-3).with_rayleigh_damping(kd))
+    if cheb:
+        d = d.with_chebyshev_acceleration(cheb)
+    d = d.construct()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VBDX_DATAFLOW", mode)
+        vbd = pbat.gpu.vbd.Integrator(d, kernel_variant=3)
+        contacts = 0
+        for s in range(40):
+            vbd.step(0.01, 8, substeps)
+            contacts = max(contacts, int((vbd.contact_state()[1] >= 0).any(axis=1).sum()))
+        out[mode] = (vbd.x.copy(), vbd.v.copy(), vbd.contact_state(), contacts, vbd.info["blockThreads"])
+    assert out["1"][3] > 50, "the bodies never touched"
+    assert out["1"][4] != out["0"][4]                     # the lean kernel (no barrier warp) did run
+    assert np.isfinite(out["1"][0]).all()
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    for a, b in zip(out["1"][2], out["0"][2]):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("accel", ["anderson", "broyden"])
 def test_windowed_accelerators_with_contact(accel):
     """The reference's example (python/examples/vbd.py:297-330) combines a surface mesh with Anderson / Broyden
