@@ -11,9 +11,21 @@
 
 namespace vbdx {
 
+// workspace of the one-launch radix sort (lbvh.cuh): zeroed barrier counter + chunk sums, the SM count as the CTA limit
+inline void InitSortSync(DevBuf<uint32_t>& aux, RadixSortSync& sync, int64_t* bytes)
+{
+    aux.Alloc(1 + kSortMaxCtas, bytes);
+    VBDX_CUDA(cudaMemset(aux.p, 0, (1 + kSortMaxCtas) * sizeof(uint32_t)));
+    int dev = 0, sms = 0;
+    VBDX_CUDA(cudaGetDevice(&dev));
+    VBDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sync.aux = aux.p, sync.base = 0, sync.maxCtas = sms;
+}
+
 struct DeviceBvh {
     uint32_t n = 0;
-    DevBuf<uint32_t> codes, inds, codesTmp, indsTmp, counts, scanScratch, visits;
+    DevBuf<uint32_t> codes, inds, codesTmp, indsTmp, counts, visits, sortAux;
+    RadixSortSync sortSync;
     DevBuf<int32_t> child0, child1, parent, right0, right1;
     DevBuf<float4> nodeLo, nodeHi;
 
@@ -22,7 +34,7 @@ struct DeviceBvh {
         n = nLeaves;
         codes.Alloc(n, bytes), inds.Alloc(n, bytes), codesTmp.Alloc(n, bytes), indsTmp.Alloc(n, bytes);
         counts.Alloc(RadixSortCountsSize(n), bytes);
-        scanScratch.Alloc(RadixSortCountsSize(n) / kScanTile + 2, bytes);
+        InitSortSync(sortAux, sortSync, bytes);
         size_t const ni = n > 1 ? n - 1 : 1;
         visits.Alloc(ni, bytes);
         child0.Alloc(ni, bytes), child1.Alloc(ni, bytes), right0.Alloc(ni, bytes), right1.Alloc(ni, bytes);
@@ -53,7 +65,7 @@ struct DeviceBvh {
     void Build(const float4* primLo, const float4* primHi, const WorldBox* world, cudaStream_t s, int64_t* launches)
     {
         MortonOfBoxes<<<Blocks(n, 256), 256, 0, s>>>(primLo, primHi, n, world, codes.p, inds.p);
-        RadixSortPairs(codes.p, inds.p, codesTmp.p, indsTmp.p, n, counts.p, scanScratch.p, s, launches);
+        RadixSortPairs(codes.p, inds.p, codesTmp.p, indsTmp.p, n, counts.p, sortSync, s, launches);
         VBDX_CUDA(cudaMemsetAsync(parent.p, 0xff, 2 * static_cast<size_t>(n) * sizeof(int32_t), s));
         if (n > 1)
             BvhHierarchy<<<Blocks(n - 1, 256), 256, 0, s>>>(View());
@@ -79,7 +91,8 @@ struct ContactState {
     DevBuf<float4> snap;
     // detector
     DeviceBvh bvh;
-    DevBuf<uint32_t> ids, idsTmp, codes, codesTmp, counts, scanScratch, flags, offsets, nActive;
+    DevBuf<uint32_t> ids, idsTmp, codes, codesTmp, counts, scanScratch, flags, offsets, nActive, sortAux;
+    RadixSortSync sortSync;
     DevBuf<float4> ptLo, ptHi, triLo, triHi;
     DevBuf<uint8_t> active;
     DevBuf<float> dupper;
@@ -94,7 +107,8 @@ struct ContactState {
         bvh.Alloc(nF, bytes);
         ids.Alloc(nCV, bytes), idsTmp.Alloc(nCV, bytes), codes.Alloc(nCV, bytes), codesTmp.Alloc(nCV, bytes);
         counts.Alloc(RadixSortCountsSize(nCV), bytes);
-        scanScratch.Alloc(std::max<size_t>(RadixSortCountsSize(nCV), nCV + 1) / kScanTile + 2, bytes);
+        InitSortSync(sortAux, sortSync, bytes);
+        scanScratch.Alloc((static_cast<size_t>(nCV) + 1) / kScanTile + 2, bytes);
         flags.Alloc(nCV + 1, bytes), offsets.Alloc(nCV + 1, bytes), nActive.Alloc(1, bytes);
         ptLo.Alloc(nCV, bytes), ptHi.Alloc(nCV, bytes), triLo.Alloc(nF, bytes), triHi.Alloc(nF, bytes);
         active.Alloc(nCV, bytes), dupper.Alloc(nCV, bytes), av.Alloc(nCV, bytes);
@@ -143,7 +157,7 @@ struct ContactState {
         // swept vertices: boxes in the current order -> codes -> sort ids -> boxes in sorted order
         SweptPointBoxes<<<Blocks(nCV, 256), 256, 0, s>>>(mesh, ids.p, x, vel, aext, dt, ptLo.p, ptHi.p);
         MortonOfBoxes<<<Blocks(nCV, 256), 256, 0, s>>>(ptLo.p, ptHi.p, nCV, world.p, codes.p, nullptr);
-        RadixSortPairs(codes.p, ids.p, codesTmp.p, idsTmp.p, nCV, counts.p, scanScratch.p, s, launches);
+        RadixSortPairs(codes.p, ids.p, codesTmp.p, idsTmp.p, nCV, counts.p, sortSync, s, launches);
         SweptPointBoxes<<<Blocks(nCV, 256), 256, 0, s>>>(mesh, ids.p, x, vel, aext, dt, ptLo.p, ptHi.p);
         // swept triangles and their BVH
         TriangleBoxes<<<Blocks(nF, 256), 256, 0, s>>>(mesh, x, vel, aext, dt, triLo.p, triHi.p);

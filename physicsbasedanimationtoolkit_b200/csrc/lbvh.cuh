@@ -13,97 +13,206 @@
 
 #include "setup_kernels.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cuda_runtime.h>
 
 namespace vbdx {
 
 // ------------------------------------------------------------------------------------------
-// stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass
+// stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass, ONE cooperative launch
 //   one warp owns a contiguous segment of kSortSegment items and walks it in chunks of 32, so that
-//   ranks within a digit follow item order (stability) without any cross-warp bookkeeping
+//   ranks within a digit follow item order (stability) without any cross-warp bookkeeping;
+//   per pass: per-segment digit counts -> grid barrier -> exclusive scan of the (digit-major) count table, every CTA
+//   its own contiguous chunk -> grid barrier -> scatter (offset = scanned count + sum of the chunks before) -> grid
+//   barrier.  The collision meshes of the contact path are 1e5 keys: 20 small launches per sort cost more in launch
+//   gaps than in work (profiles/r02g_config3_launches.csv), twelve grid barriers of <= 148 CTAs do not.
+//   Everything another CTA wrote during the launch is read with ld.global.cg (the L1 is not coherent).
 // ------------------------------------------------------------------------------------------
 constexpr int kSortSegment     = 256;   // 8 chunks per warp: short dependent chains, n/256 warps in flight
 constexpr int kSortWarpsPerCta = 8;
+constexpr int kSortMaxCtas     = 512;   // chunk sums of the scan live in shared memory
 
-__global__ void RadixCount(const uint32_t* keys, uint32_t n, int shift, uint32_t nSeg, uint32_t* counts)
+// per call site: grid barrier counter [0] + chunk sums [1 ..]; `base` = value of the counter when the next launch starts
+struct RadixSortSync {
+    unsigned int* aux = nullptr;  // 1 + kSortMaxCtas words, zeroed once
+    unsigned int base = 0;
+    int maxCtas       = 0;        // co-resident CTAs the launch may use (<= SM count: a cheap barrier)
+};
+
+__device__ __forceinline__ void SortGridSync(unsigned int* counter, unsigned int& target)
 {
-    __shared__ uint32_t hist[kSortWarpsPerCta][256];
-    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t const seg  = blockIdx.x * kSortWarpsPerCta + warp;
-    for (uint32_t d = lane; d < 256; d += 32)
-        hist[warp][d] = 0;
-    __syncwarp();
-    if (seg < nSeg)
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        uint32_t const begin = seg * kSortSegment;
-        uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
-        for (uint32_t base = begin; base < end; base += 32)
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        while (static_cast<int>(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// exclusive scan of one value per thread over the CTA (kSortWarpsPerCta warps); total = sum over the CTA
+__device__ __forceinline__ uint32_t SortBlockScan(uint32_t v, uint32_t* warpSums, uint32_t& total)
+{
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1)
+    {
+        uint32_t const t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    __syncthreads();  // the previous round's readers of warpSums are done
+    if (lane == 31)
+        warpSums[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kSortWarpsPerCta; ++w)
+    {
+        uint32_t const sum = warpSums[w];
+        before += w < warp ? sum : 0u;
+        all += sum;
+    }
+    total = all;
+    return inc - v + before;
+}
+
+__global__ void __launch_bounds__(kSortWarpsPerCta * 32)
+    RadixSortFused(uint32_t* keys, uint32_t* vals, uint32_t* keysTmp, uint32_t* valsTmp, uint32_t n, uint32_t nSeg, uint32_t* counts,
+                   unsigned int* aux, unsigned int target)
+{
+    __shared__ uint32_t tab[kSortWarpsPerCta][256];
+    __shared__ uint32_t warpSums[kSortWarpsPerCta];
+    __shared__ uint32_t chunkBefore[kSortMaxCtas];
+    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t const L     = 256u * nSeg;                                  // the count table, digit-major
+    uint32_t const chunk = ((L + gridDim.x - 1) / gridDim.x + 3u) & ~3u;  // per CTA, a multiple of 4
+    uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
+    for (int pass = 0; pass < 4; ++pass)
+    {
+        int const shift = 8 * pass;
+        // digit counts of every segment
+        for (uint32_t seg = blockIdx.x * kSortWarpsPerCta + warp; seg < nSeg; seg += gridDim.x * kSortWarpsPerCta)
         {
-            uint32_t const i    = base + lane;
-            bool const in       = i < end;
-            uint32_t const mask = __ballot_sync(0xffffffffu, in);
-            if (in)
+            for (uint32_t d = lane; d < 256; d += 32)
+                tab[warp][d] = 0;
+            __syncwarp();
+            uint32_t const begin = seg * kSortSegment;
+            uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
+            for (uint32_t base = begin; base < end; base += 32)
             {
-                uint32_t const d     = (keys[i] >> shift) & 255u;
-                uint32_t const peers = __match_any_sync(mask, d);
-                if (lane == static_cast<uint32_t>(__ffs(peers) - 1))
-                    hist[warp][d] += __popc(peers);
+                uint32_t const i    = base + lane;
+                bool const in       = i < end;
+                uint32_t const mask = __ballot_sync(0xffffffffu, in);
+                if (in)
+                {
+                    uint32_t const d     = (__ldcg(kin + i) >> shift) & 255u;
+                    uint32_t const peers = __match_any_sync(mask, d);
+                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1))
+                        tab[warp][d] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            for (uint32_t d = lane; d < 256; d += 32)
+                counts[d * nSeg + seg] = tab[warp][d];
+            __syncwarp();
+        }
+        SortGridSync(aux, target);
+        // exclusive scan of this CTA's chunk of the table, in place; the chunk's sum goes to aux[1 + CTA]
+        {
+            uint32_t const cb = min(blockIdx.x * chunk, L), ce = min(cb + chunk, L);
+            uint32_t carry    = 0;
+            for (uint32_t base = cb; base < ce; base += kSortWarpsPerCta * 32 * 4)
+            {
+                uint32_t const i = base + threadIdx.x * 4u;
+                uint32_t v[4];
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    v[j] = i + j < ce ? __ldcg(counts + i + j) : 0u;
+                uint32_t total;
+                uint32_t run = carry + SortBlockScan(v[0] + v[1] + v[2] + v[3], warpSums, total);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                {
+                    if (i + j < ce)
+                        counts[i + j] = run;
+                    run += v[j];
+                }
+                carry += total;
+            }
+            if (threadIdx.x == 0)
+                aux[1 + blockIdx.x] = carry;
+        }
+        SortGridSync(aux, target);
+        // what the chunks before a chunk add up to
+        {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < gridDim.x; base += kSortWarpsPerCta * 32)
+            {
+                uint32_t const c = base + threadIdx.x;
+                uint32_t total;
+                uint32_t const ex = SortBlockScan(c < gridDim.x ? __ldcg(aux + 1 + c) : 0u, warpSums, total);
+                if (c < gridDim.x)
+                    chunkBefore[c] = carry + ex;
+                carry += total;
+            }
+            __syncthreads();
+        }
+        // scatter
+        for (uint32_t seg = blockIdx.x * kSortWarpsPerCta + warp; seg < nSeg; seg += gridDim.x * kSortWarpsPerCta)
+        {
+            for (uint32_t d = lane; d < 256; d += 32)
+            {
+                uint32_t const at = d * nSeg + seg;
+                tab[warp][d]      = __ldcg(counts + at) + chunkBefore[at / chunk];
+            }
+            __syncwarp();
+            uint32_t const begin = seg * kSortSegment;
+            uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
+            for (uint32_t base = begin; base < end; base += 32)
+            {
+                uint32_t const i    = base + lane;
+                bool const in       = i < end;
+                uint32_t const mask = __ballot_sync(0xffffffffu, in);
+                uint32_t key = 0, val = 0, d = 0, peers = 0, dst = 0;
+                if (in)
+                {
+                    key   = __ldcg(kin + i);
+                    val   = __ldcg(vin + i);
+                    d     = (key >> shift) & 255u;
+                    peers = __match_any_sync(mask, d);
+                    dst   = tab[warp][d] + __popc(peers & ((1u << lane) - 1u));
+                }
+                __syncwarp();
+                if (in && lane == static_cast<uint32_t>(__ffs(peers) - 1))
+                    tab[warp][d] += __popc(peers);
+                __syncwarp();
+                if (in)
+                {
+                    kout[dst] = key;
+                    vout[dst] = val;
+                }
             }
             __syncwarp();
         }
-        for (uint32_t d = lane; d < 256; d += 32)
-            counts[d * nSeg + seg] = hist[warp][d];
+        SortGridSync(aux, target);
+        uint32_t* t = kin;
+        kin         = kout;
+        kout        = t;
+        t           = vin;
+        vin         = vout;
+        vout        = t;
     }
 }
 
-__global__ void RadixScatter(
-    const uint32_t* keys,
-    const uint32_t* vals,
-    uint32_t n,
-    int shift,
-    uint32_t nSeg,
-    const uint32_t* offsets,
-    uint32_t* keysOut,
-    uint32_t* valsOut)
-{
-    __shared__ uint32_t run[kSortWarpsPerCta][256];
-    uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t const seg  = blockIdx.x * kSortWarpsPerCta + warp;
-    if (seg >= nSeg)
-        return;
-    for (uint32_t d = lane; d < 256; d += 32)
-        run[warp][d] = offsets[d * nSeg + seg];
-    __syncwarp();
-    uint32_t const begin = seg * kSortSegment;
-    uint32_t const end   = min(begin + static_cast<uint32_t>(kSortSegment), n);
-    for (uint32_t base = begin; base < end; base += 32)
-    {
-        uint32_t const i    = base + lane;
-        bool const in       = i < end;
-        uint32_t const mask = __ballot_sync(0xffffffffu, in);
-        uint32_t key = 0, val = 0, d = 0, peers = 0, dst = 0;
-        if (in)
-        {
-            key   = keys[i];
-            val   = vals[i];
-            d     = (key >> shift) & 255u;
-            peers = __match_any_sync(mask, d);
-            dst   = run[warp][d] + __popc(peers & ((1u << lane) - 1u));
-        }
-        __syncwarp();
-        if (in && lane == static_cast<uint32_t>(__ffs(peers) - 1))
-            run[warp][d] += __popc(peers);
-        __syncwarp();
-        if (in)
-        {
-            keysOut[dst] = key;
-            valsOut[dst] = val;
-        }
-    }
-}
-
-// Sorts in place (4 passes ping-pong through the temporaries).  counts: 256 * nSeg (+ scan scratch).
+// Sorts in place (4 passes ping-pong through the temporaries).  counts: 256 * ceil(n / kSortSegment) words.
 inline void RadixSortPairs(
     uint32_t* keys,
     uint32_t* vals,
@@ -111,29 +220,20 @@ inline void RadixSortPairs(
     uint32_t* valsTmp,
     uint32_t n,
     uint32_t* counts,
-    uint32_t* scanScratch,
+    RadixSortSync& sync,
     cudaStream_t s,
     int64_t* launches = nullptr)
 {
     if (n < 2)
         return;
-    uint32_t const nSeg = (n + kSortSegment - 1) / kSortSegment;
-    int const ctas      = static_cast<int>((nSeg + kSortWarpsPerCta - 1) / kSortWarpsPerCta);
-    uint32_t *kin = keys, *vin = vals, *kout = keysTmp, *vout = valsTmp;
-    for (int pass = 0; pass < 4; ++pass)
-    {
-        RadixCount<<<ctas, kSortWarpsPerCta * 32, 0, s>>>(kin, n, 8 * pass, nSeg, counts);
-        ExclusiveScanU32(counts, counts, 256 * static_cast<int64_t>(nSeg), scanScratch, s);
-        RadixScatter<<<ctas, kSortWarpsPerCta * 32, 0, s>>>(kin, vin, n, 8 * pass, nSeg, counts, kout, vout);
-        uint32_t* t = kin;
-        kin         = kout;
-        kout        = t;
-        t           = vin;
-        vin         = vout;
-        vout        = t;
-        if (launches)
-            *launches += 5;
-    }
+    uint32_t nSeg   = (n + kSortSegment - 1) / kSortSegment;
+    int const need  = static_cast<int>((nSeg + kSortWarpsPerCta - 1) / kSortWarpsPerCta);
+    int const ctas  = std::max(1, std::min({need, sync.maxCtas, kSortMaxCtas}));
+    void* args[]    = {&keys, &vals, &keysTmp, &valsTmp, &n, &nSeg, &counts, &sync.aux, &sync.base};
+    VBDX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(RadixSortFused), dim3(ctas), dim3(kSortWarpsPerCta * 32), args, 0, s));
+    sync.base += 12u * static_cast<unsigned int>(ctas);  // three barriers per pass
+    if (launches)
+        *launches += 1;
 }
 
 inline size_t RadixSortCountsSize(uint32_t n)
