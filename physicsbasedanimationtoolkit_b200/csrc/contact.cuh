@@ -74,48 +74,69 @@ __device__ __forceinline__ float PointTriangleDistance2(float3 P, float3 A, floa
     return Dot(D, D);
 }
 
+// The same operations with every rounding spelled out: the contact term below is inlined into several kernels (barrier,
+// barrier-free, XPBD-free paths ...), and left to itself the compiler contracts a * b + c into an fma differently from one
+// inlining context to the next -- one ulp that flips a borderline inside-the-triangle decision and makes two kernels that
+// must agree bit for bit diverge (seen on BASELINE configs[2], where stacked identical grids project vertex onto vertex).
+__device__ __forceinline__ float3 SubR(float3 a, float3 b) { return make_float3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ float3 MulR(float s, float3 a) { return make_float3(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z)); }
+__device__ __forceinline__ float DotR(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, __fmul_rn(a.x, b.x))); }
+__device__ __forceinline__ float3 CrossR(float3 a, float3 b)
+{
+    return make_float3(fmaf(a.y, b.z, -__fmul_rn(a.z, b.y)), fmaf(a.z, b.x, -__fmul_rn(a.x, b.z)), fmaf(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+// u a + v b + w c
+__device__ __forceinline__ float3 Blend(float u, float3 a, float v, float3 b, float w, float3 c)
+{
+    return make_float3(fmaf(w, c.x, fmaf(v, b.x, __fmul_rn(u, a.x))), fmaf(w, c.y, fmaf(v, b.y, __fmul_rn(u, a.y))),
+                       fmaf(w, c.z, fmaf(v, b.z, __fmul_rn(u, a.z))));
+}
+
 // Contact energy derivatives of one (vertex, triangle) pair (sim/vbd/Kernels.h:223-302).
 // g += dE/dx_v, H (symmetric, 6 entries h00 h01 h02 h11 h12 h22) += d2E/dx_v2
 __device__ __forceinline__ void AccumulateVertexTriangleContact(
     float3 xtv, float3 xv, float3 const xtf[3], float3 const xf[3], float dt, float k, float muF, float epsv,
     float g[3], float H[6])
 {
-    float3 T0 = Sub(xf[1], xf[0]), T1 = Sub(xf[2], xf[0]);
-    float3 n             = Cross(T0, T1);
-    float const dblarea  = sqrtf(Dot(n, n));
+    float3 T0 = SubR(xf[1], xf[0]), T1 = SubR(xf[2], xf[0]);
+    float3 n             = CrossR(T0, T1);
+    float const dblarea  = __fsqrt_rn(DotR(n, n));
     if (dblarea <= 1e-8f)
         return;
-    n               = Mul(1.f / dblarea, n);
-    float3 const xc = Sub(xv, Mul(Dot(n, Sub(xv, xf[0])), n));
+    n               = MulR(__fdiv_rn(1.f, dblarea), n);
+    float3 const xc = SubR(xv, MulR(DotR(n, SubR(xv, xf[0])), n));
     // barycentric coordinates of the projection (geometry/IntersectionQueries.h:45-67)
-    float3 const AP = Sub(xc, xf[0]);
-    float const d00 = Dot(T0, T0), d01 = Dot(T0, T1), d11 = Dot(T1, T1), d20 = Dot(AP, T0), d21 = Dot(AP, T1);
-    float const denom = d00 * d11 - d01 * d01;
-    float const bv = (d11 * d20 - d01 * d21) / denom, bw = (d00 * d21 - d01 * d20) / denom, bu = 1.f - bv - bw;
+    float3 const AP = SubR(xc, xf[0]);
+    float const d00 = DotR(T0, T0), d01 = DotR(T0, T1), d11 = DotR(T1, T1), d20 = DotR(AP, T0), d21 = DotR(AP, T1);
+    float const denom = fmaf(d00, d11, -__fmul_rn(d01, d01));
+    float const bv = __fdiv_rn(fmaf(d11, d20, -__fmul_rn(d01, d21)), denom), bw = __fdiv_rn(fmaf(d00, d21, -__fmul_rn(d01, d20)), denom);
+    float const bu = __fsub_rn(__fsub_rn(1.f, bv), bw);
     bool const inside = bu >= 0.f && bu <= 1.f && bv >= 0.f && bv <= 1.f && bw >= 0.f && bw <= 1.f;
     if (!inside)
         return;
-    float3 const xb    = Add(Add(Mul(bu, xf[0]), Mul(bv, xf[1])), Mul(bw, xf[2]));
-    float const d      = fminf(0.f, Dot(Sub(xv, xb), n));
-    float const lambda = k * d;
-    g[0] += lambda * n.x, g[1] += lambda * n.y, g[2] += lambda * n.z;
-    H[0] += k * n.x * n.x, H[1] += k * n.x * n.y, H[2] += k * n.x * n.z;
-    H[3] += k * n.y * n.y, H[4] += k * n.y * n.z, H[5] += k * n.z * n.z;
+    float3 const xb    = Blend(bu, xf[0], bv, xf[1], bw, xf[2]);
+    float const d      = fminf(0.f, DotR(SubR(xv, xb), n));
+    float const lambda = __fmul_rn(k, d);
+    g[0] = fmaf(lambda, n.x, g[0]), g[1] = fmaf(lambda, n.y, g[1]), g[2] = fmaf(lambda, n.z, g[2]);
+    float3 const kn = MulR(k, n);
+    H[0] = fmaf(kn.x, n.x, H[0]), H[1] = fmaf(kn.x, n.y, H[1]), H[2] = fmaf(kn.x, n.z, H[2]);
+    H[3] = fmaf(kn.y, n.y, H[3]), H[4] = fmaf(kn.y, n.z, H[4]), H[5] = fmaf(kn.z, n.z, H[5]);
     // IPC smooth friction: tangent basis = (unnormalised edge, n x edge) as the reference has it
-    T1                  = Cross(n, T0);
-    float3 const xtb    = Add(Add(Mul(bu, xtf[0]), Mul(bv, xtf[1])), Mul(bw, xtf[2]));
-    float3 const dx     = Sub(Sub(xv, xtv), Sub(xb, xtb));
-    float const u0 = Dot(T0, dx), u1 = Dot(T1, dx);
-    float const unorm   = sqrtf(u0 * u0 + u1 * u1) + FLT_EPSILON;
-    float const epsvh   = epsv * dt;
-    float const muFl    = muF * fabsf(lambda);
-    float const y       = unorm / epsvh;
-    float const f1      = (y < 1.f) ? 2.f * y - y * y : 1.f;
-    float const c       = muFl * f1 / unorm;
-    float3 const Tu     = Add(Mul(u0, T0), Mul(u1, T1));
-    g[0] += c * Tu.x, g[1] += c * Tu.y, g[2] += c * Tu.z;
-    H[0] += c * (T0.x * T0.x + T1.x * T1.x), H[1] += c * (T0.x * T0.y + T1.x * T1.y), H[2] += c * (T0.x * T0.z + T1.x * T1.z);
-    H[3] += c * (T0.y * T0.y + T1.y * T1.y), H[4] += c * (T0.y * T0.z + T1.y * T1.z), H[5] += c * (T0.z * T0.z + T1.z * T1.z);
+    T1                  = CrossR(n, T0);
+    float3 const xtb    = Blend(bu, xtf[0], bv, xtf[1], bw, xtf[2]);
+    float3 const dx     = SubR(SubR(xv, xtv), SubR(xb, xtb));
+    float const u0 = DotR(T0, dx), u1 = DotR(T1, dx);
+    float const unorm   = __fadd_rn(__fsqrt_rn(fmaf(u1, u1, __fmul_rn(u0, u0))), FLT_EPSILON);
+    float const epsvh   = __fmul_rn(epsv, dt);
+    float const muFl    = __fmul_rn(muF, fabsf(lambda));
+    float const y       = __fdiv_rn(unorm, epsvh);
+    float const f1      = (y < 1.f) ? fmaf(-y, y, __fmul_rn(2.f, y)) : 1.f;
+    float const c       = __fdiv_rn(__fmul_rn(muFl, f1), unorm);
+    float3 const Tu     = make_float3(fmaf(u1, T1.x, __fmul_rn(u0, T0.x)), fmaf(u1, T1.y, __fmul_rn(u0, T0.y)), fmaf(u1, T1.z, __fmul_rn(u0, T0.z)));
+    g[0] = fmaf(c, Tu.x, g[0]), g[1] = fmaf(c, Tu.y, g[1]), g[2] = fmaf(c, Tu.z, g[2]);
+    H[0] = fmaf(c, fmaf(T1.x, T1.x, __fmul_rn(T0.x, T0.x)), H[0]), H[1] = fmaf(c, fmaf(T1.x, T1.y, __fmul_rn(T0.x, T0.y)), H[1]);
+    H[2] = fmaf(c, fmaf(T1.x, T1.z, __fmul_rn(T0.x, T0.z)), H[2]), H[3] = fmaf(c, fmaf(T1.y, T1.y, __fmul_rn(T0.y, T0.y)), H[3]);
+    H[4] = fmaf(c, fmaf(T1.y, T1.z, __fmul_rn(T0.y, T0.z)), H[4]), H[5] = fmaf(c, fmaf(T1.z, T1.z, __fmul_rn(T0.z, T0.z)), H[5]);
 }
 
 // Area-scaled penalty of a vertex' contacts (ContactPenalty, gpu/impl/vbd/Kernels.cuh:80-114): the triangles listed in
@@ -134,8 +155,8 @@ __device__ __forceinline__ float ContactPenaltyScale(const int* __restrict__ fcv
             ++nContacts;
     }
     for (int c = 0; c < nContacts; ++c)
-        sumfa += __ldg(FA + f[c]);
-    return nContacts > 0 ? xva * muC / sumfa : 0.f;
+        sumfa = __fadd_rn(sumfa, __ldg(FA + f[c]));
+    return nContacts > 0 ? __fdiv_rn(__fmul_rn(xva, muC), sumfa) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -7,9 +7,87 @@
 #include "contact.cuh"
 #include "device_buffer.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace vbdx {
+
+// A fixed sequence of small launches recorded once as a CUDA graph and replayed: the active-set prologue is ~20 kernels
+// of a few microseconds each, whose launch gaps and host cost exceed their work.  `key` = everything the recorded launches
+// were given by value (pointers, dt, ...): a different key records anew.  VBDX_CONTACT_GRAPH=0 launches directly.
+struct ReplayedLaunches {
+    cudaGraphExec_t exec = nullptr;
+    int64_t kernels      = 0;
+    std::vector<uint64_t> key;
+    ~ReplayedLaunches()
+    {
+        if (exec != nullptr)
+            cudaGraphExecDestroy(exec);
+    }
+    ReplayedLaunches()                                   = default;
+    ReplayedLaunches(ReplayedLaunches const&)            = delete;
+    ReplayedLaunches& operator=(ReplayedLaunches const&) = delete;
+
+    static bool Enabled()
+    {
+        static bool const on = [] {
+            char const* e = std::getenv("VBDX_CONTACT_GRAPH");
+            return e == nullptr || std::atoi(e) != 0;
+        }();
+        return on;
+    }
+    template <class Body>
+    void Run(std::vector<uint64_t> const& k, cudaStream_t s, int64_t* launches, Body&& body)
+    {
+        cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+        bool const legacy = s == nullptr || s == cudaStreamLegacy;  // cannot be captured
+        if (!Enabled() || legacy || cudaStreamIsCapturing(s, &status) != cudaSuccess || status != cudaStreamCaptureStatusNone)
+        {
+            body(launches);
+            return;
+        }
+        if (exec == nullptr || k != key)
+        {
+            if (exec != nullptr)
+                cudaGraphExecDestroy(exec), exec = nullptr;
+            int64_t counted = 0;
+            VBDX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            cudaGraph_t graph = nullptr;
+            try
+            {
+                body(&counted);
+            }
+            catch (...)
+            {
+                cudaStreamEndCapture(s, &graph);
+                if (graph != nullptr)
+                    cudaGraphDestroy(graph);
+                throw;
+            }
+            VBDX_CUDA(cudaStreamEndCapture(s, &graph));
+            cudaError_t const e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess)
+            {
+                exec = nullptr;
+                VBDX_CUDA(e);
+            }
+            kernels = counted;
+            key     = k;
+        }
+        VBDX_CUDA(cudaGraphLaunch(exec, s));
+        *launches += kernels;
+    }
+};
+
+inline uint64_t KeyOf(void const* p) { return static_cast<uint64_t>(reinterpret_cast<uintptr_t>(p)); }
+inline uint64_t KeyOf(float f)
+{
+    uint32_t u;
+    std::memcpy(&u, &f, sizeof(u));
+    return u;
+}
 
 // workspace of the one-launch radix sort (lbvh.cuh): zeroed barrier counter + chunk sums, the SM count as the CTA limit
 inline void InitSortSync(DevBuf<uint32_t>& aux, RadixSortSync& sync, int64_t* bytes)
@@ -19,7 +97,7 @@ inline void InitSortSync(DevBuf<uint32_t>& aux, RadixSortSync& sync, int64_t* by
     int dev = 0, sms = 0;
     VBDX_CUDA(cudaGetDevice(&dev));
     VBDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    sync.aux = aux.p, sync.base = 0, sync.maxCtas = sms;
+    sync.aux = aux.p, sync.maxCtas = sms;
 }
 
 struct DeviceBvh {
@@ -144,7 +222,17 @@ struct ContactState {
     }
 
     // VertexTriangleMixedCcdDcd::InitializeActiveSet with the predictor of gpu/impl/vbd/Integrator.cu:163-188
+    ReplayedLaunches replayInit, replayNearest[2];
     void InitializeActiveSet(const float4* x, const float4* vel, const float4* aext, int64_t nV, float dt, cudaStream_t s, int64_t* launches)
+    {
+        replayInit.Run({KeyOf(x), KeyOf(vel), KeyOf(aext), static_cast<uint64_t>(nV), KeyOf(dt), hasWorldBox ? 1u : 0u}, s, launches,
+                       [&](int64_t* n) { InitializeActiveSetNow(x, vel, aext, nV, dt, s, n); });
+    }
+    void NearestPass(const float4* x, int mode, cudaStream_t s, int64_t* launches)
+    {
+        replayNearest[mode != 0].Run({KeyOf(x), KeyOf(eps)}, s, launches, [&](int64_t* n) { NearestPassNow(x, mode, s, n); });
+    }
+    void InitializeActiveSetNow(const float4* x, const float4* vel, const float4* aext, int64_t nV, float dt, cudaStream_t s, int64_t* launches)
     {
         if (!hasWorldBox)
         {
@@ -172,7 +260,7 @@ struct ContactState {
     }
 
     // refit with current positions, then k-NN: mode 0 = UpdateActiveSet (+ contact lists), 1 = FinalizeActiveSet
-    void NearestPass(const float4* x, int mode, cudaStream_t s, int64_t* launches)
+    void NearestPassNow(const float4* x, int mode, cudaStream_t s, int64_t* launches)
     {
         TriangleBoxes<<<Blocks(nF, 256), 256, 0, s>>>(mesh, x, nullptr, nullptr, 0.f, triLo.p, triHi.p);
         bvh.Refit(triLo.p, triHi.p, s, launches);

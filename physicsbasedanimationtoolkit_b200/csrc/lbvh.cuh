@@ -33,10 +33,9 @@ constexpr int kSortSegment     = 256;   // 8 chunks per warp: short dependent ch
 constexpr int kSortWarpsPerCta = 8;
 constexpr int kSortMaxCtas     = 512;   // chunk sums of the scan live in shared memory
 
-// per call site: grid barrier counter [0] + chunk sums [1 ..]; `base` = value of the counter when the next launch starts
+// per call site: grid barrier counter [0] (zeroed before every launch: the launch may be a replayed graph node) + chunk sums [1 ..]
 struct RadixSortSync {
-    unsigned int* aux = nullptr;  // 1 + kSortMaxCtas words, zeroed once
-    unsigned int base = 0;
+    unsigned int* aux = nullptr;  // 1 + kSortMaxCtas words
     int maxCtas       = 0;        // co-resident CTAs the launch may use (<= SM count: a cheap barrier)
 };
 
@@ -229,9 +228,10 @@ inline void RadixSortPairs(
     uint32_t nSeg   = (n + kSortSegment - 1) / kSortSegment;
     int const need  = static_cast<int>((nSeg + kSortWarpsPerCta - 1) / kSortWarpsPerCta);
     int const ctas  = std::max(1, std::min({need, sync.maxCtas, kSortMaxCtas}));
-    void* args[]    = {&keys, &vals, &keysTmp, &valsTmp, &n, &nSeg, &counts, &sync.aux, &sync.base};
+    unsigned int zero = 0;
+    void* args[]      = {&keys, &vals, &keysTmp, &valsTmp, &n, &nSeg, &counts, &sync.aux, &zero};
+    VBDX_CUDA(cudaMemsetAsync(sync.aux, 0, sizeof(unsigned int), s));
     VBDX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(RadixSortFused), dim3(ctas), dim3(kSortWarpsPerCta * 32), args, 0, s));
-    sync.base += 12u * static_cast<unsigned int>(ctas);  // three barriers per pass
     if (launches)
         *launches += 1;
 }

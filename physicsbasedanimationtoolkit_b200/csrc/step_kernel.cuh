@@ -477,6 +477,15 @@ __device__ __forceinline__ void ProcessTile(
     if constexpr (kChebyshev)
         if (k > 1)
             h2 = __ldcg(p.hist + vi);
+    // damping / contact: the substep's start position and the head of the vertex' contact list (-1: no contacts), likewise
+    [[maybe_unused]] float4 xtv = make_float4(0.f, 0.f, 0.f, 0.f);
+    [[maybe_unused]] int fc0    = -1;
+    if constexpr (kDamping)
+    {
+        xtv = __ldcg(p.xt + vi);
+        if (p.fc != nullptr)
+            fc0 = __ldcg(p.fc + static_cast<size_t>(vi) * kMaxContacts);
+    }
 
     float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f, hd = 0.f;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -609,7 +618,7 @@ __device__ __forceinline__ void ProcessTile(
         float x = xi.x, y = xi.y, z = xi.z;
         if constexpr (kDamping)
         {
-            float4 const xt = __ldcg(p.xt + vi);
+            float4 const xt = xtv;
             float const D   = p.dampD;
             float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
             g0 = fmaf(D, fmaf(h02, ez, fmaf(h01, ey, __fmul_rn(h00, ex))), g0);
@@ -627,7 +636,7 @@ __device__ __forceinline__ void ProcessTile(
             // Triangle vertices are read as the reference's per-colour write buffer makes them visible: colours
             // already swept in this iteration -> current values, later colours -> previous iterate, the colour
             // being swept -> the values it had when the iteration started (snapshot).
-            if (p.fc != nullptr)
+            if (fc0 >= 0)
             {
                 int f[kMaxContacts];
                 int nContacts  = 0;
@@ -642,7 +651,7 @@ __device__ __forceinline__ void ProcessTile(
                             if (__ldg(p.colorVertexBegin + c + 1) <= vi)
                                 cb = __ldg(p.colorVertexBegin + c + 1);
                     float4 const* snapK = p.snap + static_cast<size_t>(k & 1) * p.nVerts;
-                    float3 const xtv    = F3(__ldcg(p.xt + vi));
+                    float3 const xtv3   = F3(xtv);
                     float gC[3] = {0.f, 0.f, 0.f}, HC[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     for (int c = 0; c < nContacts; ++c)
                     {
@@ -662,7 +671,7 @@ __device__ __forceinline__ void ProcessTile(
                             xf[a]            = F3(q);
                             xtf[a]           = F3(__ldcg(p.xt + j));
                         }
-                        AccumulateVertexTriangleContact(xtv, make_float3(x, y, z), xtf, xf, p.sdt, kC * __ldg(p.FA + f[c]), p.muF,
+                        AccumulateVertexTriangleContact(xtv3, make_float3(x, y, z), xtf, xf, p.sdt, __fmul_rn(kC, __ldg(p.FA + f[c])), p.muF,
                                                         p.epsv, gC, HC);
                     }
                     g0 = __fadd_rn(g0, gC[0]), g1 = __fadd_rn(g1, gC[1]), g2 = __fadd_rn(g2, gC[2]);

@@ -1,0 +1,16 @@
+import sys, os
+sys.path.insert(0,'/root/repo')
+import numpy as np
+import physicsbasedanimationtoolkit_b200 as pbat
+from physicsbasedanimationtoolkit_b200 import meshes
+n=29
+Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+X, T, B = meshes.stack_bodies(Xb, Tb, 16, axis=2, gap_frac=0.1)
+F = meshes.boundary_facets(T); V = np.unique(F)
+dbc = np.flatnonzero(X[2] <= X[2].min() + 0.01)
+d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B)
+     .with_dirichlet_vertices(dbc).with_contact_parameters(1e6, 0.3, 1e-3).construct())
+vbd = pbat.gpu.vbd.Integrator(d)
+for s in range(int(sys.argv[1]) if len(sys.argv)>1 else 52):
+    vbd.step(0.01,20,1)
+print(vbd.info["lastStepMs"], int(vbd.contact_state()[2]))
