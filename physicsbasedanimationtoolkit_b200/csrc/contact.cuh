@@ -165,7 +165,7 @@ __device__ __forceinline__ float ContactPenaltyScale(const int* __restrict__ fcv
 struct ContactMesh {
     const int32_t* B;  // body of every internal vertex
     const int32_t* V;  // collision vertices (internal ids)
-    const int4* F;     // collision triangles (internal vertex ids)
+    const int4* F;     // collision triangles (internal vertex ids; .w = the triangle's body)
     uint32_t nCV, nF;
 };
 
@@ -289,7 +289,7 @@ __global__ void MarkActive(ContactMesh m, BvhView t, const uint32_t* ids, const 
     float4 const lo = qlo[q], hi = qhi[q];
     float best = -1.f;
     BvhForEachOverlap(t, lo, hi, [&](int, uint32_t f) {
-        if (m.B[m.F[f].x] == body)
+        if (m.F[f].w == body)
             return;  // no self collision
         float4 const tl = triLo[f], th = triHi[f];
         float const dx = fmaxf(hi.x, th.x) - fminf(lo.x, tl.x), dy = fmaxf(hi.y, th.y) - fminf(lo.y, tl.y),
@@ -344,7 +344,7 @@ __global__ void NearestTriangles(ContactMesh m, BvhView t, const int32_t* av, co
         t, p, dupper[v], eps,
         [&](int f) {
             int4 const tri = m.F[f];
-            if (m.B[tri.x] == body)
+            if (tri.w == body)
                 return FLT_MAX;
             return PointTriangleDistance2(p, F3(x[tri.x]), F3(x[tri.y]), F3(x[tri.z]));
         },

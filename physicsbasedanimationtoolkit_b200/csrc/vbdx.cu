@@ -656,7 +656,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         {
             int64_t const a = d.F[3 * f], b = d.F[3 * f + 1], c = d.F[3 * f + 2];
             Require(a >= 0 && a < nV && b >= 0 && b < nV && c >= 0 && c < nV, "collision triangle index out of range");
-            Fh[f] = make_int4(plan.old2new[a], plan.old2new[b], plan.old2new[c], 0);
+            Fh[f] = make_int4(plan.old2new[a], plan.old2new[b], plan.old2new[c], Bh[plan.old2new[a]]);  // .w: the triangle's body
             double ab[3], ac[3];
             for (int k = 0; k < 3; ++k)
             {
@@ -2235,7 +2235,7 @@ vbdx_status vbdx_contact_create(int64_t nV, const int64_t* B, const int64_t* V, 
         {
             for (int k = 0; k < 3; ++k)
                 vbdx::Require(F[3 * f + k] >= 0 && F[3 * f + k] < nV, "collision triangle index out of range");
-            Fh[f] = make_int4(static_cast<int>(F[3 * f]), static_cast<int>(F[3 * f + 1]), static_cast<int>(F[3 * f + 2]), 0);
+            Fh[f] = make_int4(static_cast<int>(F[3 * f]), static_cast<int>(F[3 * f + 1]), static_cast<int>(F[3 * f + 2]), Bh[F[3 * f]]);
         }
         cudaStream_t s = nullptr;
         cs.B.Alloc(nV, &c.bytes), cs.V.Alloc(nCV, &c.bytes), cs.F.Alloc(nF, &c.bytes);
@@ -2846,7 +2846,7 @@ void XpbdIntegrator::Create(vbdx_xpbd_desc const& d)
         {
             for (int k = 0; k < 3; ++k)
                 Require(d.F[3 * f + k] >= 0 && d.F[3 * f + k] < nV, "collision triangle index out of range");
-            Fh[f] = make_int4(static_cast<int>(d.F[3 * f]), static_cast<int>(d.F[3 * f + 1]), static_cast<int>(d.F[3 * f + 2]), 0);
+            Fh[f] = make_int4(static_cast<int>(d.F[3 * f]), static_cast<int>(d.F[3 * f + 1]), static_cast<int>(d.F[3 * f + 2]), Bh[d.F[3 * f]]);
         }
         cs.B.Alloc(nV, &deviceBytes), cs.V.Alloc(nCV, &deviceBytes), cs.F.Alloc(nF, &deviceBytes);
         cs.B.Upload(Bh.data(), nV, stream), cs.V.Upload(Vh.data(), nCV, stream), cs.F.Upload(Fh.data(), nF, stream);

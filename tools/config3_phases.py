@@ -1,3 +1,6 @@
+"""BASELINE configs[2] (16 stacked bodies, contact): device ms of every step, barrier-free sweep vs colour barriers, and the number
+of active vertices every 10 steps -- shows the two phases (free fall, then contact) and that both sweeps take the same
+contact decisions.   python tools/config3_phases.py"""
 import sys, time, os
 sys.path.insert(0,'/root/repo')
 import numpy as np
