@@ -190,10 +190,13 @@ class DomainDecomposedIntegrator:
             mine = torch.as_tensor(self.vbd.ipc_handles(), device=dev)
             handles = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(handles, mine)
-            nv = torch.tensor([lp.l2g.size, lp.ghost_local.size], dtype=torch.int64, device=dev)
+            nv = torch.tensor([lp.l2g.size, lp.ghost_local.size, int(self.vbd.info["nColors"])], dtype=torch.int64, device=dev)
             nvs = [torch.zeros_like(nv) for _ in range(self.world)]
             dist.all_gather(nvs, nv)
             nvs = torch.stack(nvs).cpu().numpy()
+            # barrier sweeps count epochs per colour: every rank must sweep the same number of colours (empty ones included)
+            if len(set(nvs[:, 2].tolist())) != 1:
+                raise RuntimeError(f"ranks disagree on the number of colours: {nvs[:, 2].tolist()}")
             self.vbd.dist_connect(self.rank, self.world, torch.stack(handles).cpu().numpy(),
                                   nvs[:, 0], nvs[:, 1], sl, sp, sr,
                                   sum(1 << int(r) for r in np.unique(lp.ghost_owner)))
