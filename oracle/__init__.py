@@ -100,6 +100,15 @@ def have_ref() -> bool:
     return os.path.exists(REF_LIB)
 
 
+def default_kind() -> str:
+    """The checker the tests use when they do not name one: the build over the reference's own headers where it exists
+    (``oracle/_ref`` travels to the GPU box with the repository snapshot), else the port.  ``VBD_ORACLE_KIND`` overrides."""
+    k = os.environ.get("VBD_ORACLE_KIND", "")
+    if k in ("port", "reference"):
+        return k
+    return "reference" if have_ref() else "port"
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -112,14 +121,15 @@ class Oracle:
     """Double-precision CPU VBD integrator with the reference's semantics.
 
     ``X`` is 3 x nV, ``E`` is 4 x nT (the reference's column-per-vertex / column-per-tet
-    convention, sim/vbd/Data.h:167-170).  ``kind`` = "port" | "reference".
+    convention, sim/vbd/Data.h:167-170).  ``kind`` = "port" | "reference" (default: ``default_kind()``).
     """
 
     def __init__(self, X, E, *, v=None, aext=None, rhoe=None, mue=None, lambdae=None, dbc=None,
                  colors=None, ordering=ORDER_LARGEST_DEGREE, selection=SELECT_LEAST_USED,
                  strategy=ADAPTIVE_PBAT, accel=ACCEL_NONE, rho=1.0, omega_mode=0, kD=0.0,
-                 detH_zero=1e-7, kind="port", B=None, V=None, F=None, muC=1e6, muF=0.3, epsv=1e-3,
+                 detH_zero=1e-7, kind=None, B=None, V=None, F=None, muC=1e6, muF=0.3, epsv=1e-3,
                  active_set_update_frequency=1, material=MATERIAL_STABLE_NEO_HOOKEAN):
+        kind = kind or default_kind()
         self.lib = _load("port" if kind == "port" else "ref")
         X = np.asarray(X, dtype=np.float64)
         E = np.asarray(E, dtype=np.int64)

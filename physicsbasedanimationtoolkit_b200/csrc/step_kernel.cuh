@@ -49,7 +49,8 @@ struct StepParams {
     float detHZero;
     int strategy;
     int iterations, substeps;
-    unsigned int* barrier;  // zeroed before launch; [1]: warps x sweeps finished (barrier-free sweeps with contact)
+    unsigned int* barrier;  // zeroed before launch
+    unsigned int* sweepDone;  // barrier-free sweeps with contact: per sweep of the launch, the warps that have finished it (zeroed before launch)
     unsigned int* nonFinite;  // sentinel: owned vertices whose final position is NaN/Inf (counted by the velocity update; zeroed per step)
     // vertex-triangle contact (fc == nullptr: disabled)
     const int32_t* __restrict__ fc;      // 8 triangle ids per internal vertex, -1 terminated

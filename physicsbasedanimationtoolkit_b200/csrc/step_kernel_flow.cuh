@@ -253,8 +253,10 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
     int omegaOf            = -1;
     // Contact (p.hist4 != nullptr; launched per substep, after PreStepKernel and the active-set update): readers of the
     // write history (step_kernel.cuh, HistSlot) must find the slot they need un-overwritten, so no warp starts sweep k
-    // before every warp that has tiles finished sweep k - 2.  One relaxed add per warp and sweep; the counter is looked
-    // at when a warp finishes a sweep, a sweep ahead of its use, and in steady state never waited for.
+    // before every warp that has tiles finished sweep k - 2.  One counter per sweep of the launch (p.sweepDone[k] = warps that
+    // have finished sweep k; a single running total would let fast warps vouch for slow ones -- the CPU model check,
+    // tests/test_dataflow_protocol.py, found exactly that), one relaxed add per warp and sweep; the counter a warp needs is
+    // looked at when it finishes a sweep, a sweep ahead of its use, and in steady state never waited for.
     bool const lagBound     = p.hist4 != nullptr;
     unsigned int sweepsSeen = 0;
     int sweepOf             = 0;  // the sweep the tile about to run belongs to, as far as the bound was checked
@@ -298,11 +300,11 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
                 sweepOf = k0;
                 if (k0 >= 2 && !dead)
                 {
-                    unsigned int const need = pp.flowActiveWarps * static_cast<unsigned int>(k0 - 1);
+                    unsigned int const need = pp.flowActiveWarps;
                     unsigned long long t0   = 0;
                     for (uint32_t polls = 1; sweepsSeen < need; ++polls)
                     {
-                        sweepsSeen = LoadRelaxedGpu(p.barrier + 1);
+                        sweepsSeen = LoadRelaxedGpu(p.sweepDone + (k0 - 2));
                         if ((polls & 255u) == 0u)
                         {
                             if (t0 == 0)
@@ -369,8 +371,8 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
             {
                 // this warp's last tile of sweep k0 (its history reads are done: their values were used)
                 if (lane == 0)
-                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier + 1) : "memory");
-                sweepsSeen = LoadRelaxedGpu(p.barrier + 1);
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.sweepDone + k0) : "memory");
+                sweepsSeen = k1 >= 2 ? LoadRelaxedGpu(p.sweepDone + (k1 - 2)) : 0u;  // what the next sweep will ask for
             }
             if (k1 >= 0)
                 Gather(td1, idA, idB, tagSub + static_cast<uint32_t>(k1));

@@ -109,6 +109,7 @@ struct Integrator {
     size_t flowSmemBytes = 0;
     uint32_t flowActiveWarps = 0;  // warps of the lean kernel's grid that have tiles
     DevBuf<float4> dHist4;         // contact under barrier-free sweeps: every vertex' last four writes (step_kernel.cuh, HistSlot)
+    DevBuf<unsigned int> dSweepDone;  // ... and per sweep of a launch the warps that have finished it (the sweep-lag bound)
     void BuildFlowSchedule();
 
     // state
@@ -609,7 +610,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     dAext.Alloc(nV, &deviceBytes);
     if (flags & VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY)
         dVtm1.Alloc(nV, &deviceBytes);
-    dBarrier.Alloc(3, &deviceBytes);  // [0] grid barrier counter, [1] finished warp-sweeps (contact, barrier-free), [2] non-finite sentinel
+    dBarrier.Alloc(3, &deviceBytes);  // [0] grid barrier counter, [1] spare, [2] non-finite sentinel
     VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 3 * sizeof(unsigned int), stream));
     dDistFlags.Alloc(16, &deviceBytes);
     VBDX_CUDA(cudaMemsetAsync(dDistFlags.p, 0, 16 * sizeof(unsigned int), stream));
@@ -1016,7 +1017,12 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
         q.substeps    = 1;
         q.skipPreStep = 1;
         if (UseFlow(iterations))
+        {
             q.hist4 = dHist4.p, q.snap = nullptr;  // barrier-free sweeps: contact reads go to the write history
+            if (dSweepDone.n < static_cast<size_t>(iterations))
+                dSweepDone.Alloc(static_cast<size_t>(iterations) + 64, &deviceBytes);
+            q.sweepDone = dSweepDone.p;
+        }
         for (int s = 0; s < substeps; ++s)
         {
             q.tagBase = p.tagBase + static_cast<unsigned int>(s) * (static_cast<unsigned int>(iterations) + 1u);  // write numbers of this substep
@@ -1033,6 +1039,8 @@ void Integrator::RunStep(StepParams const& p, double dt, int iterations, int sub
                 NvtxRange const z("pbat.gpu.impl.vbd.Integrator.UpdateActiveSet");
                 contact.NearestPass(xFinal, 0, stream, &kernelLaunches);
             }
+            if (q.sweepDone != nullptr)
+                VBDX_CUDA(cudaMemsetAsync(q.sweepDone, 0, static_cast<size_t>(iterations) * sizeof(unsigned int), stream));
             launchStep(q);
         }
         contact.NearestPass(xFinal, 1, stream, &kernelLaunches);

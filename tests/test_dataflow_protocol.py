@@ -275,3 +275,180 @@ def test_protocol_across_gpus_with_many_neighbours(world):
     X, T = meshes.tet_grid(6, 6, 6, 0.1)
     dbc = np.flatnonzero(X[2] == 0)
     assert simulate_ranks(X, T, dbc, world, 3, 5, np.random.default_rng(world), partition="rcb") > 500
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# contact: a triangle corner is a vertex of ANOTHER body -- no ring dependency ties its tile to the reader's.
+# Every write also goes to the history of the vertex' last four writes (slot = write number & 3); a reader polls the slot of
+# the write it needs; no warp starts sweep k before every warp with tiles has finished sweep k - 2 (csrc/step_kernel_flow.cuh).
+# ---------------------------------------------------------------------------------------------------------------------
+def simulate_contact(plan, colors, iterations, n_warps, rng, contacts, lag_bound=True, favoured=None, warp_of=None):
+    """`contacts`: internal vertex -> array of corner vertices (internal ids) its contact term reads.  Ring reads happen when
+    the ring dependencies are met, contact reads some time later, the write later still.  `favoured`: warps the scheduler
+    prefers (the others only run when no favoured warp can) -- lets one body run as far ahead as the protocol allows.
+    `warp_of(colour, index within the colour, tile)`: which warp runs a tile (default: dealt round-robin like the kernel's
+    schedule; the protocol must hold for ANY assignment in which a warp runs its tiles in (sweep, colour) order)."""
+    tiles, ids, ctb = plan["tiles"], plan["ids"], plan["ctb"]
+    n_active, n_colors, new2old = plan["n_active"], plan["n_colors"], plan["new2old"]
+    icolor = np.asarray(colors)[new2old]
+    nV = new2old.size
+    T0 = 9
+    tagQ = np.full(nV, T0, np.int64)
+    tagP = np.full(nV, T0, np.int64)
+    hist = np.full((4, nV), -1, np.int64)
+    hist[T0 & 3] = T0                                          # the pre-step primes the history
+    prog = [[] for _ in range(n_warps)]
+    for k in range(iterations):
+        for c in range(n_colors):
+            for j, t in enumerate(range(int(ctb[c]), int(ctb[c + 1]))):
+                prog[warp_of(c, j, t) if warp_of else j % n_warps].append((k, t))
+    active_warps = sum(1 for p in prog if p)
+    pc = [0] * n_warps
+    stage = [0] * n_warps                                      # 0: waiting for the ring, 1: ring read, 2: contacts read
+    sweeps_done = [0] * iterations                             # per sweep: warps that have finished it (one add per warp and sweep)
+    remaining = sum(len(p) for p in prog)
+    contact_reads = 0
+    max_lead = 0
+    while remaining:
+        order = list(rng.permutation(n_warps))
+        if favoured is not None:
+            order.sort(key=lambda w: w not in favoured)
+        progressed = False
+        for w in order:
+            if favoured is not None and w not in favoured and progressed:
+                break                                          # the others run only when no favoured warp can
+            if pc[w] >= len(prog[w]):
+                continue
+            k, t = prog[w][pc[w]]
+            vbase, meta, ring_start = int(tiles[t, 1]), int(tiles[t, 2]), int(tiles[t, 3])
+            nverts = (meta >> 3) & 63
+            if stage[w] == 0:
+                first_of_sweep = pc[w] == 0 or prog[w][pc[w] - 1][0] != k
+                if lag_bound and first_of_sweep and k >= 2 and sweeps_done[k - 2] < active_warps:
+                    continue                                   # polls the counter
+                entries = ids[ring_start:ring_start + 32 * ((meta >> 9) & 63)]
+                base = (entries & ~np.uint32(PREV)).astype(np.int64)
+                prev = (entries & np.uint32(PREV)) != 0
+                checked = (base < n_active) & ~((base == vbase) & ~prev)
+                expect = T0 + k + np.where(prev, 0, 1)
+                have = np.where(prev, tagP[base], tagQ[base])
+                assert not (checked & (have > expect)).any(), "ring overwrite hazard"
+                if (checked & (have != expect)).any():
+                    continue
+                stage[w] = 1
+                progressed = True
+                if favoured is None or w not in favoured:
+                    continue                                   # (favoured warps go on at once: as far ahead as possible)
+            if stage[w] == 1:
+                if favoured is None and rng.random() < 0.5:
+                    progressed = True
+                    continue                                   # the contact reads come some time after the ring reads
+                ready = True
+                for v in range(vbase, vbase + nverts):
+                    for j in contacts.get(v, ()):
+                        if j >= n_active:
+                            continue                           # never swept: read in place
+                        lower = icolor[j] < icolor[v]
+                        want = T0 + k + (1 if lower else 0)
+                        have = hist[want & 3, j]
+                        assert have <= want, (f"history overwritten: vertex {v} (sweep {k}) needs write {want} of vertex {j}, "
+                                              f"its slot already holds write {have}")
+                        if have != want:
+                            ready = False
+                        else:
+                            contact_reads += 1
+                if not ready:
+                    continue                                   # keeps polling (AwaitHist)
+                stage[w] = 2
+                progressed = True
+                if favoured is None or w not in favoured:
+                    continue
+            # stage 2: the write
+            if favoured is None and rng.random() < 0.5:
+                progressed = True
+                continue
+            tag = T0 + k + 1
+            tagQ[vbase:vbase + nverts] = tag
+            tagP[vbase:vbase + nverts] = tag
+            hist[tag & 3, vbase:vbase + nverts] = tag
+            stage[w] = 0
+            pc[w] += 1
+            remaining -= 1
+            progressed = True
+            if pc[w] == len(prog[w]) or prog[w][pc[w]][0] != k:
+                sweeps_done[k] += 1                            # this warp's last tile of sweep k
+            lo = min((prog[x][pc[x]][0] if pc[x] < len(prog[x]) else iterations) for x in range(n_warps) if prog[x])
+            max_lead = max(max_lead, k - lo)
+        assert progressed, "deadlock: no warp can proceed"
+    assert (tagQ[:n_active] == T0 + iterations).all()
+    return contact_reads, max_lead
+
+
+def contact_scene(seed, one_way=False, tile_iters=0):
+    """Two grids that share no tet; random contact lists (<= 8 triangles = 24 corners) between them."""
+    Xa, Ta = meshes.tet_grid(4, 4, 2, 0.1)
+    Xb, Tb = meshes.tet_grid(4, 3, 2, 0.1, origin=(0.0, 0.0, 0.25))
+    X = np.concatenate([Xa, Xb], axis=1)
+    T = np.concatenate([Ta, Tb + Xa.shape[1]], axis=1)
+    nA, nV = Xa.shape[1], X.shape[1]
+    colors = pbat.graph.mesh_greedy_color(T, nV)
+    constrained = np.zeros(nV, np.uint8)
+    constrained[np.flatnonzero(X[2] == 0)] = 1
+    plan = plan_of(X, T, colors, constrained, tile_iters)
+    old2new = np.empty(nV, np.int64)
+    old2new[plan["new2old"]] = np.arange(nV)
+    rng = np.random.default_rng(seed)
+    contacts = {}
+    body = np.arange(nV) >= nA
+    for v in rng.choice(nV, 30, replace=False):
+        if one_way and body[v]:
+            continue                                           # only body A reads body B
+        other = np.flatnonzero(body != body[v])
+        iv = int(old2new[v])
+        if iv < plan["n_active"]:
+            contacts[iv] = old2new[rng.choice(other, 3 * int(rng.integers(1, 9)))]
+    tile_body = []                                             # None: the tile holds vertices of both bodies
+    for t in plan["tiles"]:
+        b = body[plan["new2old"][int(t[1]):int(t[1]) + ((int(t[2]) >> 3) & 63)]]
+        tile_body.append(bool(b[0]) if (b == b[0]).all() else None)
+    return plan, colors, contacts, tile_body
+
+
+@pytest.mark.parametrize("n_warps,seed", [(2, 1), (7, 2), (64, 3), (500, 4)])
+def test_contact_history_protocol(n_warps, seed):
+    plan, colors, contacts, _ = contact_scene(seed)
+    reads, lead = simulate_contact(plan, colors, 7, n_warps, np.random.default_rng(seed), contacts)
+    assert reads > 500 and lead <= 1
+
+
+def test_contact_history_needs_the_sweep_lag_bound():
+    """Two bodies that share no tile (a hand-made plan: two paths of six vertices, two colours, one vertex per tile and warp);
+    A's contact lists read B, B reads nothing, and the scheduler lets B's warps go whenever they can.  With the bound B is
+    never more than a sweep ahead of the slowest warp and every history read finds its write; without it B finishes all
+    its sweeps before A starts, laps the four slots, and the model check reports the overwrite -- the bound is what makes
+    the history safe, not luck."""
+    # internal ids: colour 0 = A0 A2 A4 B0 B2 B4 (0..5), colour 1 = A1 A3 A5 B1 B3 B5 (6..11); position along the path:
+    pos = {0: ("A", 0), 1: ("A", 2), 2: ("A", 4), 3: ("B", 0), 4: ("B", 2), 5: ("B", 4),
+           6: ("A", 1), 7: ("A", 3), 8: ("A", 5), 9: ("B", 1), 10: ("B", 3), 11: ("B", 5)}
+    at = {v: k for k, v in pos.items()}
+    colors = np.array([0] * 6 + [1] * 6)
+    ids, tiles = [], []
+    for v in range(12):
+        body, i = pos[v]
+        ring = [v | PREV]                                      # the tile's own start value
+        for j in (i - 1, i + 1):
+            if (body, j) in at:
+                u = at[(body, j)]
+                ring.append(u if colors[u] < colors[v] else u | PREV)
+        ring += [v] * (32 - len(ring))                         # padding: the tile's first vertex without the flag
+        tiles.append([0, v, (1 << 3) | (1 << 9), len(ids)])    # one vertex, one chunk
+        ids += ring
+    plan = dict(tiles=np.array(tiles, np.uint32), ids=np.array(ids, np.uint32), ctb=np.array([0, 6, 12], np.uint32),
+                new2old=np.arange(12, dtype=np.int32), n_active=12, n_colors=2)
+    b_verts = np.array([v for v in range(12) if pos[v][0] == "B"])
+    contacts = {v: np.random.default_rng(v).choice(b_verts, 6) for v in range(12) if pos[v][0] == "A"}
+    kw = dict(favoured={int(v) for v in b_verts}, warp_of=lambda c, j, t: t)
+    reads, lead = simulate_contact(plan, colors, 12, 12, np.random.default_rng(0), contacts, lag_bound=True, **kw)
+    assert reads == 6 * 6 * 12 and lead == 1                   # as far ahead as the bound allows (sweep k starts when all finished k - 2)
+    with pytest.raises(AssertionError, match="history overwritten"):
+        simulate_contact(plan, colors, 12, 12, np.random.default_rng(0), contacts, lag_bound=False, **kw)
