@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-iters", type=int, default=0)
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of domain decomposition")
-    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the parity / strong-scaling / batch sub-records")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (N > 1: parity / strong scaling / batch; N = 1: the other colouring)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -471,6 +471,24 @@ def main():
                 "timing": "CUDA events around the steps on every rank, max over ranks; the single-GPU time is the median of 5 steps of the same block on rank 0 in this same run"}
         del dds
         barrier()
+    if world == 1 and not args.no_extras:
+        # The same workload under the reference's other colour selection (with_vertex_coloring_strategy(LargestDegree,
+        # FirstAvailable), graph/Color.h:45-135): 4 colours instead of 7 on this grid = fewer dependent tile rounds per sweep
+        # (SURVEY.md 8f rank 2).  A sub-record: the headline keeps the reference's default colouring.
+        data4 = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_dirichlet_vertices(dbc).with_chebyshev_acceleration(RHO)
+                 .with_vertex_coloring_strategy(pbat.graph.GreedyColorOrderingStrategy.LargestDegree,
+                                                pbat.graph.GreedyColorSelectionStrategy.FirstAvailable).construct())
+        vbd4 = pbat.gpu.vbd.Integrator(data4, device=local_rank, tile_iters=args.tile_iters)
+        vbd4.x = np.ascontiguousarray(x0, dtype=np.float32)
+        c_steps = 10
+        ms_c, _, _ = device_timed(vbd4, c_steps, 3)
+        info4 = vbd4.info
+        extras["colouring_first_available"] = {
+            "what": "same workload, vertex colouring LargestDegree / FirstAvailable (a reference option) instead of the default LeastUsed",
+            "colours": int(info4["nColors"]), "steps": c_steps, "ms_per_step": ms_c / c_steps,
+            "value": info4["nActiveVertices"] * ITERS * c_steps / (ms_c * 1e-3), "unit": "vertex-iterations/s",
+            "finite": bool(np.isfinite(vbd4.x).all())}
+        del vbd4
     if world > 1 and not args.no_extras and not args.replicas:
         # scene batches (configs[4]): 512 independent 10^3-cube scenes per GPU, one persistent launch per step and GPU
         from physicsbasedanimationtoolkit_b200 import meshes
