@@ -170,9 +170,10 @@ vbdx_status vbdx_batch_offsets(vbdx_integrator* h, int32_t* n_scenes, int64_t* v
 vbdx_status vbdx_destroy(vbdx_integrator* h);
 
 /* Integrator::Step(dt, iterations, substeps)   gpu/vbd/Integrator.h:72, sim/vbd/Integrator.h:29
- * One persistent launch per call.  Without damping / contact the colours of a sweep follow each other without a grid
- * barrier (every position carries the number of its write; a tile waits for exactly its 1-ring), with results bit-identical
- * to the barrier sweep; environment: VBDX_DATAFLOW=0 selects colour barriers, VBDX_DATAFLOW_TIMEOUT_S (2) bounds a dependency
+ * One persistent launch per call (with contact: per substep, behind the active-set kernels, which are replayed as CUDA
+ * graphs).  The colours of a sweep follow each other without a grid barrier (every position carries the number of its write; a
+ * tile waits for exactly its 1-ring; contact terms read other bodies' vertices from a history of their last four writes), with
+ * results bit-identical to the barrier sweep; environment: VBDX_DATAFLOW=0 selects colour barriers, VBDX_DATAFLOW_TIMEOUT_S (2) bounds a dependency
  * wait (exceeded = VBDX_CUDA_ERROR with a diagnostic, and the handle falls back to barriers). */
 vbdx_status vbdx_step(vbdx_integrator* h, double dt, int32_t iterations, int32_t substeps);
 /* same, returns once the work is enqueued on the handle's stream */
