@@ -36,8 +36,8 @@ constexpr uint32_t kFlowStatic  = 0x40000000u;  // never changes (constrained ve
 constexpr uint32_t kFlowGhost   = 0x20000000u;  // written by a peer GPU; index = ghost number (two copies by parity of the write)
 constexpr uint32_t kFlowIndex   = 0x1fffffffu;
 
-// kDist: domain decomposition (ghost entries exist)
-template <bool kChebyshev, bool kDamping, bool kDist>
+// kDist: domain decomposition (ghost entries exist); kStvk: St. Venant-Kirchhoff records (two blocks per incident tet)
+template <bool kChebyshev, bool kDamping, bool kDist, bool kStvk = false>
 __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __grid_constant__ PipeParams pp)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
                 if (k1 >= 0)
                     IssueRecords(td1);
             };
-            ProcessTile<kChebyshev, kDamping, false, SmemRecords, decltype(afterAccumulate), false>(
+            ProcessTile<kChebyshev, kDamping, false, SmemRecords, decltype(afterAccumulate), kStvk>(
                 p, td0, stage, src, 0, k0, omega, lane, tr, afterAccumulate, tagLow + 1u);
             __syncwarp();  // ... and with the staged positions
             if (lagBound && k1 != k0)

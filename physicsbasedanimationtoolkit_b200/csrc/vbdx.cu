@@ -181,6 +181,12 @@ struct Integrator {
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
         bool const damp = kD != 0.0 || contact.enabled;  // the damping variants carry the contact term
+        if (material == VBDX_MATERIAL_STVK)  // (single GPU; domain decomposition keeps the pipelined kernel for StVK)
+        {
+            if (cheb)
+                return damp ? StepKernelFlow<true, true, false, true> : StepKernelFlow<true, false, false, true>;
+            return damp ? StepKernelFlow<false, true, false, true> : StepKernelFlow<false, false, false, true>;
+        }
         if (distWorld > 1 || nGhost > 0)
         {
             if (cheb)
@@ -194,7 +200,8 @@ struct Integrator {
     bool UseFlow(int iterations) const
     {
         return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterMode &&
-               (!contact.enabled || dHist4.p != nullptr) && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && iterations > 0;
+               (!contact.enabled || dHist4.p != nullptr) &&
+               (material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN || (distWorld == 1 && nGhost == 0)) && iterations > 0;
     }
 
     TmaKernelFn KernelTma() const
@@ -503,13 +510,19 @@ void Integrator::Create(vbdx_data_desc const& d)
             perSm = std::min(perSm, n);
         }
         // the lean barrier-free kernel has its own launch shape: no barrier warp, no id buffers
-        if (!stvk && flowSmemBytes <= static_cast<size_t>(maxOptin))
+        if (flowSmemBytes <= static_cast<size_t>(maxOptin) && !(stvk && d.nGhosts > 0))
         {
             int flowPerSm = 1 << 30;
-            for (PipeKernelFn fn : {cheb0 ? StepKernelFlow<true, false, false> : StepKernelFlow<false, false, false>,
-                                    cheb0 ? StepKernelFlow<true, true, false> : StepKernelFlow<false, true, false>,
-                                    cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
-                                    cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>})
+            std::vector<PipeKernelFn> fns;
+            if (stvk)
+                fns = {cheb0 ? StepKernelFlow<true, false, false, true> : StepKernelFlow<false, false, false, true>,
+                       cheb0 ? StepKernelFlow<true, true, false, true> : StepKernelFlow<false, true, false, true>};
+            else
+                fns = {cheb0 ? StepKernelFlow<true, false, false> : StepKernelFlow<false, false, false>,
+                       cheb0 ? StepKernelFlow<true, true, false> : StepKernelFlow<false, true, false>,
+                       cheb0 ? StepKernelFlow<true, false, true> : StepKernelFlow<false, false, true>,
+                       cheb0 ? StepKernelFlow<true, true, true> : StepKernelFlow<false, true, true>};
+            for (PipeKernelFn fn : fns)
             {
                 VBDX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));
                 int n = 0;
@@ -566,7 +579,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     PartitionTiles(plan, gridBlocks);
     if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && flowGridBlocks > 0)
         flowGridBlocks = std::max(1, std::min(std::atoi(e), flowGridBlocks));
-    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN && flowGridBlocks > 0)
+    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && flowGridBlocks > 0)
         BuildFlowSchedule();
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
