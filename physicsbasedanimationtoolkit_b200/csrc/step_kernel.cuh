@@ -442,7 +442,8 @@ __device__ __forceinline__ void ProcessTile(
     uint32_t lane,
     unsigned long long* trace = nullptr,
     AfterAccumulate afterAccumulate = AfterAccumulate{},  // runs once the tile's records have been consumed
-    uint32_t sendTag = 0u)                                // domain decomposition: tag of this sweep's writes
+    uint32_t sendTag = 0u,                                // domain decomposition: tag of this sweep's writes
+    float4 const* xtStaged = nullptr)                     // damping / contact: xt of this lane's vertex, staged with the tile's gather
 {
     float4 const* __restrict__ posQ = p.pos;
     uint32_t const lw         = TileLog2W(td.z);
@@ -483,7 +484,8 @@ __device__ __forceinline__ void ProcessTile(
     [[maybe_unused]] int fc0    = -1;
     if constexpr (kDamping)
     {
-        xtv = __ldcg(p.xt + vi);
+        if (xtStaged == nullptr)
+            xtv = __ldcg(p.xt + vi);
         if (p.fc != nullptr)
             fc0 = __ldcg(p.fc + static_cast<size_t>(vi) * kMaxContacts);
     }
@@ -619,7 +621,7 @@ __device__ __forceinline__ void ProcessTile(
         float x = xi.x, y = xi.y, z = xi.z;
         if constexpr (kDamping)
         {
-            float4 const xt = xtv;
+            float4 const xt = xtStaged != nullptr ? xtStaged[lane] : xtv;
             float const D   = p.dampD;
             float const ex = x - xt.x, ey = y - xt.y, ez = z - xt.z;
             g0 = fmaf(D, fmaf(h02, ez, fmaf(h01, ey, __fmul_rn(h00, ex))), g0);
@@ -652,7 +654,7 @@ __device__ __forceinline__ void ProcessTile(
                             if (__ldg(p.colorVertexBegin + c + 1) <= vi)
                                 cb = __ldg(p.colorVertexBegin + c + 1);
                     float4 const* snapK = p.snap + static_cast<size_t>(k & 1) * p.nVerts;
-                    float3 const xtv3   = F3(xtv);
+                    float3 const xtv3   = F3(xtStaged != nullptr ? xtStaged[lane] : xtv);
                     float gC[3] = {0.f, 0.f, 0.f}, HC[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     for (int c = 0; c < nContacts; ++c)
                     {

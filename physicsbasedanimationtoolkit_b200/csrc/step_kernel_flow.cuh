@@ -48,13 +48,14 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
     uint32_t const nC     = static_cast<uint32_t>(p.nColors);
     uint32_t const gwarp  = warp * gridDim.x + blockIdx.x;
 
-    // per warp (FlowWarpBytes): record buffer | staged positions | 4 descriptors | mbarrier | 4 sweep numbers
+    // per warp (FlowWarpBytes): record buffer | staged positions | 4 descriptors | mbarrier | 4 sweep numbers | 32 x xt
     unsigned char* mine   = smem + static_cast<size_t>(warp) * FlowWarpBytes(SE, pp.maxIters);
     float4* const recBuf  = reinterpret_cast<float4*>(mine);
     float4* const stage   = recBuf + static_cast<size_t>(pp.maxIters) * kBlockFloat4;
     uint4* const tdRing   = reinterpret_cast<uint4*>(stage + SE);  // descriptors of tiles seq .. seq+3 of this warp's sequence
     uint32_t const barRec = SmemAddr(tdRing + 4);                   // completion of the bulk copy of a tile's records
     int* const kkRing     = reinterpret_cast<int*>(tdRing + 5);     // their sweep numbers within the substep (-1: no tile)
+    float4* const xtStage = reinterpret_cast<float4*>(tdRing + 6);  // xt of the tile's vertices, per lane (damping / contact)
 
     if (lane == 0)
     {
@@ -135,6 +136,13 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
     auto Gather = [&](uint4 const td, uint4 const a, uint4 const b, uint32_t tagLow) {
         uint32_t const dst    = SmemAddr(stage + lane);
         uint32_t const chunks = TileChunks(td.z);
+        if constexpr (kDamping)
+        {
+            // the epilogue's xt (constant during the sweeps): staged with the ring instead of an L2 round trip on the tile's
+            // critical path or four registers held across the accumulation loop
+            uint32_t const g = lane >> TileLog2W(td.z);
+            CpAsync16(SmemAddr(xtStage + lane), p.xt + td.y + (g < TileVerts(td.z) ? g : 0u));
+        }
         uint32_t const e[8]   = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (uint32_t u = 0; u < 8; ++u)
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(kFlowMaxThreads, 1) StepKernelFlow(const __gri
                     IssueRecords(td1);
             };
             ProcessTile<kChebyshev, kDamping, false, SmemRecords, decltype(afterAccumulate), kStvk>(
-                p, td0, stage, src, 0, k0, omega, lane, tr, afterAccumulate, tagLow + 1u);
+                p, td0, stage, src, 0, k0, omega, lane, tr, afterAccumulate, tagLow + 1u, kDamping ? xtStage : nullptr);
             __syncwarp();  // ... and with the staged positions
             if (lagBound && k1 != k0)
             {

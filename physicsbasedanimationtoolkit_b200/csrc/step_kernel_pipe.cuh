@@ -45,9 +45,10 @@ __host__ __device__ inline size_t PipeSmemBytes(uint32_t nColors, uint32_t warps
 }
 
 // ... of the lean barrier-free kernel (step_kernel_flow.cuh): no id buffers (the ring entries live in registers)
+// (+ 512 B: the substep's start positions of the tile's vertices, one slot per lane -- read by the damping / contact epilogue)
 __host__ __device__ inline size_t FlowWarpBytes(uint32_t stageEntries, uint32_t maxIters)
 {
-    return kPipeWarpFixed + static_cast<size_t>(stageEntries) * 16 + static_cast<size_t>(maxIters) * kBlockBytes;
+    return kPipeWarpFixed + 512 + static_cast<size_t>(stageEntries) * 16 + static_cast<size_t>(maxIters) * kBlockBytes;
 }
 __host__ __device__ inline size_t FlowSmemBytes(uint32_t warps, uint32_t stageEntries, uint32_t maxIters)
 {
