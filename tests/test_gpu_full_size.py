@@ -145,6 +145,31 @@ def test_config3_stack_stays_ordered_and_lands():
     assert (B[V[vi]] != B[F[0, nn[vi, slot]]]).all()
 
 
+def test_config3_barrier_free_equals_colour_barriers_at_full_size(monkeypatch):
+    """configs[2] at its size, 45 steps (free fall, first impacts, ~2,000 active vertices): the barrier-free sweep with the
+    write history (default) and the sweep with colour barriers take the same contact decisions and produce the same bits
+    -- also on the degenerate geometry of identical grids stacked exactly above each other, where one ulp flips a contact."""
+    n = 29
+    Xb, Tb = meshes.tet_grid(n, n, n, 1.0 / n)
+    X, T, B = meshes.stack_bodies(Xb, Tb, 16, axis=2, gap_frac=0.1)
+    F = meshes.boundary_facets(T)
+    V = np.unique(F)
+    dbc = np.flatnonzero(X[2] <= X[2].min() + 0.01)
+    d = (pbat.sim.vbd.Data().with_volume_mesh(X, T).with_surface_mesh(V, F).with_bodies(B)
+         .with_dirichlet_vertices(dbc).with_contact_parameters(1e6, 0.3, 1e-3).construct())
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VBDX_DATAFLOW", mode)
+        vbd = pbat.gpu.vbd.Integrator(d)
+        for _ in range(45):
+            vbd.step(DT, 20, 1)
+        out[mode] = (vbd.x.copy(), vbd.v.copy(), vbd.contact_state(), vbd.info["blockThreads"])
+    assert out["1"][3] != out["0"][3]                       # the lean kernel (no barrier warp) ran the default
+    assert out["1"][2][2] > 1000                            # vertices in the active set
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    assert np.array_equal(out["1"][2][0], out["0"][2][0]) and np.array_equal(out["1"][2][1], out["0"][2][1])
+
+
 def test_config5_scene_in_a_batch_equals_the_scene_alone():
     n_scenes = 256
     Xs, Ts = meshes.tet_grid(10, 10, 10, 0.1)
