@@ -193,7 +193,66 @@ class VertexTriangleMixedCcdDcd
 };
 
 }  // namespace contact
+
+namespace xpbd {
+
+/// Constraint kinds of pbat::sim::xpbd::EConstraint (sim/xpbd/Enums.h)
+enum class EConstraint { StableNeoHookean = 0, Collision = 1 };
+
+/// pbat::gpu::xpbd::Integrator (gpu/xpbd/Integrator.h:33-140) over raw 3 x nV column-major double arrays
+class Integrator
+{
+  public:
+    explicit Integrator(vbdx_xpbd_desc const& data) : mNV(data.nV) { vbd::Integrator::Check(vbdx_xpbd_create(&data, &mImpl)); }
+    Integrator(Integrator const&)            = delete;
+    Integrator& operator=(Integrator const&) = delete;
+    ~Integrator() { vbdx_xpbd_destroy(mImpl); }
+    void Step(double dt, int iterations, int substeps) { vbd::Integrator::Check(vbdx_xpbd_step(mImpl, dt, iterations, substeps)); }
+    void SetPositions(double const* x) { vbd::Integrator::Check(vbdx_xpbd_set_positions(mImpl, x, mNV)); }
+    void SetVelocities(double const* v) { vbd::Integrator::Check(vbdx_xpbd_set_velocities(mImpl, v, mNV)); }
+    void SetExternalAcceleration(double const* a) { vbd::Integrator::Check(vbdx_xpbd_set_external_acceleration(mImpl, a, mNV)); }
+    void SetCompliance(double const* alpha, int64_t n, EConstraint c)
+    {
+        vbd::Integrator::Check(vbdx_xpbd_set_compliance(mImpl, static_cast<int32_t>(c), alpha, n));
+    }
+    void SetFrictionCoefficients(double muS, double muD) { vbd::Integrator::Check(vbdx_xpbd_set_friction_coefficients(mImpl, muS, muD)); }
+    void SetSceneBoundingBox(float const min3[3], float const max3[3])
+    {
+        vbd::Integrator::Check(vbdx_xpbd_set_scene_bounding_box(mImpl, min3, max3));
+    }
+    std::vector<double> GetPositions() const
+    {
+        std::vector<double> x(static_cast<std::size_t>(3 * mNV));
+        vbd::Integrator::Check(vbdx_xpbd_get_positions(mImpl, x.data(), mNV));
+        return x;
+    }
+    std::vector<double> GetVelocities() const
+    {
+        std::vector<double> v(static_cast<std::size_t>(3 * mNV));
+        vbd::Integrator::Check(vbdx_xpbd_get_velocities(mImpl, v.data(), mNV));
+        return v;
+    }
+
+  private:
+    vbdx_xpbd* mImpl{nullptr};
+    int64_t mNV{0};
+};
+
+}  // namespace xpbd
 }  // namespace gpu
+
+namespace graph {
+
+/// pbat::graph::GreedyColor (graph/Color.h:45-135) on a graph in compressed sparse format; host only
+inline std::vector<int64_t> GreedyColor(std::vector<int64_t> const& ptr, std::vector<int64_t> const& adj, int ordering = 2, int selection = 0)
+{
+    std::vector<int64_t> colors(ptr.empty() ? 0 : ptr.size() - 1);
+    gpu::vbd::Integrator::Check(
+        vbdx_graph_greedy_color(static_cast<int64_t>(colors.size()), ptr.data(), adj.data(), ordering, selection, colors.data()));
+    return colors;
+}
+
+}  // namespace graph
 }  // namespace pbat_b200
 
 #endif  // VBDX_HPP
