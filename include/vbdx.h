@@ -142,7 +142,8 @@ typedef enum vbdx_kernel_variant {
                                  the current one (the default when the per-warp buffers fit in shared memory) */
     VBDX_KERNEL_CLUSTER = 4   /* small meshes: the whole problem is swept by ONE thread-block cluster (8 CTAs x 16 warps)
                                  and colours are separated by the hardware cluster barrier instead of a grid barrier
-                                 through L2 (the default when a colour has at most a few tiles per warp of the cluster) */
+                                 through L2 (by default the shape of the launches that keep colour barriers on such meshes:
+                                 partial launches, VBDX_DATAFLOW=0; whole steps run the barrier-free kernel) */
 } vbdx_kernel_variant;
 
 #define VBDX_FLAG_ADAPTIVE_VBD_GPU_HISTORY 1 /* AdaptiveVbd uses the stored v(t-1) like the reference's GPU

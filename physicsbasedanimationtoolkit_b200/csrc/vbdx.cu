@@ -63,6 +63,7 @@ struct Integrator {
     bool usedDataflow  = false;
     unsigned int dfTag = 1;    // write numbers used by earlier launches (single GPU)
     bool clusterMode = false;  // the pipelined kernel launched as ONE thread-block cluster (VBDX_KERNEL_CLUSTER)
+    bool clusterOnly = false;  // ... because the caller asked for it (kernel_variant): whole steps too; chosen by default, it serves partial launches only
     uint32_t ringSlots = 0, maxTileIters = 1;
     size_t smemBytes   = 0;
     int64_t nRecordSlots = 0;
@@ -199,7 +200,7 @@ struct Integrator {
     }
     bool UseFlow(int iterations) const
     {
-        return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterMode &&
+        return dataflow && flowKernel && dFlowTiles.p != nullptr && variant == VBDX_KERNEL_PIPELINED && !clusterOnly &&
                (!contact.enabled || dHist4.p != nullptr) &&
                (material == VBDX_MATERIAL_STABLE_NEO_HOOKEAN || (distWorld == 1 && nGhost == 0)) && iterations > 0;
     }
@@ -466,10 +467,12 @@ void Integrator::Create(vbdx_data_desc const& d)
     if (variant == VBDX_KERNEL_DEFAULT)
     {
         variant = pipeSmem <= static_cast<size_t>(maxOptin) || material == VBDX_MATERIAL_STVK ? VBDX_KERNEL_PIPELINED : VBDX_KERNEL_DIRECT;
-        // Tiny meshes: when every colour leaves at least half the warps of ONE thread-block cluster idle, the phase is
-        // pure latency; running the same kernel as one cluster replaces the grid barrier (fence + atomic + poll through
-        // L2) by the hardware cluster barrier.  Measured: 4-5 % per step on a 10 k-tet mesh (0.507 vs 0.528 ms), a loss
-        // from ~20 k tets on (8 SMs of gather bandwidth instead of 148), hence the tight threshold.
+        // Tiny meshes: when every colour leaves at least half the warps of ONE thread-block cluster idle, a phase of the
+        // BARRIER sweep is pure latency; running the same kernel as one cluster replaces the grid barrier (fence + atomic +
+        // poll through L2) by the hardware cluster barrier.  Measured: 4-5 % per step on a 10 k-tet mesh (0.507 vs 0.528 ms),
+        // a loss from ~20 k tets on (8 SMs of gather bandwidth instead of 148), hence the tight threshold.  Since round 2
+        // this shape serves the launches that keep barriers (partial launches of the accelerators and traces); whole steps
+        // run the lean barrier-free kernel, which is faster at every size (one cube: 0.19 vs 0.37 ms; 10 k tets: 0.31 vs 0.51).
         uint32_t maxColorTiles = 0;
         for (int32_t c = 0; c < plan.nColors; ++c)
             maxColorTiles = std::max(maxColorTiles, plan.colorTileBegin[c + 1] - plan.colorTileBegin[c]);
@@ -481,6 +484,7 @@ void Integrator::Create(vbdx_data_desc const& d)
         dataflow = std::atoi(e) != 0;
     if (char const* e = std::getenv("VBDX_FLOW"))
         flowKernel = std::atoi(e) != 0;
+    clusterOnly = d.kernel_variant == VBDX_KERNEL_CLUSTER;
     clusterMode = variant == VBDX_KERNEL_CLUSTER;
     if (clusterMode)
     {
@@ -579,7 +583,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     PartitionTiles(plan, gridBlocks);
     if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && flowGridBlocks > 0)
         flowGridBlocks = std::max(1, std::min(std::atoi(e), flowGridBlocks));
-    if (variant == VBDX_KERNEL_PIPELINED && !clusterMode && flowGridBlocks > 0)
+    if (variant == VBDX_KERNEL_PIPELINED && !clusterOnly && flowGridBlocks > 0)
         BuildFlowSchedule();
 
     dTiles.Alloc(plan.tiles.size() + 1, &deviceBytes);
@@ -930,7 +934,9 @@ void Integrator::LaunchStepKernel(StepParams const& q)
 {
     {
         VBDX_CUDA(cudaMemsetAsync(dBarrier.p, 0, 2 * sizeof(unsigned int), stream));
-        if (variant == VBDX_KERNEL_PIPELINED && !clusterMode)
+        bool const wholeStepBarrierFree = variant == VBDX_KERNEL_PIPELINED && UseFlow(q.iterations) && !q.skipPostStep && q.iterBegin == 0 &&
+                                          (contact.enabled ? q.hist4 != nullptr : !q.skipPreStep);
+        if (variant == VBDX_KERNEL_PIPELINED && (!clusterMode || wholeStepBarrierFree))
         {
             PipeParams pp{};
             pp.base      = q;

@@ -279,16 +279,29 @@ def test_three_sweep_kernels_agree_bitwise_over_sizes_and_damping(shape, kd, mon
     assert np.isfinite(out[0][0]).all()
 
 
-def test_small_meshes_default_to_one_cluster_and_large_ones_do_not():
-    """VBDX_KERNEL_DEFAULT: a mesh whose colours fit one thread-block cluster is swept by 8 CTAs behind the hardware
-    cluster barrier; anything larger takes the whole GPU.  Contact, damping, substeps run on either."""
+def test_small_meshes_run_whole_steps_barrier_free_and_keep_the_cluster_for_barrier_launches(monkeypatch):
+    """VBDX_KERNEL_DEFAULT on a mesh whose colours fit one thread-block cluster: whole steps are swept by the lean
+    barrier-free kernel on the whole GPU (faster at every size since round 2); the 8-CTA cluster behind the hardware barrier
+    serves what keeps colour barriers (VBDX_DATAFLOW=0, partial launches) and remains selectable (kernel_variant=4).
+    Same bits whichever runs.  Contact, damping, substeps run on either."""
     X, T = meshes.tet_grid(25, 9, 9, 0.04)
-    d, vbd, ref = make(X, T, dbc=np.flatnonzero(X[0] == 0), cheb=0.9, kD=1e-4)
-    assert vbd.info["gridBlocks"] == 8
+    dbc = np.flatnonzero(X[0] == 0)
+    d, vbd, ref = make(X, T, dbc=dbc, cheb=0.9, kD=1e-4)
+    assert vbd.info["gridBlocks"] >= 100 and vbd.info["blockThreads"] % 32 == 0
     for _ in range(10):
         vbd.step(0.01, 20, 2)
         ref.step(0.01, 20, 2)
     assert rel_l2(vbd.x, ref.x) < TOL
+    _, one_cluster, _ = make(X, T, dbc=dbc, cheb=0.9, kD=1e-4, kernel_variant=4)
+    assert one_cluster.info["gridBlocks"] == 8
+    monkeypatch.setenv("VBDX_DATAFLOW", "0")
+    _, barriers, _ = make(X, T, dbc=dbc, cheb=0.9, kD=1e-4)
+    assert barriers.info["gridBlocks"] == 8
+    for other in (one_cluster, barriers):
+        for _ in range(10):
+            other.step(0.01, 20, 2)
+        assert np.array_equal(other.x, vbd.x) and np.array_equal(other.v, vbd.v)
+    monkeypatch.delenv("VBDX_DATAFLOW")
     Xl, Tl = meshes.tet_grid(40, 40, 40, 1 / 40)
     dl = pbat.sim.vbd.Data().with_volume_mesh(Xl, Tl).construct()
     assert pbat.gpu.vbd.Integrator(dl).info["gridBlocks"] >= 100
