@@ -328,27 +328,88 @@ __global__ void CompactActive(const uint32_t* ids, const uint32_t* flags, const 
 // k-nearest triangles of the active vertices (VertexTriangleMixedCcdDcd.cuh:108-162).
 // mode 0: UpdateActiveSet -> nn rows, and the contact lists fc of the vertices (gpu/impl/vbd/Integrator.cu:250-273)
 // mode 1: FinalizeActiveSet -> active[v] = vertex is on the negative side of (the last of) its nearest triangles
+//
+// One WARP per active vertex.  The depth-first branch and bound of BvhNearest (lbvh.cuh; Bvh.cuh:347-474) is walked by
+// all lanes in lockstep (same loads: broadcasts), but leaves are not evaluated one by one: the triangles whose box
+// passes the bound are collected, 32 at a time, their point-triangle distances -- triangle row, three corner positions,
+// Ericson's region walk: what the query's time goes into -- are computed one per lane, and the reference's sequential
+// update (nearest so far, ties within +-eps, at most 8, in discovery order) is then replayed over them in that order.
+// While a batch is collected the bound is the one of the previous batch, so more leaves pass than in the one-by-one
+// walk; a leaf that the tighter bound would have skipped has d >= box distance > bound and changes nothing when it is
+// replayed -- the result is the sequential one, list order included.
 __global__ void NearestTriangles(ContactMesh m, BvhView t, const int32_t* av, const uint32_t* nActive, const float4* x, const float* dupper,
                                  float eps, int mode, int32_t* nn, int32_t* fc, uint8_t* active)
 {
-    uint32_t const q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= *nActive)
-        return;
+    uint32_t const lane = threadIdx.x & 31u;
+    uint32_t const nAct = *nActive;
+    // (grid-stride over the active list: its length is known on the device only, the grid is sized for a full GPU)
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nAct; q += (gridDim.x * blockDim.x) >> 5)
+    {
     int const v    = av[q];
     int const i    = m.V[v];
     int const body = m.B[i];
     float3 const p = F3(x[i]);
     int found[kMaxContacts];
-    float dmin;
-    int const count = BvhNearest<kMaxContacts>(
-        t, p, dupper[v], eps,
-        [&](int f) {
-            int4 const tri = m.F[f];
-            if (tri.w == body)
-                return FLT_MAX;
-            return PointTriangleDistance2(p, F3(x[tri.x]), F3(x[tri.y]), F3(x[tri.z]));
-        },
-        found, dmin);
+    int count   = 0;
+    float dmin  = dupper[v];
+    int mine    = -1;  // the candidate this lane evaluates
+    int pending = 0;   // candidates collected since the last evaluation
+    auto evaluate = [&]() {
+        float d = FLT_MAX;
+        if (static_cast<int>(lane) < pending)
+        {
+            int4 const tri = m.F[mine];
+            if (tri.w != body)
+                d = PointTriangleDistance2(p, F3(x[tri.x]), F3(x[tri.y]), F3(x[tri.z]));
+        }
+        for (int c = 0; c < pending; ++c)
+        {
+            float const dc  = __shfl_sync(0xffffffffu, d, c);
+            int const prim  = __shfl_sync(0xffffffffu, mine, c);
+            float const lo = dmin - eps, hi = dmin + eps;
+            if (dc < lo)
+            {
+                count          = 0;
+                found[count++] = prim;
+                dmin           = dc;
+            }
+            else if (dc <= hi && count < kMaxContacts)
+                found[count++] = prim;
+        }
+        pending = 0;
+    };
+    int stack[kBvhStack];
+    int top         = 0;
+    stack[top++]    = 0;
+    int const leaf0 = static_cast<int>(t.n) - 1;
+    do
+    {
+        int const node = stack[--top];
+        float const db = PointBoxDistance2(p, t.nodeLo[node], t.nodeHi[node]);
+        if (db <= dmin + eps)
+        {
+            if (node < leaf0)
+            {
+                if (top + 2 <= kBvhStack)
+                {
+                    stack[top++] = t.child[0][node];
+                    stack[top++] = t.child[1][node];
+                }
+            }
+            else
+            {
+                int const prim = static_cast<int>(t.inds[node - leaf0]);
+                if (static_cast<int>(lane) == pending)
+                    mine = prim;
+                if (++pending == 32)
+                    evaluate();
+            }
+        }
+        if (top == 0 && pending > 0)
+            evaluate();  // (may not push anything: the walk ends)
+    } while (top > 0);
+    if (lane != 0)
+        continue;
     if (mode == 0)
     {
         for (int k = 0; k < kMaxContacts; ++k)
@@ -364,6 +425,7 @@ __global__ void NearestTriangles(ContactMesh m, BvhView t, const int32_t* av, co
         float3 const A = F3(x[tri.x]), Bq = F3(x[tri.y]), C = F3(x[tri.z]);
         float3 const n  = Cross(Sub(Bq, A), Sub(C, A));
         active[v]       = Dot(Sub(p, A), n) < 0.f ? 1 : 0;  // sign of geometry/DistanceQueries.h PointPlane
+    }
     }
 }
 

@@ -269,7 +269,7 @@ struct ContactState {
             FillI32<<<Blocks(static_cast<int64_t>(nCV) * kMaxContacts, 256), 256, 0, s>>>(nn.p, -1, static_cast<size_t>(nCV) * kMaxContacts);
             ++*launches;
         }
-        NearestTriangles<<<Blocks(nCV, 128), 128, 0, s>>>(mesh, bvh.View(), av.p, nActive.p, x, dupper.p, eps, mode, nn.p, fc.p, active.p);
+        NearestTriangles<<<std::min(Blocks(static_cast<int64_t>(nCV) * 32, 128), 2368), 128, 0, s>>>(mesh, bvh.View(), av.p, nActive.p, x, dupper.p, eps, mode, nn.p, fc.p, active.p);  // a warp per vertex
         *launches += 2;
     }
 };
