@@ -106,6 +106,7 @@ struct DeviceBvh {
     RadixSortSync sortSync;
     DevBuf<int32_t> child0, child1, parent, right0, right1;
     DevBuf<float4> nodeLo, nodeHi;
+    DevBuf<int2> up;
 
     void Alloc(uint32_t nLeaves, int64_t* bytes)
     {
@@ -115,6 +116,8 @@ struct DeviceBvh {
         InitSortSync(sortAux, sortSync, bytes);
         size_t const ni = n > 1 ? n - 1 : 1;
         visits.Alloc(ni, bytes);
+        VBDX_CUDA(cudaMemset(visits.p, 0, ni * sizeof(uint32_t)));  // arrival counters: never reset afterwards (BvhRefit)
+        up.Alloc(2 * static_cast<size_t>(n), bytes);
         child0.Alloc(ni, bytes), child1.Alloc(ni, bytes), right0.Alloc(ni, bytes), right1.Alloc(ni, bytes);
         parent.Alloc(2 * static_cast<size_t>(n), bytes);
         nodeLo.Alloc(2 * static_cast<size_t>(n), bytes), nodeHi.Alloc(2 * static_cast<size_t>(n), bytes);
@@ -125,19 +128,14 @@ struct DeviceBvh {
         v.n = n, v.codes = codes.p, v.inds = inds.p;
         v.child[0] = child0.p, v.child[1] = child1.p, v.parent = parent.p;
         v.rightmost[0] = right0.p, v.rightmost[1] = right1.p;
-        v.nodeLo = nodeLo.p, v.nodeHi = nodeHi.p, v.visits = visits.p;
+        v.nodeLo = nodeLo.p, v.nodeHi = nodeHi.p, v.visits = visits.p, v.up = up.p;
         return v;
     }
     // internal boxes from per-primitive boxes, keeping the topology (Bvh::ConstructBoxes)
     void Refit(const float4* primLo, const float4* primHi, cudaStream_t s, int64_t* launches)
     {
-        BvhGatherLeafBoxes<<<Blocks(n, 256), 256, 0, s>>>(View(), primLo, primHi);
-        if (n > 1)
-        {
-            VBDX_CUDA(cudaMemsetAsync(visits.p, 0, (n - 1) * sizeof(uint32_t), s));
-            BvhInternalBoxes<<<Blocks(n, 256), 256, 0, s>>>(View());
-        }
-        *launches += 2;
+        BvhRefit<<<Blocks(n, 256), 256, 0, s>>>(View(), primLo, primHi);
+        *launches += 1;
     }
     // Bvh::Build: Morton codes of the box centroids, stable sort, hierarchy, boxes
     void Build(const float4* primLo, const float4* primHi, const WorldBox* world, cudaStream_t s, int64_t* launches)
@@ -145,6 +143,7 @@ struct DeviceBvh {
         MortonOfBoxes<<<Blocks(n, 256), 256, 0, s>>>(primLo, primHi, n, world, codes.p, inds.p);
         RadixSortPairs(codes.p, inds.p, codesTmp.p, indsTmp.p, n, counts.p, sortSync, s, launches);
         VBDX_CUDA(cudaMemsetAsync(parent.p, 0xff, 2 * static_cast<size_t>(n) * sizeof(int32_t), s));
+        VBDX_CUDA(cudaMemsetAsync(up.p, 0xff, 2 * static_cast<size_t>(n) * sizeof(int2), s));
         if (n > 1)
             BvhHierarchy<<<Blocks(n - 1, 256), 256, 0, s>>>(View());
         *launches += 2;

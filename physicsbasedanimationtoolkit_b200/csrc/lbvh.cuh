@@ -292,7 +292,8 @@ struct BvhView {
     int32_t* rightmost[2]; // n-1
     float4* nodeLo;        // 2n-1: internal boxes then leaf boxes (sorted order)
     float4* nodeHi;
-    uint32_t* visits;      // n-1
+    uint32_t* visits;      // n-1: arrivals at the node, two per box computation (never reset: an odd count = one child is done)
+    int2* up;              // 2n-1: (parent, sibling) of every node, (-1, -1) for the root
 };
 
 __device__ __forceinline__ int BvhDelta(const uint32_t* codes, int n, int i, int j)
@@ -343,41 +344,43 @@ __global__ void BvhHierarchy(BvhView t)
     t.child[1][in]      = rc;
     t.parent[lc]        = in;
     t.parent[rc]        = in;
+    t.up[lc]            = make_int2(in, rc);
+    t.up[rc]            = make_int2(in, lc);
     t.rightmost[0][in]  = leafBegin + gamma;
     t.rightmost[1][in]  = leafBegin + hi;
 }
 
-// leaf boxes in sorted order from the per-primitive boxes
-__global__ void BvhGatherLeafBoxes(BvhView t, const float4* primLo, const float4* primHi)
+// Boxes of all nodes from the per-primitive boxes, one launch (Bvh::ConstructBoxes, gpu/impl/geometry/Bvh.cu:175-233): a
+// thread per leaf writes the leaf's box and climbs; at every node the second thread to arrive merges the box it carries
+// in registers with its sibling's and goes on.  Per level the dependent chain is one ordered atomic (acq_rel: the box
+// this thread wrote below is released with it, the sibling's -- written by the thread that arrived first -- acquired)
+// and one box load; (parent, sibling) of the next level are requested before the atomic.  The arrival counters are
+// never reset: two arrivals per box computation, so an odd count before the add means "the other child is done".
+__global__ void BvhRefit(BvhView t, const float4* primLo, const float4* primHi)
 {
     uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= t.n)
         return;
-    uint32_t const f       = t.inds[k];
-    t.nodeLo[t.n - 1 + k]  = primLo[f];
-    t.nodeHi[t.n - 1 + k]  = primHi[f];
-}
-
-// internal boxes bottom-up: the second thread to reach a node merges its children and moves on
-__global__ void BvhInternalBoxes(BvhView t)
-{
-    uint32_t const k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= t.n)
-        return;
-    int p = t.parent[t.n - 1 + k];
-    while (p >= 0)
+    uint32_t const f = t.inds[k];
+    int cur          = static_cast<int>(t.n - 1 + k);
+    float4 lo = primLo[f], hi = primHi[f];
+    t.nodeLo[cur] = lo;
+    t.nodeHi[cur] = hi;
+    int2 u        = t.up[cur];
+    while (u.x >= 0)
     {
-        // acq_rel arrival: the box this thread wrote one level below is released with it, and the sibling's box (written
-        // by the thread that arrived first) is acquired with it -- one ordered atomic instead of two full fences
+        int2 const next = t.up[u.x];
         unsigned int old;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(t.visits + p), "r"(1u) : "memory");
-        if (old == 0u)
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(t.visits + u.x), "r"(1u) : "memory");
+        if ((old & 1u) == 0u)
             break;
-        int const lc = t.child[0][p], rc = t.child[1][p];
-        float4 const al = __ldcg(t.nodeLo + lc), ah = __ldcg(t.nodeHi + lc), bl = __ldcg(t.nodeLo + rc), bh = __ldcg(t.nodeHi + rc);
-        t.nodeLo[p] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
-        t.nodeHi[p] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
-        p           = t.parent[p];
+        float4 const sl = __ldcg(t.nodeLo + u.y), sh = __ldcg(t.nodeHi + u.y);
+        lo = make_float4(fminf(lo.x, sl.x), fminf(lo.y, sl.y), fminf(lo.z, sl.z), 0.f);
+        hi = make_float4(fmaxf(hi.x, sh.x), fmaxf(hi.y, sh.y), fmaxf(hi.z, sh.z), 0.f);
+        cur           = u.x;
+        t.nodeLo[cur] = lo;
+        t.nodeHi[cur] = hi;
+        u             = next;
     }
 }
 

@@ -2151,12 +2151,17 @@ vbdx_status vbdx_bvh_get(vbdx_bvh* h, int32_t* child, int32_t* parent, int32_t* 
             b.bvh.inds.Download(reinterpret_cast<uint32_t*>(inds), n, s);
         if (codes)
             b.bvh.codes.Download(codes, n, s);
+        std::vector<uint32_t> arrivals(visits && ni ? ni : 0);
         if (visits && ni)
-            b.bvh.visits.Download(reinterpret_cast<uint32_t*>(visits), ni, s);
+            b.bvh.visits.Download(arrivals.data(), ni, s);
         std::vector<float4> nl(2 * n - 1), nh(2 * n - 1);
         b.bvh.nodeLo.Download(nl.data(), 2 * n - 1, s);
         b.bvh.nodeHi.Download(nh.data(), 2 * n - 1, s);
         VBDX_CUDA(cudaStreamSynchronize(s));
+        // the reference resets its visit counters per box computation (2 = both children arrived, gpu/impl/geometry/Bvh.cu:209);
+        // the counters here run on, two arrivals per computation: report the last computation's
+        for (size_t k = 0; k < arrivals.size(); ++k)
+            visits[k] = arrivals[k] == 0u ? 0 : 2 - static_cast<int32_t>(arrivals[k] & 1u);
         for (int64_t k = 0; k < 2 * n - 1; ++k)
         {
             if (node_lo)
