@@ -271,8 +271,10 @@ __global__ void TriangleBoxes(ContactMesh m, const float4* x, const float4* vel,
             h[0] = fmaxf(h[0], p1.x), h[1] = fmaxf(h[1], p1.y), h[2] = fmaxf(h[2], p1.z);
         }
     }
-    lo[f] = make_float4(l[0], l[1], l[2], 0.f);
-    hi[f] = make_float4(h[0], h[1], h[2], 0.f);
+    // .w: the triangle's body, as the range [lo.w, hi.w] (integer bits) that BvhRefit merges up the tree -- a node whose
+    // range is one body can be skipped as a whole by a query of that body (MarkActive)
+    lo[f] = make_float4(l[0], l[1], l[2], __int_as_float(t.w));
+    hi[f] = make_float4(h[0], h[1], h[2], __int_as_float(t.w));
 }
 
 // VertexTriangleMixedCcdDcd.cu:107-140: a vertex becomes active when its swept box overlaps the swept box
@@ -288,6 +290,7 @@ __global__ void MarkActive(ContactMesh m, BvhView t, const uint32_t* ids, const 
     int const body   = m.B[i];
     float4 const lo = qlo[q], hi = qhi[q];
     float best = -1.f;
+    // (nodes that hold triangles of the query's own body only are not descended into: their leaves would all be rejected)
     BvhForEachOverlap(t, lo, hi, [&](int, uint32_t f) {
         if (m.F[f].w == body)
             return;  // no self collision
@@ -295,7 +298,7 @@ __global__ void MarkActive(ContactMesh m, BvhView t, const uint32_t* ids, const 
         float const dx = fmaxf(hi.x, th.x) - fminf(lo.x, tl.x), dy = fmaxf(hi.y, th.y) - fminf(lo.y, tl.y),
                     dz = fmaxf(hi.z, th.z) - fminf(lo.z, tl.z);
         best = fmaxf(best, dx * dx + dy * dy + dz * dz);
-    });
+    }, body);
     if (best >= 0.f)
     {
         active[v] = 1;

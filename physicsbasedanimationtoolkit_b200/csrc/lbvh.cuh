@@ -375,8 +375,9 @@ __global__ void BvhRefit(BvhView t, const float4* primLo, const float4* primHi)
         if ((old & 1u) == 0u)
             break;
         float4 const sl = __ldcg(t.nodeLo + u.y), sh = __ldcg(t.nodeHi + u.y);
-        lo = make_float4(fminf(lo.x, sl.x), fminf(lo.y, sl.y), fminf(lo.z, sl.z), 0.f);
-        hi = make_float4(fmaxf(hi.x, sh.x), fmaxf(hi.y, sh.y), fmaxf(hi.z, sh.z), 0.f);
+        // (.w: an integer range carried with the box -- the bodies of the triangles below the node on the contact path)
+        lo = make_float4(fminf(lo.x, sl.x), fminf(lo.y, sl.y), fminf(lo.z, sl.z), __int_as_float(min(__float_as_int(lo.w), __float_as_int(sl.w))));
+        hi = make_float4(fmaxf(hi.x, sh.x), fmaxf(hi.y, sh.y), fmaxf(hi.z, sh.z), __int_as_float(max(__float_as_int(hi.w), __float_as_int(sh.w))));
         cur           = u.x;
         t.nodeLo[cur] = lo;
         t.nodeHi[cur] = hi;
@@ -396,8 +397,9 @@ __device__ __forceinline__ bool BoxesOverlap(float4 al, float4 ah, float4 bl, fl
 }
 
 // calls f(leafSlot, primitive) for every leaf whose box overlaps [qlo, qhi]  (Bvh.cuh:282-345)
+// skipOnly >= 0: nodes whose .w range (see BvhRefit) is exactly [skipOnly, skipOnly] are not descended into
 template <class F>
-__device__ __forceinline__ void BvhForEachOverlap(BvhView const& t, float4 qlo, float4 qhi, F f)
+__device__ __forceinline__ void BvhForEachOverlap(BvhView const& t, float4 qlo, float4 qhi, F f, int skipOnly = -1)
 {
     int stack[kBvhStack];
     int top        = 0;
@@ -406,7 +408,10 @@ __device__ __forceinline__ void BvhForEachOverlap(BvhView const& t, float4 qlo, 
     do
     {
         int const node = stack[--top];
-        if (!BoxesOverlap(t.nodeLo[node], t.nodeHi[node], qlo, qhi))
+        float4 const nl = t.nodeLo[node], nh = t.nodeHi[node];
+        if (!BoxesOverlap(nl, nh, qlo, qhi))
+            continue;
+        if (skipOnly >= 0 && __float_as_int(nl.w) == skipOnly && __float_as_int(nh.w) == skipOnly)
             continue;
         if (node >= leaf0)
             f(node - leaf0, t.inds[node - leaf0]);
