@@ -246,9 +246,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: NCCL's version banner / warnings (NCCL_DEBUG=VERSION or WARN print there) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
