@@ -157,7 +157,7 @@ struct Integrator {
         return damp ? StepKernel<false, true> : StepKernel<false, false>;
     }
 
-    // dataflowSweep = the barrier-free instantiation (no damping / contact: their reads go beyond the 1-rings)
+    // dataflowSweep = the round-1 kernel's barrier-free instantiation (VBDX_FLOW=0; it has no damping / contact form)
     PipeKernelFn KernelPipe(bool dataflowSweep = false) const
     {
         bool const cheb = acceleration == VBDX_ACCEL_CHEBYSHEV;
