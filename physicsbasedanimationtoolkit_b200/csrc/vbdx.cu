@@ -109,6 +109,7 @@ struct Integrator {
     int flowWarps = 16, flowGridBlocks = 0;  // launch shape of the lean kernel (no barrier warp, no id buffers)
     size_t flowSmemBytes = 0;
     uint32_t flowActiveWarps = 0;  // warps of the lean kernel's grid that have tiles
+    uint32_t flowBoundarySms = 0, flowBoundaryWarps = 0;  // domain decomposition: CTAs (and their warps in use) that run the tiles next to another GPU
     DevBuf<float4> dHist4;         // contact under barrier-free sweeps: every vertex' last four writes (step_kernel.cuh, HistSlot)
     DevBuf<unsigned int> dSweepDone;  // ... and per sweep of a launch the warps that have finished it (the sweep-lag bound)
     void BuildFlowSchedule();
@@ -583,6 +584,7 @@ void Integrator::Create(vbdx_data_desc const& d)
     PartitionTiles(plan, gridBlocks);
     if (char const* e = std::getenv("VBDX_GRID_BLOCKS"); e && flowGridBlocks > 0)
         flowGridBlocks = std::max(1, std::min(std::atoi(e), flowGridBlocks));
+    nGhost = static_cast<int64_t>(nV) - plan.ghostBegin;  // (the schedule treats the tiles next to another GPU specially)
     if (variant == VBDX_KERNEL_PIPELINED && !clusterOnly && flowGridBlocks > 0)
         BuildFlowSchedule();
 
@@ -758,13 +760,13 @@ void Integrator::BuildFlowSchedule()
                 ids[idsStart[t] + (j >> 2) * 128u + lane * 4u + (j & 3u)] = e;
             }
     }
-    // Deal order of a colour's tiles: the planner's (heaviest first).  Domain decomposition: the tiles next to another GPU's
-    // vertices go first -- their vertices are what the peers wait for, and the ghosts THEY read were sent at the start of
-    // the peers' previous colour, so both directions of the halo get a whole colour's worth of time to cross NVLink.
+    // Deal order of a colour's tiles: the planner's (heaviest first).  Optionally (domain decomposition) the tiles next to
+    // another GPU's vertices first; with about one tile per warp and colour the order within a colour decides little, and
+    // it measured slower.
     std::vector<uint32_t> order(nTiles);
-    bool boundaryFirst = nGhost > 0;
+    bool boundaryFirst = false;  // (measured on 2 GPUs: 1.045 ms/step with it, 1.021 without -- off unless VBDX_BOUNDARY_FIRST=1)
     if (char const* e = std::getenv("VBDX_BOUNDARY_FIRST"))
-        boundaryFirst = boundaryFirst && std::atoi(e) != 0;
+        boundaryFirst = nGhost > 0 && std::atoi(e) != 0;
     for (int32_t c = 0; c < plan.nColors; ++c)
     {
         uint32_t const tb = plan.colorTileBegin[c], te = plan.colorTileBegin[c + 1];
@@ -777,10 +779,56 @@ void Integrator::BuildFlowSchedule()
             for (uint32_t t = tb; t < te; ++t)
                 order[t] = t;
     }
-    std::vector<uint32_t> wBegin(static_cast<size_t>(gWarps) + 1, 0);
+    // Which warp runs which tile (home = warp-in-CTA * CTAs + CTA): a colour's tiles round-robin over all warps of the grid.
+    // Experiment, opt-in (VBDX_BOUNDARY_WARPS=n, domain decomposition, at most one tile per warp and colour): the tiles next
+    // to another GPU go to a few CTAs of their own with only n of their warps in use.  A tile's colour-to-colour chain
+    // there includes the NVLink hop of the ghosts it waits for (~0.5 us more than a local dependency), and a tile runs
+    // faster on an SM that runs fewer of them.  Only the placement changes: same tiles, same arithmetic, same bits.
+    // Measured on 2 GPUs: 1.021 ms/step without, 1.003-1.009 with n = 11-12, 1.04 with n = 9 or 16 -- the grid has only 8 %
+    // more warps than a colour has tiles, so the boundary SMs cannot be made light enough; off by default.
+    uint32_t const G = static_cast<uint32_t>(flowGridBlocks), W = static_cast<uint32_t>(flowWarps);
+    uint32_t boundarySms = 0, boundaryWarps = 0;
+    {
+        char const* e      = std::getenv("VBDX_BOUNDARY_WARPS");  // unset / 0: off; n: warps in use per boundary SM; -1: the fewest that fit, from 4
+        int const wanted   = e ? std::atoi(e) : 0;
+        uint32_t nbMax = 0, niMax = 0;
+        for (int32_t c = 0; c < plan.nColors; ++c)
+        {
+            uint32_t nb = 0;
+            for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
+                nb += TileReadsGhosts(plan.tiles[t].meta) ? 1u : 0u;
+            nbMax = std::max(nbMax, nb);
+            niMax = std::max(niMax, plan.colorTileBegin[c + 1] - plan.colorTileBegin[c] - nb);
+        }
+        if (nGhost > 0 && nbMax > 0 && wanted != 0)
+            for (uint32_t wb = wanted > 0 ? static_cast<uint32_t>(wanted) : 4u; wb <= (wanted > 0 ? static_cast<uint32_t>(wanted) : W) && wb <= W; ++wb)
+            {
+                uint32_t const sb = (nbMax + wb - 1) / wb;
+                if (sb < G && static_cast<uint64_t>(niMax) <= static_cast<uint64_t>(G - sb) * W)
+                {
+                    boundarySms = sb, boundaryWarps = wb;
+                    break;
+                }
+            }
+    }
+    std::vector<uint32_t> home(nTiles);
     for (int32_t c = 0; c < plan.nColors; ++c)
+    {
+        uint32_t ib = 0, ii = 0;
         for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
-            ++wBegin[(t - plan.colorTileBegin[c]) % gWarps + 1];
+        {
+            if (boundarySms == 0)
+                home[t] = (t - plan.colorTileBegin[c]) % gWarps;
+            else if (TileReadsGhosts(plan.tiles[order[t]].meta))
+                home[t] = (ib / boundarySms) * G + ib % boundarySms, ++ib;
+            else
+                home[t] = (ii / (G - boundarySms)) * G + boundarySms + ii % (G - boundarySms), ++ii;
+        }
+    }
+    flowBoundarySms = boundarySms, flowBoundaryWarps = boundaryWarps;
+    std::vector<uint32_t> wBegin(static_cast<size_t>(gWarps) + 1, 0);
+    for (size_t t = 0; t < nTiles; ++t)
+        ++wBegin[home[t] + 1];
     for (uint32_t w = 0; w < gWarps; ++w)
         wBegin[w + 1] += wBegin[w];
     std::vector<uint4> seqTiles(nTiles);
@@ -789,7 +837,7 @@ void Integrator::BuildFlowSchedule()
         for (uint32_t t = plan.colorTileBegin[c]; t < plan.colorTileBegin[c + 1]; ++t)
         {
             TileDesc const& td = plan.tiles[order[t]];
-            seqTiles[cursor[(t - plan.colorTileBegin[c]) % gWarps]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[order[t]]);
+            seqTiles[cursor[home[t]]++] = make_uint4(td.blockStart, td.vbase, td.meta, idsStart[order[t]]);
         }
     flowActiveWarps = 0;
     for (uint32_t w = 0; w < gWarps; ++w)
