@@ -210,6 +210,12 @@ typedef enum vbdx_dtype { VBDX_F32 = 0, VBDX_F64 = 1 } vbdx_dtype;
 typedef enum vbdx_layout { VBDX_LAYOUT_COLUMNS = 0, VBDX_LAYOUT_ROWS = 1 } vbdx_layout;
 vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV);
 vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV);
+/* The same, enqueued on the handle's stream without waiting (extension, like vbdx_step_async): the host array should be
+ * page-locked (vbdx_host_alloc; a pageable one makes the copy synchronous) and must not be touched -- read after a get,
+ * written after a set -- before vbdx_synchronize returns.  set_async, step_async, get_async, synchronize is one host
+ * round trip per step instead of three. */
+vbdx_status vbdx_set_vertex_field_async(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV);
+vbdx_status vbdx_get_vertex_field_async(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV);
 /* Page-locked host memory for the arrays above (cudaHostAlloc / cudaFreeHost). */
 vbdx_status vbdx_host_alloc(void** out, int64_t bytes);
 vbdx_status vbdx_host_free(void* p);

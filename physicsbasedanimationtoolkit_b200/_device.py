@@ -177,6 +177,23 @@ class DeviceIntegrator:
         """``x`` with an optional preallocated (pinned) destination."""
         return self._get("positions", out)
 
+    def _check_async_array(self, a):
+        if not (isinstance(a, np.ndarray) and a.shape == (3, self.nV) and a.dtype == self._dtype and a.flags.c_contiguous):
+            raise ValueError(f"need a C-contiguous 3 x {self.nV} array of {np.dtype(self._dtype).name} (ideally from pinned_empty)")
+
+    def set_positions_async(self, a):
+        """Enqueue the upload of ``a`` (page-locked, see ``host.pinned_empty``) on the integrator's stream without waiting;
+        ``a`` must stay untouched until ``synchronize()``.  With ``step_async`` and ``positions_async`` a step costs the host one
+        round trip instead of three."""
+        self._check_async_array(a)
+        _lib.check(self._L.vbdx_set_vertex_field_async(self._h, 0, int(self._dtype == np.float64), 1, a.ctypes.data, self.nV))
+
+    def positions_async(self, out):
+        """Enqueue the download of ``x`` into ``out`` (page-locked); valid after ``synchronize()``."""
+        self._check_async_array(out)
+        _lib.check(self._L.vbdx_get_vertex_field_async(self._h, 0, int(self._dtype == np.float64), 1, out.ctypes.data, self.nV))
+        return out
+
     def velocities(self, out=None):
         return self._get("velocities", out)
 

@@ -84,6 +84,8 @@ SYMBOLS = {
     "vbdx_objective": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "vbdx_set_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_get_vertex_field": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "vbdx_set_vertex_field_async": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "vbdx_get_vertex_field_async": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "vbdx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "vbdx_host_free": (C.c_int, [C.c_void_p]),
     "vbdx_set_positions_f32": (C.c_int, [_H, C.c_void_p, C.c_int64]),

@@ -253,9 +253,9 @@ struct Integrator {
     void StepPartial(double sdt, int kBegin, int kEnd, int totalIterations, int flags);
     void Objective(const double* xk, const double* xtilde, double dt, double* f, double* grad);
     template <class T>
-    void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows = false);
+    void SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows = false, bool sync = true);
     template <class T>
-    void GetVertexField(float4 const* src, T* dst, int64_t n, bool rows = false);
+    void GetVertexField(float4 const* src, T* dst, int64_t n, bool rows = false, bool sync = true);
 };
 
 void Integrator::Create(vbdx_data_desc const& d)
@@ -1490,7 +1490,7 @@ void Integrator::Objective(const double* xk, const double* xtilde, double dt, do
 }
 
 template <class T>
-void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows)
+void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* dst1, bool rows, bool sync)
 {
     Require(src != nullptr && n == nV, "expected a 3 x nV array");  // gpu/impl/common/Eigen.cuh:28-35
     VBDX_CUDA(cudaSetDevice(device));
@@ -1499,11 +1499,12 @@ void Integrator::SetVertexField(T const* src, int64_t n, float4* dst0, float4* d
     ScatterFromCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, staging, rows ? nV : 1, rows ? 1 : 3, dst0, dst1,
                                                                  distWorld > 1 ? plan.ghostBegin : nV);
     ++kernelLaunches;
-    VBDX_CUDA(cudaStreamSynchronize(stream));
+    if (sync)
+        VBDX_CUDA(cudaStreamSynchronize(stream));
 }
 
 template <class T>
-void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n, bool rows)
+void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n, bool rows, bool sync)
 {
     Require(dst != nullptr && n == nV, "expected a 3 x nV array");
     VBDX_CUDA(cudaSetDevice(device));
@@ -1511,7 +1512,8 @@ void Integrator::GetVertexField(float4 const* src, T* dst, int64_t n, bool rows)
     GatherToCaller<T><<<Blocks(nV, 256), 256, 0, stream>>>(nV, dOld2New.p, src, staging, rows ? nV : 1, rows ? 1 : 3);
     ++kernelLaunches;
     VBDX_CUDA(cudaMemcpyAsync(dst, staging, 3 * nV * sizeof(T), cudaMemcpyDeviceToHost, stream));
-    VBDX_CUDA(cudaStreamSynchronize(stream));
+    if (sync)
+        VBDX_CUDA(cudaStreamSynchronize(stream));
 }
 
 }  // namespace vbdx
@@ -1797,7 +1799,7 @@ VBDX_GETTER(vbdx_get_positions_f64, double, (VBDX_POS_P ? VBDX_POS_P : VBDX_POS_
 VBDX_GETTER(vbdx_get_velocities_f32, float, h->impl.dVel.p)
 VBDX_GETTER(vbdx_get_velocities_f64, double, h->impl.dVel.p)
 
-vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV)
+static vbdx_status SetVertexFieldImpl(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV, bool sync)
 {
     if (vbdx_status s = NeedHandle(h))
         return s;
@@ -1809,13 +1811,21 @@ vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dty
         float4* dst1 = field == VBDX_FIELD_POSITIONS ? VBDX_POS_P : nullptr;
         bool const rows = layout == VBDX_LAYOUT_ROWS;
         if (dtype == VBDX_F32)
-            h->impl.SetVertexField<float>(static_cast<const float*>(src), nV, dst0, dst1, rows);
+            h->impl.SetVertexField<float>(static_cast<const float*>(src), nV, dst0, dst1, rows, sync);
         else
-            h->impl.SetVertexField<double>(static_cast<const double*>(src), nV, dst0, dst1, rows);
+            h->impl.SetVertexField<double>(static_cast<const double*>(src), nV, dst0, dst1, rows, sync);
     });
 }
+vbdx_status vbdx_set_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV)
+{
+    return SetVertexFieldImpl(h, field, dtype, layout, src, nV, true);
+}
+vbdx_status vbdx_set_vertex_field_async(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, const void* src, int64_t nV)
+{
+    return SetVertexFieldImpl(h, field, dtype, layout, src, nV, false);
+}
 
-vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV)
+static vbdx_status GetVertexFieldImpl(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV, bool sync)
 {
     if (vbdx_status s = NeedHandle(h))
         return s;
@@ -1831,10 +1841,18 @@ vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dty
                                                                      : h->impl.dXt.p;
         bool const rows   = layout == VBDX_LAYOUT_ROWS;
         if (dtype == VBDX_F32)
-            h->impl.GetVertexField<float>(src, static_cast<float*>(dst), nV, rows);
+            h->impl.GetVertexField<float>(src, static_cast<float*>(dst), nV, rows, sync);
         else
-            h->impl.GetVertexField<double>(src, static_cast<double*>(dst), nV, rows);
+            h->impl.GetVertexField<double>(src, static_cast<double*>(dst), nV, rows, sync);
     });
+}
+vbdx_status vbdx_get_vertex_field(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV)
+{
+    return GetVertexFieldImpl(h, field, dtype, layout, dst, nV, true);
+}
+vbdx_status vbdx_get_vertex_field_async(vbdx_integrator* h, int32_t field, int32_t dtype, int32_t layout, void* dst, int64_t nV)
+{
+    return GetVertexFieldImpl(h, field, dtype, layout, dst, nV, false);
 }
 
 vbdx_status vbdx_host_alloc(void** out, int64_t bytes)

@@ -360,6 +360,32 @@ def test_host_layouts_and_pinned_buffers():
     assert np.array_equal(sim.x, xd.astype(np.float32).astype(np.float64))
 
 
+def test_async_upload_step_download_equals_the_synchronous_calls():
+    """vbdx_set_vertex_field_async / vbdx_step_async / vbdx_get_vertex_field_async / vbdx_synchronize: one host round trip per
+    step instead of three (what bench.py's end-to-end leg does), same bits as the synchronous calls."""
+    X, T = meshes.tet_grid(12, 10, 8, 0.1)
+    dbc = np.flatnonzero(X[2] == 0)
+    d, a, _ = make(X, T, dbc=dbc, cheb=0.9)
+    _, b, _ = make(X, T, dbc=dbc, cheb=0.9)
+    nV = X.shape[1]
+    xin, xout = pbat.host.pinned_empty((3, nV), np.float32), pbat.host.pinned_empty((3, nV), np.float32)
+    xin[...] = X + 0.003 * np.random.default_rng(2).uniform(-1, 1, X.shape)
+    xin[:, dbc] = X[:, dbc]
+    xs = xin.copy()
+    for _ in range(6):
+        a.set_positions_async(xin)
+        a.step_async(0.01, 10, 1)
+        a.positions_async(xout)
+        a.synchronize()
+        b.x = xs
+        b.step(0.01, 10, 1)
+        xs = b.x
+        assert np.array_equal(xout, xs)
+        xin, xout = xout, xin
+    with pytest.raises(ValueError):
+        a.set_positions_async(np.zeros((3, nV + 1), np.float32))
+
+
 def test_anderson_acceleration():
     """AndersonIntegrator (sim/vbd/AndersonIntegrator.cpp:24-58): the reference's cube known answer and parity with
     the oracle on a cantilever where the window wraps around."""
