@@ -425,6 +425,13 @@ vbdx_status vbdx_xpbd_get_info(vbdx_xpbd* h, int64_t* out8);
 vbdx_status vbdx_xpbd_get_contact_state(vbdx_xpbd* h, int32_t* active, int32_t* nn, int64_t* nActive);
 /* graph/Color.h:45-135 on a graph in compressed sparse format (bindings/pypbat/graph/Color.cpp:28-60 greedy_color); host only */
 vbdx_status vbdx_graph_greedy_color(int64_t n, const int64_t* ptr, const int64_t* adj, int32_t ordering, int32_t selection, int64_t* colors_out);
+/* The same colouring computed on the device, for the selection that parallelises (FirstAvailable = 1: the smallest colour
+ * missing among the neighbours that come earlier in the visiting order depends on those neighbours only, so vertices are
+ * coloured in rounds as soon as theirs are -- the sequential result, vertex for vertex; rounds_out: how many rounds).
+ * LeastUsed (0), the reference's default, picks by a global running count and is inherently sequential: VBDX_UNSUPPORTED.
+ * E: 4 x nT column-major like vbdx_greedy_color (sim/vbd/Data.cpp:228-231 -> graph/Color.h:45-135). */
+vbdx_status vbdx_greedy_color_device(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int32_t device,
+                                     int64_t* colors_out, int32_t* rounds_out);
 
 /* Test hooks (GPU): the sweep's vertex-triangle contact term (csrc/contact.cuh, restating sim/vbd/Kernels.h:223-302) and its
  * area-scaled penalties (gpu/impl/vbd/Kernels.cuh:80-114) on caller-supplied inputs.  in28 = per pair xtv(3) xv(3) xtf(3 x 3,

@@ -135,6 +135,7 @@ SYMBOLS = {
     "vbdx_get_element_data": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbdx_get_colors": (C.c_int, [_H, C.c_void_p]),
     "vbdx_greedy_color": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vbdx_greedy_color_device": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vbdx_debug_contact_pairs": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
     "vbdx_debug_contact_penalties": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "vbdx_xpbd_desc_init": (None, [C.POINTER(XpbdDesc)]),

@@ -2719,6 +2719,74 @@ vbdx_status vbdx_greedy_color(int64_t nV, int64_t nT, const int64_t* E, int32_t 
 }  // extern "C"
 
 // ============================================================================================
+// greedy colouring on the device (coloring.cuh)
+// ============================================================================================
+#include "coloring.cuh"
+
+extern "C" vbdx_status vbdx_greedy_color_device(int64_t nV, int64_t nT, const int64_t* E, int32_t ordering, int32_t selection, int32_t device,
+                                                int64_t* colors_out, int32_t* rounds_out)
+{
+    using namespace vbdx;
+    return Guard([&] {
+        Require(nV > 0 && nT >= 0 && E && colors_out, "vbdx_greedy_color_device: bad arguments");
+        Require(ordering >= 0 && ordering <= 2, "unknown ordering strategy");
+        if (selection != 1)
+            throw Error(VBDX_UNSUPPORTED,
+                        "device colouring reproduces the sequential result for the FirstAvailable selection only: LeastUsed picks by a global running "
+                        "count of vertices per colour and is inherently sequential (use vbdx_greedy_color)");
+        Require(nV < (int64_t(1) << 31) && 4 * nT < (int64_t(1) << 32), "mesh too large");
+        std::vector<int32_t> E32(4 * static_cast<size_t>(nT));
+        for (int64_t k = 0; k < 4 * nT; ++k)
+        {
+            Require(E[k] >= 0 && E[k] < nV, "element index out of range");
+            E32[k] = static_cast<int32_t>(E[k]);
+        }
+        VBDX_CUDA(cudaSetDevice(device));
+        cudaStream_t s = nullptr;
+        DevBuf<int32_t> dE, dColors;
+        DevBuf<uint32_t> dPtr, dCursor, dAdj, dDeg, dScratch, dSmall;
+        int64_t const nEntries = 4 * nT;
+        dE.Alloc(std::max<size_t>(E32.size(), 1)), dColors.Alloc(nV), dPtr.Alloc(nV + 1), dCursor.Alloc(nV + 1), dAdj.Alloc(std::max<int64_t>(nEntries, 1));
+        dDeg.Alloc(nV), dScratch.Alloc((nV + 1) / kScanTile + 2), dSmall.Alloc(4);  // [0] max degree, [1] overflow, [2] coloured, [3] too many colours
+        if (nEntries)
+            dE.Upload(E32.data(), E32.size(), s);
+        VBDX_CUDA(cudaMemsetAsync(dCursor.p, 0, (nV + 1) * sizeof(uint32_t), s));
+        VBDX_CUDA(cudaMemsetAsync(dSmall.p, 0, 4 * sizeof(uint32_t), s));
+        VBDX_CUDA(cudaMemsetAsync(dColors.p, 0xff, nV * sizeof(int32_t), s));
+        if (nEntries)
+            CountIncidences<<<Blocks(nEntries, 256), 256, 0, s>>>(dE.p, nEntries, dCursor.p);
+        ExclusiveScanU32(dCursor.p, dPtr.p, nV + 1, dScratch.p, s);
+        VBDX_CUDA(cudaMemsetAsync(dCursor.p, 0, (nV + 1) * sizeof(uint32_t), s));
+        if (nEntries)
+            FillIncidences<<<Blocks(nEntries, 256), 256, 0, s>>>(dE.p, nEntries, dPtr.p, dCursor.p, dAdj.p);
+        ColorDegrees<<<Blocks(nV, 128), 128, 0, s>>>(nV, dE.p, dPtr.p, dAdj.p, dDeg.p, dSmall.p, dSmall.p + 1);
+        uint32_t small[4] = {0, 0, 0, 0};
+        int rounds        = 0;
+        for (;;)
+        {
+            for (int r = 0; r < 8; ++r, ++rounds)  // a few rounds per look at the counter
+                ColorRound<<<Blocks(nV, 128), 128, 0, s>>>(nV, dE.p, dPtr.p, dAdj.p, dDeg.p, dSmall.p, ordering, dColors.p, dSmall.p + 2, dSmall.p + 3);
+            VBDX_CUDA(cudaMemcpyAsync(small, dSmall.p, sizeof(small), cudaMemcpyDeviceToHost, s));
+            VBDX_CUDA(cudaStreamSynchronize(s));
+            if (small[1] != 0u)
+                throw Error(VBDX_UNSUPPORTED, "a vertex has more distinct neighbours than the device colouring handles (use vbdx_greedy_color)");
+            if (small[3] != 0u)
+                throw Error(VBDX_UNSUPPORTED, "more colours than the device colouring handles (use vbdx_greedy_color)");
+            if (static_cast<int64_t>(small[2]) >= nV)
+                break;
+            Require(rounds <= nV + 8, "internal error: device colouring does not progress");
+        }
+        std::vector<int32_t> c32(nV);
+        dColors.Download(c32.data(), nV, s);
+        VBDX_CUDA(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < nV; ++i)
+            colors_out[i] = c32[i];
+        if (rounds_out)
+            *rounds_out = rounds;
+    });
+}
+
+// ============================================================================================
 // XPBD (xpbd.cuh): host driver and C ABI
 // ============================================================================================
 #include "xpbd.cuh"

@@ -20,12 +20,18 @@ class GreedyColorSelectionStrategy(enum.IntEnum):
 
 
 def mesh_greedy_color(T, n_vertices, ordering=GreedyColorOrderingStrategy.LargestDegree,
-                      selection=GreedyColorSelectionStrategy.LeastUsed):
+                      selection=GreedyColorSelectionStrategy.LeastUsed, device=None):
     """Greedy colouring of the primal graph of a tet mesh ``T`` (4 x nT), exactly as
     ``Data::Construct`` obtains it (sim/vbd/Data.cpp:228-231 -> graph/Mesh.h:116-123,
-    graph/Color.h:45-135).  Host-only; needs no GPU."""
+    graph/Color.h:45-135).  On the host by default (needs no GPU); ``device=<cuda ordinal>`` computes the
+    same colouring on that GPU -- for ``FirstAvailable`` only (``LeastUsed`` is inherently sequential:
+    ``NotImplementedError``)."""
     T = np.ascontiguousarray(np.asarray(T, dtype=np.int64).T)  # column-major 4 x nT
     out = np.empty(n_vertices, dtype=np.int64)
+    if device is not None:
+        _lib.check(_lib.lib().vbdx_greedy_color_device(n_vertices, T.shape[0], T.ctypes.data, int(ordering), int(selection), int(device),
+                                                       out.ctypes.data, None))
+        return out
     _lib.check(_lib.lib().vbdx_greedy_color(n_vertices, T.shape[0], T.ctypes.data, int(ordering),
                                             int(selection), out.ctypes.data))
     return out

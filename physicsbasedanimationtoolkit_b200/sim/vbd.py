@@ -252,7 +252,9 @@ class Data:
         return self
 
     # ---- Data::Construct (sim/vbd/Data.cpp:179-308) --------------------------------------
-    def construct(self, validate=True):
+    def construct(self, validate=True, coloring_device=None):
+        """``Data::Construct`` (sim/vbd/Data.cpp:179-243).  ``coloring_device=<cuda ordinal>`` (extension) computes the vertex
+        colouring on that GPU instead of the host -- same colours; for the FirstAvailable selection only."""
         X, E = self.X, self.E
         nV, nT = X.shape[1], E.shape[1]
         if nT and (E.min() < 0 or E.max() >= nV):
@@ -285,7 +287,7 @@ class Data:
         self._lazy = {"GP", "GVG"}
         # colouring and partitions (sim/vbd/Data.cpp:228-231)
         self.colors = _graph.mesh_greedy_color(E, nV, self.vertex_coloring_ordering,
-                                               self.vertex_coloring_selection)
+                                               self.vertex_coloring_selection, device=coloring_device)
         nC = int(self.colors.max()) + 1 if nV else 0
         keep = np.ones(nV, dtype=bool)
         if self.dbc.size:  # sim/vbd/Data.cpp:236-243

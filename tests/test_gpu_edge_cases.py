@@ -185,3 +185,35 @@ def test_invalid_problems_are_rejected():
             vbd.step(*bad)
     vbd.step(0.01, 1, 1)                                                  # the handle survives the rejected calls
     assert np.isfinite(vbd.x).all()
+
+
+@pytest.mark.parametrize("ordering", [0, 1, 2])
+def test_device_colouring_equals_the_sequential_one(ordering):
+    """the greedy colouring on the device.  With the FirstAvailable selection a vertex' colour depends only
+    on the neighbours that come earlier in the visiting order, so colouring in rounds reproduces the sequential result
+    (graph/Color.h:45-135) vertex for vertex -- all three orderings; a grid, disconnected stacked bodies, a vertex of valence 80
+    next to isolated pieces.  LeastUsed, the reference's default, is inherently sequential and refused."""
+    G = pbat.graph
+    Xs, Ts = icosphere_star()
+    Xa, Ta = meshes.tet_grid(3, 3, 2, 0.2, origin=(2.0, 0.0, 0.0))
+    Xg, Tg = meshes.tet_grid(14, 11, 9, 0.1)
+    Xb, Tb, _ = meshes.stack_bodies(*meshes.tet_grid(5, 4, 3, 0.1), 3)
+    cases = [(Xg, Tg), (Xb, Tb), (np.concatenate([Xs, Xa], axis=1), np.concatenate([Ts, Ta + Xs.shape[1]], axis=1))]
+    for X, T in cases:
+        nV = X.shape[1]
+        host = G.mesh_greedy_color(T, nV, ordering, G.GreedyColorSelectionStrategy.FirstAvailable)
+        dev = G.mesh_greedy_color(T, nV, ordering, G.GreedyColorSelectionStrategy.FirstAvailable, device=0)
+        assert np.array_equal(host, dev)
+        for a in range(4):
+            for b in range(a + 1, 4):
+                assert (dev[T[a]] != dev[T[b]]).all()
+    with pytest.raises(NotImplementedError):
+        G.mesh_greedy_color(Tg, Xg.shape[1], 2, G.GreedyColorSelectionStrategy.LeastUsed, device=0)
+    # through Data.construct, and stepping with it
+    d = (pbat.sim.vbd.Data().with_volume_mesh(Xg, Tg).with_dirichlet_vertices(np.flatnonzero(Xg[2] == 0))
+         .with_vertex_coloring_strategy(G.GreedyColorOrderingStrategy(ordering), G.GreedyColorSelectionStrategy.FirstAvailable)
+         .construct(coloring_device=0))
+    assert np.array_equal(d.colors, G.mesh_greedy_color(Tg, Xg.shape[1], ordering, G.GreedyColorSelectionStrategy.FirstAvailable))
+    vbd = pbat.gpu.vbd.Integrator(d)
+    vbd.step(0.01, 5, 1)
+    assert np.isfinite(vbd.x).all()
