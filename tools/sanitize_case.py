@@ -69,4 +69,6 @@ bvh = pbat.gpu.geometry.Bvh(F.shape[1], 64 * F.shape[1])
 bvh.build(aabbs, Xc.min(axis=1), Xc.max(axis=1))
 bvh.detect_overlaps(aabbs)
 bvh.point_triangle_nearest_neighbours(aabbs, Xc[:, :5], Xc, F)
+# greedy colouring on the device (FirstAvailable)
+assert np.array_equal(pbat.graph.mesh_greedy_color(T, X.shape[1], 2, 1, device=0), pbat.graph.mesh_greedy_color(T, X.shape[1], 2, 1))
 print("sanitize_case: done")
