@@ -246,9 +246,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries ONE JSON line: NCCL's version banner / warnings (NCCL_DEBUG=VERSION or WARN print there) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries ONE JSON line: NCCL prints its version banner there when the first communicator is created
+        # (NCCL_DEBUG=VERSION/WARN) -- send file descriptor 1 to stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         torch.cuda.synchronize()
