@@ -177,3 +177,11 @@ def test_graph_helpers_and_xpbd_data():
         pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_mass_inverse(np.ones(3)).construct()
     with pytest.raises(ValueError):
         pbat.sim.xpbd.Data().with_volume_mesh(X, T).with_surface_mesh(np.arange(4), np.zeros((3, 1), int)).with_collision_penalties(np.ones(2)).construct()
+
+
+def test_device_colouring_refuses_the_sequential_selection_without_touching_a_gpu():
+    """vbdx_greedy_color_device: the LeastUsed selection is inherently sequential (a global running count per colour) and is
+    refused up front -- VBDX_UNSUPPORTED -> NotImplementedError, before any CUDA call (so also on a box without a GPU)."""
+    X, T = meshes.tet_grid(3, 2, 2, 0.1)
+    with pytest.raises(NotImplementedError, match="sequential"):
+        pbat.graph.mesh_greedy_color(T, X.shape[1], 2, pbat.graph.GreedyColorSelectionStrategy.LeastUsed, device=0)
