@@ -9,11 +9,13 @@ Stable Neo-Hookean, 30 iterations/step, Chebyshev rho = 0.9, z = 0 face fixed.
 
   value      vertex-iterations/s, state resident in HBM, device-timed (CUDA events), max over ranks
   e2e        same metric through the public Python/C-ABI call with HOST buffers: every step
-             uploads positions from pinned host memory, steps, and reads positions back
+             uploads positions from pinned host memory, steps, and reads positions back (enqueued with the
+             asynchronous calls, one vbdx_synchronize per step: the host holds the result when the step returns)
   roofline   bytes the record format must move per launch / kernel time, with the SURVEY.md 8(d)
              figure beside it (frac_survey_formula) and the DRAM traffic ncu measured for this configuration
              (profiles/traffic.json, keyed by workload and GPU count)
   cpu_baseline  the reference's CPU arithmetic (oracle/_ref, OpenMP over each colour) on this host
+  colouring_first_available   (N = 1) the same workload under the reference's other colour selection (4 colours instead of 7)
 
 N > 1 (one process per GPU, torch.distributed/NCCL for set-up and timing only):
   main line  one mesh domain-decomposed over the GPUs: a beam of N x 58^3 cubes, one 58^3 slab (the N = 1
